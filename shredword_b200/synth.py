@@ -1,0 +1,192 @@
+"""Seeded synthetic corpora for the BPE trainer/encoder hot path.
+
+The reference ships no corpus; BASELINE.json's configs are all "synthetic Zipfian" text.
+This module is the single generator used by tests/, bench.py and the golden-vector script,
+so that a (config, seed) pair names exactly one byte string everywhere.
+
+Shape of the text: lines of 12 space-separated words, '\\n'-terminated. Word types are drawn
+once per corpus; a type's rank-k probability is proportional to k**-s (Zipf, s = 1.1).
+  * alphabet "ascii":  letters a-z, letter i drawn with probability ~ 1/(i+1), length U[1,11].
+  * alphabet "multi":  60 % ASCII types + 40 % types over Cyrillic / Greek / CJK code points
+                       (2-3 byte UTF-8), for config 5's long low-frequency tail.
+"""
+from __future__ import annotations
+
+import io
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+WORDS_PER_LINE = 12
+MAX_LEN = 11
+
+
+@dataclass(frozen=True)
+class CorpusSpec:
+  name: str
+  nbytes: int
+  n_types: int
+  alphabet: str = "ascii"
+  zipf_s: float = 1.1
+  seed: int = 7
+
+
+# BASELINE.json configs -> generator parameters.
+CONFIGS = {
+  "config1_10MB": CorpusSpec("config1_10MB", 10 * 1000 * 1000, 200_000, "ascii", 1.1, 7),
+  "config2_1GB": CorpusSpec("config2_1GB", 1000 * 1000 * 1000, 2_000_000, "ascii", 1.1, 11),
+  "config3_10GB": CorpusSpec("config3_10GB", 10 * 1000 * 1000 * 1000, 5_000_000, "ascii", 1.1, 13),
+  "config5_50GB": CorpusSpec("config5_50GB", 50 * 1000 * 1000 * 1000, 20_000_000, "multi", 1.1, 17),
+}
+
+
+def _ascii_types(rng: np.random.Generator, n: int):
+  """n word types over a-z; returns (padded uint8 matrix [n, W], lengths [n])."""
+  lens = rng.integers(1, MAX_LEN + 1, size=n)
+  p = 1.0 / np.arange(1, 27)
+  p /= p.sum()
+  letters = rng.choice(26, size=(n, MAX_LEN), p=p).astype(np.uint8) + ord("a")
+  return letters, lens.astype(np.int64)
+
+
+_MULTI_RANGES = [
+  (0x0430, 0x044F),  # Cyrillic small letters (2-byte UTF-8)
+  (0x03B1, 0x03C9),  # Greek small letters (2-byte)
+  (0x4E00, 0x4FFF),  # CJK unified ideographs, first 512 (3-byte)
+]
+
+
+def _multi_types(rng: np.random.Generator, n: int):
+  """n word types over non-ASCII scripts; each type is 1..5 code points of one script."""
+  width = 15
+  mat = np.zeros((n, width), dtype=np.uint8)
+  lens = np.zeros(n, dtype=np.int64)
+  script = rng.integers(0, len(_MULTI_RANGES), size=n)
+  ncp = rng.integers(1, 6, size=n)
+  for s, (lo, hi) in enumerate(_MULTI_RANGES):
+    rows = np.nonzero(script == s)[0]
+    if rows.size == 0:
+      continue
+    span = hi - lo + 1
+    pr = 1.0 / np.arange(1, span + 1)
+    pr /= pr.sum()
+    cps = rng.choice(span, size=(rows.size, 5), p=pr) + lo
+    if hi < 0x800:  # 2-byte sequences
+      b0 = (0xC0 | (cps >> 6)).astype(np.uint8)
+      b1 = (0x80 | (cps & 0x3F)).astype(np.uint8)
+      enc = np.stack([b0, b1], axis=2).reshape(rows.size, 10)
+      per = 2
+    else:  # 3-byte sequences
+      b0 = (0xE0 | (cps >> 12)).astype(np.uint8)
+      b1 = (0x80 | ((cps >> 6) & 0x3F)).astype(np.uint8)
+      b2 = (0x80 | (cps & 0x3F)).astype(np.uint8)
+      enc = np.stack([b0, b1, b2], axis=2).reshape(rows.size, 15)
+      per = 3
+    mat[rows, : enc.shape[1]] = enc
+    lens[rows] = ncp[rows] * per
+  return mat, lens
+
+
+def make_types(spec: CorpusSpec, rng: np.random.Generator):
+  """Returns (matrix [n_types, W+1] with a separator slot after each word, lens)."""
+  if spec.alphabet == "ascii":
+    mat, lens = _ascii_types(rng, spec.n_types)
+  elif spec.alphabet == "multi":
+    n_multi = int(spec.n_types * 0.4)
+    a_mat, a_lens = _ascii_types(rng, spec.n_types - n_multi)
+    m_mat, m_lens = _multi_types(rng, n_multi)
+    width = max(a_mat.shape[1], m_mat.shape[1])
+    mat = np.zeros((spec.n_types, width), dtype=np.uint8)
+    mat[: a_mat.shape[0], : a_mat.shape[1]] = a_mat
+    mat[a_mat.shape[0]:, : m_mat.shape[1]] = m_mat
+    lens = np.concatenate([a_lens, m_lens])
+    perm = rng.permutation(spec.n_types)  # interleave scripts over the Zipf ranks
+    mat, lens = mat[perm], lens[perm]
+  else:
+    raise ValueError(f"unknown alphabet {spec.alphabet!r}")
+  out = np.zeros((mat.shape[0], mat.shape[1] + 1), dtype=np.uint8)
+  out[:, : mat.shape[1]] = mat
+  return out, lens
+
+
+def generate(spec: CorpusSpec, chunk_words: int = 2_000_000):
+  """Yields consecutive uint8 chunks of the corpus; total length == spec.nbytes exactly.
+
+  The last line is cut at spec.nbytes and terminated with '\\n' (a cut word is still a word)."""
+  rng = np.random.default_rng(spec.seed)
+  mat, lens = make_types(spec, rng)
+  width = mat.shape[1]
+  ranks = np.arange(1, spec.n_types + 1, dtype=np.float64)
+  cdf = np.cumsum(ranks ** (-spec.zipf_s))
+  cdf /= cdf[-1]
+  cols = np.arange(width)[None, :]
+  produced = 0
+  word_no = 0
+  while produced < spec.nbytes:
+    u = rng.random(chunk_words)
+    idx = np.searchsorted(cdf, u, side="right")
+    np.minimum(idx, spec.n_types - 1, out=idx)
+    rows = mat[idx]  # [chunk, width]
+    l = lens[idx]
+    sep = np.full(chunk_words, ord(" "), dtype=np.uint8)
+    eol = (np.arange(word_no, word_no + chunk_words) % WORDS_PER_LINE) == WORDS_PER_LINE - 1
+    sep[eol] = ord("\n")
+    rows[np.arange(chunk_words), l] = sep
+    flat = rows[cols <= l[:, None]]
+    word_no += chunk_words
+    if produced + flat.size >= spec.nbytes:
+      flat = flat[: spec.nbytes - produced].copy()
+      flat[-1] = ord("\n")
+    produced += flat.size
+    yield flat
+
+
+def corpus_bytes(spec: CorpusSpec) -> np.ndarray:
+  """Whole corpus as one uint8 array (use only for sizes that fit in host memory)."""
+  out = np.empty(spec.nbytes, dtype=np.uint8)
+  pos = 0
+  for chunk in generate(spec):
+    out[pos: pos + chunk.size] = chunk
+    pos += chunk.size
+  assert pos == spec.nbytes
+  return out
+
+
+def write_corpus(spec: CorpusSpec, path: str) -> str:
+  """Writes the corpus to `path` unless a file of the right size is already there."""
+  if os.path.exists(path) and os.path.getsize(path) == spec.nbytes:
+    return path
+  tmp = path + ".tmp"
+  with open(tmp, "wb") as f:
+    for chunk in generate(spec):
+      f.write(chunk.tobytes())
+  os.replace(tmp, path)
+  return path
+
+
+def small_spec(nbytes: int, n_types: int, seed: int, alphabet: str = "ascii", name: str | None = None) -> CorpusSpec:
+  return CorpusSpec(name or f"synth_{alphabet}_{nbytes}_{n_types}_{seed}", nbytes, n_types, alphabet, 1.1, seed)
+
+
+def reference_test_corpus() -> bytes:
+  """The fixture of the reference's own test (reference test/bpe_test.cpp:31-56), restated."""
+  buf = io.StringIO()
+  for line in (
+    "the quick brown fox jumps over the lazy dog",
+    "the brown fox is quick and the dog is lazy",
+    "quick brown foxes jump over lazy dogs",
+    "the the the quick quick brown brown fox fox",
+    "jumping foxes are quick brown animals",
+    "lazy dogs sleep under the brown tree",
+    "the quick fox and the lazy dog are friends",
+    "brown and quick describe the fox perfectly",
+    "the lazy dog watches the quick brown fox",
+    "quick movements by the brown fox surprise the dog",
+  ):
+    buf.write(line + "\n")
+  for _ in range(20):
+    buf.write("hello world hello world programming programming\n")
+    buf.write("testing testing the the quick quick brown brown\n")
+    buf.write("algorithm algorithm implementation implementation\n")
+  return buf.getvalue().encode("ascii")
