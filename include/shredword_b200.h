@@ -1,0 +1,181 @@
+/* shredword_b200.h -- C-ABI of shredword_b200/libtrainer.so
+ *
+ * A B200-native (sm_100a) replacement for the native core behind ShredWord's
+ * `shredword.trainer.BPETrainer`. Part 1 below is, symbol for symbol, what the
+ * reference's ctypes binding loads (reference shredword/cbase.py:44-59, declared in
+ * reference shredword/csrc/bpe/bpe.h:62-72): a maintainer drops this library into the
+ * reference package directory as `libtrainer.so` and nothing else changes
+ * (INTEGRATION.md). Part 2 is additive (the reference has no such entry points):
+ * host/device buffer loading, result accessors, the rank-ordered encoder, and the
+ * building blocks of the multi-GPU merge loop.
+ *
+ * All signatures are plain C: pointers, sizes, fixed-width integers. No torch types.
+ * Every compute entry point needs a CUDA device; without one it fails loudly
+ * (error return + message from swb_last_error()), never by falling back to the CPU.
+ */
+#ifndef SHREDWORD_B200_H
+#define SHREDWORD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ Part 1: reference ABI */
+
+/* reference csrc/bpe/hash.h:27-29 */
+typedef struct PairKey { int32_t first, second; } PairKey;
+
+/* reference csrc/bpe/heap.h:17-21 (24 bytes) */
+typedef struct HeapEntry { PairKey key; uint64_t freq; uint32_t version; } HeapEntry;
+
+/* reference csrc/bpe/heap.h:23-27. Live: `data[0..size)` is the exact binary-heap array the
+ * reference would hold at the same point (same order, same ties). */
+typedef struct MaxHeap { HeapEntry *data; size_t size; size_t cap; } MaxHeap;
+
+/* reference csrc/bpe/bpe.h:37-41. `vocab_size` (unique words) and `word_counts` (host mirror, in
+ * reference word order) are live. `words` is an OPAQUE non-NULL handle once a corpus is loaded:
+ * the word table lives in HBM, not in malloc'd Symbol chains; use swb_get_words(). */
+typedef struct Corpus { void **words; uint64_t *word_counts; size_t vocab_size; } Corpus;
+
+/* reference csrc/bpe/hash.h:41-44 (field-less in cbase.py:33). Not populated: the pair table
+ * is an open-addressing map inside the handle. nbuckets is kept at 4096 for readers. */
+typedef struct BIMap { void **buckets; size_t nbuckets; } BIMap;
+
+/* reference csrc/bpe/bpe.h:43-48, cbase.py:40 (24 bytes: size_t @0, int32 @8, float @12, uint64 @16) */
+typedef struct BPEConfig {
+  size_t target_vocab_size;
+  int32_t unk_id;            /* id given to bytes dropped by character_coverage */
+  float character_coverage;  /* outside (0,1) -> 0.995 (reference bpe.cpp:124-126) */
+  uint64_t min_pair_freq;    /* 0 -> 2000 (reference bpe.cpp:128-130) */
+} BPEConfig;
+
+/* reference csrc/bpe/bpe.h:50-60: same field order and offsets (config 0, heap 24, corpus 48,
+ * bigram_map 72, next_token 88, num_merges 96, merge_ops 104, token_strs 112, token_freq 120),
+ * so code that peeks at config / heap / num_merges / merge_ops (reference test/bpe_test.cpp)
+ * keeps working. `impl` (offset 128) is private. */
+typedef struct Trainer {
+  BPEConfig config;
+  MaxHeap heap;
+  Corpus corpus;
+  BIMap bigram_map;
+  size_t next_token;
+  size_t num_merges;
+  PairKey *merge_ops;   /* merge_ops[m] = pair merged into id 256+m, m < num_merges */
+  char **token_strs;    /* unused by the reference too (bpe.h:58) */
+  uint64_t *token_freq; /* unused by the reference too (bpe.h:59) */
+  void *impl;
+} Trainer;
+
+/* reference bpe.cpp:112-136. NULL config -> returns NULL (the reference exit()s; trainer.py:14
+ * already turns NULL into RuntimeError). */
+Trainer *create_trainer(const BPEConfig *config);
+/* reference bpe.cpp:148-158. NULL is ignored (the reference exit()s). */
+void bpe_trainer_destroy(Trainer *trainer);
+/* reference bpe.cpp:208-297. 0 on success, -1 on error (missing file, no CUDA device,
+ * NUL byte in the corpus). Reads the file, builds the unique-word table in HBM. */
+int bpe_load_corpus(Trainer *trainer, const char *input_path);
+/* reference bpe.cpp:171-185: reset pair table + heap, recount. */
+void bpe_init(Trainer *trainer);
+/* reference bpe.cpp:315-370: count adjacent pairs, push those with freq >= min_pair_freq. */
+void bpe_count_bigrams(Trainer *trainer);
+/* reference bpe.cpp:391-535: up to batch_size merges; returns merges done, -1 on NULL / device error. */
+int bpe_merge_batch(Trainer *trainer, int batch_size);
+/* reference bpe.cpp:597-655: bpe_init + merges until target_vocab_size-256 or heap exhausted. */
+int bpe_train(Trainer *trainer);
+/* reference bpe.cpp:678-739: vocab text file + binary merge file, byte-identical formats. */
+void bpe_save(const Trainer *trainer, const char *model_path, const char *vocab_path);
+
+/* ------------------------------------------------------------------ Part 2: additive */
+
+/* Last error message of the calling thread ("" if none). */
+const char *swb_last_error(void);
+/* 0 = silent (default), 1 = the reference's [INFO]/[MERGE] lines on stdout. Env SHREDWORD_LOG=1 too. */
+void swb_set_log_level(int level);
+/* Number of visible CUDA devices (0 when there is none / no driver). Never throws. */
+int swb_device_count(void);
+/* Select the device used by handles created afterwards on this thread (default 0). */
+int swb_set_device(int device);
+
+/* Same as bpe_load_corpus but from memory. `data` is a HOST pointer (pinned or pageable) for
+ * _buffer and a DEVICE pointer for _device (the bytes are only read, never kept). */
+int swb_load_corpus_buffer(Trainer *trainer, const void *data, size_t nbytes);
+int swb_load_corpus_device(Trainer *trainer, const void *device_data, size_t nbytes);
+
+/* Results. Merges are (a, b, new_id) triples in rank order (README.md:95 of the reference). */
+size_t swb_num_merges(const Trainer *trainer);
+size_t swb_get_merges(const Trainer *trainer, int32_t *out_triples, size_t cap_triples);
+/* Bytes of token `id` (true bytes: unlike the .vocab file, not cut at NUL). Returns the length. */
+size_t swb_token_bytes(const Trainer *trainer, int32_t id, uint8_t *out, size_t cap);
+/* byte -> initial id map after character_coverage (identity for kept bytes, unk_id otherwise). */
+void swb_get_byte_map(const Trainer *trainer, int32_t *out256);
+/* Token histogram of the current segmentation (the .vocab frequency column), ids < 256+num_merges. */
+int swb_token_freq(const Trainer *trainer, uint64_t *out, size_t cap);
+
+/* Word table, in reference word order (device -> host copy; for tests and tools).
+ * Pass NULL for parts you do not need. Sizes: swb_num_words / swb_num_symbols / swb_word_bytes_total. */
+size_t swb_num_words(const Trainer *trainer);
+size_t swb_num_symbols(const Trainer *trainer); /* live symbols */
+size_t swb_word_bytes_total(const Trainer *trainer);
+int swb_get_words(const Trainer *trainer, uint64_t *byte_off /*[W+1]*/, uint8_t *bytes,
+                  uint64_t *sym_off /*[W+1]*/, int32_t *syms, uint64_t *counts /*[W]*/);
+
+/* Counters of the device work done so far by this handle. */
+typedef struct SwbStats {
+  uint64_t kernel_launches;   /* kernels of this library launched */
+  uint64_t merge_launches;    /* launches of the merge-scan kernel */
+  double load_ms, count_ms, merge_ms;  /* host wall time per phase (includes syncs) */
+  double merge_kernel_ms;     /* device time of the merge-scan kernel (CUDA events), if enabled */
+  uint64_t merge_scan_bytes;  /* sum over merges of bytes the scan kernel was launched over */
+  uint64_t merge_alg_bytes;   /* sum over merges of 4*S_live + 8*W */
+  uint64_t rows, live_symbols, words, long_words;
+  uint64_t repacks;
+} SwbStats;
+void swb_get_stats(const Trainer *trainer, SwbStats *out);
+/* 1: bracket every merge-scan launch with CUDA events (adds a little latency); 0: off (default). */
+void swb_set_kernel_timing(Trainer *trainer, int enabled);
+
+/* ---- encoder (no reference entry point exists; semantics: reference base.py:10-36 applied
+ * lowest merge rank first, per whitespace-delimited word; delimiters \t \r \n space) ---- */
+typedef struct SwbEncoder SwbEncoder;
+SwbEncoder *swb_encoder_create(const int32_t *merge_triples, size_t n_merges, const int32_t *byte_map256);
+SwbEncoder *swb_encoder_from_trainer(const Trainer *trainer);
+void swb_encoder_destroy(SwbEncoder *enc);
+/* Encodes host text. Token ids of all words, in order, go to out_ids (capacity cap_ids);
+ * if word_ntok != NULL it receives the token count of each word (capacity cap_words).
+ * Returns the number of tokens, or -1 on error (then see swb_last_error; capacity too small
+ * is an error: nothing partial is returned). *n_words receives the number of words. */
+int64_t swb_encode(SwbEncoder *enc, const void *text, size_t nbytes, int32_t *out_ids, size_t cap_ids,
+                   uint32_t *word_ntok, size_t cap_words, size_t *n_words);
+/* Same with device pointers (text, out_ids, word_ntok all in device memory). */
+int64_t swb_encode_device(SwbEncoder *enc, const void *d_text, size_t nbytes, int32_t *d_out_ids, size_t cap_ids,
+                          uint32_t *d_word_ntok, size_t cap_words, size_t *n_words);
+/* ids -> bytes on the host (table lookup; not a device path). Returns the byte count. */
+size_t swb_decode(const SwbEncoder *enc, const int32_t *ids, size_t n, uint8_t *out, size_t cap);
+uint64_t swb_encoder_kernel_launches(const SwbEncoder *enc);
+
+/* ---- building blocks of the multi-GPU merge loop ----
+ * Unique words are sharded over ranks (word wi belongs to rank wi % nranks); every rank keeps an
+ * identical replica of the pair table + heap. A record is 4 x int64: first, second, delta, key
+ * (key = global first-touch order; for the count pass delta is the weighted frequency).
+ * The swb_dist_* host functions need no GPU; the swb_shard_* functions run this rank's kernels. */
+int swb_set_shard(Trainer *trainer, int rank, int nranks);     /* before loading the corpus */
+/* Reduce concatenated per-rank record lists by pair: sum delta, min key. Returns the new count. */
+size_t swb_dist_reduce_records(int64_t *recs, size_t n);
+/* Replica step 1: reset pair table + heap and seed them from the reduced count records. */
+void swb_dist_seed(Trainer *trainer, const int64_t *recs, size_t n);
+/* Replica step 2: pop until a valid pair; 1 = (a, b, new_id) filled and recorded, 0 = heap exhausted. */
+int swb_dist_next_merge(Trainer *trainer, int32_t *a, int32_t *b, int32_t *new_id);
+/* Replica step 3: apply the reduced delta records of the merge returned by step 2. */
+void swb_dist_apply(Trainer *trainer, const int64_t *recs, size_t n);
+/* This rank's kernels: local pair count / local merge of (a,b)->new_id. Return the record count
+ * (-1 on error); records are written to recs (capacity cap records). */
+int64_t swb_shard_count(Trainer *trainer, int64_t *recs, size_t cap);
+int64_t swb_shard_merge(Trainer *trainer, int32_t a, int32_t b, int32_t new_id, int64_t *recs, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHREDWORD_B200_H */

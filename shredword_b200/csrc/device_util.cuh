@@ -1,0 +1,118 @@
+// device_util.cuh -- error handling, RAII device/pinned buffers, shared constants.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace swb {
+
+struct Error : std::runtime_error {
+  explicit Error(const std::string &m) : std::runtime_error(m) {}
+};
+
+#define SWB_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      throw ::swb::Error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " +       \
+                         __FILE__ + ":" + std::to_string(__LINE__) + " (" #call ")");           \
+  } while (0)
+
+template <typename T>
+class DevBuf {
+ public:
+  DevBuf() = default;
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) { release(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    if (n) {
+      void *p = nullptr;
+      cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+      if (e != cudaSuccess)
+        throw Error(std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e));
+      p_ = (T *)p;
+    }
+    n_ = n;
+  }
+  void release() {
+    if (p_) cudaFree(p_);
+    p_ = nullptr; n_ = 0;
+  }
+  T *get() const { return p_; }
+  size_t size() const { return n_; }
+  size_t bytes() const { return n_ * sizeof(T); }
+
+ private:
+  T *p_ = nullptr;
+  size_t n_ = 0;
+};
+
+// Pinned, device-mapped host memory: kernels write results straight into it, the host reads them
+// after one stream synchronize (no separate D2H copy on the per-merge critical path).
+template <typename T>
+class PinnedBuf {
+ public:
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf &) = delete;
+  PinnedBuf &operator=(const PinnedBuf &) = delete;
+  ~PinnedBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    if (n) {
+      void *p = nullptr;
+      SWB_CUDA(cudaHostAlloc(&p, n * sizeof(T), cudaHostAllocMapped));
+      h_ = (T *)p;
+      void *d = nullptr;
+      SWB_CUDA(cudaHostGetDevicePointer(&d, p, 0));
+      d_ = (T *)d;
+    }
+    n_ = n;
+  }
+  void release() {
+    if (h_) cudaFreeHost(h_);
+    h_ = nullptr; d_ = nullptr; n_ = 0;
+  }
+  T *host() const { return h_; }
+  T *dev() const { return d_; }
+  size_t size() const { return n_; }
+
+ private:
+  T *h_ = nullptr, *d_ = nullptr;
+  size_t n_ = 0;
+};
+
+// ---- symbol stream constants (see DESIGN.md "Data layout in HBM")
+constexpr int ROW = 128;                       // symbols per row; a word never straddles a row
+constexpr int32_t PAD = (int32_t)0x80000000;   // filler after the last live symbol of a word / row
+constexpr int32_t UNK_CODE = 0x7FFFFFFE;       // device-side stand-in for a NEGATIVE unk_id
+// header of word with local index w is ~w (negative, never PAD)
+
+__host__ __device__ __forceinline__ uint64_t dmix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+__host__ __device__ __forceinline__ bool is_delim(uint8_t c) {  // reference bpe.cpp:247 "\t\r\n "
+  return c == ' ' || c == '\n' || c == '\t' || c == '\r';
+}
+// first-touch key: word index major, then position, then slot (order of the 4 delta adds of a match)
+__host__ __device__ __forceinline__ uint64_t touch_key(uint64_t wi, uint32_t pos, uint32_t slot) {
+  return (wi << 30) | ((uint64_t)pos << 2) | slot;
+}
+
+struct CastU32ToU64 {
+  __host__ __device__ unsigned long long operator()(const uint32_t &x) const { return (unsigned long long)x; }
+};
+
+}  // namespace swb

@@ -1,0 +1,388 @@
+// encoder_impl.cuh -- rank-ordered BPE encoder on the device.
+//
+// The reference has no encoder (reference shredword/base.py:107-109 raises NotImplementedError);
+// the step is defined by its helpers get_stats (base.py:10-20) and merge (base.py:22-36): per
+// whitespace-delimited word, repeatedly take the adjacent pair with the lowest merge rank and replace
+// all its non-overlapping occurrences left to right. Applied to a training word this reproduces the
+// trainer's final segmentation of that word (a merge of rank r only creates pairs containing id
+// 256+r, which can only match ranks > r), which is how the tests pin it.
+//
+// Three kernels per chunk of text:
+//   enc_words  : 16 bytes per thread -> delimiter bit-mask -> word list in shared memory -> one thread
+//                encodes one word in shared memory (merge-rank table: 16-byte slots, L2 resident) and
+//                parks the tokens in tmp[word start ...] (a word of L bytes yields <= L tokens, so the
+//                regions never collide); tmp[start+L-1] = -(ntok)-1 when ntok < L.
+//   (scan)     : per-tile token / word totals -> exclusive offsets
+//   enc_gather : re-derives the word starts, block-scans the per-word token counts and writes the
+//                compact id stream plus the optional per-word token counts.
+#pragma once
+
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "device_util.cuh"
+
+namespace swb {
+
+constexpr int ENC_THREADS = 256;
+constexpr int ENC_TILE = ENC_THREADS * 16;  // bytes per block iteration
+constexpr int ENC_SHORT = 64;               // words up to this many bytes are encoded in shared memory
+constexpr uint32_t RANK_NONE = 0xFFFFFFFFu;
+
+struct RankSlot { unsigned long long key; unsigned long long val; };  // val = rank << 32 | new_id
+struct RankTableDev { const RankSlot *slots; uint32_t mask; };
+
+__device__ __forceinline__ unsigned long long enc_lookup(const RankTableDev &t, int a, int b) {
+  const unsigned long long k = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
+  uint32_t h = (uint32_t)dmix64(k) & t.mask;
+  for (;;) {
+    const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2 *>(t.slots + h));
+    if (s.x == k) return s.y;
+    if (s.x == ~0ull) return ~0ull;
+    h = (h + 1) & t.mask;
+  }
+}
+
+// In-place rank-ordered merge of ids[0..L). Returns the new length.
+__device__ __forceinline__ uint32_t enc_word(int *ids, uint32_t L, const RankTableDev &t) {
+  while (L >= 2) {
+    unsigned long long best = ~0ull;
+    uint32_t kb = 0;
+    for (uint32_t k = 0; k + 1 < L; k++) {
+      const unsigned long long v = enc_lookup(t, ids[k], ids[k + 1]);
+      if (v < best) { best = v; kb = k; }  // rank is in the high half: lowest rank wins, leftmost on ties
+    }
+    if (best == ~0ull) break;
+    const int a = ids[kb], b = ids[kb + 1], nid = (int)(uint32_t)(best & 0xFFFFFFFFu);
+    uint32_t w = 0, r = 0;
+    while (r < L) {
+      if (r + 1 < L && ids[r] == a && ids[r + 1] == b) { ids[w++] = nid; r += 2; }
+      else ids[w++] = ids[r++];
+    }
+    L = w;
+  }
+  return L;
+}
+
+__device__ __forceinline__ uint32_t enc_delim_bits(uint32_t w) {
+  const uint32_t m = __vcmpeq4(w, 0x20202020u) | __vcmpeq4(w, 0x0a0a0a0au) | __vcmpeq4(w, 0x09090909u) |
+                     __vcmpeq4(w, 0x0d0d0d0du);
+  return ((m & 0x01010101u) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint32_t enc_starts(const uint8_t *__restrict__ text, uint64_t seg) {
+  const uint4 v = *reinterpret_cast<const uint4 *>(text + seg * 16);
+  const uint32_t dm = enc_delim_bits(v.x) | (enc_delim_bits(v.y) << 4) | (enc_delim_bits(v.z) << 8) | (enc_delim_bits(v.w) << 12);
+  const uint32_t prev_delim = (seg == 0) ? 1u : (is_delim(text[seg * 16 - 1]) ? 1u : 0u);
+  return ~dm & ((dm << 1) | prev_delim) & 0xFFFFu;
+}
+__device__ __forceinline__ uint32_t enc_word_len(const uint8_t *__restrict__ text, uint64_t off, uint64_t n) {
+  uint64_t i = off;
+  while (i < n && !is_delim(text[i])) ++i;
+  return (uint32_t)(i - off);
+}
+
+// text: n bytes, 16-byte aligned, followed by >= 16 bytes of ' '. One tile per block iteration.
+__global__ void __launch_bounds__(ENC_THREADS)
+enc_words(const uint8_t *__restrict__ text, uint64_t n, RankTableDev tbl, const int32_t *__restrict__ byte_map,
+          int32_t *__restrict__ tmp, uint32_t *__restrict__ tile_ntok, uint32_t *__restrict__ tile_nwords) {
+  __shared__ int stok[ENC_TILE + ENC_SHORT];
+  __shared__ uint16_t wstart[ENC_TILE / 2];
+  __shared__ int32_t bmap[256];
+  __shared__ unsigned int s_nwords, s_ntok;
+  for (int i = threadIdx.x; i < 256; i += ENC_THREADS) bmap[i] = byte_map[i];
+  const uint64_t n_tiles = (n + ENC_TILE - 1) / ENC_TILE;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (threadIdx.x == 0) { s_nwords = 0; s_ntok = 0; }
+    __syncthreads();
+    const uint64_t seg = tile * ENC_THREADS + threadIdx.x;
+    if (seg * 16 < n) {
+      uint32_t starts = enc_starts(text, seg);
+      if (starts) {
+        const int c = __popc(starts);
+        unsigned int base = atomicAdd(&s_nwords, (unsigned int)c);  // order inside the tile is irrelevant here
+        while (starts) {
+          const int s = __ffs(starts) - 1;
+          starts &= starts - 1;
+          if (seg * 16 + s < n) wstart[base++] = (uint16_t)(threadIdx.x * 16 + s);
+          else atomicSub(&s_nwords, 1u);
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned int nw = s_nwords;
+    unsigned int my_tok = 0;
+    for (unsigned int j = threadIdx.x; j < nw; j += ENC_THREADS) {
+      const uint32_t rel = wstart[j];
+      const uint64_t off = tile * ENC_TILE + rel;
+      const uint32_t L = enc_word_len(text, off, n);
+      uint32_t nt;
+      if (L <= ENC_SHORT) {
+        int *ids = stok + rel;
+        for (uint32_t k = 0; k < L; k++) ids[k] = bmap[text[off + k]];
+        nt = enc_word(ids, L, tbl);
+        for (uint32_t k = 0; k < nt; k++) tmp[off + k] = ids[k];
+      } else {  // long word: encode in place in global memory
+        int *ids = tmp + off;
+        for (uint32_t k = 0; k < L; k++) ids[k] = bmap[text[off + k]];
+        nt = enc_word(ids, L, tbl);
+      }
+      if (nt < L) tmp[off + L - 1] = -(int)nt - 1;
+      my_tok += nt;
+    }
+    if (my_tok) atomicAdd(&s_ntok, my_tok);
+    __syncthreads();
+    if (threadIdx.x == 0) { tile_ntok[tile] = s_ntok; tile_nwords[tile] = nw; }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_tot /* [ENC_THREADS/32] shared */, uint32_t &total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < ENC_THREADS / 32; i++) { if (i < w) base += warp_tot[i]; tot += warp_tot[i]; }
+  __syncthreads();
+  total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS)
+enc_gather(const uint8_t *__restrict__ text, uint64_t n, const int32_t *__restrict__ tmp,
+           const unsigned long long *__restrict__ tile_tok_off, const unsigned long long *__restrict__ tile_word_off,
+           unsigned long long tok_base, unsigned long long word_base, int32_t *__restrict__ out, uint64_t cap_ids,
+           uint32_t *__restrict__ word_ntok, uint64_t cap_words, int32_t neg_id) {
+  __shared__ uint32_t wt[ENC_THREADS / 32];
+  const uint64_t n_tiles = (n + ENC_TILE - 1) / ENC_TILE;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t seg = tile * ENC_THREADS + threadIdx.x;
+    uint32_t starts = (seg * 16 < n) ? enc_starts(text, seg) : 0u;
+    uint32_t ntoks[8];  // at most 8 word starts in 16 bytes
+    uint32_t nmine = 0, tok_sum = 0;
+    uint32_t st = starts;
+    while (st) {
+      const int s = __ffs(st) - 1;
+      st &= st - 1;
+      const uint64_t off = seg * 16 + s;
+      if (off >= n) { starts &= ~(1u << s); continue; }
+      const uint32_t L = enc_word_len(text, off, n);
+      const int last = tmp[off + L - 1];
+      const uint32_t nt = last >= 0 ? L : (uint32_t)(-last - 1);
+      ntoks[nmine] = nt; nmine++;
+      tok_sum += nt;
+    }
+    uint32_t tot_t, tot_w;
+    const uint32_t tbase = block_excl_scan(tok_sum, wt, tot_t);
+    const uint32_t wbase = block_excl_scan(nmine, wt, tot_w);
+    uint64_t to = tok_base + tile_tok_off[tile] + tbase;
+    uint64_t wo = word_base + tile_word_off[tile] + wbase;
+    uint32_t j = 0;
+    st = starts;
+    while (st) {
+      const int s = __ffs(st) - 1;
+      st &= st - 1;
+      const uint64_t off = seg * 16 + s;
+      const uint32_t nt = ntoks[j];
+      for (uint32_t k = 0; k < nt; k++)
+        if (to + k < cap_ids) { const int v = tmp[off + k]; out[to + k] = (v == UNK_CODE) ? neg_id : v; }
+      if (word_ntok && wo < cap_words) word_ntok[wo] = nt;
+      to += nt; wo++; j++;
+    }
+  }
+}
+
+class EncoderImpl {
+ public:
+  EncoderImpl(const int32_t *triples, size_t M, const int32_t *byte_map256, int32_t unk_for_negative) {
+    merges_.assign(triples, triples + 3 * M);
+    for (int i = 0; i < 256; i++) bmap_[i] = byte_map256 ? byte_map256[i] : i;
+    // a negative id (only a negative unk_id can produce one) travels as UNK_CODE on the device
+    neg_id_ = unk_for_negative;
+    for (int i = 0; i < 256; i++) if (bmap_[i] < 0) { neg_id_ = bmap_[i]; dev_bmap_[i] = UNK_CODE; } else dev_bmap_[i] = bmap_[i];
+    // host decode table
+    tok_off_.assign(256 + M + 1, 0);
+    std::vector<std::vector<uint8_t>> toks(256 + M);
+    for (int i = 0; i < 256; i++) toks[i] = {(uint8_t)i};
+    for (size_t m = 0; m < M; m++) {
+      const int32_t a = triples[3 * m], b = triples[3 * m + 1];
+      std::vector<uint8_t> v;
+      if (a >= 0 && (size_t)a < 256 + m) v = toks[a];
+      if (b >= 0 && (size_t)b < 256 + m) v.insert(v.end(), toks[b].begin(), toks[b].end());
+      toks[256 + m] = std::move(v);
+    }
+    for (size_t i = 0; i < toks.size(); i++) {
+      tok_off_[i] = tok_bytes_.size();
+      tok_bytes_.insert(tok_bytes_.end(), toks[i].begin(), toks[i].end());
+    }
+    tok_off_[toks.size()] = tok_bytes_.size();
+  }
+  ~EncoderImpl() { if (stream_) cudaStreamDestroy(stream_); }
+
+  uint64_t launches = 0;
+
+  void ensure_device() {
+    if (stream_) return;
+    int nd = 0;
+    cudaError_t e = cudaGetDeviceCount(&nd);
+    if (e != cudaSuccess || nd == 0)
+      throw Error(std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                  " (this library has no CPU fallback)");
+    int dev = 0;
+    SWB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    SWB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    sms_ = prop.multiProcessorCount;
+    SWB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    // merge-rank table (a repeated pair keeps its lowest rank)
+    const size_t M = merges_.size() / 3;
+    uint64_t cap = 64;
+    while (cap < 4 * M + 16) cap <<= 1;
+    std::vector<RankSlot> h(cap, RankSlot{~0ull, ~0ull});
+    for (size_t r = 0; r < M; r++) {
+      const int32_t ma = merges_[3 * r] < 0 ? UNK_CODE : merges_[3 * r], mb = merges_[3 * r + 1] < 0 ? UNK_CODE : merges_[3 * r + 1];
+      const unsigned long long k = ((unsigned long long)(uint32_t)ma << 32) | (uint32_t)mb;
+      uint64_t hh = dmix64(k) & (cap - 1);
+      bool dup = false;
+      while (h[hh].key != ~0ull) { if (h[hh].key == k) { dup = true; break; } hh = (hh + 1) & (cap - 1); }
+      if (!dup) h[hh] = RankSlot{k, ((unsigned long long)r << 32) | (uint32_t)merges_[3 * r + 2]};
+    }
+    slots_.alloc(cap);
+    SWB_CUDA(cudaMemcpyAsync(slots_.get(), h.data(), cap * sizeof(RankSlot), cudaMemcpyHostToDevice, stream_));
+    d_bmap_.alloc(256);
+    SWB_CUDA(cudaMemcpyAsync(d_bmap_.get(), dev_bmap_, sizeof dev_bmap_, cudaMemcpyHostToDevice, stream_));
+    SWB_CUDA(cudaStreamSynchronize(stream_));
+    tbl_ = RankTableDev{slots_.get(), (uint32_t)(cap - 1)};
+  }
+
+  // Encodes one device-resident piece [d_text, d_text+n) that is 16-byte aligned and padded with 16 ' '.
+  // Appends to d_out at tok_base / d_word_ntok at word_base. Returns (tokens, words) of the piece.
+  void encode_piece(const uint8_t *d_text, uint64_t n, int32_t *d_out, uint64_t cap_ids, uint64_t tok_base,
+                    uint32_t *d_word_ntok, uint64_t cap_words, uint64_t word_base, uint64_t *ntok, uint64_t *nwords) {
+    *ntok = 0; *nwords = 0;
+    if (n == 0) return;
+    const uint64_t n_tiles = (n + ENC_TILE - 1) / ENC_TILE;
+    if (tmp_.size() < n + 16) tmp_.alloc(n + 16);
+    if (tile_tok_.size() < n_tiles + 1) {
+      tile_tok_.alloc(n_tiles + 1); tile_words_.alloc(n_tiles + 1);
+      tile_tok_off_.alloc(n_tiles + 1); tile_word_off_.alloc(n_tiles + 1);
+    }
+    SWB_CUDA(cudaMemsetAsync(tile_tok_.get() + n_tiles, 0, 4, stream_));
+    SWB_CUDA(cudaMemsetAsync(tile_words_.get() + n_tiles, 0, 4, stream_));
+    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)sms_ * 4);
+    enc_words<<<grid, ENC_THREADS, 0, stream_>>>(d_text, n, tbl_, d_bmap_.get(), tmp_.get(), tile_tok_.get(), tile_words_.get());
+    launches++;
+    SWB_CUDA(cudaGetLastError());
+    scan(tile_tok_.get(), tile_tok_off_.get(), n_tiles + 1);
+    scan(tile_words_.get(), tile_word_off_.get(), n_tiles + 1);
+    unsigned long long totals[2];
+    SWB_CUDA(cudaMemcpyAsync(&totals[0], tile_tok_off_.get() + n_tiles, 8, cudaMemcpyDeviceToHost, stream_));
+    SWB_CUDA(cudaMemcpyAsync(&totals[1], tile_word_off_.get() + n_tiles, 8, cudaMemcpyDeviceToHost, stream_));
+    SWB_CUDA(cudaStreamSynchronize(stream_));
+    *ntok = totals[0]; *nwords = totals[1];
+    if (tok_base + totals[0] > cap_ids) throw Error("swb_encode: output capacity too small");
+    if (d_word_ntok && word_base + totals[1] > cap_words) throw Error("swb_encode: word_ntok capacity too small");
+    enc_gather<<<grid, ENC_THREADS, 0, stream_>>>(d_text, n, tmp_.get(), tile_tok_off_.get(), tile_word_off_.get(), tok_base,
+                                                  word_base, d_out, cap_ids, d_word_ntok, cap_words, neg_id_);
+    launches++;
+    SWB_CUDA(cudaGetLastError());
+  }
+
+  // host text -> host ids, streamed through the device in pieces that end on a delimiter
+  int64_t encode_host(const uint8_t *text, uint64_t n, int32_t *out, uint64_t cap_ids, uint32_t *word_ntok,
+                      uint64_t cap_words, size_t *n_words) {
+    ensure_device();
+    const uint64_t PIECE = 256ull << 20;
+    DevBuf<uint8_t> d_text(std::min<uint64_t>(n, PIECE + (1ull << 20)) + 64);
+    uint64_t pos = 0, tok_total = 0, word_total = 0;
+    DevBuf<int32_t> d_out;
+    DevBuf<uint32_t> d_wn;
+    while (pos < n) {
+      uint64_t end = std::min<uint64_t>(n, pos + PIECE);
+      if (end < n) {  // cut on a delimiter so that no word is split
+        uint64_t e = end;
+        while (e > pos && !is_delim(text[e - 1])) --e;
+        if (e == pos) { e = end; while (e < n && !is_delim(text[e])) ++e; }
+        end = e;
+      }
+      const uint64_t len = end - pos;
+      if (d_text.size() < len + 64) d_text.alloc(len + 64);
+      if (d_out.size() < len) d_out.alloc(len);
+      if (word_ntok && d_wn.size() < len / 2 + 1) d_wn.alloc(len / 2 + 1);
+      SWB_CUDA(cudaMemcpyAsync(d_text.get(), text + pos, len, cudaMemcpyHostToDevice, stream_));
+      SWB_CUDA(cudaMemsetAsync(d_text.get() + len, ' ', 64, stream_));
+      uint64_t nt = 0, nw = 0;
+      encode_piece(d_text.get(), len, d_out.get(), len, 0, word_ntok ? d_wn.get() : nullptr, len / 2 + 1, 0, &nt, &nw);
+      if (tok_total + nt > cap_ids) throw Error("swb_encode: output capacity too small");
+      if (word_ntok && word_total + nw > cap_words) throw Error("swb_encode: word_ntok capacity too small");
+      if (nt) SWB_CUDA(cudaMemcpyAsync(out + tok_total, d_out.get(), nt * 4, cudaMemcpyDeviceToHost, stream_));
+      if (word_ntok && nw) SWB_CUDA(cudaMemcpyAsync(word_ntok + word_total, d_wn.get(), nw * 4, cudaMemcpyDeviceToHost, stream_));
+      SWB_CUDA(cudaStreamSynchronize(stream_));
+      tok_total += nt; word_total += nw;
+      pos = end;
+    }
+    if (n_words) *n_words = word_total;
+    return (int64_t)tok_total;
+  }
+
+  // device text -> device ids (the text is copied once into an aligned, padded buffer)
+  int64_t encode_device(const uint8_t *d_text_in, uint64_t n, int32_t *d_out, uint64_t cap_ids, uint32_t *d_word_ntok,
+                        uint64_t cap_words, size_t *n_words) {
+    ensure_device();
+    if (dtext_.size() < n + 64) dtext_.alloc(n + 64);
+    if (n) SWB_CUDA(cudaMemcpyAsync(dtext_.get(), d_text_in, n, cudaMemcpyDeviceToDevice, stream_));
+    SWB_CUDA(cudaMemsetAsync(dtext_.get() + n, ' ', 64, stream_));
+    uint64_t nt = 0, nw = 0;
+    encode_piece(dtext_.get(), n, d_out, cap_ids, 0, d_word_ntok, cap_words, 0, &nt, &nw);
+    SWB_CUDA(cudaStreamSynchronize(stream_));
+    if (n_words) *n_words = nw;
+    return (int64_t)nt;
+  }
+
+  size_t decode(const int32_t *ids, size_t n, uint8_t *out, size_t cap) const {
+    size_t pos = 0;
+    const size_t T = tok_off_.size() - 1;
+    for (size_t i = 0; i < n; i++) {
+      if (ids[i] < 0 || (size_t)ids[i] >= T) continue;
+      const size_t a = tok_off_[ids[i]], b = tok_off_[ids[i] + 1];
+      for (size_t k = a; k < b; k++) { if (out && pos < cap) out[pos] = tok_bytes_[k]; pos++; }
+    }
+    return pos;
+  }
+
+ private:
+  void scan(const uint32_t *in, unsigned long long *out, uint64_t count) {
+    cub::TransformInputIterator<unsigned long long, CastU32ToU64, const uint32_t *> it(in, CastU32ToU64());
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, (int64_t)count, stream_);
+    if (scan_tmp_.size() < bytes) scan_tmp_.alloc(bytes);
+    SWB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp_.get(), bytes, it, out, (int64_t)count, stream_));
+    launches += 2;
+  }
+
+  std::vector<int32_t> merges_;
+  int32_t bmap_[256], dev_bmap_[256];
+  int32_t neg_id_ = -1;
+  std::vector<uint8_t> tok_bytes_;
+  std::vector<size_t> tok_off_;
+  cudaStream_t stream_ = nullptr;
+  int sms_ = 148;
+  DevBuf<RankSlot> slots_;
+  DevBuf<int32_t> d_bmap_;
+  RankTableDev tbl_{};
+  DevBuf<int32_t> tmp_;
+  DevBuf<uint32_t> tile_tok_, tile_words_;
+  DevBuf<unsigned long long> tile_tok_off_, tile_word_off_;
+  DevBuf<uint8_t> scan_tmp_, dtext_;
+};
+
+}  // namespace swb

@@ -1,0 +1,270 @@
+// host_core.hpp -- host half of the BPE merge loop: pair table, exact heap replica, delta application.
+//
+// The merge order of the reference is not a pure function of (freq, pair): equal-frequency ties
+// are broken by the physical history of its binary heap and by the iteration orders of its three
+// hash maps. This file replays exactly those orders from the compact
+// per-merge records the GPU kernels produce: (pair, net delta, first-touch key). It is tiny and
+// sequential by nature (a heap), so it lives on the host; the O(corpus) work lives in the kernels.
+//
+// Pure C++17, no CUDA, so the multi-rank logic (swb_dist_*) can be exercised without a GPU.
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/shredword_b200.h"
+
+namespace swb {
+
+struct Rec { int64_t first, second, delta, key; };  // wire format of a record: 4 x int64
+static_assert(sizeof(Rec) == 32, "record must be 4 x int64");
+
+static inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+static inline uint64_t pack_pair(int32_t a, int32_t b) { return ((uint64_t)(uint32_t)a << 32) | (uint32_t)b; }
+
+// pair -> {freq, version}; entries live in creation order because the reference's BIMap iteration
+// order (bucket ascending, chain in creation order; reference hash.cpp:104-130) is observable
+// through bpe_count_bigrams' push pass (reference bpe.cpp:359-366).
+struct PairInfo { int32_t first, second; uint64_t freq; uint32_t version; };
+
+class PairTable {
+ public:
+  PairTable() { clear(); }
+  void clear() {
+    entries_.clear();
+    slots_.assign(4096, 0);
+  }
+  size_t size() const { return entries_.size(); }
+  PairInfo &at(size_t i) { return entries_[i]; }
+  const PairInfo &at(size_t i) const { return entries_[i]; }
+  // find-or-create (reference bimap_get: a missing pair reads as freq 0, version 0)
+  size_t get(int32_t a, int32_t b) {
+    const uint64_t k = pack_pair(a, b);
+    size_t mask = slots_.size() - 1, h = (size_t)mix64(k) & mask;
+    while (slots_[h]) {
+      const PairInfo &p = entries_[slots_[h] - 1];
+      if (p.first == a && p.second == b) return slots_[h] - 1;
+      h = (h + 1) & mask;
+    }
+    entries_.push_back(PairInfo{a, b, 0, 0});
+    slots_[h] = (uint32_t)entries_.size();
+    if (entries_.size() * 2 > slots_.size()) rehash(slots_.size() * 4);
+    return entries_.size() - 1;
+  }
+
+ private:
+  void rehash(size_t n) {
+    slots_.assign(n, 0);
+    for (size_t i = 0; i < entries_.size(); i++) {
+      size_t h = (size_t)mix64(pack_pair(entries_[i].first, entries_[i].second)) & (n - 1);
+      while (slots_[h]) h = (h + 1) & (n - 1);
+      slots_[h] = (uint32_t)(i + 1);
+    }
+  }
+  std::vector<PairInfo> entries_;
+  std::vector<uint32_t> slots_;
+};
+
+// FNV-1a over the 8 little-endian bytes of {first, second} (reference hash.cpp:7-16)
+static inline uint32_t ref_pair_hash(int32_t first, int32_t second) {
+  uint32_t h = 2166136261u;
+  const uint32_t w[2] = {(uint32_t)first, (uint32_t)second};
+  for (int k = 0; k < 2; k++)
+    for (int i = 0; i < 4; i++) { h ^= (w[k] >> (8 * i)) & 0xffu; h *= 16777619u; }
+  return h;
+}
+
+// Reduce records by pair: sum delta, min key. Order of the output is unspecified. Returns new count.
+static inline size_t reduce_records(Rec *recs, size_t n) {
+  if (n < 2) return n;
+  size_t nslots = 16;
+  while (nslots < 2 * n) nslots *= 2;
+  std::vector<uint32_t> slots(nslots, 0);
+  size_t out = 0;
+  for (size_t i = 0; i < n; i++) {
+    const Rec r = recs[i];
+    size_t h = (size_t)mix64(pack_pair((int32_t)r.first, (int32_t)r.second)) & (nslots - 1);
+    for (;;) {
+      if (!slots[h]) { recs[out] = r; slots[h] = (uint32_t)(++out); break; }
+      Rec &q = recs[slots[h] - 1];
+      if (q.first == r.first && q.second == r.second) {
+        q.delta += r.delta;
+        if ((uint64_t)r.key < (uint64_t)q.key) q.key = r.key;
+        break;
+      }
+      h = (h + 1) & (nslots - 1);
+    }
+  }
+  return out;
+}
+
+class HostCore {
+ public:
+  explicit HostCore(Trainer *tr) : tr_(tr) {}
+  ~HostCore() { free(tr_->heap.data); tr_->heap.data = nullptr; tr_->heap.size = tr_->heap.cap = 0; }
+
+  int log_level = 0;
+
+  // ---- heap: the exact array heap of reference heap.cpp:53-114, stored in the public Trainer fields
+  void heap_reset() {  // heap_free + heap_init(4096), reference bpe.cpp:182-183
+    MaxHeap &h = tr_->heap;
+    if (!h.data) { h.cap = 4096; h.data = (HeapEntry *)malloc(h.cap * sizeof(HeapEntry)); }
+    h.size = 0;
+  }
+  void heap_push(int32_t a, int32_t b, uint64_t freq, uint32_t version) {
+    MaxHeap &h = tr_->heap;
+    if (!h.data) heap_reset();
+    if (h.size == h.cap) {
+      h.cap *= 2;
+      h.data = (HeapEntry *)realloc(h.data, h.cap * sizeof(HeapEntry));
+      if (!h.data) { fprintf(stderr, "[ERROR]\t heap reallocation failed\n"); abort(); }
+    }
+    size_t i = h.size++;
+    h.data[i].key.first = a; h.data[i].key.second = b; h.data[i].freq = freq; h.data[i].version = version;
+    while (i > 0) {  // stop as soon as parent.freq >= child.freq (reference heap.cpp:74-79)
+      size_t p = (i - 1) >> 1;
+      if (h.data[p].freq >= h.data[i].freq) break;
+      std::swap(h.data[p], h.data[i]);
+      i = p;
+    }
+  }
+  HeapEntry heap_pop() {
+    MaxHeap &h = tr_->heap;
+    HeapEntry top = h.data[0];
+    h.data[0] = h.data[--h.size];
+    size_t i = 0;
+    for (;;) {  // left child if strictly larger, then right if strictly larger than that (heap.cpp:97-111)
+      size_t l = 2 * i + 1, r = l + 1, best = i;
+      if (l < h.size && h.data[l].freq > h.data[best].freq) best = l;
+      if (r < h.size && h.data[r].freq > h.data[best].freq) best = r;
+      if (best == i) break;
+      std::swap(h.data[i], h.data[best]);
+      i = best;
+    }
+    return top;
+  }
+  bool heap_empty() const { return tr_->heap.size == 0; }
+
+  // ---- reference bpe_init's table part (bpe.cpp:177-183)
+  void reset_tables() {
+    pairs_.clear();
+    heap_reset();
+  }
+
+  // ---- reference bpe_count_bigrams (bpe.cpp:315-370), fed with the reduced count records.
+  // Pass 1 creates/accumulates entries in first-touch order; pass 2 pushes every entry of the
+  // table with freq >= min_pair_freq in (FNV bucket, creation) order.
+  void seed_counts(const Rec *recs, size_t n) {
+    std::vector<Rec> v(recs, recs + n);
+    std::sort(v.begin(), v.end(), [](const Rec &x, const Rec &y) { return (uint64_t)x.key < (uint64_t)y.key; });
+    for (const Rec &r : v) {
+      PairInfo &p = pairs_.at(pairs_.get((int32_t)r.first, (int32_t)r.second));
+      if (p.freq == 0) p.version = 0;  // bpe.cpp:342-345
+      p.freq += (uint64_t)r.delta;
+    }
+    const size_t P = pairs_.size();
+    std::vector<uint32_t> order(P);
+    for (size_t i = 0; i < P; i++) order[i] = (uint32_t)i;
+    std::vector<uint32_t> bucket(P);
+    for (size_t i = 0; i < P; i++) bucket[i] = ref_pair_hash(pairs_.at(i).first, pairs_.at(i).second) & 4095u;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return bucket[x] < bucket[y]; });
+    const uint64_t minf = tr_->config.min_pair_freq;
+    size_t pushed = 0;
+    for (uint32_t i : order) {
+      const PairInfo &p = pairs_.at(i);
+      if (p.freq >= minf) { heap_push(p.first, p.second, p.freq, p.version); pushed++; }
+    }
+    if (log_level > 0) {
+      printf("[INFO]\t Counted %zu unique pairs\n", P);
+      printf("[INFO]\t Added %zu pairs to heap (freq >= %llu)\n", pushed, (unsigned long long)minf);
+    }
+  }
+
+  // ---- reference bpe_merge_batch, decision part (bpe.cpp:405-429): pop until a live entry.
+  bool next_merge(int32_t *a, int32_t *b, int32_t *new_id) {
+    const uint64_t minf = tr_->config.min_pair_freq;
+    while (!heap_empty()) {
+      HeapEntry top = heap_pop();
+      PairInfo &info = pairs_.at(pairs_.get(top.key.first, top.key.second));
+      if (top.version != info.version) continue;  // stale (bpe.cpp:412-415)
+      if (info.freq < minf) continue;             // bpe.cpp:418-421
+      cur_a_ = top.key.first; cur_b_ = top.key.second;
+      cur_new_ = (int32_t)(256 + tr_->num_merges);  // bpe.cpp:424
+      merges_.push_back(PairKey{cur_a_, cur_b_});
+      tr_->merge_ops = merges_.data();
+      pending_ = true;
+      if (log_level > 0)
+        printf("[MERGE]\t Merging (%d,%d) freq=%llu -> new_id=%d (merge %zu)\n", cur_a_, cur_b_,
+               (unsigned long long)info.freq, cur_new_, tr_->num_merges + 1);
+      *a = cur_a_; *b = cur_b_; *new_id = cur_new_;
+      return true;
+    }
+    return false;
+  }
+
+  // ---- reference bpe_merge_batch, bookkeeping part (bpe.cpp:486-526) for the pending merge.
+  // recs: (first, second) are the raw ids of the touched pair, delta its net change, key the
+  // first-touch order of the pair inside this merge.
+  void apply(const Rec *recs, size_t n) {
+    if (!pending_) return;
+    scratch_.assign(recs, recs + n);
+    bool any_negative = false;
+    for (Rec &r : scratch_) {
+      // The reference keys its per-merge delta map by ((uint64_t)first << 32) | (uint64_t)second with
+      // int32 operands (bpe.cpp:456-457): a negative `second` sign-extends over `first`. Replayed here
+      // so that negative unk ids behave identically.
+      const uint64_t ph = ((uint64_t)(int64_t)(int32_t)r.first << 32) | (uint64_t)(int64_t)(int32_t)r.second;
+      const int32_t f = (int32_t)(ph >> 32), s = (int32_t)(ph & 0xFFFFFFFFu);
+      if (f != (int32_t)r.first) any_negative = true;
+      r.first = f; r.second = s;
+    }
+    size_t m = scratch_.size();
+    if (any_negative) { m = reduce_records(scratch_.data(), m); scratch_.resize(m); }
+    // Delta-map iteration order (bpe.cpp:30, 41-45, 486-487): bucket = pair_hash % 1024 ascending;
+    // inside a bucket entries were prepended, so the most recently first-touched pair comes first.
+    std::sort(scratch_.begin(), scratch_.end(), [](const Rec &x, const Rec &y) {
+      const uint32_t bx = (uint32_t)x.second & 1023u, by = (uint32_t)y.second & 1023u;
+      if (bx != by) return bx < by;
+      return (uint64_t)x.key > (uint64_t)y.key;
+    });
+    const uint64_t minf = tr_->config.min_pair_freq;
+    for (const Rec &r : scratch_) {
+      const int32_t f = (int32_t)r.first, s = (int32_t)r.second;
+      if (f == cur_a_ && s == cur_b_) continue;  // bpe.cpp:494-496
+      PairInfo &p = pairs_.at(pairs_.get(f, s));
+      if (r.delta < 0) {  // clamp at zero on the NET delta (bpe.cpp:500-509)
+        const uint64_t ad = (uint64_t)(-r.delta);
+        p.freq = p.freq >= ad ? p.freq - ad : 0;
+      } else {
+        p.freq += (uint64_t)r.delta;
+      }
+      if (p.freq >= minf) { p.version++; heap_push(f, s, p.freq, p.version); }  // bpe.cpp:512-515
+    }
+    PairInfo &info = pairs_.at(pairs_.get(cur_a_, cur_b_));
+    info.freq = 0; info.version++;  // bpe.cpp:523-524
+    tr_->num_merges++;
+    tr_->next_token = 256 + tr_->num_merges;
+    pending_ = false;
+  }
+
+  const std::vector<PairKey> &merges() const { return merges_; }
+  PairTable &pairs() { return pairs_; }
+  bool pending() const { return pending_; }
+
+ private:
+  Trainer *tr_;
+  PairTable pairs_;
+  std::vector<PairKey> merges_;
+  std::vector<Rec> scratch_;
+  int32_t cur_a_ = 0, cur_b_ = 0, cur_new_ = 0;
+  bool pending_ = false;
+};
+
+}  // namespace swb

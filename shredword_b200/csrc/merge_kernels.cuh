@@ -1,0 +1,369 @@
+// merge_kernels.cuh -- the per-merge hot path over the row-packed symbol stream.
+//
+// Replaces reference bpe_count_bigrams' first pass (reference csrc/bpe/bpe.cpp:329-350), the scan +
+// splice + delta bookkeeping of bpe_merge_batch (bpe.cpp:437-483, FreqChangeMap bpe.cpp:10-46) and
+// bpe_save's token histogram (bpe.cpp:704-712).
+//
+// Stream layout: rows of ROW=128 int32. A word is [~local_index][sym ...][PAD ...]; it never
+// straddles a row, so one warp owns whole words: lane l holds symbols 4l..4l+3 of a row (one 16-byte
+// coalesced load), adjacency is a shuffle, and a row without the pair (a, b) -- almost all of them --
+// costs one load, one shuffle, a few compares and one vote. Rows with a match take the slow path:
+// the row is staged in shared memory and every word is rewritten left to right by the lane that holds
+// its header, which reproduces the reference's sequential semantics exactly (already-merged left
+// neighbour, not-yet-merged right neighbour, greedy self-pairs) and emits the four signed deltas of
+// each match into a global open-addressing pair table together with a first-touch key.
+#pragma once
+
+#include "device_util.cuh"
+#include "host_core.hpp"
+
+namespace swb {
+
+constexpr uint64_t PT_EMPTY = ~0ull;
+
+struct PairTableDev {
+  unsigned long long *keys;    // (first << 32) | second, PT_EMPTY when free
+  unsigned long long *val;     // net delta (two's complement) or frequency
+  unsigned long long *minkey;  // smallest first-touch key
+  unsigned int *touched;       // slots claimed since the last emit
+  unsigned int *n_touched;
+  unsigned int *flags;         // bit 0: table full
+  unsigned int *done_blocks;   // emit kernel bookkeeping
+  uint32_t mask;
+};
+
+__device__ __forceinline__ void pt_add(const PairTableDev &t, int32_t a, int32_t b, long long delta, uint64_t key) {
+  const unsigned long long k = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
+  uint32_t h = (uint32_t)dmix64(k) & t.mask;
+  for (uint32_t probe = 0; probe <= t.mask; probe++) {
+    unsigned long long cur = t.keys[h];
+    if (cur == PT_EMPTY) {
+      cur = atomicCAS(&t.keys[h], PT_EMPTY, k);
+      if (cur == PT_EMPTY) {
+        const unsigned int idx = atomicAdd(t.n_touched, 1u);
+        t.touched[idx] = h;
+        if (idx >= (t.mask >> 1)) atomicOr(t.flags, 1u);  // past 50 % load: the host grows the table and reruns
+        cur = k;
+      }
+    }
+    if (cur == k) {
+      atomicAdd(&t.val[h], (unsigned long long)delta);
+      atomicMin(&t.minkey[h], (unsigned long long)key);
+      return;
+    }
+    h = (h + 1) & t.mask;
+    if (probe > 64 && *(volatile unsigned int *)t.flags) return;  // overflow already declared: do not crawl
+  }
+  atomicOr(t.flags, 1u);
+}
+
+__global__ void pt_clear(PairTableDev t) {
+  const uint64_t cap = (uint64_t)t.mask + 1;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    t.keys[i] = PT_EMPTY; t.val[i] = 0; t.minkey[i] = ~0ull;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *t.n_touched = 0; *t.flags = 0; *t.done_blocks = 0; }
+}
+
+// touched slots -> records in mapped host memory; frees the slots. The last block to finish resets
+// the counters, so the next merge needs no extra memset on the critical path.
+// out_hdr[0] = number of records, out_hdr[1] = flags, out_hdr[2] = removed symbols of this merge.
+__global__ void __launch_bounds__(256)
+pt_emit(PairTableDev t, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
+        unsigned long long *removed) {
+  const unsigned int n = *t.n_touched;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned int h = t.touched[i];
+    const unsigned long long k = t.keys[h];
+    if (i < out_cap) {
+      Rec r;
+      r.first = (int32_t)(k >> 32); r.second = (int32_t)(k & 0xFFFFFFFFu);
+      r.delta = (long long)t.val[h]; r.key = (long long)t.minkey[h];
+      out[i] = r;
+    }
+    t.keys[h] = PT_EMPTY; t.val[h] = 0; t.minkey[h] = ~0ull;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int d = atomicAdd(t.done_blocks, 1u);
+    if (d == gridDim.x - 1) {
+      out_hdr[0] = n;
+      out_hdr[1] = *t.flags | (n > out_cap ? 4u : 0u);
+      out_hdr[2] = removed ? *removed : 0ull;
+      if (removed) *removed = 0;
+      *t.n_touched = 0; *t.flags = 0; *t.done_blocks = 0;
+      __threadfence_system();
+    }
+  }
+}
+
+struct StreamDev {
+  int4 *rows;                 // n_rows * ROW int32
+  uint64_t n_rows;
+  const unsigned long long *cnt;   // [W] word count, indexed by the (global, reference-order) word index
+  // long words (more than ROW-1 symbols): CSR, one warp per word
+  int32_t *long_syms;
+  const uint64_t *long_off;
+  uint32_t *long_len;         // live length
+  const uint32_t *long_word;  // word index of long word j
+  uint32_t n_long;
+};
+
+__device__ __forceinline__ uint64_t word_gwi(const StreamDev &, uint32_t wi) { return (uint64_t)wi; }
+
+// ---------------------------------------------------------------- merge (a, b) -> new_id
+// Sequential rewrite of one word living in shared memory at sm[p+1 ...]; p = header position.
+__device__ __forceinline__ uint32_t merge_word_smem(int *sm, int p, const StreamDev &s, const PairTableDev &t,
+                                                    int32_t a, int32_t b, int32_t new_id) {
+  const uint32_t li = (uint32_t)(~sm[p]);
+  int r = p + 1, w = p + 1;
+  long long c = 0; uint64_t g = 0;
+  uint32_t nmatch = 0;
+  while (r < ROW) {
+    const int x = sm[r];
+    if (x < 0) break;
+    if (x == a && r + 1 < ROW && sm[r + 1] == b) {
+      if (nmatch == 0) { c = (long long)s.cnt[li]; g = word_gwi(s, li); }
+      if (w > p + 1) {  // left neighbour: the already rewritten symbol (reference bpe.cpp:453-460)
+        const int L = sm[w - 1];
+        pt_add(t, L, a, -c, touch_key(g, r, 0));
+        pt_add(t, L, new_id, c, touch_key(g, r, 1));
+      }
+      if (r + 2 < ROW && sm[r + 2] >= 0) {  // right neighbour: not yet rewritten (bpe.cpp:463-470)
+        const int R = sm[r + 2];
+        pt_add(t, b, R, -c, touch_key(g, r, 2));
+        pt_add(t, new_id, R, c, touch_key(g, r, 3));
+      }
+      sm[w++] = new_id;
+      r += 2;
+      nmatch++;
+    } else {
+      if (w != r) sm[w] = x;
+      w++; r++;
+    }
+  }
+  for (int q = w; q < r; q++) sm[q] = PAD;
+  return nmatch;
+}
+
+constexpr int MERGE_THREADS = 256;
+constexpr int MERGE_UNROLL = 4;
+
+// Slow path of one row (warp-uniform): stage in shared memory, rewrite word by word, store back.
+__device__ __noinline__ uint32_t merge_row_slow(int *sm, int4 v, int lane, int4 *row_gmem, const StreamDev &s,
+                                                const PairTableDev &t, int32_t a, int32_t b, int32_t new_id) {
+  *reinterpret_cast<int4 *>(&sm[lane * 4]) = v;
+  __syncwarp();
+  uint32_t removed = 0;
+  const int h[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (h[k] < 0 && h[k] != PAD) removed += merge_word_smem(sm, lane * 4 + k, s, t, a, b, new_id);
+  __syncwarp();
+  row_gmem[lane] = *reinterpret_cast<const int4 *>(&sm[lane * 4]);
+  __syncwarp();
+  return removed;
+}
+
+__global__ void __launch_bounds__(MERGE_THREADS)
+merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, unsigned long long *removed_total) {
+  __shared__ __align__(16) int sm[MERGE_THREADS / 32][ROW];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint64_t warp = (blockIdx.x * (uint64_t)MERGE_THREADS + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * MERGE_THREADS) >> 5;
+  uint32_t removed = 0;
+  for (uint64_t r0 = warp * MERGE_UNROLL; r0 < s.n_rows; r0 += n_warps * MERGE_UNROLL) {
+    int4 v[MERGE_UNROLL];
+#pragma unroll
+    for (int u = 0; u < MERGE_UNROLL; u++)
+      if (r0 + u < s.n_rows) v[u] = s.rows[(r0 + u) * (ROW / 4) + lane];
+      else v[u] = make_int4(PAD, PAD, PAD, PAD);
+#pragma unroll
+    for (int u = 0; u < MERGE_UNROLL; u++) {
+      int nxt = __shfl_down_sync(0xffffffffu, v[u].x, 1);
+      if (lane == 31) nxt = PAD;
+      const bool m = (v[u].x == a && v[u].y == b) || (v[u].y == a && v[u].z == b) || (v[u].z == a && v[u].w == b) ||
+                     (v[u].w == a && nxt == b);
+      if (__any_sync(0xffffffffu, m)) {
+        removed += merge_row_slow(sm[wib], v[u], lane, s.rows + (r0 + u) * (ROW / 4), s, t, a, b, new_id);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) removed += __shfl_down_sync(0xffffffffu, removed, d);
+  if (lane == 0 && removed) atomicAdd(removed_total, (unsigned long long)removed);
+}
+
+// long words: lanes stride over the word to detect; the rare word with a match is rewritten by lane 0
+__global__ void __launch_bounds__(128)
+merge_long(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, unsigned long long *removed_total) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t j = warp; j < s.n_long; j += n_warps) {
+    int32_t *sym = s.long_syms + s.long_off[j];
+    const uint32_t L = s.long_len[j];
+    bool m = false;
+    for (uint32_t i = lane; i + 1 < L; i += 32) m |= (sym[i] == a && sym[i + 1] == b);
+    if (!__any_sync(0xffffffffu, m)) continue;
+    if (lane == 0) {
+      const uint32_t li = s.long_word[j];
+      const long long c = (long long)s.cnt[li];
+      const uint64_t g = word_gwi(s, li);
+      uint32_t r = 0, w = 0, nmatch = 0;
+      while (r < L) {
+        const int x = sym[r];
+        if (x == a && r + 1 < L && sym[r + 1] == b) {
+          if (w > 0) {
+            const int Lf = sym[w - 1];
+            pt_add(t, Lf, a, -c, touch_key(g, r, 0));
+            pt_add(t, Lf, new_id, c, touch_key(g, r, 1));
+          }
+          if (r + 2 < L) {
+            const int R = sym[r + 2];
+            pt_add(t, b, R, -c, touch_key(g, r, 2));
+            pt_add(t, new_id, R, c, touch_key(g, r, 3));
+          }
+          sym[w++] = new_id; r += 2; nmatch++;
+        } else {
+          if (w != r) sym[w] = x;
+          w++; r++;
+        }
+      }
+      s.long_len[j] = w;
+      atomicAdd(removed_total, (unsigned long long)nmatch);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- initial pair count
+// reference bpe.cpp:329-350: every adjacent pair of every word, weighted by the word count, pairs
+// containing unk_id skipped. key = (word, position) so the host can replay first-touch order.
+__global__ void __launch_bounds__(MERGE_THREADS)
+count_rows(StreamDev s, PairTableDev t, int32_t unk) {
+  __shared__ __align__(16) int sm[MERGE_THREADS / 32][ROW];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint64_t warp = (blockIdx.x * (uint64_t)MERGE_THREADS + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * MERGE_THREADS) >> 5;
+  int *row = sm[wib];
+  for (uint64_t r0 = warp; r0 < s.n_rows; r0 += n_warps) {
+    const int4 v = s.rows[r0 * (ROW / 4) + lane];
+    *reinterpret_cast<int4 *>(&row[lane * 4]) = v;
+    __syncwarp();
+    const int h[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (h[k] < 0 && h[k] != PAD) {
+        const int p = lane * 4 + k;
+        const uint32_t li = (uint32_t)(~h[k]);
+        const long long c = (long long)s.cnt[li];
+        const uint64_t g = word_gwi(s, li);
+        for (int r = p + 1; r + 1 < ROW; r++) {
+          const int x = row[r], y = row[r + 1];
+          if (y < 0) break;
+          if (x == unk || y == unk) continue;
+          pt_add(t, x, y, c, touch_key(g, r, 0));
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(128)
+count_long(StreamDev s, PairTableDev t, int32_t unk) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t j = warp; j < s.n_long; j += n_warps) {
+    const int32_t *sym = s.long_syms + s.long_off[j];
+    const uint32_t L = s.long_len[j];
+    if (L < 2) continue;
+    const uint32_t li = s.long_word[j];
+    const long long c = (long long)s.cnt[li];
+    const uint64_t g = word_gwi(s, li);
+    for (uint32_t i = lane; i + 1 < L; i += 32) {
+      const int x = sym[i], y = sym[i + 1];
+      if (x == unk || y == unk) continue;
+      pt_add(t, x, y, c, touch_key(g, i, 0));
+    }
+  }
+}
+
+// ---------------------------------------------------------------- token histogram (bpe_save)
+__global__ void __launch_bounds__(MERGE_THREADS)
+tokfreq_rows(StreamDev s, unsigned long long *__restrict__ freq, uint32_t T) {
+  __shared__ __align__(16) int sm[MERGE_THREADS / 32][ROW];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint64_t warp = (blockIdx.x * (uint64_t)MERGE_THREADS + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * MERGE_THREADS) >> 5;
+  int *row = sm[wib];
+  for (uint64_t r0 = warp; r0 < s.n_rows; r0 += n_warps) {
+    const int4 v = s.rows[r0 * (ROW / 4) + lane];
+    *reinterpret_cast<int4 *>(&row[lane * 4]) = v;
+    __syncwarp();
+    const int h[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (h[k] < 0 && h[k] != PAD) {
+        const unsigned long long c = s.cnt[(uint32_t)(~h[k])];
+        for (int r = lane * 4 + k + 1; r < ROW; r++) {
+          const int x = row[r];
+          if (x < 0) break;
+          if ((uint32_t)x < T) atomicAdd(&freq[x], c);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void tokfreq_long(StreamDev s, unsigned long long *__restrict__ freq, uint32_t T) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t j = warp; j < s.n_long; j += n_warps) {
+    const int32_t *sym = s.long_syms + s.long_off[j];
+    const uint32_t L = s.long_len[j];
+    const unsigned long long c = s.cnt[s.long_word[j]];
+    for (uint32_t i = lane; i < L; i += 32)
+      if ((uint32_t)sym[i] < T) atomicAdd(&freq[sym[i]], c);
+  }
+}
+
+// ---------------------------------------------------------------- word extraction (accessors)
+// live length of every word of this rank (0 for other ranks' words)
+__global__ void words_live_len(StreamDev s, const uint64_t *__restrict__ wloc, const uint32_t *__restrict__ long_index,
+                               uint32_t W, int rank, int nranks, uint32_t *__restrict__ out_len) {
+  const int32_t *flat = reinterpret_cast<const int32_t *>(s.rows);
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
+    if ((int)(w % (uint32_t)nranks) != rank) { out_len[w] = 0; continue; }
+    const uint32_t j = long_index[w];
+    if (j != 0xFFFFFFFFu) { out_len[w] = s.long_len[j]; continue; }
+    const uint64_t base = wloc[w];
+    const int pos = (int)(base % ROW);
+    uint32_t n = 0;
+    for (int r = pos + 1; r < ROW && flat[base - pos + r] >= 0; r++) n++;
+    out_len[w] = n;
+  }
+}
+
+__global__ void words_copy_syms(StreamDev s, const uint64_t *__restrict__ wloc, const uint32_t *__restrict__ long_index,
+                                uint32_t W, int rank, int nranks, const uint64_t *__restrict__ out_off,
+                                int32_t *__restrict__ out) {
+  const int32_t *flat = reinterpret_cast<const int32_t *>(s.rows);
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
+    if ((int)(w % (uint32_t)nranks) != rank) continue;
+    const uint32_t j = long_index[w];
+    int32_t *dst = out + out_off[w];
+    if (j != 0xFFFFFFFFu) {
+      const int32_t *src = s.long_syms + s.long_off[j];
+      for (uint32_t k = 0; k < s.long_len[j]; k++) dst[k] = src[k];
+      continue;
+    }
+    const uint64_t base = wloc[w];
+    const int pos = (int)(base % ROW);
+    for (int r = pos + 1, k = 0; r < ROW && flat[base - pos + r] >= 0; r++, k++) dst[k] = flat[base - pos + r];
+  }
+}
+
+}  // namespace swb

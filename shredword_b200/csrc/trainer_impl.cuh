@@ -1,0 +1,510 @@
+// trainer_impl.cuh -- device-side state of one Trainer handle and the orchestration of the kernels.
+//
+// Phases (reference file:line each one replaces):
+//   load   : file/host/device bytes -> HBM -> wt_tokenize -> sort -> keep rule -> row packing
+//            (reference csrc/bpe/bpe.cpp:208-297)
+//   count  : count_rows/count_long -> pt_emit -> HostCore::seed_counts      (bpe.cpp:315-370)
+//   merge  : HostCore::next_merge -> merge_rows/merge_long -> pt_emit -> HostCore::apply (bpe.cpp:391-535)
+//   save   : tokfreq_rows -> host writes the two files                       (bpe.cpp:678-739)
+#pragma once
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <chrono>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "device_util.cuh"
+#include "host_core.hpp"
+#include "merge_kernels.cuh"
+#include "word_table.cuh"
+
+namespace swb {
+
+static inline double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+static inline uint64_t pow2_ceil(uint64_t x) {
+  uint64_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+class TrainerImpl {
+ public:
+  explicit TrainerImpl(Trainer *tr) : tr_(tr), core(tr) {
+    for (int i = 0; i < 256; i++) { byte_map[i] = i; keep[i] = 1; }
+    memset(&stats, 0, sizeof stats);
+  }
+  ~TrainerImpl() {
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_) cudaStreamDestroy(stream_);
+  }
+
+  HostCore core;
+  SwbStats stats;
+  int32_t byte_map[256];  // byte -> initial id as the caller sees it (unk_id for dropped bytes)
+  uint8_t keep[256];
+  int rank = 0, nranks = 1;
+  bool timing = false;
+  uint64_t W = 0;  // unique words (global)
+  std::vector<uint64_t> h_counts;  // host mirror of the word counts (Corpus.word_counts)
+
+  // ---------------------------------------------------------------- device bring-up
+  void ensure_device() {
+    if (stream_) return;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      throw Error(std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                  " (this library has no CPU fallback)");
+    SWB_CUDA(cudaGetDevice(&device_));
+    cudaDeviceProp prop;
+    SWB_CUDA(cudaGetDeviceProperties(&prop, device_));
+    sms_ = prop.multiProcessorCount;
+    SWB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    SWB_CUDA(cudaEventCreate(&ev0_));
+    SWB_CUDA(cudaEventCreate(&ev1_));
+    scalars_.alloc(16);
+    SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
+    hdr_.alloc(8);
+    SWB_CUDA(cudaFuncSetAttribute(wt_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
+  }
+  void sync() { SWB_CUDA(cudaStreamSynchronize(stream_)); }
+  void launched(uint64_t n = 1) { stats.kernel_launches += n; }
+  int32_t unk_dev() const { return tr_->config.unk_id < 0 ? UNK_CODE : tr_->config.unk_id; }
+
+  // ---------------------------------------------------------------- load
+  // Copies host bytes into a padded device buffer (double-buffered through pinned staging when the
+  // source is a file) and builds the word table.
+  void load_file(const char *path) {
+    ensure_device();
+    const double t0 = now_ms();
+    FILE *f = fopen(path, "rb");
+    if (!f) throw Error(std::string("Couldn't open file: ") + path);
+    fseeko(f, 0, SEEK_END);
+    const uint64_t n = (uint64_t)ftello(f);
+    fseeko(f, 0, SEEK_SET);
+    DevBuf<uint8_t> corpus(n + 64);
+    const size_t CH = 64ull << 20;
+    PinnedBuf<uint8_t> stage[2];
+    cudaEvent_t done[2];
+    for (int i = 0; i < 2; i++) { stage[i].alloc(std::min<uint64_t>(CH, n ? n : 1)); SWB_CUDA(cudaEventCreate(&done[i])); }
+    uint64_t pos = 0;
+    int b = 0;
+    bool ok = true;
+    while (pos < n) {
+      const size_t want = (size_t)std::min<uint64_t>(CH, n - pos);
+      SWB_CUDA(cudaEventSynchronize(done[b]));  // staging buffer free again
+      const size_t got = fread(stage[b].host(), 1, want, f);
+      if (got != want) { ok = false; break; }
+      SWB_CUDA(cudaMemcpyAsync(corpus.get() + pos, stage[b].host(), got, cudaMemcpyHostToDevice, stream_));
+      SWB_CUDA(cudaEventRecord(done[b], stream_));
+      pos += got;
+      b ^= 1;
+    }
+    fclose(f);
+    sync();
+    for (int i = 0; i < 2; i++) cudaEventDestroy(done[i]);
+    if (!ok) throw Error(std::string("short read on ") + path);
+    SWB_CUDA(cudaMemsetAsync(corpus.get() + n, ' ', 64, stream_));
+    build_word_table(corpus, n);
+    stats.load_ms += now_ms() - t0;
+  }
+  void load_host(const void *data, uint64_t n) {
+    ensure_device();
+    const double t0 = now_ms();
+    DevBuf<uint8_t> corpus(n + 64);
+    if (n) SWB_CUDA(cudaMemcpyAsync(corpus.get(), data, n, cudaMemcpyHostToDevice, stream_));
+    SWB_CUDA(cudaMemsetAsync(corpus.get() + n, ' ', 64, stream_));
+    build_word_table(corpus, n);
+    stats.load_ms += now_ms() - t0;
+  }
+  void load_device(const void *d_data, uint64_t n) {
+    ensure_device();
+    const double t0 = now_ms();
+    DevBuf<uint8_t> corpus(n + 64);
+    if (n) SWB_CUDA(cudaMemcpyAsync(corpus.get(), d_data, n, cudaMemcpyDeviceToDevice, stream_));
+    SWB_CUDA(cudaMemsetAsync(corpus.get() + n, ' ', 64, stream_));
+    build_word_table(corpus, n);
+    stats.load_ms += now_ms() - t0;
+  }
+
+  // corpus: n bytes + >= 16 bytes of ' ' padding, 16-byte aligned (cudaMalloc)
+  void build_word_table(DevBuf<uint8_t> &corpus, uint64_t n) {
+    if (n >= (1ull << 40)) throw Error("corpus larger than 1 TiB is not supported (40-bit offsets)");
+    free_corpus_state();
+    unsigned int *d_nuniq = scalars_.get() + 0, *d_flags = scalars_.get() + 1, *d_cursor = scalars_.get() + 2,
+                 *d_nlong = scalars_.get() + 3;
+    unsigned long long *d_u64 = reinterpret_cast<unsigned long long *>(scalars_.get() + 8);  // [0]=long syms [1]=bytes [2]=cursor
+    // ---- 1. tokenise + dedupe
+    uint64_t cap = std::max<uint64_t>(1ull << 16, pow2_ceil(n / 64));
+    DevBuf<unsigned long long> keys, counts;
+    unsigned int h_scal[4];
+    for (;;) {
+      keys.alloc(cap); counts.alloc(cap);
+      wt_fill<<<sms_ * 8, 256, 0, stream_>>>(keys.get(), counts.get(), cap); launched();
+      SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
+      WordTableDev tbl{keys.get(), counts.get(), cap - 1, d_nuniq, d_flags, (uint64_t)(cap * 0.6)};
+      if (n) { wt_tokenize<<<sms_ * 4, WT_THREADS, WT_SMEM_BYTES, stream_>>>(corpus.get(), n, tbl); launched(); }
+      SWB_CUDA(cudaGetLastError());
+      SWB_CUDA(cudaMemcpyAsync(h_scal, scalars_.get(), sizeof h_scal, cudaMemcpyDeviceToHost, stream_));
+      sync();
+      if (h_scal[1] & 2u) throw Error("NUL byte in corpus: outside the parity domain (the reference drops a libc-buffer-dependent span)");
+      if (!(h_scal[1] & 1u)) break;
+      cap *= 8;  // more unique words than expected: bigger table, run again
+    }
+    W = h_scal[0];
+    if (W >= (1ull << 31)) throw Error("more than 2^31 unique words");
+    // ---- 2. reference word order: (djb2 bucket, first occurrence)
+    DevBuf<unsigned long long> skeys(W), scnt(W), skeys2(W);
+    cnt_.alloc(W);
+    if (W) {
+      wt_compact<<<sms_ * 8, 256, 0, stream_>>>(keys.get(), counts.get(), cap, skeys.get(), scnt.get(), d_cursor); launched();
+      size_t tmp_bytes = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, skeys.get(), skeys2.get(), scnt.get(), cnt_.get(), (int64_t)W, 0, 52, stream_);
+      DevBuf<uint8_t> tmp(tmp_bytes);
+      SWB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), tmp_bytes, skeys.get(), skeys2.get(), scnt.get(), cnt_.get(), (int64_t)W, 0, 52, stream_));
+      launched(8);
+      sync();
+    }
+    keys.release(); counts.release(); skeys.release(); scnt.release();
+    // ---- 3. lengths, byte histogram, long words
+    DevBuf<uint64_t> woff(W);
+    DevBuf<uint32_t> wlen(W);
+    long_index_.alloc(W);
+    DevBuf<unsigned long long> hist(256);
+    SWB_CUDA(cudaMemsetAsync(hist.get(), 0, hist.bytes(), stream_));
+    if (W) {
+      wt_word_info<<<std::min<uint64_t>(sms_ * 8, (W + 255) / 256), 256, 0, stream_>>>(
+          corpus.get(), n, skeys2.get(), W, woff.get(), wlen.get(), hist.get(), d_nlong, d_u64 + 0, long_index_.get(), d_u64 + 1);
+      launched();
+    }
+    unsigned long long h_hist[256], h_u64[3];
+    SWB_CUDA(cudaMemcpyAsync(h_hist, hist.get(), sizeof h_hist, cudaMemcpyDeviceToHost, stream_));
+    SWB_CUDA(cudaMemcpyAsync(h_scal, scalars_.get(), sizeof h_scal, cudaMemcpyDeviceToHost, stream_));
+    SWB_CUDA(cudaMemcpyAsync(h_u64, d_u64, sizeof h_u64, cudaMemcpyDeviceToHost, stream_));
+    sync();
+    skeys2.release();
+    n_long_ = h_scal[3];
+    const uint64_t long_total = h_u64[0];
+    word_bytes_total_ = h_u64[1];
+    // ---- 4. character coverage rule on the host (256 values; reference bpe.cpp:257-279)
+    apply_keep_rule(h_hist);
+    DevBuf<int32_t> d_bmap(256);
+    int32_t dev_map[256];
+    for (int i = 0; i < 256; i++) dev_map[i] = keep[i] ? i : unk_dev();
+    SWB_CUDA(cudaMemcpyAsync(d_bmap.get(), dev_map, sizeof dev_map, cudaMemcpyHostToDevice, stream_));
+    // ---- 5. pack this rank's words into rows
+    const uint64_t n_batches = (W + PACK_BATCH - 1) / PACK_BATCH;
+    wloc_.alloc(W);
+    n_rows_ = 0;
+    if (W) {
+      DevBuf<uint32_t> batch_rows(n_batches);
+      const int pgrid = (int)std::min<uint64_t>(sms_ * 4, (n_batches + 7) / 8);
+      wt_pack<false><<<pgrid, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), long_index_.get(), W, rank, nranks,
+                                                 d_bmap.get(), batch_rows.get(), nullptr, nullptr);
+      launched();
+      std::vector<uint32_t> h_rows(n_batches);
+      SWB_CUDA(cudaMemcpyAsync(h_rows.data(), batch_rows.get(), n_batches * 4, cudaMemcpyDeviceToHost, stream_));
+      sync();
+      uint64_t acc = 0;
+      for (uint64_t i = 0; i < n_batches; i++) { const uint32_t c = h_rows[i]; h_rows[i] = (uint32_t)acc; acc += c; }
+      if (acc >= (1ull << 32)) throw Error("too many rows");
+      n_rows_ = acc;
+      rows_.alloc(n_rows_ * (ROW / 4));
+      SWB_CUDA(cudaMemcpyAsync(batch_rows.get(), h_rows.data(), n_batches * 4, cudaMemcpyHostToDevice, stream_));
+      wt_pack<true><<<pgrid, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), long_index_.get(), W, rank, nranks,
+                                                d_bmap.get(), batch_rows.get(), rows_.get(), wloc_.get());
+      launched();
+      sync();
+    }
+    // ---- 6. long words
+    long_off_.alloc(n_long_); long_len_.alloc(n_long_); long_word_.alloc(n_long_); long_syms_.alloc(long_total);
+    if (n_long_) {
+      wt_long_offsets<<<sms_ * 4, 256, 0, stream_>>>(wlen.get(), long_index_.get(), W, d_u64 + 2, long_off_.get());
+      wt_fill_long<<<sms_ * 4, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), long_index_.get(), W, rank, nranks,
+                                                  d_bmap.get(), long_off_.get(), long_syms_.get(), long_len_.get(), long_word_.get());
+      launched(2);
+    }
+    // ---- 7. keep the bytes of the unique words (accessors, encoder pin checks); release the corpus
+    word_boff_.alloc(W + 1);
+    word_bytes_.alloc(word_bytes_total_);
+    if (W) {
+      cub::TransformInputIterator<unsigned long long, CastU32ToU64, const uint32_t *> it(wlen.get(), CastU32ToU64());
+      size_t tmp_bytes = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, (unsigned long long *)word_boff_.get(), (int64_t)W, stream_);
+      DevBuf<uint8_t> tmp(tmp_bytes);
+      SWB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(), tmp_bytes, it, (unsigned long long *)word_boff_.get(), (int64_t)W, stream_));
+      launched(2);
+      wt_gather_bytes<<<sms_ * 8, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), word_boff_.get(), W, word_bytes_.get());
+      launched();
+      sync();
+    }
+    SWB_CUDA(cudaMemcpyAsync(word_boff_.get() + W, &word_bytes_total_, 8, cudaMemcpyHostToDevice, stream_));
+    h_counts.resize(W);
+    if (W) SWB_CUDA(cudaMemcpyAsync(h_counts.data(), cnt_.get(), W * 8, cudaMemcpyDeviceToHost, stream_));
+    sync();
+    // live symbols of this rank
+    live_symbols_ = 0;
+    if (nranks == 1) live_symbols_ = word_bytes_total_;
+    else {
+      std::vector<uint32_t> h_len(W);
+      if (W) SWB_CUDA(cudaMemcpy(h_len.data(), wlen.get(), W * 4, cudaMemcpyDeviceToHost));
+      for (uint64_t w = rank; w < W; w += nranks) live_symbols_ += h_len[w];
+    }
+    corpus.release();
+    SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
+    // public mirror fields (reference Corpus)
+    tr_->corpus.vocab_size = W;
+    tr_->corpus.word_counts = h_counts.data();
+    tr_->corpus.words = reinterpret_cast<void **>(this);  // opaque, non-NULL
+    stats.words = W; stats.rows = n_rows_; stats.long_words = n_long_; stats.live_symbols = live_symbols_;
+    loaded_ = true;
+    // reference bpe.cpp:295: a fresh pair table after every load
+    core.pairs().clear();
+  }
+
+  // reference bpe.cpp:262-279 + histogram.cpp:47-53: bytes listed in the bucket
+  // order of a 256-bucket djb2 map of 1-byte strings, stable-sorted by count descending, the first
+  // (size_t)(c * coverage) kept -- the product is taken in float, as in the reference.
+  void apply_keep_rule(const unsigned long long *hist) {
+    uint8_t order[256];
+    size_t c = 0;
+    for (int b = 0; b < 256; b++) {
+      const uint8_t byte = (uint8_t)((b - 165) & 255);
+      if (hist[byte]) order[c++] = byte;
+    }
+    std::stable_sort(order, order + c, [&](uint8_t x, uint8_t y) { return hist[x] > hist[y]; });
+    const size_t nkeep = (size_t)((float)c * tr_->config.character_coverage);
+    memset(keep, 0, sizeof keep);
+    for (size_t i = 0; i < nkeep && i < c; i++) keep[order[i]] = 1;
+    for (int i = 0; i < 256; i++) byte_map[i] = keep[i] ? i : tr_->config.unk_id;
+    if (core.log_level > 0) printf("[DEBUG]\t Character histogram built with %zu unique characters.\n", c);
+  }
+
+  // ---------------------------------------------------------------- pair table plumbing
+  void ensure_pair_table(uint64_t min_cap) {
+    ensure_device();
+    uint64_t cap = std::max<uint64_t>(1ull << 20, pow2_ceil(min_cap));
+    if (pt_cap_ >= cap) return;
+    if (cap > (1ull << 31)) throw Error("pair table would exceed 2^31 slots");
+    sync();
+    pt_keys_.alloc(cap); pt_val_.alloc(cap); pt_min_.alloc(cap); pt_touched_.alloc(cap);
+    pt_scal_.alloc(4);
+    recs_.alloc(cap / 2);
+    removed_.alloc(1);
+    SWB_CUDA(cudaMemsetAsync(removed_.get(), 0, 8, stream_));
+    pt_cap_ = cap;
+    pt_ = PairTableDev{pt_keys_.get(), pt_val_.get(), pt_min_.get(), pt_touched_.get(), pt_scal_.get() + 0,
+                       pt_scal_.get() + 1, pt_scal_.get() + 2, (uint32_t)(cap - 1)};
+    pt_clear<<<sms_ * 8, 256, 0, stream_>>>(pt_); launched();
+  }
+  StreamDev stream_dev() {
+    return StreamDev{rows_.get(), n_rows_, cnt_.get(), long_syms_.get(), long_off_.get(), long_len_.get(),
+                     long_word_.get(), n_long_};
+  }
+  // runs pt_emit, waits, returns the records (in mapped host memory, valid until the next emit)
+  size_t emit_and_wait(unsigned int *flags_out, uint64_t *removed_out) {
+    pt_emit<<<32, 256, 0, stream_>>>(pt_, recs_.dev(), recs_.size(), hdr_.dev(), removed_.get()); launched();
+    SWB_CUDA(cudaGetLastError());
+    sync();
+    const size_t n = (size_t)hdr_.host()[0];
+    *flags_out = (unsigned int)hdr_.host()[1];
+    if (removed_out) *removed_out = hdr_.host()[2];
+    return n;
+  }
+  // device ids -> caller ids (a negative unk_id travels as UNK_CODE on the device)
+  void translate_out(Rec *r, size_t n) const {
+    if (tr_->config.unk_id >= 0) return;
+    for (size_t i = 0; i < n; i++) {
+      if (r[i].first == UNK_CODE) r[i].first = tr_->config.unk_id;
+      if (r[i].second == UNK_CODE) r[i].second = tr_->config.unk_id;
+    }
+  }
+
+  // ---------------------------------------------------------------- count (this rank's words)
+  // Returns the records (pair, weighted frequency, first-touch key) of this rank's share.
+  const Rec *shard_count(size_t *n_out) {
+    ensure_pair_table(1);
+    const double t0 = now_ms();
+    if (!loaded_) { *n_out = 0; return recs_.host(); }
+    for (;;) {
+      StreamDev s = stream_dev();
+      if (n_rows_) {
+        const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 8, (n_rows_ + 7) / 8);
+        count_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, unk_dev()); launched();
+      }
+      if (n_long_) { count_long<<<std::min<uint32_t>(sms_ * 4, (n_long_ + 3) / 4), 128, 0, stream_>>>(s, pt_, unk_dev()); launched(); }
+      unsigned int flags = 0;
+      const size_t n = emit_and_wait(&flags, nullptr);
+      if (flags & 5u) {  // table (or record buffer) too small for the number of distinct pairs: grow, recount
+        const uint64_t want = pt_cap_ * 4;
+        pt_cap_ = 0;
+        ensure_pair_table(want);
+        continue;
+      }
+      translate_out(recs_.host(), n);
+      *n_out = n;
+      stats.count_ms += now_ms() - t0;
+      return recs_.host();
+    }
+  }
+
+  // ---------------------------------------------------------------- merge (this rank's words)
+  const Rec *shard_merge(int32_t a, int32_t b, int32_t new_id, size_t *n_out) {
+    // at most 4 distinct pairs per distinct neighbour symbol: size the table so that it cannot fill up
+    ensure_pair_table(8ull * (258ull + tr_->num_merges + 2));
+    *n_out = 0;
+    if (!loaded_) return recs_.host();
+    const int32_t unk = tr_->config.unk_id;
+    if ((a < 0 && a != unk) || (b < 0 && b != unk)) return recs_.host();  // such ids exist in no word
+    const int32_t da = a < 0 ? UNK_CODE : a, db = b < 0 ? UNK_CODE : b;
+    StreamDev s = stream_dev();
+    if (timing) SWB_CUDA(cudaEventRecord(ev0_, stream_));
+    if (n_rows_) {
+      const uint64_t warps_needed = (n_rows_ + MERGE_UNROLL - 1) / MERGE_UNROLL;
+      const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 8, (warps_needed + 7) / 8);
+      merge_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, da, db, new_id, removed_.get()); launched();
+      stats.merge_launches++;
+    }
+    if (timing) SWB_CUDA(cudaEventRecord(ev1_, stream_));
+    if (n_long_) { merge_long<<<std::min<uint32_t>(sms_ * 4, (n_long_ + 3) / 4), 128, 0, stream_>>>(s, pt_, da, db, new_id, removed_.get()); launched(); }
+    unsigned int flags = 0;
+    uint64_t removed = 0;
+    const size_t n = emit_and_wait(&flags, &removed);
+    if (flags) throw Error("pair table overflow during a merge (internal sizing error)");
+    if (timing) {
+      float ms = 0;
+      SWB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+      stats.merge_kernel_ms += ms;
+    }
+    stats.merge_scan_bytes += n_rows_ * ROW * 4;
+    stats.merge_alg_bytes += 4 * live_symbols_ + 8 * (nranks == 1 ? W : (W + nranks - 1 - rank) / nranks);
+    live_symbols_ -= removed;
+    stats.live_symbols = live_symbols_;
+    translate_out(recs_.host(), n);
+    *n_out = n;
+    return recs_.host();
+  }
+
+  // ---------------------------------------------------------------- single-process drivers
+  void count_bigrams() {  // reference bpe_count_bigrams
+    size_t n = 0;
+    const Rec *r = shard_count(&n);
+    core.seed_counts(r, n);
+  }
+  void init() {  // reference bpe_init
+    core.reset_tables();
+    count_bigrams();
+  }
+  int merge_batch(int batch) {  // reference bpe_merge_batch
+    const double t0 = now_ms();
+    int done = 0;
+    while (done < batch && !core.heap_empty()) {
+      int32_t a, b, nid;
+      if (!core.next_merge(&a, &b, &nid)) break;
+      size_t n = 0;
+      const Rec *r = shard_merge(a, b, nid, &n);
+      core.apply(r, n);
+      done++;
+    }
+    stats.merge_ms += now_ms() - t0;
+    return done;
+  }
+
+  // ---------------------------------------------------------------- results
+  void token_freq(std::vector<uint64_t> &freq) {
+    const size_t T = 256 + tr_->num_merges;
+    freq.assign(T, 0);
+    if (!loaded_) return;
+    DevBuf<unsigned long long> d(T);
+    SWB_CUDA(cudaMemsetAsync(d.get(), 0, d.bytes(), stream_));
+    StreamDev s = stream_dev();
+    if (n_rows_) { tokfreq_rows<<<(int)std::min<uint64_t>((uint64_t)sms_ * 8, (n_rows_ + 7) / 8), MERGE_THREADS, 0, stream_>>>(s, d.get(), (uint32_t)T); launched(); }
+    if (n_long_) { tokfreq_long<<<std::min<uint32_t>(sms_ * 4, (n_long_ + 3) / 4), 128, 0, stream_>>>(s, d.get(), (uint32_t)T); launched(); }
+    SWB_CUDA(cudaMemcpyAsync(freq.data(), d.get(), T * 8, cudaMemcpyDeviceToHost, stream_));
+    sync();
+  }
+  uint64_t num_symbols() const { return live_symbols_; }
+  uint64_t word_bytes_total() const { return word_bytes_total_; }
+  bool loaded() const { return loaded_; }
+
+  // word table -> host (this rank's words have their symbols; other ranks' words come back empty)
+  void get_words(uint64_t *byte_off, uint8_t *bytes, uint64_t *sym_off, int32_t *syms, uint64_t *counts) {
+    if (!loaded_ || W == 0) {
+      if (byte_off) byte_off[0] = 0;
+      if (sym_off) sym_off[0] = 0;
+      return;
+    }
+    if (byte_off) SWB_CUDA(cudaMemcpyAsync(byte_off, word_boff_.get(), (W + 1) * 8, cudaMemcpyDeviceToHost, stream_));
+    if (bytes && word_bytes_total_) SWB_CUDA(cudaMemcpyAsync(bytes, word_bytes_.get(), word_bytes_total_, cudaMemcpyDeviceToHost, stream_));
+    if (counts) memcpy(counts, h_counts.data(), W * 8);
+    if (sym_off || syms) {
+      StreamDev s = stream_dev();
+      DevBuf<uint32_t> len(W);
+      words_live_len<<<sms_ * 4, 256, 0, stream_>>>(s, wloc_.get(), long_index_.get(), (uint32_t)W, rank, nranks, len.get()); launched();
+      std::vector<uint32_t> h_len(W);
+      SWB_CUDA(cudaMemcpyAsync(h_len.data(), len.get(), W * 4, cudaMemcpyDeviceToHost, stream_));
+      sync();
+      std::vector<uint64_t> off(W + 1);
+      uint64_t acc = 0;
+      for (uint64_t w = 0; w < W; w++) { off[w] = acc; acc += h_len[w]; }
+      off[W] = acc;
+      if (sym_off) memcpy(sym_off, off.data(), (W + 1) * 8);
+      if (syms && acc) {
+        DevBuf<uint64_t> d_off(W + 1);
+        DevBuf<int32_t> d_out(acc);
+        SWB_CUDA(cudaMemcpyAsync(d_off.get(), off.data(), (W + 1) * 8, cudaMemcpyHostToDevice, stream_));
+        words_copy_syms<<<sms_ * 4, 256, 0, stream_>>>(s, wloc_.get(), long_index_.get(), (uint32_t)W, rank, nranks, d_off.get(), d_out.get()); launched();
+        SWB_CUDA(cudaMemcpyAsync(syms, d_out.get(), acc * 4, cudaMemcpyDeviceToHost, stream_));
+        sync();
+        if (tr_->config.unk_id < 0)
+          for (uint64_t i = 0; i < acc; i++) if (syms[i] == UNK_CODE) syms[i] = tr_->config.unk_id;
+      }
+    }
+    sync();
+  }
+
+ private:
+  void free_corpus_state() {
+    rows_.release(); cnt_.release(); wloc_.release(); long_index_.release(); long_syms_.release(); long_off_.release();
+    long_len_.release(); long_word_.release(); word_bytes_.release(); word_boff_.release();
+    n_rows_ = 0; n_long_ = 0; W = 0; live_symbols_ = 0; word_bytes_total_ = 0; loaded_ = false;
+    h_counts.clear();
+  }
+
+  Trainer *tr_;
+  int device_ = 0, sms_ = 148;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  bool loaded_ = false;
+  DevBuf<unsigned int> scalars_;
+  PinnedBuf<unsigned long long> hdr_;
+  // symbol stream
+  DevBuf<int4> rows_;
+  uint64_t n_rows_ = 0;
+  DevBuf<unsigned long long> cnt_;
+  DevBuf<uint64_t> wloc_;
+  DevBuf<uint32_t> long_index_;
+  DevBuf<int32_t> long_syms_;
+  DevBuf<uint64_t> long_off_;
+  DevBuf<uint32_t> long_len_, long_word_;
+  uint32_t n_long_ = 0;
+  uint64_t live_symbols_ = 0, word_bytes_total_ = 0;
+  DevBuf<uint8_t> word_bytes_;
+  DevBuf<uint64_t> word_boff_;
+  // pair table
+  uint64_t pt_cap_ = 0;
+  PairTableDev pt_{};
+  DevBuf<unsigned long long> pt_keys_, pt_val_, pt_min_, removed_;
+  DevBuf<unsigned int> pt_touched_, pt_scal_;
+  PinnedBuf<Rec> recs_;
+};
+
+}  // namespace swb
