@@ -132,6 +132,8 @@ typedef struct SwbStats {
   uint64_t merge_alg_bytes;   /* sum over merges of 4*S_live + 8*W */
   uint64_t rows, live_symbols, words, long_words;
   uint64_t repacks;
+  double host_pop_ms, host_launch_ms, host_wait_ms, host_apply_ms; /* merge loop split on the host */
+  uint64_t records, heap_pushes, heap_pops, heap_peak;             /* host replica counters */
 } SwbStats;
 void swb_get_stats(const Trainer *trainer, SwbStats *out);
 /* 1: bracket every merge-scan launch with CUDA events (adds a little latency); 0: off (default). */
@@ -174,6 +176,10 @@ void swb_dist_apply(Trainer *trainer, const int64_t *recs, size_t n);
  * (-1 on error); records are written to recs (capacity cap records). */
 int64_t swb_shard_count(Trainer *trainer, int64_t *recs, size_t cap);
 int64_t swb_shard_merge(Trainer *trainer, int32_t a, int32_t b, int32_t new_id, int64_t *recs, size_t cap);
+/* bpe_save with a caller-supplied token histogram (the all-reduced one when words are sharded).
+ * freq must hold 256+num_merges entries. 0 on success. */
+int swb_save_with_freq(const Trainer *trainer, const char *model_path, const char *vocab_path, const uint64_t *freq,
+                       size_t n_freq);
 
 #ifdef __cplusplus
 }

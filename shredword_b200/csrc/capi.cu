@@ -140,15 +140,10 @@ static void build_c_tokens(const Trainer *t, std::vector<std::string> &tok) {
   }
 }
 
-void bpe_save(const Trainer *trainer, const char *model_path, const char *vocab_path) {
-  if (!trainer || !model_path || !vocab_path) { set_err("Trainer pointer is NULL!"); return; }
-  SWB_TRY
-  TrainerImpl *im = impl_of(trainer);
+static void save_files(const Trainer *trainer, const char *model_path, const char *vocab_path, const uint64_t *freq) {
   const size_t M = trainer->num_merges, T = 256 + M;
   std::vector<std::string> tok;
   build_c_tokens(trainer, tok);
-  std::vector<uint64_t> freq;
-  im->token_freq(freq);
   FILE *vf = fopen(vocab_path, "w");
   if (!vf) throw swb::Error(std::string("cannot open ") + vocab_path);
   for (size_t i = 0; i < T; i++) fprintf(vf, "%s %llu\n", tok[i].c_str(), (unsigned long long)freq[i]);
@@ -161,6 +156,14 @@ void bpe_save(const Trainer *trainer, const char *model_path, const char *vocab_
   }
   fclose(mf);
   if (log_level() > 0) printf("[INFO]\tSaved %zu-token vocab to %s and %zu merges to %s\n", T, vocab_path, M, model_path);
+}
+
+void bpe_save(const Trainer *trainer, const char *model_path, const char *vocab_path) {
+  if (!trainer || !model_path || !vocab_path) { set_err("Trainer pointer is NULL!"); return; }
+  SWB_TRY
+  std::vector<uint64_t> freq;
+  impl_of(trainer)->token_freq(freq);
+  save_files(trainer, model_path, vocab_path, freq.data());
   SWB_CATCH()
 }
 
@@ -245,7 +248,10 @@ int swb_get_words(const Trainer *trainer, uint64_t *byte_off, uint8_t *bytes, ui
 }
 void swb_get_stats(const Trainer *trainer, SwbStats *out) {
   if (!trainer || !out) return;
-  *out = impl_of(trainer)->stats;
+  TrainerImpl *im = impl_of(trainer);
+  im->stats.records = im->core.n_records; im->stats.heap_pushes = im->core.n_pushes;
+  im->stats.heap_pops = im->core.n_pops; im->stats.heap_peak = im->core.heap_peak;
+  *out = im->stats;
 }
 void swb_set_kernel_timing(Trainer *trainer, int enabled) {
   if (trainer) impl_of(trainer)->timing = enabled != 0;
@@ -337,6 +343,16 @@ int64_t swb_shard_merge(Trainer *trainer, int32_t a, int32_t b, int32_t new_id, 
   if (n > cap) throw swb::Error("swb_shard_merge: record buffer too small");
   if (n) memcpy(recs, r, n * sizeof(Rec));
   return (int64_t)n;
+  SWB_CATCH(-1)
+}
+
+int swb_save_with_freq(const Trainer *trainer, const char *model_path, const char *vocab_path, const uint64_t *freq,
+                       size_t n_freq) {
+  if (!trainer || !model_path || !vocab_path || !freq) { set_err("swb_save_with_freq: NULL argument"); return -1; }
+  if (n_freq < 256 + trainer->num_merges) { set_err("swb_save_with_freq: freq too short"); return -1; }
+  SWB_TRY
+  save_files(trainer, model_path, vocab_path, freq);
+  return 0;
   SWB_CATCH(-1)
 }
 

@@ -29,47 +29,60 @@ static inline uint64_t mix64(uint64_t x) {
 }
 static inline uint64_t pack_pair(int32_t a, int32_t b) { return ((uint64_t)(uint32_t)a << 32) | (uint32_t)b; }
 
-// pair -> {freq, version}; entries live in creation order because the reference's BIMap iteration
-// order (bucket ascending, chain in creation order; reference hash.cpp:104-130) is observable
-// through bpe_count_bigrams' push pass (reference bpe.cpp:359-366).
-struct PairInfo { int32_t first, second; uint64_t freq; uint32_t version; };
+// pair -> {freq, version}. One 24-byte open-addressing slot per pair (a lookup is one cache miss, and
+// the misses of a whole delta list are overlapped by prefetching). `order` is the creation rank:
+// the reference's BIMap iteration order (bucket ascending, chain in creation order; reference
+// hash.cpp:104-130) is observable through bpe_count_bigrams' push pass (reference bpe.cpp:359-366).
+struct PairInfo { int32_t first, second; uint64_t freq; uint32_t version; uint32_t order; /* 0 = free slot */ };
+static_assert(sizeof(PairInfo) == 24, "PairInfo is one 24-byte slot");
 
 class PairTable {
  public:
   PairTable() { clear(); }
   void clear() {
-    entries_.clear();
-    slots_.assign(4096, 0);
+    slots_.assign(1u << 14, PairInfo{0, 0, 0, 0, 0});
+    n_ = 0;
   }
-  size_t size() const { return entries_.size(); }
-  PairInfo &at(size_t i) { return entries_[i]; }
-  const PairInfo &at(size_t i) const { return entries_[i]; }
-  // find-or-create (reference bimap_get: a missing pair reads as freq 0, version 0)
-  size_t get(int32_t a, int32_t b) {
-    const uint64_t k = pack_pair(a, b);
-    size_t mask = slots_.size() - 1, h = (size_t)mix64(k) & mask;
-    while (slots_[h]) {
-      const PairInfo &p = entries_[slots_[h] - 1];
-      if (p.first == a && p.second == b) return slots_[h] - 1;
+  size_t size() const { return n_; }
+  size_t home(int32_t a, int32_t b) const { return (size_t)mix64(pack_pair(a, b)) & (slots_.size() - 1); }
+  void prefetch(int32_t a, int32_t b) const { __builtin_prefetch(&slots_[home(a, b)]); }
+  // find-or-create (reference bimap_get: a missing pair reads as freq 0, version 0).
+  // The reference is valid until the next get().
+  PairInfo &get(int32_t a, int32_t b) {
+    if ((n_ + 1) * 2 > slots_.size()) rehash(slots_.size() * 4);
+    const size_t mask = slots_.size() - 1;
+    size_t h = home(a, b);
+    for (;;) {
+      PairInfo &p = slots_[h];
+      if (!p.order) {
+        p.first = a; p.second = b; p.freq = 0; p.version = 0; p.order = (uint32_t)(++n_);
+        return p;
+      }
+      if (p.first == a && p.second == b) return p;
       h = (h + 1) & mask;
     }
-    entries_.push_back(PairInfo{a, b, 0, 0});
-    slots_[h] = (uint32_t)entries_.size();
-    if (entries_.size() * 2 > slots_.size()) rehash(slots_.size() * 4);
-    return entries_.size() - 1;
+  }
+  // all entries in creation order
+  void in_creation_order(std::vector<PairInfo> &out) const {
+    out.resize(n_);
+    for (const PairInfo &p : slots_)
+      if (p.order) out[p.order - 1] = p;
   }
 
  private:
   void rehash(size_t n) {
-    slots_.assign(n, 0);
-    for (size_t i = 0; i < entries_.size(); i++) {
-      size_t h = (size_t)mix64(pack_pair(entries_[i].first, entries_[i].second)) & (n - 1);
-      while (slots_[h]) h = (h + 1) & (n - 1);
-      slots_[h] = (uint32_t)(i + 1);
+    std::vector<PairInfo> old;
+    old.swap(slots_);
+    slots_.assign(n, PairInfo{0, 0, 0, 0, 0});
+    for (const PairInfo &p : old) {
+      if (!p.order) continue;
+      size_t h = home(p.first, p.second);
+      while (slots_[h].order) h = (h + 1) & (n - 1);
+      slots_[h] = p;
     }
   }
-  std::vector<PairInfo> entries_;
-  std::vector<uint32_t> slots_;
+  std::vector<PairInfo> slots_;
+  size_t n_ = 0;
 };
 
 // FNV-1a over the 8 little-endian bytes of {first, second} (reference hash.cpp:7-16)
@@ -111,6 +124,7 @@ class HostCore {
   ~HostCore() { free(tr_->heap.data); tr_->heap.data = nullptr; tr_->heap.size = tr_->heap.cap = 0; }
 
   int log_level = 0;
+  uint64_t n_records = 0, n_pushes = 0, n_pops = 0, heap_peak = 0;
 
   // ---- heap: the exact array heap of reference heap.cpp:53-114, stored in the public Trainer fields
   void heap_reset() {  // heap_free + heap_init(4096), reference bpe.cpp:182-183
@@ -127,6 +141,8 @@ class HostCore {
       if (!h.data) { fprintf(stderr, "[ERROR]\t heap reallocation failed\n"); abort(); }
     }
     size_t i = h.size++;
+    n_pushes++;
+    if (h.size > heap_peak) heap_peak = h.size;
     h.data[i].key.first = a; h.data[i].key.second = b; h.data[i].freq = freq; h.data[i].version = version;
     while (i > 0) {  // stop as soon as parent.freq >= child.freq (reference heap.cpp:74-79)
       size_t p = (i - 1) >> 1;
@@ -138,6 +154,7 @@ class HostCore {
   HeapEntry heap_pop() {
     MaxHeap &h = tr_->heap;
     HeapEntry top = h.data[0];
+    n_pops++;
     h.data[0] = h.data[--h.size];
     size_t i = 0;
     for (;;) {  // left child if strictly larger, then right if strictly larger than that (heap.cpp:97-111)
@@ -165,20 +182,20 @@ class HostCore {
     std::vector<Rec> v(recs, recs + n);
     std::sort(v.begin(), v.end(), [](const Rec &x, const Rec &y) { return (uint64_t)x.key < (uint64_t)y.key; });
     for (const Rec &r : v) {
-      PairInfo &p = pairs_.at(pairs_.get((int32_t)r.first, (int32_t)r.second));
+      PairInfo &p = pairs_.get((int32_t)r.first, (int32_t)r.second);
       if (p.freq == 0) p.version = 0;  // bpe.cpp:342-345
       p.freq += (uint64_t)r.delta;
     }
-    const size_t P = pairs_.size();
-    std::vector<uint32_t> order(P);
-    for (size_t i = 0; i < P; i++) order[i] = (uint32_t)i;
-    std::vector<uint32_t> bucket(P);
-    for (size_t i = 0; i < P; i++) bucket[i] = ref_pair_hash(pairs_.at(i).first, pairs_.at(i).second) & 4095u;
+    std::vector<PairInfo> all;
+    pairs_.in_creation_order(all);
+    const size_t P = all.size();
+    std::vector<uint32_t> order(P), bucket(P);
+    for (size_t i = 0; i < P; i++) { order[i] = (uint32_t)i; bucket[i] = ref_pair_hash(all[i].first, all[i].second) & 4095u; }
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return bucket[x] < bucket[y]; });
     const uint64_t minf = tr_->config.min_pair_freq;
     size_t pushed = 0;
     for (uint32_t i : order) {
-      const PairInfo &p = pairs_.at(i);
+      const PairInfo &p = all[i];
       if (p.freq >= minf) { heap_push(p.first, p.second, p.freq, p.version); pushed++; }
     }
     if (log_level > 0) {
@@ -192,7 +209,7 @@ class HostCore {
     const uint64_t minf = tr_->config.min_pair_freq;
     while (!heap_empty()) {
       HeapEntry top = heap_pop();
-      PairInfo &info = pairs_.at(pairs_.get(top.key.first, top.key.second));
+      PairInfo &info = pairs_.get(top.key.first, top.key.second);
       if (top.version != info.version) continue;  // stale (bpe.cpp:412-415)
       if (info.freq < minf) continue;             // bpe.cpp:418-421
       cur_a_ = top.key.first; cur_b_ = top.key.second;
@@ -214,31 +231,55 @@ class HostCore {
   // first-touch order of the pair inside this merge.
   void apply(const Rec *recs, size_t n) {
     if (!pending_) return;
-    scratch_.assign(recs, recs + n);
-    bool any_negative = false;
-    for (Rec &r : scratch_) {
+    n_records += n;
+    if (tr_->config.unk_id < 0 && n) {
       // The reference keys its per-merge delta map by ((uint64_t)first << 32) | (uint64_t)second with
       // int32 operands (bpe.cpp:456-457): a negative `second` sign-extends over `first`. Replayed here
-      // so that negative unk ids behave identically.
-      const uint64_t ph = ((uint64_t)(int64_t)(int32_t)r.first << 32) | (uint64_t)(int64_t)(int32_t)r.second;
-      const int32_t f = (int32_t)(ph >> 32), s = (int32_t)(ph & 0xFFFFFFFFu);
-      if (f != (int32_t)r.first) any_negative = true;
-      r.first = f; r.second = s;
+      // so that negative unk ids behave identically (distinct raw pairs can collapse into one entry).
+      scratch_.assign(recs, recs + n);
+      for (Rec &r : scratch_) {
+        const uint64_t ph = ((uint64_t)(int64_t)(int32_t)r.first << 32) | (uint64_t)(int64_t)(int32_t)r.second;
+        r.first = (int32_t)(ph >> 32); r.second = (int32_t)(ph & 0xFFFFFFFFu);
+      }
+      n = reduce_records(scratch_.data(), n);
+      recs = scratch_.data();
     }
-    size_t m = scratch_.size();
-    if (any_negative) { m = reduce_records(scratch_.data(), m); scratch_.resize(m); }
     // Delta-map iteration order (bpe.cpp:30, 41-45, 486-487): bucket = pair_hash % 1024 ascending;
     // inside a bucket entries were prepended, so the most recently first-touched pair comes first.
-    std::sort(scratch_.begin(), scratch_.end(), [](const Rec &x, const Rec &y) {
-      const uint32_t bx = (uint32_t)x.second & 1023u, by = (uint32_t)y.second & 1023u;
-      if (bx != by) return bx < by;
-      return (uint64_t)x.key > (uint64_t)y.key;
-    });
+    // Counting sort by bucket, then an insertion sort of each (tiny) bucket by key descending.
+    uint32_t start[1025];
+    memset(start, 0, sizeof start);
+    for (size_t i = 0; i < n; i++) start[((uint32_t)recs[i].second & 1023u) + 1]++;
+    for (int b = 0; b < 1024; b++) start[b + 1] += start[b];
+    order_.resize(n);
+    {
+      uint32_t fill[1024];
+      memcpy(fill, start, sizeof fill);
+      for (size_t i = 0; i < n; i++) order_[fill[(uint32_t)recs[i].second & 1023u]++] = KeyIdx{(uint64_t)recs[i].key, (uint32_t)i};
+    }
+    for (int b = 0; b < 1024; b++) {  // (L, new_id) for every L share one bucket: runs can be long
+      const uint32_t lo = start[b], hi = start[b + 1];
+      if (hi - lo < 2) continue;
+      if (hi - lo <= 8) {
+        for (uint32_t x = lo + 1; x < hi; x++) {
+          const KeyIdx v = order_[x];
+          uint32_t y = x;
+          while (y > lo && order_[y - 1].key < v.key) { order_[y] = order_[y - 1]; y--; }
+          order_[y] = v;
+        }
+      } else {
+        std::sort(order_.begin() + lo, order_.begin() + hi, [](const KeyIdx &x, const KeyIdx &y) { return x.key > y.key; });
+      }
+    }
     const uint64_t minf = tr_->config.min_pair_freq;
-    for (const Rec &r : scratch_) {
+    constexpr size_t PF = 12;  // slot prefetch distance: keeps ~a dozen cache misses in flight
+    for (size_t k = 0; k < n && k < PF; k++) pairs_.prefetch((int32_t)recs[order_[k].idx].first, (int32_t)recs[order_[k].idx].second);
+    for (size_t k = 0; k < n; k++) {
+      if (k + PF < n) pairs_.prefetch((int32_t)recs[order_[k + PF].idx].first, (int32_t)recs[order_[k + PF].idx].second);
+      const Rec &r = recs[order_[k].idx];
       const int32_t f = (int32_t)r.first, s = (int32_t)r.second;
       if (f == cur_a_ && s == cur_b_) continue;  // bpe.cpp:494-496
-      PairInfo &p = pairs_.at(pairs_.get(f, s));
+      PairInfo &p = pairs_.get(f, s);
       if (r.delta < 0) {  // clamp at zero on the NET delta (bpe.cpp:500-509)
         const uint64_t ad = (uint64_t)(-r.delta);
         p.freq = p.freq >= ad ? p.freq - ad : 0;
@@ -247,7 +288,7 @@ class HostCore {
       }
       if (p.freq >= minf) { p.version++; heap_push(f, s, p.freq, p.version); }  // bpe.cpp:512-515
     }
-    PairInfo &info = pairs_.at(pairs_.get(cur_a_, cur_b_));
+    PairInfo &info = pairs_.get(cur_a_, cur_b_);
     info.freq = 0; info.version++;  // bpe.cpp:523-524
     tr_->num_merges++;
     tr_->next_token = 256 + tr_->num_merges;
@@ -263,6 +304,8 @@ class HostCore {
   PairTable pairs_;
   std::vector<PairKey> merges_;
   std::vector<Rec> scratch_;
+  struct KeyIdx { uint64_t key; uint32_t idx; };
+  std::vector<KeyIdx> order_;
   int32_t cur_a_ = 0, cur_b_ = 0, cur_new_ = 0;
   bool pending_ = false;
 };

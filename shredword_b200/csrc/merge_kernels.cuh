@@ -65,38 +65,53 @@ __global__ void pt_clear(PairTableDev t) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { *t.n_touched = 0; *t.flags = 0; *t.done_blocks = 0; }
 }
 
-// touched slots -> records in mapped host memory; frees the slots. The last block to finish resets
-// the counters, so the next merge needs no extra memset on the critical path.
-// out_hdr[0] = number of records, out_hdr[1] = flags, out_hdr[2] = removed symbols of this merge.
-__global__ void __launch_bounds__(256)
-pt_emit(PairTableDev t, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
-        unsigned long long *removed) {
-  const unsigned int n = *t.n_touched;
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned int h = t.touched[i];
-    const unsigned long long k = t.keys[h];
+// touched slots -> records in mapped host memory; frees the slots. The last block to finish publishes
+// the header and resets the counters, so the next merge needs no extra memset on the critical path.
+// out_hdr[0] = number of records, [1] = flags, [2] = removed symbols of this merge, [3] = sequence
+// number (written last, after a system-scope fence: the host polls it instead of synchronising).
+// flags: 1 = table full, 4 = more records than out_cap, 8 = records not emitted (fused tail only).
+__device__ __forceinline__ void pt_emit_range(const PairTableDev &t, Rec *__restrict__ out, size_t out_cap,
+                                              unsigned int n, unsigned int first, unsigned int stride) {
+  for (unsigned int i = first; i < n; i += stride) {
+    const unsigned int h = __ldcg(&t.touched[i]);
+    const unsigned long long k = __ldcg(&t.keys[h]);
     if (i < out_cap) {
       Rec r;
       r.first = (int32_t)(k >> 32); r.second = (int32_t)(k & 0xFFFFFFFFu);
-      r.delta = (long long)t.val[h]; r.key = (long long)t.minkey[h];
+      r.delta = (long long)__ldcg(&t.val[h]); r.key = (long long)__ldcg(&t.minkey[h]);
       out[i] = r;
     }
     t.keys[h] = PT_EMPTY; t.val[h] = 0; t.minkey[h] = ~0ull;
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int d = atomicAdd(t.done_blocks, 1u);
-    if (d == gridDim.x - 1) {
-      out_hdr[0] = n;
-      out_hdr[1] = *t.flags | (n > out_cap ? 4u : 0u);
-      out_hdr[2] = removed ? *removed : 0ull;
-      if (removed) *removed = 0;
-      *t.n_touched = 0; *t.flags = 0; *t.done_blocks = 0;
-      __threadfence_system();
-    }
-  }
 }
+__device__ __forceinline__ void pt_publish(const PairTableDev &t, unsigned int n, size_t out_cap, unsigned int extra_flags,
+                                           volatile unsigned long long *out_hdr, unsigned long long *removed,
+                                           unsigned long long seq) {
+  out_hdr[0] = n;
+  out_hdr[1] = __ldcg(t.flags) | (n > out_cap ? 4u : 0u) | extra_flags;
+  out_hdr[2] = removed ? __ldcg(removed) : 0ull;
+  if (removed && !(extra_flags & 8u)) *removed = 0;
+  if (!(extra_flags & 8u)) { *t.n_touched = 0; *t.flags = 0; }
+  *t.done_blocks = 0;
+  __threadfence_system();
+  out_hdr[3] = seq;
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256)
+pt_emit(PairTableDev t, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
+        unsigned long long *removed, unsigned long long seq) {
+  __shared__ bool is_last;
+  const unsigned int n = __ldcg(t.n_touched);
+  pt_emit_range(t, out, out_cap, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) pt_publish(t, n, out_cap, 0u, out_hdr, removed, seq);
+}
+
+constexpr unsigned int FUSED_EMIT_MAX = 8192;  // above this the records are emitted by a full-grid pt_emit
 
 struct StreamDev {
   int4 *rows;                 // n_rows * ROW int32
@@ -166,9 +181,14 @@ __device__ __noinline__ uint32_t merge_row_slow(int *sm, int4 v, int lane, int4 
   return removed;
 }
 
+// fused != 0: the last block to finish also emits the records and publishes the header (one launch per
+// merge); used when there are no long words to process after this kernel.
 __global__ void __launch_bounds__(MERGE_THREADS)
-merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, unsigned long long *removed_total) {
+merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, unsigned long long *removed_total,
+           int fused, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
+           unsigned long long seq) {
   __shared__ __align__(16) int sm[MERGE_THREADS / 32][ROW];
+  __shared__ bool is_last;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint64_t warp = (blockIdx.x * (uint64_t)MERGE_THREADS + threadIdx.x) >> 5;
   const uint64_t n_warps = ((uint64_t)gridDim.x * MERGE_THREADS) >> 5;
@@ -185,14 +205,27 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
       if (lane == 31) nxt = PAD;
       const bool m = (v[u].x == a && v[u].y == b) || (v[u].y == a && v[u].z == b) || (v[u].z == a && v[u].w == b) ||
                      (v[u].w == a && nxt == b);
-      if (__any_sync(0xffffffffu, m)) {
+      if (__any_sync(0xffffffffu, m))
         removed += merge_row_slow(sm[wib], v[u], lane, s.rows + (r0 + u) * (ROW / 4), s, t, a, b, new_id);
-      }
     }
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) removed += __shfl_down_sync(0xffffffffu, removed, d);
   if (lane == 0 && removed) atomicAdd(removed_total, (unsigned long long)removed);
+  if (!fused) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  const unsigned int n = __ldcg(t.n_touched);
+  const bool small = n <= FUSED_EMIT_MAX;
+  if (small) {
+    pt_emit_range(t, out, out_cap, n, threadIdx.x, MERGE_THREADS);
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) pt_publish(t, n, out_cap, small ? 0u : 8u, out_hdr, removed_total, seq);
 }
 
 // long words: lanes stride over the word to detect; the rare word with a match is rewritten by lane 0

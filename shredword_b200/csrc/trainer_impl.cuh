@@ -73,6 +73,7 @@ class TrainerImpl {
     scalars_.alloc(16);
     SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
     hdr_.alloc(8);
+    memset(hdr_.host(), 0, 8 * sizeof(unsigned long long));
     SWB_CUDA(cudaFuncSetAttribute(wt_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
   }
   void sync() { SWB_CUDA(cudaStreamSynchronize(stream_)); }
@@ -309,11 +310,32 @@ class TrainerImpl {
     return StreamDev{rows_.get(), n_rows_, cnt_.get(), long_syms_.get(), long_off_.get(), long_len_.get(),
                      long_word_.get(), n_long_};
   }
-  // runs pt_emit, waits, returns the records (in mapped host memory, valid until the next emit)
+  // Waits until the kernels of this merge have published header sequence `seq` in mapped host memory.
+  // Polling the flag is cheaper than cudaStreamSynchronize on a loop that runs once per merge; the
+  // stream is queried from time to time so that a failed launch cannot hang the host.
+  void wait_seq(unsigned long long seq) {
+    volatile unsigned long long *h = hdr_.host();
+    for (uint64_t spin = 0;; spin++) {
+      if (h[3] == seq) return;
+      if ((spin & 0x3FFF) == 0x3FFF) {
+        cudaError_t e = cudaStreamQuery(stream_);
+        if (e == cudaSuccess) {
+          if (h[3] == seq) return;
+          throw Error("merge kernels finished without publishing their result");
+        }
+        if (e != cudaErrorNotReady) SWB_CUDA(e);
+      }
+    }
+  }
+  // runs pt_emit, waits, returns the record count (records are in mapped host memory until the next emit)
   size_t emit_and_wait(unsigned int *flags_out, uint64_t *removed_out) {
-    pt_emit<<<32, 256, 0, stream_>>>(pt_, recs_.dev(), recs_.size(), hdr_.dev(), removed_.get()); launched();
+    const unsigned long long seq = ++seq_;
+    pt_emit<<<32, 256, 0, stream_>>>(pt_, recs_.dev(), recs_.size(), hdr_.dev(), removed_.get(), seq); launched();
     SWB_CUDA(cudaGetLastError());
-    sync();
+    const double tw0 = now_ms();
+    stats.host_launch_ms += tw0 - t_launch0_;
+    wait_seq(seq);
+    stats.host_wait_ms += now_ms() - tw0;
     const size_t n = (size_t)hdr_.host()[0];
     *flags_out = (unsigned int)hdr_.host()[1];
     if (removed_out) *removed_out = hdr_.host()[2];
@@ -336,6 +358,7 @@ class TrainerImpl {
     if (!loaded_) { *n_out = 0; return recs_.host(); }
     for (;;) {
       StreamDev s = stream_dev();
+      t_launch0_ = now_ms();
       if (n_rows_) {
         const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 8, (n_rows_ + 7) / 8);
         count_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, unk_dev()); launched();
@@ -366,21 +389,44 @@ class TrainerImpl {
     if ((a < 0 && a != unk) || (b < 0 && b != unk)) return recs_.host();  // such ids exist in no word
     const int32_t da = a < 0 ? UNK_CODE : a, db = b < 0 ? UNK_CODE : b;
     StreamDev s = stream_dev();
+    t_launch0_ = now_ms();
     if (timing) SWB_CUDA(cudaEventRecord(ev0_, stream_));
+    const bool fused = n_rows_ && !n_long_;
+    unsigned long long seq = 0;
     if (n_rows_) {
       const uint64_t warps_needed = (n_rows_ + MERGE_UNROLL - 1) / MERGE_UNROLL;
       const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 8, (warps_needed + 7) / 8);
-      merge_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, da, db, new_id, removed_.get()); launched();
+      if (fused) seq = ++seq_;
+      merge_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, da, db, new_id, removed_.get(), fused ? 1 : 0, recs_.dev(),
+                                                      recs_.size(), hdr_.dev(), seq);
+      launched();
       stats.merge_launches++;
     }
     if (timing) SWB_CUDA(cudaEventRecord(ev1_, stream_));
     if (n_long_) { merge_long<<<std::min<uint32_t>(sms_ * 4, (n_long_ + 3) / 4), 128, 0, stream_>>>(s, pt_, da, db, new_id, removed_.get()); launched(); }
     unsigned int flags = 0;
     uint64_t removed = 0;
-    const size_t n = emit_and_wait(&flags, &removed);
+    size_t n = 0;
+    if (fused) {
+      SWB_CUDA(cudaGetLastError());
+      const double tw0 = now_ms();
+      stats.host_launch_ms += tw0 - t_launch0_;
+      wait_seq(seq);
+      stats.host_wait_ms += now_ms() - tw0;
+      n = (size_t)hdr_.host()[0];
+      flags = (unsigned int)hdr_.host()[1];
+      removed = hdr_.host()[2];
+      if (flags & 8u) {  // too many records for the fused tail: emit them with a full grid
+        t_launch0_ = now_ms();
+        n = emit_and_wait(&flags, &removed);
+      }
+    } else {
+      n = emit_and_wait(&flags, &removed);
+    }
     if (flags) throw Error("pair table overflow during a merge (internal sizing error)");
     if (timing) {
       float ms = 0;
+      SWB_CUDA(cudaEventSynchronize(ev1_));
       SWB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
       stats.merge_kernel_ms += ms;
     }
@@ -408,10 +454,14 @@ class TrainerImpl {
     int done = 0;
     while (done < batch && !core.heap_empty()) {
       int32_t a, b, nid;
+      const double tp0 = now_ms();
       if (!core.next_merge(&a, &b, &nid)) break;
+      stats.host_pop_ms += now_ms() - tp0;
       size_t n = 0;
       const Rec *r = shard_merge(a, b, nid, &n);
+      const double ta0 = now_ms();
       core.apply(r, n);
+      stats.host_apply_ms += now_ms() - ta0;
       done++;
     }
     stats.merge_ms += now_ms() - t0;
@@ -484,6 +534,8 @@ class TrainerImpl {
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   bool loaded_ = false;
+  double t_launch0_ = 0;
+  unsigned long long seq_ = 0;
   DevBuf<unsigned int> scalars_;
   PinnedBuf<unsigned long long> hdr_;
   // symbol stream

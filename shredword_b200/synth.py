@@ -110,36 +110,47 @@ def make_types(spec: CorpusSpec, rng: np.random.Generator):
   return out, lens
 
 
-def generate(spec: CorpusSpec, chunk_words: int = 2_000_000):
+def _chunk(spec: CorpusSpec, mat, lens, cdf, chunk_no: int, chunk_words: int) -> np.ndarray:
+  """Chunk `chunk_no` of the corpus: chunk_words words drawn with their own counter-based RNG stream,
+  so chunks can be produced in any order / in parallel and the corpus is still one fixed byte string."""
+  rng = np.random.default_rng([spec.seed, 1 + chunk_no])
+  idx = np.searchsorted(cdf, rng.random(chunk_words), side="right")
+  np.minimum(idx, spec.n_types - 1, out=idx)
+  rows = mat[idx]  # [chunk, width]
+  l = lens[idx]
+  sep = np.full(chunk_words, ord(" "), dtype=np.uint8)
+  sep[WORDS_PER_LINE - 1:: WORDS_PER_LINE] = ord("\n")  # chunk_words is a multiple of WORDS_PER_LINE
+  rows[np.arange(chunk_words), l] = sep
+  return rows[np.arange(mat.shape[1])[None, :] <= l[:, None]]
+
+
+def generate(spec: CorpusSpec, chunk_words: int = 1_200_000, threads: int | None = None):
   """Yields consecutive uint8 chunks of the corpus; total length == spec.nbytes exactly.
 
   The last line is cut at spec.nbytes and terminated with '\\n' (a cut word is still a word)."""
+  from concurrent.futures import ThreadPoolExecutor
+  assert chunk_words % WORDS_PER_LINE == 0
   rng = np.random.default_rng(spec.seed)
   mat, lens = make_types(spec, rng)
-  width = mat.shape[1]
   ranks = np.arange(1, spec.n_types + 1, dtype=np.float64)
   cdf = np.cumsum(ranks ** (-spec.zipf_s))
   cdf /= cdf[-1]
-  cols = np.arange(width)[None, :]
+  threads = threads or min(8, os.cpu_count() or 1)
   produced = 0
-  word_no = 0
-  while produced < spec.nbytes:
-    u = rng.random(chunk_words)
-    idx = np.searchsorted(cdf, u, side="right")
-    np.minimum(idx, spec.n_types - 1, out=idx)
-    rows = mat[idx]  # [chunk, width]
-    l = lens[idx]
-    sep = np.full(chunk_words, ord(" "), dtype=np.uint8)
-    eol = (np.arange(word_no, word_no + chunk_words) % WORDS_PER_LINE) == WORDS_PER_LINE - 1
-    sep[eol] = ord("\n")
-    rows[np.arange(chunk_words), l] = sep
-    flat = rows[cols <= l[:, None]]
-    word_no += chunk_words
-    if produced + flat.size >= spec.nbytes:
-      flat = flat[: spec.nbytes - produced].copy()
-      flat[-1] = ord("\n")
-    produced += flat.size
-    yield flat
+  chunk_no = 0
+  with ThreadPoolExecutor(threads) as pool:
+    while produced < spec.nbytes:
+      futs = [pool.submit(_chunk, spec, mat, lens, cdf, chunk_no + k, chunk_words) for k in range(threads)]
+      chunk_no += threads
+      for f in futs:
+        flat = f.result()
+        if produced >= spec.nbytes:
+          continue
+        if produced + flat.size >= spec.nbytes:
+          flat = flat[: spec.nbytes - produced].copy()
+          flat[-1] = ord("\n")
+        produced += flat.size
+        yield flat
 
 
 def corpus_bytes(spec: CorpusSpec) -> np.ndarray:
