@@ -1,0 +1,81 @@
+"""CPU: the C-ABI shared library loads, exports every symbol include/*.h declares, keeps the reference's
+struct layouts, and fails loudly (never falls back) when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+  src = open(os.path.join(ROOT, "include", "shredword_b200.h")).read()
+  src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+  names = re.findall(r"\b([a-z_][a-z0-9_]*)\s*\([^;{}]*\)\s*;", src)
+  return sorted(set(n for n in names if n.startswith(("swb_", "bpe_", "create_trainer"))))
+
+
+def test_exports_every_declared_symbol(product):
+  from shredword_b200.cbase import lib
+  names = _declared_functions()
+  assert len(names) >= 40 and "create_trainer" in names and "bpe_merge_batch" in names and "swb_encode" in names
+  for n in names:
+    assert hasattr(lib, n), f"{n} is declared in include/shredword_b200.h but not exported"
+
+
+def test_reference_symbols_and_layouts(product):
+  from shredword_b200 import cbase
+  # the 8 entry points reference cbase.py:44-59 binds
+  for n in ("create_trainer", "bpe_trainer_destroy", "bpe_init", "bpe_count_bigrams", "bpe_load_corpus", "bpe_merge_batch",
+            "bpe_train", "bpe_save"):
+    assert hasattr(cbase.lib, n)
+  assert ctypes.sizeof(cbase.BPEConfig) == 24 and cbase.BPEConfig.min_pair_freq.offset == 16 and cbase.BPEConfig.character_coverage.offset == 12
+  assert ctypes.sizeof(cbase.HeapEntry) == 24
+  T = cbase.Trainer
+  assert (T.heap.offset, T.corpus.offset, T.bigram_map.offset, T.next_token.offset, T.num_merges.offset, T.merge_ops.offset) == (24, 48, 72, 88, 96, 104)
+
+
+def test_create_defaults_and_destroy(product):
+  """reference test/bpe_test.cpp:59-94: config copied, defaults applied, num_merges == 0."""
+  from shredword_b200 import cbase
+  cfg = cbase.BPEConfig(target_vocab_size=1000, unk_id=0, character_coverage=0.0, min_pair_freq=0)
+  t = cbase.lib.create_trainer(ctypes.byref(cfg))
+  assert t
+  c = t.contents
+  assert c.config.target_vocab_size == 1000 and abs(c.config.character_coverage - 0.995) < 1e-6 and c.config.min_pair_freq == 2000
+  assert c.num_merges == 0 and c.heap.size == 0 and c.heap.cap >= 4096 and bool(c.heap.data)
+  cbase.lib.bpe_trainer_destroy(t)
+  assert not cbase.lib.create_trainer(None)          # the reference exit()s here; we return NULL
+  cbase.lib.bpe_trainer_destroy(None)                # no-op
+  assert cbase.lib.bpe_merge_batch(None, 1) == -1 and cbase.lib.bpe_train(None) == -1 and cbase.lib.bpe_load_corpus(None, b"x") == -1
+
+
+def test_no_gpu_fails_loudly(product, tmp_path):
+  from shredword_b200 import cbase
+  if cbase.lib.swb_device_count() > 0:
+    pytest.skip("a CUDA device is present")
+  t = product.BPETrainer(300, min_pair_freq=2)
+  p = tmp_path / "c.txt"; p.write_bytes(b"hello world hello\n")
+  with pytest.raises(IOError):
+    t.load_corpus(str(p))
+  assert "no CUDA device" in cbase.last_error() and "no CPU fallback" in cbase.last_error()
+  with pytest.raises(IOError):
+    t.load_buffer(b"hello world")
+  enc = product.BPEEncoder([(104, 101, 256)])
+  with pytest.raises(RuntimeError):
+    enc.encode(b"hello")
+  assert enc.decode([256, 108]) == b"hel"              # decode is a host table lookup
+
+
+def test_product_never_touches_oracle():
+  """The shipped package must not import, link or load anything under oracle/."""
+  pkg = os.path.join(ROOT, "shredword_b200")
+  for dirpath, _, files in os.walk(pkg):
+    for f in files:
+      if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+        txt = open(os.path.join(dirpath, f), errors="replace").read()
+        assert "liboracle" not in txt and "oracle/" not in txt and "import oracle" not in txt, os.path.join(dirpath, f)
+  import subprocess
+  out = subprocess.run(["ldd", os.path.join(pkg, "libtrainer.so")], capture_output=True, text=True).stdout
+  assert "oracle" not in out

@@ -1,0 +1,85 @@
+"""CPU: the multi-rank merge loop. The pair table + heap replica and the record reduction are host code of
+the product (swb_dist_*), exercised here without a GPU: this rank's kernels are replaced by the oracle's
+shard functions (a CPU stand-in that emits the same records), the exchange runs over gloo with world_size 2."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleLocalOps:
+  def __init__(self, o, rank, world):
+    self.o, self.rank, self.world = o, rank, world
+
+  def count(self):
+    return np.ascontiguousarray(self.o.shard_count(self.rank, self.world))
+
+  def merge(self, a, b, new_id):
+    return np.ascontiguousarray(self.o.shard_merge(self.rank, self.world, a, b, new_id))
+
+
+def test_single_process_replica_matches_oracle(product, oracle_mod):
+  """world_size 1 through the same swb_dist_* path (no process group needed)."""
+  import ctypes
+  from shredword_b200.cbase import lib
+  from shredword_b200.trainer import _ptr
+  for name in ("ascii_ties", "multi_unk97", "self_pairs", "negative_unk"):
+    kw = cases.kwargs(name)
+    full = oracle_mod.Oracle(kw["target_vocab_size"], kw.get("unk_id", 0), kw.get("character_coverage", 0.995), kw["min_pair_freq"])
+    full.load_buffer(cases.corpus(name)); n_full = full.train()
+    sh = oracle_mod.Oracle(kw["target_vocab_size"], kw.get("unk_id", 0), kw.get("character_coverage", 0.995), kw["min_pair_freq"])
+    sh.load_buffer(cases.corpus(name))
+    t = product.BPETrainer(**kw)
+    # three emulated ranks in one process: concatenate their records, reduce, apply
+    R = 3
+    recs = np.ascontiguousarray(np.concatenate([sh.shard_count(r, R) for r in range(R)]))
+    n = lib.swb_dist_reduce_records(_ptr(recs), recs.shape[0])
+    lib.swb_dist_seed(t.trainer, _ptr(recs), n)
+    a, b, nid = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    done = 0
+    while done < kw["target_vocab_size"] - 256 and lib.swb_dist_next_merge(t.trainer, ctypes.byref(a), ctypes.byref(b), ctypes.byref(nid)):
+      parts = [sh.shard_merge(r, R, a.value, b.value, nid.value) for r in range(R)]
+      recs = np.ascontiguousarray(np.concatenate(parts)) if sum(len(p) for p in parts) else np.zeros((0, 4), np.int64)
+      n = lib.swb_dist_reduce_records(_ptr(recs), recs.shape[0]) if recs.shape[0] else 0
+      lib.swb_dist_apply(t.trainer, _ptr(recs), n)
+      done += 1
+    assert done == n_full, name
+    assert np.array_equal(full.merges, t.merges_array()), name
+
+
+def _worker(rank, world, port, name, out_dir):
+  sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+  import torch.distributed as dist
+  import oracle as O
+  from shredword_b200.distributed import DistributedBPETrainer
+  dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+  kw = cases.kwargs(name)
+  o = O.Oracle(kw["target_vocab_size"], kw.get("unk_id", 0), kw.get("character_coverage", 0.995), kw["min_pair_freq"])
+  o.load_buffer(cases.corpus(name))
+  t = DistributedBPETrainer(**kw, local_ops=OracleLocalOps(o, rank, world))
+  n = t.train_quiet()
+  np.save(os.path.join(out_dir, f"merges_{rank}.npy"), t.merges_array())
+  # every rank holds the same replica: same heap size, same merge count
+  sizes = [None] * world
+  dist.all_gather_object(sizes, (n, int(t.trainer.contents.heap.size), t.collectives))
+  assert len(set(s[:2] for s in sizes)) == 1, sizes
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["ascii_ties", "multi_ties"])
+def test_gloo_world2_matches_oracle(name, product, oracle_mod, tmp_path):
+  import socket
+  s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+  kw = cases.kwargs(name)
+  full = oracle_mod.Oracle(kw["target_vocab_size"], kw.get("unk_id", 0), kw.get("character_coverage", 0.995), kw["min_pair_freq"])
+  full.load_buffer(cases.corpus(name)); full.train()
+  mp.spawn(_worker, args=(2, port, name, str(tmp_path)), nprocs=2, join=True)
+  for r in range(2):
+    assert np.array_equal(np.load(tmp_path / f"merges_{r}.npy"), full.merges), f"rank {r}"

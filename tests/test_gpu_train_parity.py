@@ -62,6 +62,11 @@ def test_train_matches_oracle(name, product, oracle_mod, tmp_path):
   assert (tmp_path / "o.model").read_bytes() == (tmp_path / "t.model").read_bytes()
   assert (tmp_path / "o.vocab").read_bytes() == (tmp_path / "t.vocab").read_bytes()
   assert os.path.getsize(tmp_path / "t.model") == 12 * n_t  # reference test/bpe_test.cpp:262-270
+  # and against the bytes the UNMODIFIED reference wrote for this corpus (tests/golden/make_golden.py)
+  gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+  if os.path.exists(gold + ".model"):
+    assert (tmp_path / "t.model").read_bytes() == open(gold + ".model", "rb").read()
+    assert (tmp_path / "t.vocab").read_bytes() == open(gold + ".vocab", "rb").read()
 
 
 def test_merge_batch_stepwise_matches(product, oracle_mod):
