@@ -79,3 +79,37 @@ def test_product_never_touches_oracle():
   import subprocess
   out = subprocess.run(["ldd", os.path.join(pkg, "libtrainer.so")], capture_output=True, text=True).stdout
   assert "oracle" not in out
+
+
+def test_reference_python_package_binds_our_library(product, tmp_path):
+  """The drop-in claim of INTEGRATION.md: the reference's own cbase.py/trainer.py (symlinked, not copied)
+  load our libtrainer.so and drive it. Only where /root/reference exists (this container)."""
+  ref = "/root/reference/shredword"
+  if not os.path.isdir(ref):
+    pytest.skip("/root/reference is not present on this machine")
+  import subprocess
+  import sys
+  pkg = tmp_path / "shredword"
+  pkg.mkdir()
+  for f in ("__init__.py", "cbase.py", "trainer.py"):
+    os.symlink(os.path.join(ref, f), pkg / f)
+  os.symlink(os.path.join(ROOT, "shredword_b200", "libtrainer.so"), pkg / "libtrainer.so")
+  corpus = tmp_path / "c.txt"; corpus.write_bytes(b"hello world hello\n")
+  code = (
+    "import sys; sys.path.insert(0, %r)\n"
+    "from shredword.trainer import BPETrainer\n"
+    "from shredword.cbase import lib\n"
+    "t = BPETrainer(target_vocab_size=500, min_pair_freq=1000)\n"
+    "assert t.trainer and t.trainer.contents.config.target_vocab_size == 500\n"
+    "import ctypes\n"
+    "lib.swb_device_count.restype = ctypes.c_int\n"
+    "if lib.swb_device_count() == 0:\n"
+    "  try:\n"
+    "    t.load_corpus(%r); raise SystemExit('expected IOError without a GPU')\n"
+    "  except IOError: pass\n"
+    "else:\n"
+    "  t.load_corpus(%r); t.train(); t.save(%r, %r)\n"
+    "t.destroy(); print('BOUND_OK')\n"
+  ) % (str(tmp_path), str(corpus), str(corpus), str(tmp_path / "m.model"), str(tmp_path / "m.vocab"))
+  r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+  assert "BOUND_OK" in r.stdout, r.stdout + r.stderr
