@@ -111,6 +111,11 @@ __host__ __device__ __forceinline__ uint64_t touch_key(uint64_t wi, uint32_t pos
   return (wi << 30) | ((uint64_t)pos << 2) | slot;
 }
 
+// Row signature: SIG_WORDS x 32 bits per row, one bit per symbol id present (conservative: bits are only
+// ever added between rebuilds). A merge of (a, b) can only touch rows whose signature has both bits.
+constexpr int SIG_WORDS = 8;
+__host__ __device__ __forceinline__ uint32_t sig_hash(int32_t id) { return ((uint32_t)id * 0x9E3779B1u) >> 24; }  // 0..255
+
 struct CastU32ToU64 {
   __host__ __device__ unsigned long long operator()(const uint32_t &x) const { return (unsigned long long)x; }
 };

@@ -36,15 +36,14 @@ __device__ __forceinline__ void pt_add(const PairTableDev &t, int32_t a, int32_t
   const unsigned long long k = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
   uint32_t h = (uint32_t)dmix64(k) & t.mask;
   for (uint32_t probe = 0; probe <= t.mask; probe++) {
-    unsigned long long cur = t.keys[h];
+    // CAS straight away (one L2 round trip): the table is empty at the start of every merge, so the
+    // common case is a first touch
+    unsigned long long cur = atomicCAS(&t.keys[h], PT_EMPTY, k);
     if (cur == PT_EMPTY) {
-      cur = atomicCAS(&t.keys[h], PT_EMPTY, k);
-      if (cur == PT_EMPTY) {
-        const unsigned int idx = atomicAdd(t.n_touched, 1u);
-        t.touched[idx] = h;
-        if (idx >= (t.mask >> 1)) atomicOr(t.flags, 1u);  // past 50 % load: the host grows the table and reruns
-        cur = k;
-      }
+      const unsigned int idx = atomicAdd(t.n_touched, 1u);
+      t.touched[idx] = h;
+      if (idx >= (t.mask >> 1)) atomicOr(t.flags, 1u);  // past 50 % load: the host grows the table and reruns
+      cur = k;
     }
     if (cur == k) {
       atomicAdd(&t.val[h], (unsigned long long)delta);
@@ -66,12 +65,24 @@ __global__ void pt_clear(PairTableDev t) {
 }
 
 // touched slots -> records in mapped host memory; frees the slots. The last block to finish publishes
-// the header and resets the counters, so the next merge needs no extra memset on the critical path.
-// out_hdr[0] = number of records, [1] = flags, [2] = removed symbols of this merge, [3] = sequence
-// number (written last, after a system-scope fence: the host polls it instead of synchronising).
+// an 8-word header and resets the counters, so the next merge needs no extra memset on the critical path.
+//   hdr[0] = seq, [1] = number of records, [2] = flags, [3] = removed symbols of this merge,
+//   hdr[4] = XOR of all record words, [5] = SUM of all record words, [6] = header check word, [7] = seq
+// The host polls the header instead of synchronising the stream. No system-scope fence sits between the
+// record writes and the header (each one costs a PCIe round trip, ~2.3 us on this box): the header and
+// the records validate themselves -- the host accepts them only when the check word and the XOR/SUM of
+// the records it reads match, and keeps polling otherwise (the bytes are still in flight).
 // flags: 1 = table full, 4 = more records than out_cap, 8 = records not emitted (fused tail only).
+constexpr unsigned long long HDR_MAGIC = 0x9E3779B97F4A7C15ull;
+__host__ __device__ __forceinline__ unsigned long long hdr_check(unsigned long long seq, unsigned long long n,
+                                                                 unsigned long long flags, unsigned long long removed,
+                                                                 unsigned long long x, unsigned long long sm) {
+  return (seq * HDR_MAGIC) ^ (n + 0x1234567ull) ^ (flags << 48) ^ (removed * 31ull) ^ x ^ (sm << 1 | sm >> 63);
+}
+
 __device__ __forceinline__ void pt_emit_range(const PairTableDev &t, Rec *__restrict__ out, size_t out_cap,
-                                              unsigned int n, unsigned int first, unsigned int stride) {
+                                              unsigned int n, unsigned int first, unsigned int stride,
+                                              unsigned long long &cx, unsigned long long &cs) {
   for (unsigned int i = first; i < n; i += stride) {
     const unsigned int h = __ldcg(&t.touched[i]);
     const unsigned long long k = __ldcg(&t.keys[h]);
@@ -80,41 +91,68 @@ __device__ __forceinline__ void pt_emit_range(const PairTableDev &t, Rec *__rest
       r.first = (int32_t)(k >> 32); r.second = (int32_t)(k & 0xFFFFFFFFu);
       r.delta = (long long)__ldcg(&t.val[h]); r.key = (long long)__ldcg(&t.minkey[h]);
       out[i] = r;
+      cx ^= (unsigned long long)r.first ^ (unsigned long long)r.second ^ (unsigned long long)r.delta ^ (unsigned long long)r.key;
+      cs += (unsigned long long)r.first + 3ull * (unsigned long long)r.second + 5ull * (unsigned long long)r.delta +
+            7ull * (unsigned long long)r.key;
     }
     t.keys[h] = PT_EMPTY; t.val[h] = 0; t.minkey[h] = ~0ull;
   }
 }
+// block-wide XOR / SUM of per-thread checksums (all threads of the block must call)
+__device__ __forceinline__ void block_checksum(unsigned long long &cx, unsigned long long &cs, unsigned long long *sh /* [2*32] */) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { cx ^= __shfl_down_sync(0xffffffffu, cx, d); cs += __shfl_down_sync(0xffffffffu, cs, d); }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { sh[w] = cx; sh[32 + w] = cs; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long x = 0, sm = 0;
+    for (int i = 0; i < nw; i++) { x ^= sh[i]; sm += sh[32 + i]; }
+    cx = x; cs = sm;
+  }
+}
 __device__ __forceinline__ void pt_publish(const PairTableDev &t, unsigned int n, size_t out_cap, unsigned int extra_flags,
                                            volatile unsigned long long *out_hdr, unsigned long long *removed,
-                                           unsigned long long seq) {
-  out_hdr[0] = n;
-  out_hdr[1] = __ldcg(t.flags) | (n > out_cap ? 4u : 0u) | extra_flags;
-  out_hdr[2] = removed ? __ldcg(removed) : 0ull;
+                                           unsigned long long seq, unsigned long long cx, unsigned long long cs) {
+  const unsigned long long flags = __ldcg(t.flags) | (n > out_cap ? 4u : 0u) | extra_flags;
+  const unsigned long long rem = removed ? __ldcg(removed) : 0ull;
+  out_hdr[1] = n; out_hdr[2] = flags; out_hdr[3] = rem; out_hdr[4] = cx; out_hdr[5] = cs;
+  out_hdr[6] = hdr_check(seq, n, flags, rem, cx, cs);
+  out_hdr[0] = seq; out_hdr[7] = seq;
   if (removed && !(extra_flags & 8u)) *removed = 0;
   if (!(extra_flags & 8u)) { *t.n_touched = 0; *t.flags = 0; }
   *t.done_blocks = 0;
-  __threadfence_system();
-  out_hdr[3] = seq;
-  __threadfence_system();
 }
 
+// full-grid emit (more records than the fused tail takes, or long words present): every block writes its
+// share and its partial checksum; the last block to finish adds the partials up and publishes.
 __global__ void __launch_bounds__(256)
 pt_emit(PairTableDev t, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
-        unsigned long long *removed, unsigned long long seq) {
+        unsigned long long *removed, unsigned long long seq, unsigned long long *__restrict__ partial /* [2*gridDim.x] */) {
   __shared__ bool is_last;
+  __shared__ unsigned long long sh[64];
   const unsigned int n = __ldcg(t.n_touched);
-  pt_emit_range(t, out, out_cap, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
-  __threadfence_system();
+  unsigned long long cx = 0, cs = 0;
+  pt_emit_range(t, out, out_cap, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, cx, cs);
+  block_checksum(cx, cs, sh);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = cx; partial[2 * blockIdx.x + 1] = cs;
+    __threadfence();
+    is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (is_last && threadIdx.x == 0) pt_publish(t, n, out_cap, 0u, out_hdr, removed, seq);
+  if (is_last && threadIdx.x == 0) {
+    unsigned long long x = 0, sm = 0;
+    for (unsigned int i = 0; i < gridDim.x; i++) { x ^= __ldcg(&partial[2 * i]); sm += __ldcg(&partial[2 * i + 1]); }
+    pt_publish(t, n, out_cap, 0u, out_hdr, removed, seq, x, sm);
+  }
 }
 
 constexpr unsigned int FUSED_EMIT_MAX = 8192;  // above this the records are emitted by a full-grid pt_emit
 
 struct StreamDev {
   int4 *rows;                 // n_rows * ROW int32
+  uint32_t *sig;              // n_rows * SIG_WORDS: which symbol ids (hashed to 256 bits) a row may contain
   uint64_t n_rows;
   const unsigned long long *cnt;   // [W] word count, indexed by the (global, reference-order) word index
   // long words (more than ROW-1 symbols): CSR, one warp per word
@@ -128,28 +166,29 @@ struct StreamDev {
 __device__ __forceinline__ uint64_t word_gwi(const StreamDev &, uint32_t wi) { return (uint64_t)wi; }
 
 // ---------------------------------------------------------------- merge (a, b) -> new_id
+constexpr int MERGE_THREADS = 256;
+constexpr int MERGE_WARPS = MERGE_THREADS / 32;
+constexpr int MATCH_CAP = ROW / 2;  // a row of 128 symbols holds at most 64 matches
+
+// One match of the pair inside a row, recorded by the lane that rewrites the word; the four signed
+// deltas it stands for (reference bpe.cpp:453-470) are emitted afterwards, one lane per delta.
+struct Match { int32_t L, R; uint32_t wi; uint32_t pos; };  // L / R = -1: no such neighbour
+
 // Sequential rewrite of one word living in shared memory at sm[p+1 ...]; p = header position.
-__device__ __forceinline__ uint32_t merge_word_smem(int *sm, int p, const StreamDev &s, const PairTableDev &t,
-                                                    int32_t a, int32_t b, int32_t new_id) {
-  const uint32_t li = (uint32_t)(~sm[p]);
+__device__ __forceinline__ uint32_t merge_word_smem(int *sm, int p, Match *ml, unsigned int *n_match, int32_t a, int32_t b,
+                                                    int32_t new_id) {
+  const uint32_t wi = (uint32_t)(~sm[p]);
   int r = p + 1, w = p + 1;
-  long long c = 0; uint64_t g = 0;
   uint32_t nmatch = 0;
   while (r < ROW) {
     const int x = sm[r];
     if (x < 0) break;
     if (x == a && r + 1 < ROW && sm[r + 1] == b) {
-      if (nmatch == 0) { c = (long long)s.cnt[li]; g = word_gwi(s, li); }
-      if (w > p + 1) {  // left neighbour: the already rewritten symbol (reference bpe.cpp:453-460)
-        const int L = sm[w - 1];
-        pt_add(t, L, a, -c, touch_key(g, r, 0));
-        pt_add(t, L, new_id, c, touch_key(g, r, 1));
-      }
-      if (r + 2 < ROW && sm[r + 2] >= 0) {  // right neighbour: not yet rewritten (bpe.cpp:463-470)
-        const int R = sm[r + 2];
-        pt_add(t, b, R, -c, touch_key(g, r, 2));
-        pt_add(t, new_id, R, c, touch_key(g, r, 3));
-      }
+      Match m;
+      m.L = (w > p + 1) ? sm[w - 1] : -1;                      // left neighbour: the already rewritten symbol
+      m.R = (r + 2 < ROW && sm[r + 2] >= 0) ? sm[r + 2] : -1;  // right neighbour: not yet rewritten
+      m.wi = wi; m.pos = (uint32_t)r;
+      ml[atomicAdd(n_match, 1u)] = m;
       sm[w++] = new_id;
       r += 2;
       nmatch++;
@@ -162,21 +201,38 @@ __device__ __forceinline__ uint32_t merge_word_smem(int *sm, int p, const Stream
   return nmatch;
 }
 
-constexpr int MERGE_THREADS = 256;
-constexpr int MERGE_UNROLL = 4;
-
-// Slow path of one row (warp-uniform): stage in shared memory, rewrite word by word, store back.
-__device__ __noinline__ uint32_t merge_row_slow(int *sm, int4 v, int lane, int4 *row_gmem, const StreamDev &s,
-                                                const PairTableDev &t, int32_t a, int32_t b, int32_t new_id) {
+// Slow path of one row (warp-uniform): stage in shared memory, rewrite word by word (the lane that holds
+// a header rewrites that word), store back, then emit the deltas of all matches with one lane per delta.
+__device__ __noinline__ uint32_t merge_row_slow(int *sm, Match *ml, unsigned int *n_match, int4 v, int lane, int4 *row_gmem,
+                                                uint32_t *row_sig, const StreamDev &s, const PairTableDev &t, int32_t a,
+                                                int32_t b, int32_t new_id) {
   *reinterpret_cast<int4 *>(&sm[lane * 4]) = v;
+  if (lane == 0) *n_match = 0;
   __syncwarp();
   uint32_t removed = 0;
   const int h[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int k = 0; k < 4; k++)
-    if (h[k] < 0 && h[k] != PAD) removed += merge_word_smem(sm, lane * 4 + k, s, t, a, b, new_id);
+    if (h[k] < 0 && h[k] != PAD) removed += merge_word_smem(sm, lane * 4 + k, ml, n_match, a, b, new_id);
   __syncwarp();
   row_gmem[lane] = *reinterpret_cast<const int4 *>(&sm[lane * 4]);
+  const unsigned int nm = *n_match;
+  if (lane == 0 && nm) {  // the row now contains new_id
+    const uint32_t hh = sig_hash(new_id);
+    row_sig[hh >> 5] |= 1u << (hh & 31);
+  }
+  for (unsigned int i = lane; i < 4 * nm; i += 32) {
+    const Match m = ml[i >> 2];
+    const int slot = i & 3;
+    const int nb = slot < 2 ? m.L : m.R;
+    if (nb < 0) continue;
+    const long long c = (long long)s.cnt[m.wi];
+    const uint64_t key = touch_key(m.wi, m.pos, slot);
+    if (slot == 0) pt_add(t, nb, a, -c, key);
+    else if (slot == 1) pt_add(t, nb, new_id, c, key);
+    else if (slot == 2) pt_add(t, b, nb, -c, key);
+    else pt_add(t, new_id, nb, c, key);
+  }
   __syncwarp();
   return removed;
 }
@@ -187,26 +243,51 @@ __global__ void __launch_bounds__(MERGE_THREADS)
 merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, unsigned long long *removed_total,
            int fused, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
            unsigned long long seq) {
-  __shared__ __align__(16) int sm[MERGE_THREADS / 32][ROW];
+  __shared__ __align__(16) int sm[MERGE_WARPS][ROW];
+  __shared__ Match ml[MERGE_WARPS][MATCH_CAP];
+  __shared__ unsigned int n_match[MERGE_WARPS];
+  __shared__ unsigned long long csum_sh[64];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint64_t warp = (blockIdx.x * (uint64_t)MERGE_THREADS + threadIdx.x) >> 5;
   const uint64_t n_warps = ((uint64_t)gridDim.x * MERGE_THREADS) >> 5;
+  const uint32_t ha = sig_hash(a), hb = sig_hash(b);
+  const uint32_t wa = ha >> 5, ba = 1u << (ha & 31), wb = hb >> 5, bb = 1u << (hb & 31);
   uint32_t removed = 0;
-  for (uint64_t r0 = warp * MERGE_UNROLL; r0 < s.n_rows; r0 += n_warps * MERGE_UNROLL) {
-    int4 v[MERGE_UNROLL];
+  // 32 rows per warp iteration: lane l tests the signature of row base+l (8 bytes of a 32-byte signature)
+  for (uint64_t base = warp * 32; base < s.n_rows; base += n_warps * 32) {
+    const uint64_t row = base + lane;
+    bool cand = false;
+    if (row < s.n_rows) {
+      const uint32_t *sg = s.sig + row * SIG_WORDS;
+      cand = (sg[wa] & ba) && (sg[wb] & bb);
+    }
+    uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+    while (cmask) {  // candidate rows, four loads in flight at a time
+      uint64_t rr[4];
+      int4 vv[4];
+      int nc = 0;
 #pragma unroll
-    for (int u = 0; u < MERGE_UNROLL; u++)
-      if (r0 + u < s.n_rows) v[u] = s.rows[(r0 + u) * (ROW / 4) + lane];
-      else v[u] = make_int4(PAD, PAD, PAD, PAD);
+      for (int u = 0; u < 4; u++) {
+        if (cmask) {
+          rr[u] = base + (__ffs(cmask) - 1);
+          cmask &= cmask - 1;
+          vv[u] = s.rows[rr[u] * (ROW / 4) + lane];
+          nc = u + 1;
+        }
+      }
 #pragma unroll
-    for (int u = 0; u < MERGE_UNROLL; u++) {
-      int nxt = __shfl_down_sync(0xffffffffu, v[u].x, 1);
-      if (lane == 31) nxt = PAD;
-      const bool m = (v[u].x == a && v[u].y == b) || (v[u].y == a && v[u].z == b) || (v[u].z == a && v[u].w == b) ||
-                     (v[u].w == a && nxt == b);
-      if (__any_sync(0xffffffffu, m))
-        removed += merge_row_slow(sm[wib], v[u], lane, s.rows + (r0 + u) * (ROW / 4), s, t, a, b, new_id);
+      for (int u = 0; u < 4; u++) {
+        if (u < nc) {
+          const int4 v = vv[u];
+          int nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
+          if (lane == 31) nxt = PAD;
+          const bool m = (v.x == a && v.y == b) || (v.y == a && v.z == b) || (v.z == a && v.w == b) || (v.w == a && nxt == b);
+          if (__any_sync(0xffffffffu, m))
+            removed += merge_row_slow(sm[wib], ml[wib], &n_match[wib], v, lane, s.rows + rr[u] * (ROW / 4),
+                                      s.sig + rr[u] * SIG_WORDS, s, t, a, b, new_id);
+        }
+      }
     }
   }
 #pragma unroll
@@ -220,12 +301,10 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
   if (!is_last) return;
   const unsigned int n = __ldcg(t.n_touched);
   const bool small = n <= FUSED_EMIT_MAX;
-  if (small) {
-    pt_emit_range(t, out, out_cap, n, threadIdx.x, MERGE_THREADS);
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) pt_publish(t, n, out_cap, small ? 0u : 8u, out_hdr, removed_total, seq);
+  unsigned long long cx = 0, cs = 0;
+  if (small) pt_emit_range(t, out, out_cap, n, threadIdx.x, MERGE_THREADS, cx, cs);
+  block_checksum(cx, cs, csum_sh);
+  if (threadIdx.x == 0) pt_publish(t, n, out_cap, small ? 0u : 8u, out_hdr, removed_total, seq, cx, cs);
 }
 
 // long words: lanes stride over the word to detect; the rare word with a match is rewritten by lane 0

@@ -209,7 +209,7 @@ class TrainerImpl {
       DevBuf<uint32_t> batch_rows(n_batches);
       const int pgrid = (int)std::min<uint64_t>(sms_ * 4, (n_batches + 7) / 8);
       wt_pack<false><<<pgrid, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), long_index_.get(), W, rank, nranks,
-                                                 d_bmap.get(), batch_rows.get(), nullptr, nullptr);
+                                                 d_bmap.get(), batch_rows.get(), nullptr, nullptr, nullptr);
       launched();
       std::vector<uint32_t> h_rows(n_batches);
       SWB_CUDA(cudaMemcpyAsync(h_rows.data(), batch_rows.get(), n_batches * 4, cudaMemcpyDeviceToHost, stream_));
@@ -219,9 +219,10 @@ class TrainerImpl {
       if (acc >= (1ull << 32)) throw Error("too many rows");
       n_rows_ = acc;
       rows_.alloc(n_rows_ * (ROW / 4));
+      sig_.alloc(n_rows_ * SIG_WORDS);
       SWB_CUDA(cudaMemcpyAsync(batch_rows.get(), h_rows.data(), n_batches * 4, cudaMemcpyHostToDevice, stream_));
       wt_pack<true><<<pgrid, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), long_index_.get(), W, rank, nranks,
-                                                d_bmap.get(), batch_rows.get(), rows_.get(), wloc_.get());
+                                                d_bmap.get(), batch_rows.get(), rows_.get(), wloc_.get(), sig_.get());
       launched();
       sync();
     }
@@ -300,6 +301,7 @@ class TrainerImpl {
     pt_scal_.alloc(4);
     recs_.alloc(cap / 2);
     removed_.alloc(1);
+    emit_partial_.alloc(2 * 32);
     SWB_CUDA(cudaMemsetAsync(removed_.get(), 0, 8, stream_));
     pt_cap_ = cap;
     pt_ = PairTableDev{pt_keys_.get(), pt_val_.get(), pt_min_.get(), pt_touched_.get(), pt_scal_.get() + 0,
@@ -307,38 +309,58 @@ class TrainerImpl {
     pt_clear<<<sms_ * 8, 256, 0, stream_>>>(pt_); launched();
   }
   StreamDev stream_dev() {
-    return StreamDev{rows_.get(), n_rows_, cnt_.get(), long_syms_.get(), long_off_.get(), long_len_.get(),
+    return StreamDev{rows_.get(), sig_.get(), n_rows_, cnt_.get(), long_syms_.get(), long_off_.get(), long_len_.get(),
                      long_word_.get(), n_long_};
   }
-  // Waits until the kernels of this merge have published header sequence `seq` in mapped host memory.
-  // Polling the flag is cheaper than cudaStreamSynchronize on a loop that runs once per merge; the
-  // stream is queried from time to time so that a failed launch cannot hang the host.
+  // Waits until the kernels of this merge have published a valid header with sequence `seq` in mapped host
+  // memory, and until the n records it announces have all arrived (XOR/SUM check, see pt_emit_range).
+  // Polling is cheaper than cudaStreamSynchronize on a loop that runs once per merge; the stream is
+  // queried from time to time so that a failed launch cannot hang the host.
   void wait_seq(unsigned long long seq) {
     volatile unsigned long long *h = hdr_.host();
-    for (uint64_t spin = 0;; spin++) {
-      if (h[3] == seq) return;
-      if ((spin & 0x3FFF) == 0x3FFF) {
-        cudaError_t e = cudaStreamQuery(stream_);
-        if (e == cudaSuccess) {
-          if (h[3] == seq) return;
-          throw Error("merge kernels finished without publishing their result");
+    uint64_t spin = 0;
+    auto check_stream = [&]() {
+      if ((++spin & 0x3FFF) != 0) return;
+      cudaError_t e = cudaStreamQuery(stream_);
+      if (e == cudaSuccess) { if (++idle_polls_ > 64) throw Error("merge kernels finished without publishing a valid result"); }
+      else if (e != cudaErrorNotReady) SWB_CUDA(e);
+    };
+    idle_polls_ = 0;
+    for (;;) {
+      if (h[0] == seq && h[7] == seq) {
+        const unsigned long long n = h[1], fl = h[2], rem = h[3], cx = h[4], cs = h[5];
+        if (h[6] == hdr_check(seq, n, fl, rem, cx, cs)) {
+          if (fl & 8u) return;  // records were not emitted by this kernel
+          const size_t m = (size_t)std::min<unsigned long long>(n, recs_.size());
+          for (;;) {
+            const volatile long long *r = reinterpret_cast<const volatile long long *>(recs_.host());
+            unsigned long long x = 0, sm = 0;
+            for (size_t i = 0; i < m; i++) {
+              const unsigned long long a = (unsigned long long)r[4 * i], b = (unsigned long long)r[4 * i + 1],
+                                       c = (unsigned long long)r[4 * i + 2], d = (unsigned long long)r[4 * i + 3];
+              x ^= a ^ b ^ c ^ d;
+              sm += a + 3ull * b + 5ull * c + 7ull * d;
+            }
+            if (x == cx && sm == cs) return;
+            check_stream();
+          }
         }
-        if (e != cudaErrorNotReady) SWB_CUDA(e);
       }
+      check_stream();
     }
   }
   // runs pt_emit, waits, returns the record count (records are in mapped host memory until the next emit)
   size_t emit_and_wait(unsigned int *flags_out, uint64_t *removed_out) {
     const unsigned long long seq = ++seq_;
-    pt_emit<<<32, 256, 0, stream_>>>(pt_, recs_.dev(), recs_.size(), hdr_.dev(), removed_.get(), seq); launched();
+    pt_emit<<<32, 256, 0, stream_>>>(pt_, recs_.dev(), recs_.size(), hdr_.dev(), removed_.get(), seq, emit_partial_.get()); launched();
     SWB_CUDA(cudaGetLastError());
     const double tw0 = now_ms();
     stats.host_launch_ms += tw0 - t_launch0_;
     wait_seq(seq);
     stats.host_wait_ms += now_ms() - tw0;
-    const size_t n = (size_t)hdr_.host()[0];
-    *flags_out = (unsigned int)hdr_.host()[1];
-    if (removed_out) *removed_out = hdr_.host()[2];
+    const size_t n = (size_t)hdr_.host()[1];
+    *flags_out = (unsigned int)hdr_.host()[2];
+    if (removed_out) *removed_out = hdr_.host()[3];
     return n;
   }
   // device ids -> caller ids (a negative unk_id travels as UNK_CODE on the device)
@@ -394,8 +416,8 @@ class TrainerImpl {
     const bool fused = n_rows_ && !n_long_;
     unsigned long long seq = 0;
     if (n_rows_) {
-      const uint64_t warps_needed = (n_rows_ + MERGE_UNROLL - 1) / MERGE_UNROLL;
-      const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 8, (warps_needed + 7) / 8);
+      const uint64_t warps_needed = (n_rows_ + 31) / 32;  // one warp tests 32 row signatures per iteration
+      const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 4, (warps_needed + MERGE_WARPS - 1) / MERGE_WARPS);
       if (fused) seq = ++seq_;
       merge_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, da, db, new_id, removed_.get(), fused ? 1 : 0, recs_.dev(),
                                                       recs_.size(), hdr_.dev(), seq);
@@ -413,9 +435,9 @@ class TrainerImpl {
       stats.host_launch_ms += tw0 - t_launch0_;
       wait_seq(seq);
       stats.host_wait_ms += now_ms() - tw0;
-      n = (size_t)hdr_.host()[0];
-      flags = (unsigned int)hdr_.host()[1];
-      removed = hdr_.host()[2];
+      n = (size_t)hdr_.host()[1];
+      flags = (unsigned int)hdr_.host()[2];
+      removed = hdr_.host()[3];
       if (flags & 8u) {  // too many records for the fused tail: emit them with a full grid
         t_launch0_ = now_ms();
         n = emit_and_wait(&flags, &removed);
@@ -523,7 +545,7 @@ class TrainerImpl {
 
  private:
   void free_corpus_state() {
-    rows_.release(); cnt_.release(); wloc_.release(); long_index_.release(); long_syms_.release(); long_off_.release();
+    rows_.release(); sig_.release(); cnt_.release(); wloc_.release(); long_index_.release(); long_syms_.release(); long_off_.release();
     long_len_.release(); long_word_.release(); word_bytes_.release(); word_boff_.release();
     n_rows_ = 0; n_long_ = 0; W = 0; live_symbols_ = 0; word_bytes_total_ = 0; loaded_ = false;
     h_counts.clear();
@@ -540,6 +562,7 @@ class TrainerImpl {
   PinnedBuf<unsigned long long> hdr_;
   // symbol stream
   DevBuf<int4> rows_;
+  DevBuf<uint32_t> sig_;
   uint64_t n_rows_ = 0;
   DevBuf<unsigned long long> cnt_;
   DevBuf<uint64_t> wloc_;
@@ -554,7 +577,8 @@ class TrainerImpl {
   // pair table
   uint64_t pt_cap_ = 0;
   PairTableDev pt_{};
-  DevBuf<unsigned long long> pt_keys_, pt_val_, pt_min_, removed_;
+  DevBuf<unsigned long long> pt_keys_, pt_val_, pt_min_, removed_, emit_partial_;
+  int idle_polls_ = 0;
   DevBuf<unsigned int> pt_touched_, pt_scal_;
   PinnedBuf<Rec> recs_;
 };

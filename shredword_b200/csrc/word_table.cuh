@@ -254,8 +254,10 @@ wt_pack(const uint8_t *__restrict__ corpus, const uint64_t *__restrict__ woff, c
         const uint32_t *__restrict__ long_index /* [W] index into the long list or ~0 */, uint64_t W, int rank,
         int nranks, const int32_t *__restrict__ byte_map /* [256] */,
         uint32_t *__restrict__ batch_rows /* [n_batches] in: exclusive scan when WRITE; out: counts otherwise */,
-        int4 *__restrict__ rows, uint64_t *__restrict__ wloc /* [W] row*ROW+pos of the header */) {
+        int4 *__restrict__ rows, uint64_t *__restrict__ wloc /* [W] row*ROW+pos of the header */,
+        uint32_t *__restrict__ sig /* [n_rows * SIG_WORDS] */) {
   __shared__ __align__(16) int srow[8][ROW];
+  __shared__ uint32_t ssig[8][SIG_WORDS];
   __shared__ int32_t bmap[256];
   if (WRITE) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) bmap[i] = byte_map[i];
@@ -283,16 +285,23 @@ wt_pack(const uint8_t *__restrict__ corpus, const uint64_t *__restrict__ woff, c
       if (used > 0) {
         if (WRITE) {
           for (int i = lane; i < ROW; i += 32) srow[wib][i] = PAD;
+          if (lane < SIG_WORDS) ssig[wib][lane] = 0;
           __syncwarp();
           if (lane < nfit && need) {
             const uint32_t pos = ps - need;
             srow[wib][pos] = ~(int32_t)(uint32_t)mine;
             const uint8_t *src = corpus + woff[mine];
-            for (uint32_t k = 0; k < len; k++) srow[wib][pos + 1 + k] = bmap[src[k]];
+            for (uint32_t k = 0; k < len; k++) {
+              const int32_t id = bmap[src[k]];
+              srow[wib][pos + 1 + k] = id;
+              const uint32_t h = sig_hash(id);
+              atomicOr(&ssig[wib][h >> 5], 1u << (h & 31));
+            }
             wloc[mine] = row * ROW + pos;
           }
           __syncwarp();
           rows[row * (ROW / 4) + lane] = *reinterpret_cast<const int4 *>(&srow[wib][lane * 4]);
+          if (lane < SIG_WORDS) sig[row * SIG_WORDS + lane] = ssig[wib][lane];
           __syncwarp();
         }
         row++; nrows++;
