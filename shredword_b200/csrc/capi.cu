@@ -314,7 +314,8 @@ size_t swb_dist_reduce_records(int64_t *recs, size_t n) { return swb::reduce_rec
 void swb_dist_seed(Trainer *trainer, const int64_t *recs, size_t n) {
   if (!trainer) return;
   TrainerImpl *im = impl_of(trainer);
-  im->core.reset_tables();
+  im->reset_tables();
+  im->mark_used();
   im->core.seed_counts(reinterpret_cast<const Rec *>(recs), n);
 }
 int swb_dist_next_merge(Trainer *trainer, int32_t *a, int32_t *b, int32_t *new_id) {

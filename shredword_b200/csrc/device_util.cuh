@@ -97,6 +97,7 @@ class PinnedBuf {
 constexpr int ROW = 128;                       // symbols per row; a word never straddles a row
 constexpr int32_t PAD = (int32_t)0x80000000;   // filler after the last live symbol of a word / row
 constexpr int32_t UNK_CODE = 0x7FFFFFFE;       // device-side stand-in for a NEGATIVE unk_id
+constexpr int32_t NEG1_CODE = 0x7FFFFFFD;      // device-side stand-in for the id -1 a sign-extended delta key produces
 // header of word with local index w is ~w (negative, never PAD)
 
 __host__ __device__ __forceinline__ uint64_t dmix64(uint64_t x) {

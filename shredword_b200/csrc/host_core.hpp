@@ -62,6 +62,16 @@ class PairTable {
       h = (h + 1) & mask;
     }
   }
+  uint32_t find_version(int32_t a, int32_t b) const {
+    const size_t mask = slots_.size() - 1;
+    size_t h = home(a, b);
+    for (;;) {
+      const PairInfo &p = slots_[h];
+      if (!p.order) return 0;
+      if (p.first == a && p.second == b) return p.version;
+      h = (h + 1) & mask;
+    }
+  }
   // all entries in creation order
   void in_creation_order(std::vector<PairInfo> &out) const {
     out.resize(n_);
@@ -186,6 +196,18 @@ class HostCore {
       if (p.freq == 0) p.version = 0;  // bpe.cpp:342-345
       p.freq += (uint64_t)r.delta;
     }
+    const size_t P = pairs_.size();
+    const size_t pushed = push_all_in_table_order();
+    const uint64_t minf = tr_->config.min_pair_freq;
+    if (log_level > 0) {
+      printf("[INFO]\t Counted %zu unique pairs\n", P);
+      printf("[INFO]\t Added %zu pairs to heap (freq >= %llu)\n", pushed, (unsigned long long)minf);
+    }
+  }
+
+  // reference bpe.cpp:359-366: every entry of the table with freq >= min_pair_freq, FNV bucket ascending,
+  // chain in creation order
+  size_t push_all_in_table_order() {
     std::vector<PairInfo> all;
     pairs_.in_creation_order(all);
     const size_t P = all.size();
@@ -198,10 +220,7 @@ class HostCore {
       const PairInfo &p = all[i];
       if (p.freq >= minf) { heap_push(p.first, p.second, p.freq, p.version); pushed++; }
     }
-    if (log_level > 0) {
-      printf("[INFO]\t Counted %zu unique pairs\n", P);
-      printf("[INFO]\t Added %zu pairs to heap (freq >= %llu)\n", pushed, (unsigned long long)minf);
-    }
+    return pushed;
   }
 
   // ---- reference bpe_merge_batch, decision part (bpe.cpp:405-429): pop until a live entry.
@@ -244,33 +263,7 @@ class HostCore {
       n = reduce_records(scratch_.data(), n);
       recs = scratch_.data();
     }
-    // Delta-map iteration order (bpe.cpp:30, 41-45, 486-487): bucket = pair_hash % 1024 ascending;
-    // inside a bucket entries were prepended, so the most recently first-touched pair comes first.
-    // Counting sort by bucket, then an insertion sort of each (tiny) bucket by key descending.
-    uint32_t start[1025];
-    memset(start, 0, sizeof start);
-    for (size_t i = 0; i < n; i++) start[((uint32_t)recs[i].second & 1023u) + 1]++;
-    for (int b = 0; b < 1024; b++) start[b + 1] += start[b];
-    order_.resize(n);
-    {
-      uint32_t fill[1024];
-      memcpy(fill, start, sizeof fill);
-      for (size_t i = 0; i < n; i++) order_[fill[(uint32_t)recs[i].second & 1023u]++] = KeyIdx{(uint64_t)recs[i].key, (uint32_t)i};
-    }
-    for (int b = 0; b < 1024; b++) {  // (L, new_id) for every L share one bucket: runs can be long
-      const uint32_t lo = start[b], hi = start[b + 1];
-      if (hi - lo < 2) continue;
-      if (hi - lo <= 8) {
-        for (uint32_t x = lo + 1; x < hi; x++) {
-          const KeyIdx v = order_[x];
-          uint32_t y = x;
-          while (y > lo && order_[y - 1].key < v.key) { order_[y] = order_[y - 1]; y--; }
-          order_[y] = v;
-        }
-      } else {
-        std::sort(order_.begin() + lo, order_.begin() + hi, [](const KeyIdx &x, const KeyIdx &y) { return x.key > y.key; });
-      }
-    }
+    sort_delta_order(recs, n);
     const uint64_t minf = tr_->config.min_pair_freq;
     constexpr size_t PF = 12;  // slot prefetch distance: keeps ~a dozen cache misses in flight
     for (size_t k = 0; k < n && k < PF; k++) pairs_.prefetch((int32_t)recs[order_[k].idx].first, (int32_t)recs[order_[k].idx].second);
@@ -288,11 +281,88 @@ class HostCore {
       }
       if (p.freq >= minf) { p.version++; heap_push(f, s, p.freq, p.version); }  // bpe.cpp:512-515
     }
+    finish_merge();
+  }
+
+  // Delta-map iteration order (bpe.cpp:30, 41-45, 486-487): bucket = pair_hash % 1024 ascending; inside a
+  // bucket entries were prepended, so the most recently first-touched pair comes first. Counting sort by
+  // bucket, then each bucket by key descending ((L, new_id) for every L share one bucket: runs can be long).
+  void sort_delta_order(const Rec *recs, size_t n) {
+    uint32_t start[1025];
+    memset(start, 0, sizeof start);
+    for (size_t i = 0; i < n; i++) start[((uint32_t)recs[i].second & 1023u) + 1]++;
+    for (int b = 0; b < 1024; b++) start[b + 1] += start[b];
+    order_.resize(n);
+    {
+      uint32_t fill[1024];
+      memcpy(fill, start, sizeof fill);
+      for (size_t i = 0; i < n; i++) order_[fill[(uint32_t)recs[i].second & 1023u]++] = KeyIdx{(uint64_t)recs[i].key, (uint32_t)i};
+    }
+    for (int b = 0; b < 1024; b++) {
+      const uint32_t lo = start[b], hi = start[b + 1];
+      if (hi - lo < 2) continue;
+      if (hi - lo <= 8) {
+        for (uint32_t x = lo + 1; x < hi; x++) {
+          const KeyIdx v = order_[x];
+          uint32_t y = x;
+          while (y > lo && order_[y - 1].key < v.key) { order_[y] = order_[y - 1]; y--; }
+          order_[y] = v;
+        }
+      } else {
+        std::sort(order_.begin() + lo, order_.begin() + hi, [](const KeyIdx &x, const KeyIdx &y) { return x.key > y.key; });
+      }
+    }
+  }
+  void finish_merge() {
     PairInfo &info = pairs_.get(cur_a_, cur_b_);
     info.freq = 0; info.version++;  // bpe.cpp:523-524
     tr_->num_merges++;
     tr_->next_token = 256 + tr_->num_merges;
     pending_ = false;
+  }
+
+  // ---- device-table mode (single GPU): the device keeps every pair's frequency and has already applied
+  // the deltas; a record carries the pair's NEW frequency and arrives only if the old or the new value
+  // reaches min_pair_freq. Pairs below the threshold on both sides can neither be pushed nor invalidate a
+  // heap entry, so the host's view (exact for every pair >= min_pair_freq, "< min" otherwise) takes the
+  // same decisions as the reference's full table.
+  void seed_absolute(const Rec *recs, size_t n) {  // fresh table: records are the pairs with count >= min
+    std::vector<Rec> v(recs, recs + n);
+    std::sort(v.begin(), v.end(), [](const Rec &x, const Rec &y) { return (uint64_t)x.key < (uint64_t)y.key; });
+    for (const Rec &r : v) {
+      PairInfo &p = pairs_.get((int32_t)r.first, (int32_t)r.second);
+      p.version = 0;
+      p.freq = (uint64_t)r.delta;
+    }
+    push_all_in_table_order();
+  }
+  void apply_absolute(const Rec *recs, size_t n) {
+    if (!pending_) return;
+    n_records += n;
+    sort_delta_order(recs, n);
+    const uint64_t minf = tr_->config.min_pair_freq;
+    constexpr size_t PF = 12;
+    for (size_t k = 0; k < n && k < PF; k++) pairs_.prefetch((int32_t)recs[order_[k].idx].first, (int32_t)recs[order_[k].idx].second);
+    for (size_t k = 0; k < n; k++) {
+      if (k + PF < n) pairs_.prefetch((int32_t)recs[order_[k + PF].idx].first, (int32_t)recs[order_[k + PF].idx].second);
+      const Rec &r = recs[order_[k].idx];
+      const int32_t f = (int32_t)r.first, s = (int32_t)r.second;
+      PairInfo &p = pairs_.get(f, s);
+      p.freq = (uint64_t)r.delta;
+      if (p.freq >= minf) { p.version++; heap_push(f, s, p.freq, p.version); }  // bpe.cpp:512-515
+    }
+    finish_merge();
+  }
+  // Rebuilds the table from a dump of the device table (entries already in creation order), keeping the
+  // versions the host knows; used when a caller leaves the fresh-count -> merge sequence.
+  void rebuild_from_dump(const std::vector<PairInfo> &in_creation_order) {
+    PairTable old;
+    std::swap(old, pairs_);
+    for (const PairInfo &e : in_creation_order) {
+      PairInfo &p = pairs_.get(e.first, e.second);
+      p.freq = e.freq;
+      p.version = old.find_version(e.first, e.second);
+    }
   }
 
   const std::vector<PairKey> &merges() const { return merges_; }

@@ -30,9 +30,91 @@ struct PairTableDev {
   unsigned int *flags;         // bit 0: table full
   unsigned int *done_blocks;   // emit kernel bookkeeping
   uint32_t mask;
+  // device-table mode with a negative unk_id: the reference's delta-map key sign-extends a negative
+  // `second` over `first` (bpe.cpp:456-457), i.e. (X, unk) collapses to (-1, unk) for every X.
+  int32_t canon_on, canon_first;
+  // device-table mode: the frequency-table slot of a newly claimed pair is prefetched into L2 here, so
+  // that the emit tail's compare-and-swap on it does not pay an HBM miss on the critical path
+  struct GSlotRef { void *slots; uint32_t mask; } gpf;
 };
 
+// Device-resident frequency table (single-GPU mode): pair -> current frequency, for every pair ever
+// touched. With it the emit step applies the deltas itself (clamp at zero on the net delta, reference
+// bpe.cpp:500-509) and only pairs that are, or were, at or above min_pair_freq travel to the host: the
+// Zipf tail of rare pairs (most records) never crosses PCIe and never enters the host's table.
+// stamp = creation order (operation index, delta-map bucket, inverted first-touch key), kept so that the
+// reference's creation-ordered table can be rebuilt exactly on the host when it is needed.
+struct __align__(32) GSlot { unsigned long long key, freq, stamp_hi, stamp_lo; };  // one 32-byte sector per pair
+struct GlobalTableDev {
+  GSlot *slots;
+  unsigned int *n_used;
+  unsigned int *flags;  // bit 0: above 50 % load, the host grows the table before the next operation
+  uint32_t mask;
+};
+__device__ __forceinline__ uint32_t gt_home(const GlobalTableDev &g, unsigned long long k) {
+  return (uint32_t)dmix64(k + 0x632BE59BD9B4E019ull) & g.mask;
+}
+__device__ __forceinline__ void gt_prefetch(const GlobalTableDev &g, unsigned long long k) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(g.slots + gt_home(g, k)));
+}
+__device__ __forceinline__ uint32_t gt_upsert(const GlobalTableDev &g, unsigned long long k, unsigned long long sh,
+                                              unsigned long long sl) {
+  uint32_t h = gt_home(g, k);
+  for (;;) {
+    const unsigned long long cur = atomicCAS(&g.slots[h].key, PT_EMPTY, k);
+    if (cur == PT_EMPTY) {
+      g.slots[h].stamp_hi = sh; g.slots[h].stamp_lo = sl;
+      if (atomicAdd(g.n_used, 1u) >= (g.mask >> 1)) atomicOr(g.flags, 1u);
+      return h;
+    }
+    if (cur == k) return h;
+    h = (h + 1) & g.mask;
+  }
+}
+
+__global__ void gt_clear(GlobalTableDev g) {
+  const uint64_t cap = (uint64_t)g.mask + 1;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
+    g.slots[i] = GSlot{PT_EMPTY, 0, 0, 0};
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *g.n_used = 0; *g.flags = 0; }
+}
+__global__ void gt_rehash(GlobalTableDev src, GlobalTableDev dst) {
+  const uint64_t cap = (uint64_t)src.mask + 1;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const GSlot e = src.slots[i];
+    if (e.key == PT_EMPTY) continue;
+    const uint32_t h = gt_upsert(dst, e.key, e.stamp_hi, e.stamp_lo);
+    dst.slots[h].freq = e.freq;
+  }
+}
+// all entries -> host (conversion to the host-resident table): 5 words per entry
+__global__ void gt_dump(GlobalTableDev g, unsigned long long *__restrict__ out, unsigned int *cursor) {
+  const uint64_t cap = (uint64_t)g.mask + 1;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const GSlot e = g.slots[i];
+    if (e.key == PT_EMPTY) continue;
+    const unsigned int j = atomicAdd(cursor, 1u);
+    out[5ull * j] = e.key; out[5ull * j + 1] = e.freq; out[5ull * j + 2] = e.stamp_hi; out[5ull * j + 3] = e.stamp_lo;
+    out[5ull * j + 4] = 0;
+  }
+}
+
+// parameters of an emit in device-table mode (mode 0 = host-resident table: plain records)
+struct EmitMode {
+  int mode;                       // 0 host records (delta), 1 device table: merge, 2 device table: count
+  unsigned long long min_freq;
+  unsigned long long merged_key;  // mode 1: the pair being merged (skipped, then zeroed)
+  unsigned long long stamp_base;  // operation index << 10
+  int32_t neg_unk_bucket;         // >= 0: a pair whose second is UNK_CODE lives in this delta-map bucket (negative unk_id)
+  GlobalTableDev g;
+};
+__device__ __forceinline__ unsigned long long delta_bucket(const EmitMode &em, unsigned long long k) {
+  if (em.neg_unk_bucket >= 0 && (uint32_t)k == (uint32_t)UNK_CODE) return (unsigned long long)em.neg_unk_bucket;
+  return k & 1023ull;
+}
+
 __device__ __forceinline__ void pt_add(const PairTableDev &t, int32_t a, int32_t b, long long delta, uint64_t key) {
+  if (t.canon_on && b == UNK_CODE) a = t.canon_first;
   const unsigned long long k = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
   uint32_t h = (uint32_t)dmix64(k) & t.mask;
   for (uint32_t probe = 0; probe <= t.mask; probe++) {
@@ -42,6 +124,9 @@ __device__ __forceinline__ void pt_add(const PairTableDev &t, int32_t a, int32_t
     if (cur == PT_EMPTY) {
       const unsigned int idx = atomicAdd(t.n_touched, 1u);
       t.touched[idx] = h;
+      if (t.gpf.slots)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<char *>(t.gpf.slots) +
+                                                     32ull * ((uint32_t)dmix64(k + 0x632BE59BD9B4E019ull) & t.gpf.mask)));
       if (idx >= (t.mask >> 1)) atomicOr(t.flags, 1u);  // past 50 % load: the host grows the table and reruns
       cur = k;
     }
@@ -72,7 +157,8 @@ __global__ void pt_clear(PairTableDev t) {
 // record writes and the header (each one costs a PCIe round trip, ~2.3 us on this box): the header and
 // the records validate themselves -- the host accepts them only when the check word and the XOR/SUM of
 // the records it reads match, and keeps polling otherwise (the bytes are still in flight).
-// flags: 1 = table full, 4 = more records than out_cap, 8 = records not emitted (fused tail only).
+// flags: 1 = table full, 4 = more records than out_cap, 8 = records not emitted (fused tail only),
+//        16 = device frequency table past 50 % load (the host grows it before the next merge).
 constexpr unsigned long long HDR_MAGIC = 0x9E3779B97F4A7C15ull;
 __host__ __device__ __forceinline__ unsigned long long hdr_check(unsigned long long seq, unsigned long long n,
                                                                  unsigned long long flags, unsigned long long removed,
@@ -80,22 +166,42 @@ __host__ __device__ __forceinline__ unsigned long long hdr_check(unsigned long l
   return (seq * HDR_MAGIC) ^ (n + 0x1234567ull) ^ (flags << 48) ^ (removed * 31ull) ^ x ^ (sm << 1 | sm >> 63);
 }
 
-__device__ __forceinline__ void pt_emit_range(const PairTableDev &t, Rec *__restrict__ out, size_t out_cap,
+__device__ __forceinline__ void rec_out(Rec *__restrict__ out, size_t out_cap, unsigned int j, unsigned long long k,
+                                        long long v, unsigned long long mk, unsigned long long &cx, unsigned long long &cs) {
+  if (j >= out_cap) return;
+  Rec r;
+  r.first = (int32_t)(k >> 32); r.second = (int32_t)(k & 0xFFFFFFFFu);
+  r.delta = v; r.key = (long long)mk;
+  out[j] = r;
+  cx ^= (unsigned long long)r.first ^ (unsigned long long)r.second ^ (unsigned long long)r.delta ^ (unsigned long long)r.key;
+  cs += (unsigned long long)r.first + 3ull * (unsigned long long)r.second + 5ull * (unsigned long long)r.delta +
+        7ull * (unsigned long long)r.key;
+}
+
+// Emits this thread's share of the touched slots and frees them.
+//   mode 0: every touched pair -> (pair, net delta, first-touch key), record i at out[i]
+//   mode 1: deltas are applied to the device frequency table; a record (pair, NEW frequency, key) is
+//           written (compacted through *out_count) only if the old or the new frequency reaches min_freq
+//   mode 2: counts are added to the device frequency table; records only for pairs >= min_freq
+__device__ __forceinline__ void pt_emit_range(const PairTableDev &t, const EmitMode &em, Rec *__restrict__ out, size_t out_cap,
                                               unsigned int n, unsigned int first, unsigned int stride,
-                                              unsigned long long &cx, unsigned long long &cs) {
+                                              unsigned int *out_count, unsigned long long &cx, unsigned long long &cs) {
   for (unsigned int i = first; i < n; i += stride) {
     const unsigned int h = __ldcg(&t.touched[i]);
     const unsigned long long k = __ldcg(&t.keys[h]);
-    if (i < out_cap) {
-      Rec r;
-      r.first = (int32_t)(k >> 32); r.second = (int32_t)(k & 0xFFFFFFFFu);
-      r.delta = (long long)__ldcg(&t.val[h]); r.key = (long long)__ldcg(&t.minkey[h]);
-      out[i] = r;
-      cx ^= (unsigned long long)r.first ^ (unsigned long long)r.second ^ (unsigned long long)r.delta ^ (unsigned long long)r.key;
-      cs += (unsigned long long)r.first + 3ull * (unsigned long long)r.second + 5ull * (unsigned long long)r.delta +
-            7ull * (unsigned long long)r.key;
-    }
+    const long long d = (long long)__ldcg(&t.val[h]);
+    const unsigned long long mk = __ldcg(&t.minkey[h]);
     t.keys[h] = PT_EMPTY; t.val[h] = 0; t.minkey[h] = ~0ull;
+    if (em.mode == 0) { rec_out(out, out_cap, i, k, d, mk, cx, cs); continue; }
+    if (em.mode == 1 && k == em.merged_key) continue;  // reference bpe.cpp:494-496
+    const unsigned long long bucket = em.mode == 1 ? delta_bucket(em, k) : 0ull;
+    const uint32_t g = gt_upsert(em.g, k, em.stamp_base | bucket, em.mode == 1 ? ~mk : mk);
+    const unsigned long long old = em.g.slots[g].freq;
+    unsigned long long nw;
+    if (d < 0) { const unsigned long long ad = (unsigned long long)(-d); nw = old >= ad ? old - ad : 0ull; }
+    else nw = old + (unsigned long long)d;
+    em.g.slots[g].freq = nw;
+    if (old >= em.min_freq || nw >= em.min_freq) rec_out(out, out_cap, atomicAdd(out_count, 1u), k, (long long)nw, mk, cx, cs);
   }
 }
 // block-wide XOR / SUM of per-thread checksums (all threads of the block must call)
@@ -124,16 +230,17 @@ __device__ __forceinline__ void pt_publish(const PairTableDev &t, unsigned int n
   *t.done_blocks = 0;
 }
 
-// full-grid emit (more records than the fused tail takes, or long words present): every block writes its
-// share and its partial checksum; the last block to finish adds the partials up and publishes.
+// full-grid emit (more records than the fused tail takes, long words present, or the count pass): every
+// block writes its share and its partial checksum; the last block to finish adds the partials up and publishes.
 __global__ void __launch_bounds__(256)
-pt_emit(PairTableDev t, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
-        unsigned long long *removed, unsigned long long seq, unsigned long long *__restrict__ partial /* [2*gridDim.x] */) {
+pt_emit(PairTableDev t, EmitMode em, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
+        unsigned long long *removed, unsigned long long seq, unsigned long long *__restrict__ partial /* [2*gridDim.x] */,
+        unsigned int *out_count /* global, zero on entry */) {
   __shared__ bool is_last;
   __shared__ unsigned long long sh[64];
   const unsigned int n = __ldcg(t.n_touched);
   unsigned long long cx = 0, cs = 0;
-  pt_emit_range(t, out, out_cap, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, cx, cs);
+  pt_emit_range(t, em, out, out_cap, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, out_count, cx, cs);
   block_checksum(cx, cs, sh);
   if (threadIdx.x == 0) {
     partial[2 * blockIdx.x] = cx; partial[2 * blockIdx.x + 1] = cs;
@@ -144,7 +251,14 @@ pt_emit(PairTableDev t, Rec *__restrict__ out, size_t out_cap, unsigned long lon
   if (is_last && threadIdx.x == 0) {
     unsigned long long x = 0, sm = 0;
     for (unsigned int i = 0; i < gridDim.x; i++) { x ^= __ldcg(&partial[2 * i]); sm += __ldcg(&partial[2 * i + 1]); }
-    pt_publish(t, n, out_cap, 0u, out_hdr, removed, seq, x, sm);
+    unsigned int n_out = n;
+    if (em.mode != 0) {
+      n_out = __ldcg(out_count);
+      *out_count = 0;
+      if (em.mode == 1) em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull)].freq = 0;  // bpe.cpp:523
+    }
+    const unsigned int gflag = (em.mode != 0 && __ldcg(em.g.flags)) ? 16u : 0u;  // frequency table past 50 % load
+    pt_publish(t, n_out, out_cap, gflag, out_hdr, removed, seq, x, sm);
   }
 }
 
@@ -241,12 +355,13 @@ __device__ __noinline__ uint32_t merge_row_slow(int *sm, Match *ml, unsigned int
 // merge); used when there are no long words to process after this kernel.
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, unsigned long long *removed_total,
-           int fused, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
+           int fused, EmitMode em, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
            unsigned long long seq) {
   __shared__ __align__(16) int sm[MERGE_WARPS][ROW];
   __shared__ Match ml[MERGE_WARPS][MATCH_CAP];
   __shared__ unsigned int n_match[MERGE_WARPS];
   __shared__ unsigned long long csum_sh[64];
+  __shared__ unsigned int tail_count;
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint64_t warp = (blockIdx.x * (uint64_t)MERGE_THREADS + threadIdx.x) >> 5;
@@ -302,9 +417,19 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
   const unsigned int n = __ldcg(t.n_touched);
   const bool small = n <= FUSED_EMIT_MAX;
   unsigned long long cx = 0, cs = 0;
-  if (small) pt_emit_range(t, out, out_cap, n, threadIdx.x, MERGE_THREADS, cx, cs);
+  if (threadIdx.x == 0) tail_count = 0;
+  __syncthreads();
+  if (small) pt_emit_range(t, em, out, out_cap, n, threadIdx.x, MERGE_THREADS, &tail_count, cx, cs);
   block_checksum(cx, cs, csum_sh);
-  if (threadIdx.x == 0) pt_publish(t, n, out_cap, small ? 0u : 8u, out_hdr, removed_total, seq, cx, cs);
+  if (threadIdx.x == 0) {
+    unsigned int n_out = n;
+    if (small && em.mode == 1) {
+      n_out = tail_count;
+      em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull)].freq = 0;  // bpe.cpp:523
+    }
+    const unsigned int gflag = (em.mode != 0 && __ldcg(em.g.flags)) ? 16u : 0u;  // frequency table past 50 % load
+    pt_publish(t, n_out, out_cap, (small ? 0u : 8u) | gflag, out_hdr, removed_total, seq, cx, cs);
+  }
 }
 
 // long words: lanes stride over the word to detect; the rare word with a match is rewritten by lane 0

@@ -270,6 +270,10 @@ class TrainerImpl {
     loaded_ = true;
     // reference bpe.cpp:295: a fresh pair table after every load
     core.pairs().clear();
+    reset_global_table();
+    device_tables_ = false;
+    tables_fresh_ = true;
+    gt_used_estimate_ = 0;
   }
 
   // reference bpe.cpp:262-279 + histogram.cpp:47-53: bytes listed in the bucket
@@ -298,16 +302,104 @@ class TrainerImpl {
     if (cap > (1ull << 31)) throw Error("pair table would exceed 2^31 slots");
     sync();
     pt_keys_.alloc(cap); pt_val_.alloc(cap); pt_min_.alloc(cap); pt_touched_.alloc(cap);
-    pt_scal_.alloc(4);
+    pt_scal_.alloc(8);
+    SWB_CUDA(cudaMemsetAsync(pt_scal_.get(), 0, pt_scal_.bytes(), stream_));
     recs_.alloc(cap / 2);
     removed_.alloc(1);
     emit_partial_.alloc(2 * 32);
     SWB_CUDA(cudaMemsetAsync(removed_.get(), 0, 8, stream_));
     pt_cap_ = cap;
     pt_ = PairTableDev{pt_keys_.get(), pt_val_.get(), pt_min_.get(), pt_touched_.get(), pt_scal_.get() + 0,
-                       pt_scal_.get() + 1, pt_scal_.get() + 2, (uint32_t)(cap - 1)};
+                       pt_scal_.get() + 1, pt_scal_.get() + 2, (uint32_t)(cap - 1), 0, 0, {nullptr, 0}};
     pt_clear<<<sms_ * 8, 256, 0, stream_>>>(pt_); launched();
   }
+  // ---- device frequency table
+  bool want_device_tables() const {
+    static const bool forced_host = getenv("SWB_HOST_TABLE") && atoi(getenv("SWB_HOST_TABLE")) > 0;
+    return nranks == 1 && !forced_host;
+  }
+  void ensure_global_table(uint64_t min_cap) {
+    ensure_device();
+    const uint64_t cap = std::max<uint64_t>(1ull << 20, pow2_ceil(min_cap));
+    if (gt_cap_ >= cap) return;
+    if (cap > (1ull << 31)) throw Error("frequency table would exceed 2^31 slots");
+    sync();
+    DevBuf<GSlot> k(cap);
+    DevBuf<unsigned int> scal(4);
+    GlobalTableDev ng{k.get(), scal.get() + 0, scal.get() + 1, (uint32_t)(cap - 1)};
+    gt_clear<<<sms_ * 8, 256, 0, stream_>>>(ng); launched();
+    if (gt_cap_) { gt_rehash<<<sms_ * 8, 256, 0, stream_>>>(gt_, ng); launched(); }
+    sync();
+    gt_slots_ = std::move(k); gt_scal_ = std::move(scal);
+    gt_ = ng;
+    gt_cap_ = cap;
+  }
+  void reset_global_table() {
+    if (!gt_cap_) return;
+    gt_clear<<<sms_ * 8, 256, 0, stream_>>>(gt_); launched();
+  }
+  // One merge inserts at most 4 pairs per distinct neighbour symbol; the kernels raise flag 16 once the
+  // table is past 50 % load, so growing then (x4) and keeping capacity >= 16 * symbols means it never fills.
+  void maybe_grow_global_table(bool flagged) {
+    const uint64_t need = 16ull * (258ull + tr_->num_merges + 2);
+    if (flagged) ensure_global_table(std::max<uint64_t>(gt_cap_ * 4, need));
+    else if (need > gt_cap_) ensure_global_table(need);
+  }
+  EmitMode emit_mode(int mode, int32_t da, int32_t db) {
+    EmitMode em;
+    memset(&em, 0, sizeof em);
+    em.mode = device_tables_ ? mode : 0;
+    em.min_freq = tr_->config.min_pair_freq;
+    em.merged_key = ((unsigned long long)(uint32_t)da << 32) | (uint32_t)db;
+    em.stamp_base = op_index_ << 10;
+    em.neg_unk_bucket = tr_->config.unk_id < 0 ? (int32_t)((uint32_t)tr_->config.unk_id & 1023u) : -1;
+    em.g = gt_;
+    return em;
+  }
+  // caller id -> device code (negative ids: unk_id travels as UNK_CODE, the -1 of a sign-extended key as NEG1_CODE)
+  int32_t to_dev(int32_t id) const {
+    if (id >= 0) return id;
+    if (id == tr_->config.unk_id) return UNK_CODE;
+    return NEG1_CODE;  // matches nothing in the stream
+  }
+  // Leaves device-table mode: the whole device table comes to the host in creation order (stamps), with
+  // the versions the host already tracks. Needed for anything but the fresh-count -> merge sequence
+  // (a second bpe_count_bigrams without bpe_init, the swb_dist_* / swb_shard_* building blocks).
+  void convert_to_host_tables() {
+    if (!device_tables_) return;
+    device_tables_ = false;
+    if (!gt_cap_) return;
+    unsigned int used = 0;
+    SWB_CUDA(cudaMemcpyAsync(&used, gt_.n_used, 4, cudaMemcpyDeviceToHost, stream_));
+    sync();
+    std::vector<PairInfo> entries;
+    if (used) {
+      DevBuf<unsigned long long> d(5ull * used);
+      DevBuf<unsigned int> cur(1);
+      SWB_CUDA(cudaMemsetAsync(cur.get(), 0, 4, stream_));
+      gt_dump<<<sms_ * 8, 256, 0, stream_>>>(gt_, d.get(), cur.get()); launched();
+      std::vector<unsigned long long> h(5ull * used);
+      SWB_CUDA(cudaMemcpyAsync(h.data(), d.get(), h.size() * 8, cudaMemcpyDeviceToHost, stream_));
+      sync();
+      std::vector<uint32_t> idx(used);
+      for (uint32_t i = 0; i < used; i++) idx[i] = i;
+      std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {
+        if (h[5ull * x + 2] != h[5ull * y + 2]) return h[5ull * x + 2] < h[5ull * y + 2];
+        return h[5ull * x + 3] < h[5ull * y + 3];
+      });
+      entries.reserve(used);
+      for (uint32_t i : idx) {
+        int32_t f = (int32_t)(h[5ull * i] >> 32), s = (int32_t)(h[5ull * i] & 0xFFFFFFFFu);
+        if (tr_->config.unk_id < 0) {
+          if (f == UNK_CODE) f = tr_->config.unk_id; else if (f == NEG1_CODE) f = -1;
+          if (s == UNK_CODE) s = tr_->config.unk_id; else if (s == NEG1_CODE) s = -1;
+        }
+        entries.push_back(PairInfo{f, s, h[5ull * i + 1], 0, 0});
+      }
+    }
+    core.rebuild_from_dump(entries);
+  }
+
   StreamDev stream_dev() {
     return StreamDev{rows_.get(), sig_.get(), n_rows_, cnt_.get(), long_syms_.get(), long_off_.get(), long_len_.get(),
                      long_word_.get(), n_long_};
@@ -350,9 +442,11 @@ class TrainerImpl {
     }
   }
   // runs pt_emit, waits, returns the record count (records are in mapped host memory until the next emit)
-  size_t emit_and_wait(unsigned int *flags_out, uint64_t *removed_out) {
+  size_t emit_and_wait(const EmitMode &em, unsigned int *flags_out, uint64_t *removed_out) {
     const unsigned long long seq = ++seq_;
-    pt_emit<<<32, 256, 0, stream_>>>(pt_, recs_.dev(), recs_.size(), hdr_.dev(), removed_.get(), seq, emit_partial_.get()); launched();
+    pt_emit<<<32, 256, 0, stream_>>>(pt_, em, recs_.dev(), recs_.size(), hdr_.dev(), removed_.get(), seq, emit_partial_.get(),
+                                     pt_scal_.get() + 3);
+    launched();
     SWB_CUDA(cudaGetLastError());
     const double tw0 = now_ms();
     stats.host_launch_ms += tw0 - t_launch0_;
@@ -367,14 +461,16 @@ class TrainerImpl {
   void translate_out(Rec *r, size_t n) const {
     if (tr_->config.unk_id >= 0) return;
     for (size_t i = 0; i < n; i++) {
-      if (r[i].first == UNK_CODE) r[i].first = tr_->config.unk_id;
-      if (r[i].second == UNK_CODE) r[i].second = tr_->config.unk_id;
+      if (r[i].first == UNK_CODE) r[i].first = tr_->config.unk_id; else if (r[i].first == NEG1_CODE) r[i].first = -1;
+      if (r[i].second == UNK_CODE) r[i].second = tr_->config.unk_id; else if (r[i].second == NEG1_CODE) r[i].second = -1;
     }
   }
 
   // ---------------------------------------------------------------- count (this rank's words)
-  // Returns the records (pair, weighted frequency, first-touch key) of this rank's share.
-  const Rec *shard_count(size_t *n_out) {
+  // Launches the count kernels and the emit in the given mode; returns the records.
+  //   mode 0: (pair, weighted frequency, first-touch key) for every distinct pair of this rank's share
+  //   mode 2: the counts go to the device frequency table; records only for pairs >= min_pair_freq
+  const Rec *run_count(int mode, size_t *n_out) {
     ensure_pair_table(1);
     const double t0 = now_ms();
     if (!loaded_) { *n_out = 0; return recs_.host(); }
@@ -386,30 +482,57 @@ class TrainerImpl {
         count_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, unk_dev()); launched();
       }
       if (n_long_) { count_long<<<std::min<uint32_t>(sms_ * 4, (n_long_ + 3) / 4), 128, 0, stream_>>>(s, pt_, unk_dev()); launched(); }
+      unsigned int overflow = 0;  // read the flag BEFORE emitting: in mode 2 the emit writes into the frequency table
+      SWB_CUDA(cudaMemcpyAsync(&overflow, pt_.flags, 4, cudaMemcpyDeviceToHost, stream_));
+      sync();
       unsigned int flags = 0;
-      const size_t n = emit_and_wait(&flags, nullptr);
-      if (flags & 5u) {  // table (or record buffer) too small for the number of distinct pairs: grow, recount
+      if (overflow & 1u) {  // more distinct pairs than the table holds: drain it, grow, recount
+        emit_and_wait(emit_mode(0, 0, 0), &flags, nullptr);
         const uint64_t want = pt_cap_ * 4;
         pt_cap_ = 0;
         ensure_pair_table(want);
         continue;
       }
+      if (mode == 2) {
+        unsigned int n_pairs = 0;
+        SWB_CUDA(cudaMemcpyAsync(&n_pairs, pt_.n_touched, 4, cudaMemcpyDeviceToHost, stream_));
+        sync();
+        // sized up front so that growing (alloc + rehash, ~10 ms each) is rare: pairs ever touched ~ O(words)
+        ensure_global_table(std::max<uint64_t>(4ull * n_pairs + 16 * (258 + tr_->config.target_vocab_size), 4 * W));
+      }
+      EmitMode em = emit_mode(mode, 0, 0);
+      const size_t n = emit_and_wait(em, &flags, nullptr);
+      if (flags & 4u) throw Error("record buffer too small for the count pass (internal sizing error)");
+      if (flags & 16u) gt_flagged_ = true;
       translate_out(recs_.host(), n);
       *n_out = n;
       stats.count_ms += now_ms() - t0;
       return recs_.host();
     }
   }
+  const Rec *shard_count(size_t *n_out) {  // building block of the multi-rank loop: always plain records
+    convert_to_host_tables();
+    tables_fresh_ = false;
+    return run_count(0, n_out);
+  }
 
   // ---------------------------------------------------------------- merge (this rank's words)
-  const Rec *shard_merge(int32_t a, int32_t b, int32_t new_id, size_t *n_out) {
+  const Rec *run_merge(int32_t a, int32_t b, int32_t new_id, size_t *n_out) {
     // at most 4 distinct pairs per distinct neighbour symbol: size the table so that it cannot fill up
     ensure_pair_table(8ull * (258ull + tr_->num_merges + 2));
     *n_out = 0;
     if (!loaded_) return recs_.host();
     const int32_t unk = tr_->config.unk_id;
-    if ((a < 0 && a != unk) || (b < 0 && b != unk)) return recs_.host();  // such ids exist in no word
-    const int32_t da = a < 0 ? UNK_CODE : a, db = b < 0 ? UNK_CODE : b;
+    const bool absent = (a < 0 && a != unk) || (b < 0 && b != unk);  // such ids exist in no word
+    if (absent && !device_tables_) return recs_.host();
+    const int32_t da = to_dev(a), db = to_dev(b);
+    if (device_tables_) { maybe_grow_global_table(gt_flagged_); gt_flagged_ = false; }
+    op_index_++;
+    EmitMode em = emit_mode(1, da, db);
+    pt_.canon_on = (device_tables_ && unk < 0) ? 1 : 0;
+    pt_.canon_first = unk == -1 ? UNK_CODE : NEG1_CODE;
+    pt_.gpf.slots = device_tables_ ? (void *)gt_.slots : nullptr;
+    pt_.gpf.mask = gt_.mask;
     StreamDev s = stream_dev();
     t_launch0_ = now_ms();
     if (timing) SWB_CUDA(cudaEventRecord(ev0_, stream_));
@@ -419,7 +542,7 @@ class TrainerImpl {
       const uint64_t warps_needed = (n_rows_ + 31) / 32;  // one warp tests 32 row signatures per iteration
       const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 4, (warps_needed + MERGE_WARPS - 1) / MERGE_WARPS);
       if (fused) seq = ++seq_;
-      merge_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, da, db, new_id, removed_.get(), fused ? 1 : 0, recs_.dev(),
+      merge_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, da, db, new_id, removed_.get(), fused ? 1 : 0, em, recs_.dev(),
                                                       recs_.size(), hdr_.dev(), seq);
       launched();
       stats.merge_launches++;
@@ -440,12 +563,13 @@ class TrainerImpl {
       removed = hdr_.host()[3];
       if (flags & 8u) {  // too many records for the fused tail: emit them with a full grid
         t_launch0_ = now_ms();
-        n = emit_and_wait(&flags, &removed);
+        n = emit_and_wait(em, &flags, &removed);
       }
     } else {
-      n = emit_and_wait(&flags, &removed);
+      n = emit_and_wait(em, &flags, &removed);
     }
-    if (flags) throw Error("pair table overflow during a merge (internal sizing error)");
+    if (flags & 16u) gt_flagged_ = true;
+    if (flags & 5u) throw Error("pair table overflow during a merge (internal sizing error)");
     if (timing) {
       float ms = 0;
       SWB_CUDA(cudaEventSynchronize(ev1_));
@@ -460,15 +584,43 @@ class TrainerImpl {
     *n_out = n;
     return recs_.host();
   }
+  const Rec *shard_merge(int32_t a, int32_t b, int32_t new_id, size_t *n_out) {  // multi-rank building block
+    convert_to_host_tables();
+    tables_fresh_ = false;
+    return run_merge(a, b, new_id, n_out);
+  }
 
   // ---------------------------------------------------------------- single-process drivers
   void count_bigrams() {  // reference bpe_count_bigrams
     size_t n = 0;
-    const Rec *r = shard_count(&n);
+    if (tables_fresh_ && want_device_tables() && loaded_) {
+      // fresh pair table (right after a load or a reset): the device keeps the frequencies from here on
+      device_tables_ = true;
+      ensure_device();
+      ensure_global_table(1);
+      tables_fresh_ = false;
+      op_index_++;
+      const Rec *r = run_count(2, &n);
+      core.seed_absolute(r, n);
+      return;
+    }
+    // counting on top of a used table (the reference then ADDS to the existing frequencies and pushes every
+    // entry again): replay on the host-resident table, which needs every pair -> leave device mode
+    convert_to_host_tables();
+    tables_fresh_ = false;
+    const Rec *r = run_count(0, &n);
     core.seed_counts(r, n);
   }
-  void init() {  // reference bpe_init
+  void reset_tables() {  // reference bpe.cpp:177-183
     core.reset_tables();
+    if (stream_) reset_global_table();
+    device_tables_ = false;
+    tables_fresh_ = true;
+    gt_used_estimate_ = 0;
+  }
+  void mark_used() { tables_fresh_ = false; }
+  void init() {  // reference bpe_init
+    reset_tables();
     count_bigrams();
   }
   int merge_batch(int batch) {  // reference bpe_merge_batch
@@ -479,10 +631,12 @@ class TrainerImpl {
       const double tp0 = now_ms();
       if (!core.next_merge(&a, &b, &nid)) break;
       stats.host_pop_ms += now_ms() - tp0;
+      tables_fresh_ = false;
       size_t n = 0;
-      const Rec *r = shard_merge(a, b, nid, &n);
+      const Rec *r = run_merge(a, b, nid, &n);
       const double ta0 = now_ms();
-      core.apply(r, n);
+      if (device_tables_) core.apply_absolute(r, n);
+      else core.apply(r, n);
       stats.host_apply_ms += now_ms() - ta0;
       done++;
     }
@@ -579,6 +733,15 @@ class TrainerImpl {
   PairTableDev pt_{};
   DevBuf<unsigned long long> pt_keys_, pt_val_, pt_min_, removed_, emit_partial_;
   int idle_polls_ = 0;
+  uint64_t gt_used_estimate_ = 0;
+  bool gt_flagged_ = false;
+  // device-resident frequency table (single-GPU mode)
+  bool device_tables_ = false;   // true: the device owns the frequencies, the host only sees pairs >= min_pair_freq
+  bool tables_fresh_ = true;     // no count / merge since the last load or reset
+  uint64_t gt_cap_ = 0, op_index_ = 0;
+  GlobalTableDev gt_{};
+  DevBuf<GSlot> gt_slots_;
+  DevBuf<unsigned int> gt_scal_;
   DevBuf<unsigned int> pt_touched_, pt_scal_;
   PinnedBuf<Rec> recs_;
 };
