@@ -228,19 +228,25 @@ def main():
   last = {}
 
   def step(resident: bool, timing: bool):
+    w0 = time.perf_counter()
+    old = last.pop("trainer", None)
+    if old is not None:
+      old.destroy()  # the previous step's handle: its device memory goes back before the next step allocates
+    w1 = time.perf_counter()
     t = new_trainer()
     t.set_kernel_timing(timing)
     if resident:
       t.load_device(d_corpus.data_ptr(), nbytes)
     else:
       t.load_buffer(arr)
+    w2 = time.perf_counter()
     merges = t.train_quiet()
+    w3 = time.perf_counter()
     m = t.merges_array()  # the step's result, read on the host
     st = t.stats()
     st["merges"] = merges; st["merge_bytes"] = m.nbytes
-    old = last.pop("trainer", None)
-    if old is not None:
-      old.destroy()
+    st["wall_ms"] = {"destroy_prev": (w1 - w0) * 1e3, "create+load": (w2 - w1) * 1e3, "train": (w3 - w2) * 1e3,
+                     "read": (time.perf_counter() - w3) * 1e3}
     last["trainer"] = t
     return st
 
@@ -310,6 +316,7 @@ def main():
               "us_per_merge": st_res[-1]["merge_ms"] * 1e3 / max(merges, 1),
               "phase_ms": {k: st_res[-1][k] for k in ("load_ms", "count_ms", "merge_ms")},
               "e2e_phase_ms": {k: st_e2e[-1][k] for k in ("load_ms", "count_ms", "merge_ms")},
+              "wall_ms": st_res[-1]["wall_ms"], "e2e_wall_ms": st_e2e[-1]["wall_ms"],
               "unique_words": st_res[-1]["words"], "rows": st_res[-1]["rows"], "wall_ms_per_step": wall_res,
               "ms_per_step_with_kernel_timing": ms_tim},
   }

@@ -99,6 +99,10 @@ int swb_device_count(void);
 /* Select the device used by handles created afterwards on this thread (default 0). */
 int swb_set_device(int device);
 
+/* The library keeps freed device / pinned blocks for reuse by later handles (allocation calls are slow
+ * and synchronise the device). This returns them to the driver; returns the number of bytes released. */
+size_t swb_release_cached_memory(void);
+
 /* Same as bpe_load_corpus but from memory. `data` is a HOST pointer (pinned or pageable) for
  * _buffer and a DEVICE pointer for _device (the bytes are only read, never kept). */
 int swb_load_corpus_buffer(Trainer *trainer, const void *data, size_t nbytes);

@@ -43,6 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     "-shared", "-cudart", "static",
     "-o", OUT + ".tmp", SRC,
   ]
+  if os.environ.get("SWB_KERNEL_TRACE"):
+    cmd.insert(1, "-DSWB_KERNEL_TRACE")
   if verbose:
     cmd.insert(1, "-Xptxas=-v")
     print(" ".join(cmd), file=sys.stderr)

@@ -68,6 +68,7 @@ _sigs = {
   "swb_set_log_level": ([c_int], None),
   "swb_device_count": ([], c_int),
   "swb_set_device": ([c_int], c_int),
+  "swb_release_cached_memory": ([], c_size_t),
   "swb_load_corpus_buffer": ([T, c_void_p, c_size_t], c_int),
   "swb_load_corpus_device": ([T, c_void_p, c_size_t], c_int),
   "swb_num_merges": ([T], c_size_t),

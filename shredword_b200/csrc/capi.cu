@@ -182,6 +182,14 @@ int swb_set_device(int device) {
   return 0;
 }
 
+size_t swb_release_cached_memory(void) {
+  const size_t n = swb::BlockCache::device().cached_bytes() + swb::BlockCache::pinned().cached_bytes();
+  cudaDeviceSynchronize();
+  swb::BlockCache::device().release_all();
+  swb::BlockCache::pinned().release_all();
+  return n;
+}
+
 int swb_load_corpus_buffer(Trainer *trainer, const void *data, size_t nbytes) {
   if (!trainer || (!data && nbytes)) { set_err("NULL trainer or data"); return -1; }
   SWB_TRY

@@ -5,8 +5,11 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace swb {
 
@@ -22,6 +25,70 @@ struct Error : std::runtime_error {
                          __FILE__ + ":" + std::to_string(__LINE__) + " (" #call ")");           \
   } while (0)
 
+// Process-wide cache of device and pinned allocations. cudaMalloc / cudaFree / cudaHostAlloc / cudaFreeHost
+// synchronise the device and cost from 0.1 to 100+ ms each on a busy driver; a trainer handle needs ~25
+// buffers, so a handle created after another one was destroyed reuses its blocks instead. Sizes are
+// rounded up to one of four classes per power of two (<= 25 % slack). swb_release_cached_memory() gives
+// everything back.
+class BlockCache {
+ public:
+  static BlockCache &device() { static BlockCache c(false); return c; }
+  static BlockCache &pinned() { static BlockCache c(true); return c; }
+  static size_t size_class(size_t bytes) {
+    if (bytes <= 4096) return 4096;
+    size_t p = 4096;
+    while (p < bytes) p <<= 1;           // p/2 < bytes <= p
+    const size_t q = p >> 3;             // classes: 5/8, 6/8, 7/8, 8/8 of p
+    for (size_t c = (p >> 1) + q; c < p; c += q)
+      if (bytes <= c) return c;
+    return p;
+  }
+  void *get(size_t bytes, size_t *cls_out) {
+    const size_t cls = size_class(bytes);
+    *cls_out = cls;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      auto it = free_.find(cls);
+      if (it != free_.end() && !it->second.empty()) {
+        void *p = it->second.back();
+        it->second.pop_back();
+        cached_bytes_ -= cls;
+        return p;
+      }
+    }
+    void *p = nullptr;
+    cudaError_t e = pinned_ ? cudaHostAlloc(&p, cls, cudaHostAllocMapped) : cudaMalloc(&p, cls);
+    if (e != cudaSuccess) {  // out of memory: give the cache back and retry once
+      cudaGetLastError();
+      release_all();
+      e = pinned_ ? cudaHostAlloc(&p, cls, cudaHostAllocMapped) : cudaMalloc(&p, cls);
+    }
+    if (e != cudaSuccess)
+      throw Error(std::string(pinned_ ? "cudaHostAlloc" : "cudaMalloc") + " of " + std::to_string(cls) + " bytes failed: " + cudaGetErrorString(e));
+    return p;
+  }
+  void put(void *p, size_t cls) {
+    std::lock_guard<std::mutex> g(mu_);
+    free_[cls].push_back(p);
+    cached_bytes_ += cls;
+  }
+  void release_all() {
+    std::lock_guard<std::mutex> g(mu_);
+    for (auto &kv : free_)
+      for (void *p : kv.second) { if (pinned_) cudaFreeHost(p); else cudaFree(p); }
+    free_.clear();
+    cached_bytes_ = 0;
+  }
+  size_t cached_bytes() const { return cached_bytes_; }
+
+ private:
+  explicit BlockCache(bool pinned) : pinned_(pinned) {}
+  bool pinned_;
+  std::mutex mu_;
+  std::map<size_t, std::vector<void *>> free_;
+  size_t cached_bytes_ = 0;
+};
+
 template <typename T>
 class DevBuf {
  public:
@@ -29,26 +96,20 @@ class DevBuf {
   explicit DevBuf(size_t n) { alloc(n); }
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  DevBuf(DevBuf &&o) noexcept : p_(o.p_), n_(o.n_), cls_(o.cls_) { o.p_ = nullptr; o.n_ = 0; o.cls_ = 0; }
   DevBuf &operator=(DevBuf &&o) noexcept {
-    if (this != &o) { release(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+    if (this != &o) { release(); p_ = o.p_; n_ = o.n_; cls_ = o.cls_; o.p_ = nullptr; o.n_ = 0; o.cls_ = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
   void alloc(size_t n) {
     release();
-    if (n) {
-      void *p = nullptr;
-      cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-      if (e != cudaSuccess)
-        throw Error(std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e));
-      p_ = (T *)p;
-    }
+    if (n) p_ = (T *)BlockCache::device().get(n * sizeof(T), &cls_);
     n_ = n;
   }
   void release() {
-    if (p_) cudaFree(p_);
-    p_ = nullptr; n_ = 0;
+    if (p_) BlockCache::device().put(p_, cls_);
+    p_ = nullptr; n_ = 0; cls_ = 0;
   }
   T *get() const { return p_; }
   size_t size() const { return n_; }
@@ -56,11 +117,11 @@ class DevBuf {
 
  private:
   T *p_ = nullptr;
-  size_t n_ = 0;
+  size_t n_ = 0, cls_ = 0;
 };
 
 // Pinned, device-mapped host memory: kernels write results straight into it, the host reads them
-// after one stream synchronize (no separate D2H copy on the per-merge critical path).
+// without a separate D2H copy on the per-merge critical path.
 template <typename T>
 class PinnedBuf {
  public:
@@ -71,18 +132,16 @@ class PinnedBuf {
   void alloc(size_t n) {
     release();
     if (n) {
-      void *p = nullptr;
-      SWB_CUDA(cudaHostAlloc(&p, n * sizeof(T), cudaHostAllocMapped));
-      h_ = (T *)p;
+      h_ = (T *)BlockCache::pinned().get(n * sizeof(T), &cls_);
       void *d = nullptr;
-      SWB_CUDA(cudaHostGetDevicePointer(&d, p, 0));
+      SWB_CUDA(cudaHostGetDevicePointer(&d, h_, 0));
       d_ = (T *)d;
     }
     n_ = n;
   }
   void release() {
-    if (h_) cudaFreeHost(h_);
-    h_ = nullptr; d_ = nullptr; n_ = 0;
+    if (h_) BlockCache::pinned().put(h_, cls_);
+    h_ = nullptr; d_ = nullptr; n_ = 0; cls_ = 0;
   }
   T *host() const { return h_; }
   T *dev() const { return d_; }
@@ -90,7 +149,7 @@ class PinnedBuf {
 
  private:
   T *h_ = nullptr, *d_ = nullptr;
-  size_t n_ = 0;
+  size_t n_ = 0, cls_ = 0;
 };
 
 // ---- symbol stream constants (see DESIGN.md "Data layout in HBM")

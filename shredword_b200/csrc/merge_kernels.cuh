@@ -25,7 +25,7 @@ struct PairTableDev {
   unsigned long long *keys;    // (first << 32) | second, PT_EMPTY when free
   unsigned long long *val;     // net delta (two's complement) or frequency
   unsigned long long *minkey;  // smallest first-touch key
-  unsigned int *touched;       // slots claimed since the last emit
+  uint4 *touched;              // per claim: {slot, key lo, key hi, 0}: slots claimed since the last emit
   unsigned int *n_touched;
   unsigned int *flags;         // bit 0: table full
   unsigned int *done_blocks;   // emit kernel bookkeeping
@@ -57,19 +57,25 @@ __device__ __forceinline__ uint32_t gt_home(const GlobalTableDev &g, unsigned lo
 __device__ __forceinline__ void gt_prefetch(const GlobalTableDev &g, unsigned long long k) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(g.slots + gt_home(g, k)));
 }
+// `inserted` is incremented when a new slot is claimed; the caller adds its total to n_used once
+// (gt_account), instead of one same-address atomic per insertion.
 __device__ __forceinline__ uint32_t gt_upsert(const GlobalTableDev &g, unsigned long long k, unsigned long long sh,
-                                              unsigned long long sl) {
+                                              unsigned long long sl, unsigned int &inserted) {
   uint32_t h = gt_home(g, k);
   for (;;) {
     const unsigned long long cur = atomicCAS(&g.slots[h].key, PT_EMPTY, k);
     if (cur == PT_EMPTY) {
       g.slots[h].stamp_hi = sh; g.slots[h].stamp_lo = sl;
-      if (atomicAdd(g.n_used, 1u) >= (g.mask >> 1)) atomicOr(g.flags, 1u);
+      inserted++;
       return h;
     }
     if (cur == k) return h;
     h = (h + 1) & g.mask;
   }
+}
+
+__device__ __forceinline__ void gt_account(const GlobalTableDev &g, unsigned int inserted) {
+  if (inserted && atomicAdd(g.n_used, inserted) + inserted >= (g.mask >> 1)) atomicOr(g.flags, 1u);
 }
 
 __global__ void gt_clear(GlobalTableDev g) {
@@ -83,8 +89,10 @@ __global__ void gt_rehash(GlobalTableDev src, GlobalTableDev dst) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
     const GSlot e = src.slots[i];
     if (e.key == PT_EMPTY) continue;
-    const uint32_t h = gt_upsert(dst, e.key, e.stamp_hi, e.stamp_lo);
+    unsigned int ins = 0;
+    const uint32_t h = gt_upsert(dst, e.key, e.stamp_hi, e.stamp_lo, ins);
     dst.slots[h].freq = e.freq;
+    gt_account(dst, ins);
   }
 }
 // all entries -> host (conversion to the host-resident table): 5 words per entry
@@ -121,9 +129,18 @@ __device__ __forceinline__ void pt_add(const PairTableDev &t, int32_t a, int32_t
     // CAS straight away (one L2 round trip): the table is empty at the start of every merge, so the
     // common case is a first touch
     unsigned long long cur = atomicCAS(&t.keys[h], PT_EMPTY, k);
+    // claims of the lanes that are converged here share ONE atomic on the list cursor (same-address global
+    // atomics serialise in L2 at tens of ns each; a merge makes hundreds of claims)
+    const unsigned int conv = __activemask();
+    const unsigned int claimers = __ballot_sync(conv, cur == PT_EMPTY);
     if (cur == PT_EMPTY) {
-      const unsigned int idx = atomicAdd(t.n_touched, 1u);
-      t.touched[idx] = h;
+      const int leader = __ffs(claimers) - 1;
+      const int lane_id = threadIdx.x & 31;
+      unsigned int base = 0;
+      if (lane_id == leader) base = atomicAdd(t.n_touched, (unsigned int)__popc(claimers));
+      base = __shfl_sync(claimers, base, leader);
+      const unsigned int idx = base + __popc(claimers & ((1u << lane_id) - 1u));
+      t.touched[idx] = make_uint4(h, (uint32_t)k, (uint32_t)(k >> 32), 0u);
       if (t.gpf.slots)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<char *>(t.gpf.slots) +
                                                      32ull * ((uint32_t)dmix64(k + 0x632BE59BD9B4E019ull) & t.gpf.mask)));
@@ -185,18 +202,30 @@ __device__ __forceinline__ void rec_out(Rec *__restrict__ out, size_t out_cap, u
 //   mode 2: counts are added to the device frequency table; records only for pairs >= min_freq
 __device__ __forceinline__ void pt_emit_range(const PairTableDev &t, const EmitMode &em, Rec *__restrict__ out, size_t out_cap,
                                               unsigned int n, unsigned int first, unsigned int stride,
-                                              unsigned int *out_count, unsigned long long &cx, unsigned long long &cs) {
+                                              unsigned int *out_count, unsigned long long &cx, unsigned long long &cs,
+                                              unsigned int &inserted) {
   for (unsigned int i = first; i < n; i += stride) {
-    const unsigned int h = __ldcg(&t.touched[i]);
-    const unsigned long long k = __ldcg(&t.keys[h]);
+    const uint4 tc = __ldcg(&t.touched[i]);
+    const unsigned int h = tc.x;
+    const unsigned long long k = ((unsigned long long)tc.z << 32) | tc.y;
+    // the frequency-table slot and the delta-table slot are fetched together (one round trip); the slot was
+    // prefetched into L2 when the pair was claimed
+    uint32_t g = 0;
+    ulonglong2 gs = make_ulonglong2(0, 0);  // {key, freq}
+    const bool dev = em.mode != 0 && !(em.mode == 1 && k == em.merged_key);
+    if (dev) { g = gt_home(em.g, k); gs = __ldcg(reinterpret_cast<const ulonglong2 *>(em.g.slots + g)); }
     const long long d = (long long)__ldcg(&t.val[h]);
     const unsigned long long mk = __ldcg(&t.minkey[h]);
     t.keys[h] = PT_EMPTY; t.val[h] = 0; t.minkey[h] = ~0ull;
     if (em.mode == 0) { rec_out(out, out_cap, i, k, d, mk, cx, cs); continue; }
-    if (em.mode == 1 && k == em.merged_key) continue;  // reference bpe.cpp:494-496
-    const unsigned long long bucket = em.mode == 1 ? delta_bucket(em, k) : 0ull;
-    const uint32_t g = gt_upsert(em.g, k, em.stamp_base | bucket, em.mode == 1 ? ~mk : mk);
-    const unsigned long long old = em.g.slots[g].freq;
+    if (!dev) continue;  // the merged pair itself: reference bpe.cpp:494-496
+    unsigned long long old;
+    if (gs.x == k) old = gs.y;  // common case: the pair is already in the table, at its home slot
+    else {
+      const unsigned long long bucket = em.mode == 1 ? delta_bucket(em, k) : 0ull;
+      g = gt_upsert(em.g, k, em.stamp_base | bucket, em.mode == 1 ? ~mk : mk, inserted);
+      old = em.g.slots[g].freq;
+    }
     unsigned long long nw;
     if (d < 0) { const unsigned long long ad = (unsigned long long)(-d); nw = old >= ad ? old - ad : 0ull; }
     else nw = old + (unsigned long long)d;
@@ -240,7 +269,11 @@ pt_emit(PairTableDev t, EmitMode em, Rec *__restrict__ out, size_t out_cap, unsi
   __shared__ unsigned long long sh[64];
   const unsigned int n = __ldcg(t.n_touched);
   unsigned long long cx = 0, cs = 0;
-  pt_emit_range(t, em, out, out_cap, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, out_count, cx, cs);
+  unsigned int inserted = 0;
+  pt_emit_range(t, em, out, out_cap, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, out_count, cx, cs, inserted);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, d);
+  if ((threadIdx.x & 31) == 0 && em.mode != 0) gt_account(em.g, inserted);
   block_checksum(cx, cs, sh);
   if (threadIdx.x == 0) {
     partial[2 * blockIdx.x] = cx; partial[2 * blockIdx.x + 1] = cs;
@@ -255,14 +288,18 @@ pt_emit(PairTableDev t, EmitMode em, Rec *__restrict__ out, size_t out_cap, unsi
     if (em.mode != 0) {
       n_out = __ldcg(out_count);
       *out_count = 0;
-      if (em.mode == 1) em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull)].freq = 0;  // bpe.cpp:523
+      if (em.mode == 1) {
+        unsigned int ins = 0;
+        em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;  // bpe.cpp:523
+        gt_account(em.g, ins);
+      }
     }
     const unsigned int gflag = (em.mode != 0 && __ldcg(em.g.flags)) ? 16u : 0u;  // frequency table past 50 % load
     pt_publish(t, n_out, out_cap, gflag, out_hdr, removed, seq, x, sm);
   }
 }
 
-constexpr unsigned int FUSED_EMIT_MAX = 8192;  // above this the records are emitted by a full-grid pt_emit
+constexpr unsigned int FUSED_EMIT_MAX = 384;   // above this the records are emitted by a full-grid pt_emit
 
 struct StreamDev {
   int4 *rows;                 // n_rows * ROW int32
@@ -282,16 +319,18 @@ __device__ __forceinline__ uint64_t word_gwi(const StreamDev &, uint32_t wi) { r
 // ---------------------------------------------------------------- merge (a, b) -> new_id
 constexpr int MERGE_THREADS = 256;
 constexpr int MERGE_WARPS = MERGE_THREADS / 32;
-constexpr int MATCH_CAP = ROW / 2;  // a row of 128 symbols holds at most 64 matches
+constexpr int MATCH_CAP = ROW;  // matches of one warp iteration awaiting emission (a row holds at most 64)
 
 // One match of the pair inside a row, recorded by the lane that rewrites the word; the four signed
 // deltas it stands for (reference bpe.cpp:453-470) are emitted afterwards, one lane per delta.
-struct Match { int32_t L, R; uint32_t wi; uint32_t pos; };  // L / R = -1: no such neighbour
+struct Match { int32_t L, R; uint32_t wi; uint32_t pos; unsigned long long cnt; };  // L / R = -1: no such neighbour
 
 // Sequential rewrite of one word living in shared memory at sm[p+1 ...]; p = header position.
-__device__ __forceinline__ uint32_t merge_word_smem(int *sm, int p, Match *ml, unsigned int *n_match, int32_t a, int32_t b,
+__device__ __forceinline__ uint32_t merge_word_smem(int *sm, int p, Match *ml, unsigned int *n_match,
+                                                    const unsigned long long *__restrict__ cnt, int32_t a, int32_t b,
                                                     int32_t new_id) {
   const uint32_t wi = (uint32_t)(~sm[p]);
+  unsigned long long c = 0;
   int r = p + 1, w = p + 1;
   uint32_t nmatch = 0;
   while (r < ROW) {
@@ -302,6 +341,8 @@ __device__ __forceinline__ uint32_t merge_word_smem(int *sm, int p, Match *ml, u
       m.L = (w > p + 1) ? sm[w - 1] : -1;                      // left neighbour: the already rewritten symbol
       m.R = (r + 2 < ROW && sm[r + 2] >= 0) ? sm[r + 2] : -1;  // right neighbour: not yet rewritten
       m.wi = wi; m.pos = (uint32_t)r;
+      if (nmatch == 0) c = __ldg(&cnt[wi]);  // issued here so that its latency hides behind the rest of the rewrite
+      m.cnt = c;
       ml[atomicAdd(n_match, 1u)] = m;
       sm[w++] = new_id;
       r += 2;
@@ -315,37 +356,47 @@ __device__ __forceinline__ uint32_t merge_word_smem(int *sm, int p, Match *ml, u
   return nmatch;
 }
 
-// Slow path of one row (warp-uniform): stage in shared memory, rewrite word by word (the lane that holds
-// a header rewrites that word), store back, then emit the deltas of all matches with one lane per delta.
-__device__ __noinline__ uint32_t merge_row_slow(int *sm, Match *ml, unsigned int *n_match, int4 v, int lane, int4 *row_gmem,
-                                                uint32_t *row_sig, const StreamDev &s, const PairTableDev &t, int32_t a,
-                                                int32_t b, int32_t new_id) {
-  *reinterpret_cast<int4 *>(&sm[lane * 4]) = v;
-  if (lane == 0) *n_match = 0;
-  __syncwarp();
-  uint32_t removed = 0;
-  const int h[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    if (h[k] < 0 && h[k] != PAD) removed += merge_word_smem(sm, lane * 4 + k, ml, n_match, a, b, new_id);
-  __syncwarp();
-  row_gmem[lane] = *reinterpret_cast<const int4 *>(&sm[lane * 4]);
-  const unsigned int nm = *n_match;
-  if (lane == 0 && nm) {  // the row now contains new_id
-    const uint32_t hh = sig_hash(new_id);
-    row_sig[hh >> 5] |= 1u << (hh & 31);
-  }
+// Emits the four signed deltas of every recorded match, one lane per delta (reference bpe.cpp:453-470):
+// the chain of dependent global atomics is paid once per warp, not once per matched row.
+__device__ __forceinline__ void emit_matches(const Match *ml, unsigned int nm, int lane, const PairTableDev &t, int32_t a,
+                                             int32_t b, int32_t new_id) {
   for (unsigned int i = lane; i < 4 * nm; i += 32) {
     const Match m = ml[i >> 2];
     const int slot = i & 3;
     const int nb = slot < 2 ? m.L : m.R;
     if (nb < 0) continue;
-    const long long c = (long long)s.cnt[m.wi];
+    const long long c = (long long)m.cnt;
     const uint64_t key = touch_key(m.wi, m.pos, slot);
     if (slot == 0) pt_add(t, nb, a, -c, key);
     else if (slot == 1) pt_add(t, nb, new_id, c, key);
     else if (slot == 2) pt_add(t, b, nb, -c, key);
     else pt_add(t, new_id, nb, c, key);
+  }
+}
+
+// Slow path of one row (warp-uniform): stage in shared memory, rewrite word by word (the lane that holds
+// a header rewrites that word) and store back. The matches are appended to the warp's list `ml`; their
+// deltas are emitted later for all rows of this warp iteration together (emit_matches).
+__device__ __noinline__ uint32_t merge_row_slow(int *sm, Match *ml, unsigned int *n_match, int4 v, int lane, int4 *row_gmem,
+                                                uint32_t *row_sig, const StreamDev &s, const PairTableDev &t, int32_t a,
+                                                int32_t b, int32_t new_id) {
+  if (*n_match > MATCH_CAP - ROW / 2) {  // not enough room left for a full row of matches: flush first
+    emit_matches(ml, *n_match, lane, t, a, b, new_id);
+    __syncwarp();
+    if (lane == 0) *n_match = 0;
+  }
+  *reinterpret_cast<int4 *>(&sm[lane * 4]) = v;
+  __syncwarp();
+  uint32_t removed = 0;
+  const int h[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (h[k] < 0 && h[k] != PAD) removed += merge_word_smem(sm, lane * 4 + k, ml, n_match, s.cnt, a, b, new_id);
+  __syncwarp();
+  row_gmem[lane] = *reinterpret_cast<const int4 *>(&sm[lane * 4]);
+  if (lane == 0) {  // the row now contains new_id
+    const uint32_t hh = sig_hash(new_id);
+    row_sig[hh >> 5] |= 1u << (hh & 31);
   }
   __syncwarp();
   return removed;
@@ -361,11 +412,15 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
   __shared__ Match ml[MERGE_WARPS][MATCH_CAP];
   __shared__ unsigned int n_match[MERGE_WARPS];
   __shared__ unsigned long long csum_sh[64];
+  __shared__ __align__(16) Rec stage[FUSED_EMIT_MAX];  // 32 KB: the fused tail's records before they cross PCIe
   __shared__ unsigned int tail_count;
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint64_t warp = (blockIdx.x * (uint64_t)MERGE_THREADS + threadIdx.x) >> 5;
   const uint64_t n_warps = ((uint64_t)gridDim.x * MERGE_THREADS) >> 5;
+#ifdef SWB_KERNEL_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0)); out_hdr[11] = t0; }
+#endif
   const uint32_t ha = sig_hash(a), hb = sig_hash(b);
   const uint32_t wa = ha >> 5, ba = 1u << (ha & 31), wb = hb >> 5, bb = 1u << (hb & 31);
   uint32_t removed = 0;
@@ -378,6 +433,11 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
       cand = (sg[wa] & ba) && (sg[wb] & bb);
     }
     uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+    if (lane == 0) n_match[wib] = 0;
+    __syncwarp();
+#ifdef SWB_KERNEL_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt)); out_hdr[12] = tt; out_hdr[15] = __popc(cmask); }
+#endif
     while (cmask) {  // candidate rows, four loads in flight at a time
       uint64_t rr[4];
       int4 vv[4];
@@ -404,30 +464,60 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
         }
       }
     }
+    __syncwarp();
+    if (n_match[wib]) emit_matches(ml[wib], n_match[wib], lane, t, a, b, new_id);
+    __syncwarp();
   }
+#ifdef SWB_KERNEL_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt)); out_hdr[13] = tt; }
+#endif
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) removed += __shfl_down_sync(0xffffffffu, removed, d);
   if (lane == 0 && removed) atomicAdd(removed_total, (unsigned long long)removed);
   if (!fused) return;
   __threadfence();
   __syncthreads();
+#ifdef SWB_KERNEL_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt)); out_hdr[14] = tt; }
+#endif
   if (threadIdx.x == 0) is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!is_last) return;
+#ifdef SWB_KERNEL_TRACE
+  unsigned long long tr_scan_done; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_scan_done));
+#endif
   const unsigned int n = __ldcg(t.n_touched);
   const bool small = n <= FUSED_EMIT_MAX;
   unsigned long long cx = 0, cs = 0;
   if (threadIdx.x == 0) tail_count = 0;
   __syncthreads();
-  if (small) pt_emit_range(t, em, out, out_cap, n, threadIdx.x, MERGE_THREADS, &tail_count, cx, cs);
-  block_checksum(cx, cs, csum_sh);
+  // Records are staged in shared memory and copied out with lane-consecutive 16-byte stores: a store to
+  // mapped host memory becomes a PCIe write, and scattered 16-byte writes (one record per thread) cost
+  // ~16x more transactions than full 128-byte lines.
+  unsigned int inserted = 0;
+  if (small) pt_emit_range(t, em, stage, FUSED_EMIT_MAX, n, threadIdx.x, MERGE_THREADS, &tail_count, cx, cs, inserted);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, d);
+  if (lane == 0 && em.mode != 0) gt_account(em.g, inserted);
+  block_checksum(cx, cs, csum_sh);  // (contains a __syncthreads: the stage is complete after it)
+  const unsigned int n_out = !small ? n : (em.mode == 0 ? n : tail_count);
+  if (small) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(stage);
+    uint4 *dst = reinterpret_cast<uint4 *>(out);
+    const unsigned int chunks = 2u * (unsigned int)min((size_t)n_out, out_cap);
+    for (unsigned int i = threadIdx.x; i < chunks; i += MERGE_THREADS) dst[i] = src[i];
+  }
   if (threadIdx.x == 0) {
-    unsigned int n_out = n;
     if (small && em.mode == 1) {
-      n_out = tail_count;
-      em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull)].freq = 0;  // bpe.cpp:523
+      unsigned int ins = 0;
+      em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;  // bpe.cpp:523
+      gt_account(em.g, ins);
     }
     const unsigned int gflag = (em.mode != 0 && __ldcg(em.g.flags)) ? 16u : 0u;  // frequency table past 50 % load
+#ifdef SWB_KERNEL_TRACE
+    unsigned long long tr_emit_done; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_emit_done));
+    out_hdr[8] = tr_scan_done; out_hdr[9] = tr_emit_done; out_hdr[10] = n;
+#endif
     pt_publish(t, n_out, out_cap, (small ? 0u : 8u) | gflag, out_hdr, removed_total, seq, cx, cs);
   }
 }

@@ -41,6 +41,28 @@ class TrainerImpl {
     memset(&stats, 0, sizeof stats);
   }
   ~TrainerImpl() {
+    if (trace_wait_ && !wait_trace_.empty()) {  // development aid: SWB_TRACE_WAIT=1 prints launch->result latency percentiles
+      std::vector<float> v = wait_trace_;
+      const size_t n = v.size();
+      auto pct = [&](std::vector<float> &x, double p) { std::sort(x.begin(), x.end()); return x[(size_t)(p * (x.size() - 1))]; };
+      std::vector<float> head(v.begin(), v.begin() + std::min<size_t>(n, 200)), tail(v.begin() + std::min<size_t>(n, 200), v.end());
+      fprintf(stderr, "[trace] merges=%zu first200: p50=%.1f p90=%.1f max=%.1f us", n, pct(head, 0.5), pct(head, 0.9), pct(head, 1.0));
+      if (!tail.empty()) fprintf(stderr, " | rest: p10=%.1f p50=%.1f p90=%.1f p99=%.1f max=%.1f us", pct(tail, 0.1), pct(tail, 0.5), pct(tail, 0.9), pct(tail, 0.99), pct(tail, 1.0));
+      double sh = 0, st = 0; for (size_t i = 0; i < n; i++) (i < 200 ? sh : st) += wait_trace_[i];
+      fprintf(stderr, " | sum first200=%.1f ms rest=%.1f ms\n", sh / 1e3, st / 1e3);
+      if (tw_n_) fprintf(stderr, "[trace]   block0/warp0 on quiet merges: sig %.2f us, candidate rows %.2f us (%.1f candidates of 32), fence+sync %.2f us\n", tw_sig_ / tw_n_, tw_rows_ / tw_n_, tw_cand_ / tw_n_, tw_fence_ / tw_n_);
+      if (trace_removed_.size() == n) {
+        const uint32_t edges[] = {0, 10, 30, 100, 300, 1000, 3000, 10000, 100000, 0xFFFFFFFFu};
+        for (int b = 0; b + 1 < 10; b++) {
+          double sum = 0; size_t c = 0;
+          for (size_t i = 200; i < n; i++) if (trace_removed_[i] >= edges[b] && trace_removed_[i] < edges[b + 1]) { sum += wait_trace_[i]; c++; }
+          double ssc = 0, stl = 0, snr = 0;
+          if (trace_scan_.size() == n)
+            for (size_t i = 200; i < n; i++) if (trace_removed_[i] >= edges[b] && trace_removed_[i] < edges[b + 1]) { ssc += trace_scan_[i]; stl += trace_tail_[i]; snr += trace_nrec_[i]; }
+          if (c) fprintf(stderr, "[trace]   matches in [%u, %u): %zu merges, mean latency %.1f us (kernel: scan %.1f us, tail %.1f us, touched pairs %.0f)\n", edges[b], edges[b + 1], c, sum / c, ssc / c, stl / c, snr / c);
+        }
+      }
+    }
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -72,8 +94,8 @@ class TrainerImpl {
     SWB_CUDA(cudaEventCreate(&ev1_));
     scalars_.alloc(16);
     SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
-    hdr_.alloc(8);
-    memset(hdr_.host(), 0, 8 * sizeof(unsigned long long));
+    hdr_.alloc(16);
+    memset(hdr_.host(), 0, 16 * sizeof(unsigned long long));
     SWB_CUDA(cudaFuncSetAttribute(wt_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
   }
   void sync() { SWB_CUDA(cudaStreamSynchronize(stream_)); }
@@ -557,7 +579,18 @@ class TrainerImpl {
       const double tw0 = now_ms();
       stats.host_launch_ms += tw0 - t_launch0_;
       wait_seq(seq);
-      stats.host_wait_ms += now_ms() - tw0;
+      const double tw1 = now_ms();
+      stats.host_wait_ms += tw1 - tw0;
+      if (trace_wait_) {
+        wait_trace_.push_back((float)((tw1 - t_launch0_) * 1e3));
+#ifdef SWB_KERNEL_TRACE
+        const volatile unsigned long long *hh = hdr_.host();
+        trace_scan_.push_back((float)((double)(hh[8] - hh[11]) * 1e-3));
+        trace_tail_.push_back((float)((double)(hh[9] - hh[8]) * 1e-3));
+        trace_nrec_.push_back((uint32_t)hh[10]);
+        if (trace_removed_.size() > 200 && hh[10] < 10) { tw_sig_ += (double)(hh[12] - hh[11]) * 1e-3; tw_rows_ += (double)(hh[13] - hh[12]) * 1e-3; tw_fence_ += (double)(hh[14] - hh[13]) * 1e-3; tw_cand_ += (double)hh[15]; tw_n_++; }
+#endif
+      }
       n = (size_t)hdr_.host()[1];
       flags = (unsigned int)hdr_.host()[2];
       removed = hdr_.host()[3];
@@ -580,6 +613,7 @@ class TrainerImpl {
     stats.merge_alg_bytes += 4 * live_symbols_ + 8 * (nranks == 1 ? W : (W + nranks - 1 - rank) / nranks);
     live_symbols_ -= removed;
     stats.live_symbols = live_symbols_;
+    if (trace_wait_ && !wait_trace_.empty()) trace_removed_.push_back((uint32_t)removed);
     translate_out(recs_.host(), n);
     *n_out = n;
     return recs_.host();
@@ -735,6 +769,11 @@ class TrainerImpl {
   int idle_polls_ = 0;
   uint64_t gt_used_estimate_ = 0;
   bool gt_flagged_ = false;
+  bool trace_wait_ = getenv("SWB_TRACE_WAIT") != nullptr;
+  std::vector<float> wait_trace_;
+  std::vector<uint32_t> trace_removed_, trace_nrec_;
+  std::vector<float> trace_scan_, trace_tail_;
+  double tw_sig_ = 0, tw_rows_ = 0, tw_fence_ = 0, tw_cand_ = 0; size_t tw_n_ = 0;
   // device-resident frequency table (single-GPU mode)
   bool device_tables_ = false;   // true: the device owns the frequencies, the host only sees pairs >= min_pair_freq
   bool tables_fresh_ = true;     // no count / merge since the last load or reset
@@ -742,7 +781,8 @@ class TrainerImpl {
   GlobalTableDev gt_{};
   DevBuf<GSlot> gt_slots_;
   DevBuf<unsigned int> gt_scal_;
-  DevBuf<unsigned int> pt_touched_, pt_scal_;
+  DevBuf<uint4> pt_touched_;
+  DevBuf<unsigned int> pt_scal_;
   PinnedBuf<Rec> recs_;
 };
 
