@@ -138,6 +138,7 @@ typedef struct SwbStats {
   uint64_t repacks;
   double host_pop_ms, host_launch_ms, host_wait_ms, host_apply_ms; /* merge loop split on the host */
   uint64_t records, heap_pushes, heap_pops, heap_peak;             /* host replica counters */
+  uint64_t collectives, exchange_bytes;                            /* multi-GPU: NCCL all-gathers and their bytes */
 } SwbStats;
 void swb_get_stats(const Trainer *trainer, SwbStats *out);
 /* 1: bracket every merge-scan launch with CUDA events (adds a little latency); 0: off (default). */
@@ -176,6 +177,13 @@ void swb_dist_seed(Trainer *trainer, const int64_t *recs, size_t n);
 int swb_dist_next_merge(Trainer *trainer, int32_t *a, int32_t *b, int32_t *new_id);
 /* Replica step 3: apply the reduced delta records of the merge returned by step 2. */
 void swb_dist_apply(Trainer *trainer, const int64_t *recs, size_t n);
+/* In-library multi-GPU training (one process per GPU): NCCL is loaded with dlopen and the per-merge
+ * all-gather is issued from C++ on the handle's stream. Rank 0 calls swb_dist_unique_id, the caller
+ * ships the 128 bytes to every rank (any transport), every rank calls swb_dist_init before loading the
+ * corpus; afterwards bpe_init / bpe_merge_batch / bpe_train run the sharded loop (every rank must make
+ * the same calls). 0 on success, -1 on error. */
+int swb_dist_unique_id(void *out128);
+int swb_dist_init(Trainer *trainer, int rank, int nranks, const void *unique_id128);
 /* This rank's kernels: local pair count / local merge of (a,b)->new_id. Return the record count
  * (-1 on error); records are written to recs (capacity cap records). */
 int64_t swb_shard_count(Trainer *trainer, int64_t *recs, size_t cap);

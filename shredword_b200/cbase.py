@@ -41,7 +41,8 @@ class SwbStats(Structure):
               ("merge_ms", c_double), ("merge_kernel_ms", c_double), ("merge_scan_bytes", c_uint64), ("merge_alg_bytes", c_uint64),
               ("rows", c_uint64), ("live_symbols", c_uint64), ("words", c_uint64), ("long_words", c_uint64), ("repacks", c_uint64),
               ("host_pop_ms", c_double), ("host_launch_ms", c_double), ("host_wait_ms", c_double), ("host_apply_ms", c_double),
-              ("records", c_uint64), ("heap_pushes", c_uint64), ("heap_pops", c_uint64), ("heap_peak", c_uint64)]
+              ("records", c_uint64), ("heap_pushes", c_uint64), ("heap_pops", c_uint64), ("heap_peak", c_uint64),
+              ("collectives", c_uint64), ("exchange_bytes", c_uint64)]
 
 # ---- the reference's eight entry points (reference cbase.py:44-59)
 lib.create_trainer.argtypes = [POINTER(BPEConfig)]
@@ -96,6 +97,8 @@ _sigs = {
   "swb_dist_apply": ([T, c_void_p, c_size_t], None),
   "swb_shard_count": ([T, c_void_p, c_size_t], c_int64),
   "swb_shard_merge": ([T, c_int32, c_int32, c_int32, c_void_p, c_size_t], c_int64),
+  "swb_dist_unique_id": ([c_void_p], c_int),
+  "swb_dist_init": ([T, c_int, c_int, c_void_p], c_int),
   "swb_save_with_freq": ([T, c_char_p, c_char_p, c_void_p, c_size_t], c_int),
 }
 for _name, (_args, _res) in _sigs.items():

@@ -334,6 +334,26 @@ void swb_dist_apply(Trainer *trainer, const int64_t *recs, size_t n) {
   if (!trainer) return;
   impl_of(trainer)->core.apply(reinterpret_cast<const Rec *>(recs), n);
 }
+int swb_dist_unique_id(void *out128) {
+  if (!out128) return -1;
+  SWB_TRY
+  swb::NcclApi &api = swb::NcclApi::get();
+  if (!api.ok()) throw swb::Error("NCCL is not available: " + api.error());
+  swb::NcclUniqueId id;
+  api.check(api.GetUniqueId(&id), "ncclGetUniqueId");
+  memcpy(out128, &id, sizeof id);
+  return 0;
+  SWB_CATCH(-1)
+}
+int swb_dist_init(Trainer *trainer, int rank, int nranks, const void *unique_id128) {
+  if (!trainer || !unique_id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_err("swb_dist_init: bad arguments"); return -1; }
+  SWB_TRY
+  swb::NcclUniqueId id;
+  memcpy(&id, unique_id128, sizeof id);
+  impl_of(trainer)->dist_init(rank, nranks, id);
+  return 0;
+  SWB_CATCH(-1)
+}
 int64_t swb_shard_count(Trainer *trainer, int64_t *recs, size_t cap) {
   if (!trainer) return -1;
   SWB_TRY

@@ -248,14 +248,15 @@ __device__ __forceinline__ void block_checksum(unsigned long long &cx, unsigned 
 }
 __device__ __forceinline__ void pt_publish(const PairTableDev &t, unsigned int n, size_t out_cap, unsigned int extra_flags,
                                            volatile unsigned long long *out_hdr, unsigned long long *removed,
-                                           unsigned long long seq, unsigned long long cx, unsigned long long cs) {
+                                           unsigned long long seq, unsigned long long cx, unsigned long long cs,
+                                           bool keep_state = false) {
   const unsigned long long flags = __ldcg(t.flags) | (n > out_cap ? 4u : 0u) | extra_flags;
   const unsigned long long rem = removed ? __ldcg(removed) : 0ull;
   out_hdr[1] = n; out_hdr[2] = flags; out_hdr[3] = rem; out_hdr[4] = cx; out_hdr[5] = cs;
   out_hdr[6] = hdr_check(seq, n, flags, rem, cx, cs);
   out_hdr[0] = seq; out_hdr[7] = seq;
-  if (removed && !(extra_flags & 8u)) *removed = 0;
-  if (!(extra_flags & 8u)) { *t.n_touched = 0; *t.flags = 0; }
+  if (removed && !(extra_flags & 8u) && !keep_state) *removed = 0;
+  if (!(extra_flags & 8u) && !keep_state) { *t.n_touched = 0; *t.flags = 0; }
   *t.done_blocks = 0;
 }
 
@@ -299,7 +300,48 @@ pt_emit(PairTableDev t, EmitMode em, Rec *__restrict__ out, size_t out_cap, unsi
   }
 }
 
-constexpr unsigned int FUSED_EMIT_MAX = 384;   // above this the records are emitted by a full-grid pt_emit
+constexpr unsigned int FUSED_EMIT_MAX = 384;  // above this the records are emitted by a full-grid pt_emit
+
+// Tail run by ALL threads of the last block of a kernel (blockDim.x == 256): emits the touched pairs of
+// table `t` (staged in shared memory, copied out with lane-consecutive 16-byte stores: a store to mapped
+// host memory becomes a PCIe write, and scattered per-thread writes cost ~16x more transactions than full
+// lines), applies them to the device frequency table when em.mode != 0, and publishes the header.
+struct TailSmem { Rec *stage; unsigned long long *csum; unsigned int *count; };
+__device__ __forceinline__ void fused_tail(const PairTableDev &t, const EmitMode &em, const TailSmem &ts, Rec *__restrict__ out,
+                                           size_t out_cap, unsigned long long *__restrict__ out_hdr, unsigned long long *removed,
+                                           unsigned long long seq, unsigned int extra_flags) {
+  const unsigned int n = __ldcg(t.n_touched);
+  const bool small = n <= FUSED_EMIT_MAX;
+  unsigned long long cx = 0, cs = 0;
+  if (threadIdx.x == 0) *ts.count = 0;
+  __syncthreads();
+  unsigned int inserted = 0;
+  if (small) pt_emit_range(t, em, ts.stage, FUSED_EMIT_MAX, n, threadIdx.x, blockDim.x, ts.count, cx, cs, inserted);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, d);
+  if ((threadIdx.x & 31) == 0 && em.mode != 0) gt_account(em.g, inserted);
+  block_checksum(cx, cs, ts.csum);  // (contains a __syncthreads: the stage is complete after it)
+  const unsigned int n_out = !small ? n : (em.mode == 0 ? n : *ts.count);
+  if (small) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(ts.stage);
+    uint4 *dst = reinterpret_cast<uint4 *>(out);
+    const unsigned int chunks = 2u * (unsigned int)min((size_t)n_out, out_cap);
+    for (unsigned int i = threadIdx.x; i < chunks; i += blockDim.x) dst[i] = src[i];
+  }
+  if (threadIdx.x == 0) {
+    if (small && em.mode == 1) {
+      unsigned int ins = 0;
+      em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;  // bpe.cpp:523
+      gt_account(em.g, ins);
+    }
+    const unsigned int gflag = (em.mode != 0 && __ldcg(em.g.flags)) ? 16u : 0u;  // frequency table past 50 % load
+#ifdef SWB_KERNEL_TRACE
+    unsigned long long tr_emit_done; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_emit_done));
+    out_hdr[9] = tr_emit_done; out_hdr[10] = n;
+#endif
+    pt_publish(t, n_out, out_cap, (small ? 0u : 8u) | gflag | extra_flags, out_hdr, removed, seq, cx, cs);
+  }
+}
 
 struct StreamDev {
   int4 *rows;                 // n_rows * ROW int32
@@ -486,40 +528,11 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
 #ifdef SWB_KERNEL_TRACE
   unsigned long long tr_scan_done; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_scan_done));
 #endif
-  const unsigned int n = __ldcg(t.n_touched);
-  const bool small = n <= FUSED_EMIT_MAX;
-  unsigned long long cx = 0, cs = 0;
-  if (threadIdx.x == 0) tail_count = 0;
-  __syncthreads();
-  // Records are staged in shared memory and copied out with lane-consecutive 16-byte stores: a store to
-  // mapped host memory becomes a PCIe write, and scattered 16-byte writes (one record per thread) cost
-  // ~16x more transactions than full 128-byte lines.
-  unsigned int inserted = 0;
-  if (small) pt_emit_range(t, em, stage, FUSED_EMIT_MAX, n, threadIdx.x, MERGE_THREADS, &tail_count, cx, cs, inserted);
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, d);
-  if (lane == 0 && em.mode != 0) gt_account(em.g, inserted);
-  block_checksum(cx, cs, csum_sh);  // (contains a __syncthreads: the stage is complete after it)
-  const unsigned int n_out = !small ? n : (em.mode == 0 ? n : tail_count);
-  if (small) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(stage);
-    uint4 *dst = reinterpret_cast<uint4 *>(out);
-    const unsigned int chunks = 2u * (unsigned int)min((size_t)n_out, out_cap);
-    for (unsigned int i = threadIdx.x; i < chunks; i += MERGE_THREADS) dst[i] = src[i];
-  }
-  if (threadIdx.x == 0) {
-    if (small && em.mode == 1) {
-      unsigned int ins = 0;
-      em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;  // bpe.cpp:523
-      gt_account(em.g, ins);
-    }
-    const unsigned int gflag = (em.mode != 0 && __ldcg(em.g.flags)) ? 16u : 0u;  // frequency table past 50 % load
+  TailSmem ts{stage, csum_sh, &tail_count};
 #ifdef SWB_KERNEL_TRACE
-    unsigned long long tr_emit_done; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_emit_done));
-    out_hdr[8] = tr_scan_done; out_hdr[9] = tr_emit_done; out_hdr[10] = n;
+  out_hdr[8] = tr_scan_done;
 #endif
-    pt_publish(t, n_out, out_cap, (small ? 0u : 8u) | gflag, out_hdr, removed_total, seq, cx, cs);
-  }
+  fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u);
 }
 
 // long words: lanes stride over the word to detect; the rare word with a match is rewritten by lane 0
@@ -655,6 +668,83 @@ __global__ void tokfreq_long(StreamDev s, unsigned long long *__restrict__ freq,
     for (uint32_t i = lane; i < L; i += 32)
       if ((uint32_t)sym[i] < T) atomicAdd(&freq[sym[i]], c);
   }
+}
+
+// ---------------------------------------------------------------- multi-GPU exchange
+// Per merge every rank copies its local (pair, net delta, first-touch key) records into its slot of an
+// all-gather buffer [DIST_HDR_WORDS x u64 header][cap x Rec]; after the all-gather every rank reduces all
+// slots by pair into a second table and runs the same tail as the single-GPU path on it (replicated
+// frequency table -> identical records -> identical heap replica on every rank).
+constexpr int DIST_HDR_WORDS = 16;
+
+// local table -> this rank's slot, WITHOUT clearing it (a capacity overflow anywhere makes every rank grow
+// its slots and copy again; the table is cleared by dist_reduce once the exchange has succeeded).
+__global__ void __launch_bounds__(256)
+dist_copy_out(PairTableDev t, unsigned long long *__restrict__ slot, size_t cap) {
+  const unsigned int n = __ldcg(t.n_touched);
+  Rec *out = reinterpret_cast<Rec *>(slot + DIST_HDR_WORDS);
+  if (n <= cap) {
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const uint4 tc = __ldcg(&t.touched[i]);
+      Rec r;
+      r.first = (int32_t)tc.z; r.second = (int32_t)tc.y;
+      r.delta = (long long)__ldcg(&t.val[tc.x]); r.key = (long long)__ldcg(&t.minkey[tc.x]);
+      out[i] = r;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { slot[0] = n; slot[1] = (n > cap ? 4u : 0u) | (__ldcg(t.flags) & 1u); }
+}
+
+__global__ void __launch_bounds__(256)
+dist_reduce(const unsigned long long *__restrict__ slots, int nranks, size_t slot_words, PairTableDev local, PairTableDev t,
+            EmitMode em, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
+            unsigned long long *removed, unsigned long long seq) {
+  __shared__ __align__(16) Rec stage[FUSED_EMIT_MAX];
+  __shared__ unsigned long long csum_sh[64];
+  __shared__ unsigned int tail_count;
+  __shared__ bool is_last;
+  unsigned int worst = 0, fl = 0;
+  for (int r = 0; r < nranks; r++) {
+    const unsigned long long *h = slots + (size_t)r * slot_words;
+    worst = max(worst, (unsigned int)h[0]);
+    fl |= (unsigned int)h[1];
+  }
+  const bool overflow = (fl & 5u) != 0;
+  if (!overflow) {
+    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    // the exchange succeeded: the local table can be cleared now
+    const unsigned int nl = __ldcg(local.n_touched);
+    for (unsigned int i = gtid; i < nl; i += gsz) {
+      const unsigned int h = __ldcg(&local.touched[i]).x;
+      local.keys[h] = PT_EMPTY; local.val[h] = 0; local.minkey[h] = ~0ull;
+    }
+    for (int r = 0; r < nranks; r++) {
+      const unsigned long long *h = slots + (size_t)r * slot_words;
+      const unsigned int n = (unsigned int)h[0];
+      const Rec *recs = reinterpret_cast<const Rec *>(h + DIST_HDR_WORDS);
+      for (unsigned int i = gtid; i < n; i += gsz) {
+        const Rec rc = recs[i];
+        pt_add(t, (int32_t)rc.first, (int32_t)rc.second, rc.delta, (uint64_t)rc.key);
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  if (overflow) {  // nothing was consumed: report the largest list so that every rank grows its slots alike
+    if (threadIdx.x == 0) {
+      out_hdr[1] = worst; out_hdr[2] = 4u | (fl & 1u); out_hdr[3] = 0; out_hdr[4] = 0; out_hdr[5] = 0;
+      out_hdr[6] = hdr_check(seq, worst, 4u | (fl & 1u), 0, 0, 0);
+      out_hdr[0] = seq; out_hdr[7] = seq;
+      *t.done_blocks = 0;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) { *local.n_touched = 0; *local.flags = 0; }
+  TailSmem ts{stage, csum_sh, &tail_count};
+  fused_tail(t, em, ts, out, out_cap, out_hdr, removed, seq, 0u);
 }
 
 // ---------------------------------------------------------------- word extraction (accessors)

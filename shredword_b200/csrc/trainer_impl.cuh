@@ -20,6 +20,7 @@
 #include "device_util.cuh"
 #include "host_core.hpp"
 #include "merge_kernels.cuh"
+#include "nccl_dyn.hpp"
 #include "word_table.cuh"
 
 namespace swb {
@@ -63,6 +64,7 @@ class TrainerImpl {
         }
       }
     }
+    if (comm_) { NcclApi::get().CommDestroy(comm_); comm_ = nullptr; }
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -334,11 +336,18 @@ class TrainerImpl {
     pt_ = PairTableDev{pt_keys_.get(), pt_val_.get(), pt_min_.get(), pt_touched_.get(), pt_scal_.get() + 0,
                        pt_scal_.get() + 1, pt_scal_.get() + 2, (uint32_t)(cap - 1), 0, 0, {nullptr, 0}};
     pt_clear<<<sms_ * 8, 256, 0, stream_>>>(pt_); launched();
+    if (comm_) {  // second table: the cross-rank reduction target (the local one keeps the deltas until the exchange succeeded)
+      pt2_keys_.alloc(cap); pt2_val_.alloc(cap); pt2_min_.alloc(cap); pt2_touched_.alloc(cap); pt2_scal_.alloc(8);
+      SWB_CUDA(cudaMemsetAsync(pt2_scal_.get(), 0, pt2_scal_.bytes(), stream_));
+      pt2_ = PairTableDev{pt2_keys_.get(), pt2_val_.get(), pt2_min_.get(), pt2_touched_.get(), pt2_scal_.get() + 0,
+                          pt2_scal_.get() + 1, pt2_scal_.get() + 2, (uint32_t)(cap - 1), 0, 0, {nullptr, 0}};
+      pt_clear<<<sms_ * 8, 256, 0, stream_>>>(pt2_); launched();
+    }
   }
   // ---- device frequency table
   bool want_device_tables() const {
     static const bool forced_host = getenv("SWB_HOST_TABLE") && atoi(getenv("SWB_HOST_TABLE")) > 0;
-    return nranks == 1 && !forced_host;
+    return (nranks == 1 || comm_ != nullptr) && !forced_host;
   }
   void ensure_global_table(uint64_t min_cap) {
     ensure_device();
@@ -465,9 +474,12 @@ class TrainerImpl {
   }
   // runs pt_emit, waits, returns the record count (records are in mapped host memory until the next emit)
   size_t emit_and_wait(const EmitMode &em, unsigned int *flags_out, uint64_t *removed_out) {
+    return emit_and_wait(pt_, em, flags_out, removed_out);
+  }
+  size_t emit_and_wait(const PairTableDev &tbl, const EmitMode &em, unsigned int *flags_out, uint64_t *removed_out) {
     const unsigned long long seq = ++seq_;
-    pt_emit<<<32, 256, 0, stream_>>>(pt_, em, recs_.dev(), recs_.size(), hdr_.dev(), removed_.get(), seq, emit_partial_.get(),
-                                     pt_scal_.get() + 3);
+    pt_emit<<<32, 256, 0, stream_>>>(tbl, em, recs_.dev(), recs_.size(), hdr_.dev(), removed_.get(), seq, emit_partial_.get(),
+                                     (tbl.keys == pt_.keys ? pt_scal_.get() : pt2_scal_.get()) + 3);
     launched();
     SWB_CUDA(cudaGetLastError());
     const double tw0 = now_ms();
@@ -488,6 +500,61 @@ class TrainerImpl {
     }
   }
 
+  // ---------------------------------------------------------------- multi-GPU exchange (NCCL)
+  void dist_init(int rank_, int nranks_, const NcclUniqueId &id) {
+    ensure_device();
+    NcclApi &api = NcclApi::get();
+    if (!api.ok()) throw Error("NCCL is not available: " + api.error());
+    if (comm_) { api.CommDestroy(comm_); comm_ = nullptr; }
+    rank = rank_; nranks = nranks_;
+    if (nranks > 1) api.check(api.CommInitRank(&comm_, nranks, id, rank), "ncclCommInitRank");
+    pt_cap_ = 0;  // the pair tables are (re)built with the reduction table next time
+  }
+  void ensure_dist_buffers(size_t cap) {
+    if (cap <= dist_cap_ && d_all_.size()) return;
+    sync();
+    dist_cap_ = std::max<size_t>(cap, 1024);
+    dist_slot_words_ = DIST_HDR_WORDS + 4 * dist_cap_;
+    d_all_.alloc(dist_slot_words_ * (size_t)nranks);
+  }
+  // local table -> all ranks -> reduced into pt2_ -> tail in mode `em`; returns the record count on the host
+  size_t exchange_and_reduce(const EmitMode &em, unsigned int *flags_out, uint64_t *removed_out) {
+    NcclApi &api = NcclApi::get();
+    for (;;) {
+      ensure_dist_buffers(dist_cap_ ? dist_cap_ : 8192);
+      unsigned long long *self = d_all_.get() + dist_slot_words_ * (size_t)rank;
+      dist_copy_out<<<32, 256, 0, stream_>>>(pt_, self, dist_cap_); launched();
+      api.check(api.AllGather(self, d_all_.get(), dist_slot_words_ * 8, NcclApi::kChar, comm_, stream_), "ncclAllGather");
+      stats.collectives++;
+      stats.exchange_bytes += dist_slot_words_ * 8 * (uint64_t)nranks;
+      const unsigned long long seq = ++seq_;
+      pt2_.canon_on = pt_.canon_on; pt2_.canon_first = pt_.canon_first; pt2_.gpf = pt_.gpf;
+      dist_reduce<<<sms_, 256, 0, stream_>>>(d_all_.get(), nranks, dist_slot_words_, pt_, pt2_, em, recs_.dev(), recs_.size(),
+                                             hdr_.dev(), removed_.get(), seq);
+      launched();
+      SWB_CUDA(cudaGetLastError());
+      const double tw0 = now_ms();
+      stats.host_launch_ms += tw0 - t_launch0_;
+      wait_seq(seq);
+      stats.host_wait_ms += now_ms() - tw0;
+      unsigned int flags = (unsigned int)hdr_.host()[2];
+      if (flags & 4u) {  // some rank had more records than a slot holds (or a full table): every rank sees the same header
+        if (flags & 1u) { *flags_out = flags; return 0; }
+        t_launch0_ = now_ms();
+        ensure_dist_buffers(pow2_ceil(2 * (size_t)hdr_.host()[1]));
+        continue;
+      }
+      size_t n = (size_t)hdr_.host()[1];
+      if (removed_out) *removed_out = hdr_.host()[3];
+      if (flags & 8u) {
+        t_launch0_ = now_ms();
+        n = emit_and_wait(pt2_, em, &flags, removed_out);
+      }
+      *flags_out = flags;
+      return n;
+    }
+  }
+
   // ---------------------------------------------------------------- count (this rank's words)
   // Launches the count kernels and the emit in the given mode; returns the records.
   //   mode 0: (pair, weighted frequency, first-touch key) for every distinct pair of this rank's share
@@ -504,26 +571,45 @@ class TrainerImpl {
         count_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, unk_dev()); launched();
       }
       if (n_long_) { count_long<<<std::min<uint32_t>(sms_ * 4, (n_long_ + 3) / 4), 128, 0, stream_>>>(s, pt_, unk_dev()); launched(); }
-      unsigned int overflow = 0;  // read the flag BEFORE emitting: in mode 2 the emit writes into the frequency table
-      SWB_CUDA(cudaMemcpyAsync(&overflow, pt_.flags, 4, cudaMemcpyDeviceToHost, stream_));
-      sync();
       unsigned int flags = 0;
-      if (overflow & 1u) {  // more distinct pairs than the table holds: drain it, grow, recount
-        emit_and_wait(emit_mode(0, 0, 0), &flags, nullptr);
-        const uint64_t want = pt_cap_ * 4;
-        pt_cap_ = 0;
-        ensure_pair_table(want);
-        continue;
-      }
-      if (mode == 2) {
-        unsigned int n_pairs = 0;
-        SWB_CUDA(cudaMemcpyAsync(&n_pairs, pt_.n_touched, 4, cudaMemcpyDeviceToHost, stream_));
+      size_t n = 0;
+      if (comm_) {
+        if (mode == 2) {  // sized for the union of all ranks' pairs: at most nranks x the largest local list
+          unsigned int n_pairs = 0;
+          SWB_CUDA(cudaMemcpyAsync(&n_pairs, pt_.n_touched, 4, cudaMemcpyDeviceToHost, stream_));
+          sync();
+          ensure_global_table(std::max<uint64_t>(4ull * n_pairs * nranks + 16 * (258 + tr_->config.target_vocab_size), 4 * W));
+        }
+        EmitMode em = emit_mode(mode, 0, 0);
+        n = exchange_and_reduce(em, &flags, nullptr);
+        if (flags & 1u) {  // a rank's pair table was too small: every rank grows alike and recounts
+          sync();
+          const uint64_t want = pt_cap_ * 4;
+          pt_cap_ = 0;
+          ensure_pair_table(want);
+          continue;
+        }
+      } else {
+        unsigned int overflow = 0;  // read the flag BEFORE emitting: in mode 2 the emit writes into the frequency table
+        SWB_CUDA(cudaMemcpyAsync(&overflow, pt_.flags, 4, cudaMemcpyDeviceToHost, stream_));
         sync();
-        // sized up front so that growing (alloc + rehash, ~10 ms each) is rare: pairs ever touched ~ O(words)
-        ensure_global_table(std::max<uint64_t>(4ull * n_pairs + 16 * (258 + tr_->config.target_vocab_size), 4 * W));
+        if (overflow & 1u) {  // more distinct pairs than the table holds: drain it, grow, recount
+          emit_and_wait(emit_mode(0, 0, 0), &flags, nullptr);
+          const uint64_t want = pt_cap_ * 4;
+          pt_cap_ = 0;
+          ensure_pair_table(want);
+          continue;
+        }
+        if (mode == 2) {
+          unsigned int n_pairs = 0;
+          SWB_CUDA(cudaMemcpyAsync(&n_pairs, pt_.n_touched, 4, cudaMemcpyDeviceToHost, stream_));
+          sync();
+          // sized up front so that growing (alloc + rehash, ~10 ms each) is rare: pairs ever touched ~ O(words)
+          ensure_global_table(std::max<uint64_t>(4ull * n_pairs + 16 * (258 + tr_->config.target_vocab_size), 4 * W));
+        }
+        EmitMode em = emit_mode(mode, 0, 0);
+        n = emit_and_wait(em, &flags, nullptr);
       }
-      EmitMode em = emit_mode(mode, 0, 0);
-      const size_t n = emit_and_wait(em, &flags, nullptr);
       if (flags & 4u) throw Error("record buffer too small for the count pass (internal sizing error)");
       if (flags & 16u) gt_flagged_ = true;
       translate_out(recs_.host(), n);
@@ -558,7 +644,7 @@ class TrainerImpl {
     StreamDev s = stream_dev();
     t_launch0_ = now_ms();
     if (timing) SWB_CUDA(cudaEventRecord(ev0_, stream_));
-    const bool fused = n_rows_ && !n_long_;
+    const bool fused = n_rows_ && !n_long_ && !comm_;
     unsigned long long seq = 0;
     if (n_rows_) {
       const uint64_t warps_needed = (n_rows_ + 31) / 32;  // one warp tests 32 row signatures per iteration
@@ -598,6 +684,8 @@ class TrainerImpl {
         t_launch0_ = now_ms();
         n = emit_and_wait(em, &flags, &removed);
       }
+    } else if (comm_) {
+      n = exchange_and_reduce(em, &flags, &removed);
     } else {
       n = emit_and_wait(em, &flags, &removed);
     }
@@ -783,6 +871,14 @@ class TrainerImpl {
   DevBuf<unsigned int> gt_scal_;
   DevBuf<uint4> pt_touched_;
   DevBuf<unsigned int> pt_scal_;
+  // multi-GPU
+  NcclComm comm_ = nullptr;
+  PairTableDev pt2_{};
+  DevBuf<unsigned long long> pt2_keys_, pt2_val_, pt2_min_;
+  DevBuf<uint4> pt2_touched_;
+  DevBuf<unsigned int> pt2_scal_;
+  DevBuf<unsigned long long> d_all_;
+  size_t dist_cap_ = 0, dist_slot_words_ = 0;
   PinnedBuf<Rec> recs_;
 };
 

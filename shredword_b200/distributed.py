@@ -51,17 +51,34 @@ class _CudaLocalOps:
 class DistributedBPETrainer(BPETrainer):
   """BPETrainer whose word table is sharded over the ranks of `group` (default: the world)."""
 
-  def __init__(self, *args, group=None, device: torch.device | None = None, local_ops=None, **kw):
+  def __init__(self, *args, group=None, device: torch.device | None = None, local_ops=None, native: bool | None = None, **kw):
+    """native=True (default on CUDA devices): the per-merge exchange is NCCL issued from C++ inside the
+    library (swb_dist_init; bpe_train then runs the sharded loop itself). native=False: the exchange is
+    torch.distributed driven from Python (any backend; what the gloo tests use)."""
     super().__init__(*args, **kw)
     self.group = group
     self.rank = dist.get_rank(group)
     self.world = dist.get_world_size(group)
     self.device = device if device is not None else torch.device("cpu")
+    if native is None:
+      native = local_ops is None and self.device.type == "cuda"
+    self.native = bool(native)
+    self.exchange_bytes = 0
+    self.collectives = 0
+    if self.native:
+      uid = np.zeros(128, dtype=np.uint8)
+      if self.rank == 0 and lib.swb_dist_unique_id(_ptr(uid)) != 0:
+        raise RuntimeError(last_error())
+      box = [uid.tobytes()]
+      dist.broadcast_object_list(box, src=0, group=group)
+      uid = np.frombuffer(box[0], dtype=np.uint8).copy()
+      if lib.swb_dist_init(self.trainer, self.rank, self.world, _ptr(uid)) != 0:
+        raise RuntimeError(last_error())
+      self.local = None
+      return
     if lib.swb_set_shard(self.trainer, self.rank, self.world) != 0:
       raise RuntimeError(last_error())
     self.local = local_ops if local_ops is not None else _CudaLocalOps(self)
-    self.exchange_bytes = 0
-    self.collectives = 0
 
   # ---- the one exchange step: variable-length record lists -> every rank has all of them
   def _allgather_records(self, recs: np.ndarray) -> np.ndarray:
@@ -90,10 +107,14 @@ class DistributedBPETrainer(BPETrainer):
     return allrecs[:n]
 
   def init(self):
+    if self.native:
+      return super().init()
     allrecs = self._reduce(self._allgather_records(self.local.count()))
     lib.swb_dist_seed(self.trainer, _ptr(allrecs), allrecs.shape[0])
 
   def merge_batch(self, n: int) -> int:
+    if self.native:
+      return super().merge_batch(n)
     a, b, nid = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
     done = 0
     while done < n:
@@ -105,6 +126,8 @@ class DistributedBPETrainer(BPETrainer):
     return done
 
   def train_quiet(self) -> int:
+    if self.native:
+      return super().train_quiet()
     self.init()
     target = int(self.config.target_vocab_size) - 256
     total = 0

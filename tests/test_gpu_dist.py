@@ -1,0 +1,59 @@
+"""GPU, 2+ devices: the sharded merge loop with the NCCL exchange issued from inside the library (and the
+Python-driven torch.distributed exchange) must reproduce the single-GPU / oracle merge list bit for bit.
+Skipped on a single-GPU box (the round-end -m gpu run); exercised with `gpurun --gpus 2`."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, name, native, out_dir):
+  sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+  import torch
+  import torch.distributed as dist
+  torch.cuda.set_device(rank)
+  from shredword_b200.cbase import lib
+  lib.swb_set_device(rank)
+  dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  from shredword_b200.distributed import DistributedBPETrainer
+  kw = cases.kwargs(name)
+  t = DistributedBPETrainer(**kw, device=torch.device("cuda", rank), native=native)
+  t.load_buffer(cases.corpus(name))
+  n = t.train_quiet()
+  np.save(os.path.join(out_dir, f"merges_{int(native)}_{rank}.npy"), t.merges_array())
+  np.save(os.path.join(out_dir, f"freq_{int(native)}_{rank}.npy"), t.token_freq())
+  t.save(os.path.join(out_dir, f"m_{int(native)}.model"), os.path.join(out_dir, f"m_{int(native)}.vocab"))
+  st = t.stats()
+  assert n == len(t.merges_array())
+  if native:
+    assert st["collectives"] >= n
+  dist.barrier()
+  t.destroy()
+  dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("native", [True, False])
+@pytest.mark.parametrize("name", ["ascii_ties", "multi_unk97", "long_words", "negative_unk"])
+def test_two_gpus_match_oracle(name, native, product, oracle_mod, tmp_path):
+  import torch
+  import torch.multiprocessing as mp
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs 2 GPUs")
+  s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+  kw = cases.kwargs(name)
+  o = oracle_mod.Oracle(kw["target_vocab_size"], kw.get("unk_id", 0), kw.get("character_coverage", 0.995), kw["min_pair_freq"])
+  o.load_buffer(cases.corpus(name)); o.train()
+  o.save(str(tmp_path / "o.model"), str(tmp_path / "o.vocab"))
+  mp.spawn(_worker, args=(2, port, name, native, str(tmp_path)), nprocs=2, join=True)
+  for r in range(2):
+    assert np.array_equal(np.load(tmp_path / f"merges_{int(native)}_{r}.npy"), o.merges), f"rank {r}"
+    assert np.array_equal(np.load(tmp_path / f"freq_{int(native)}_{r}.npy"), o.token_freq()), f"rank {r}"
+  assert (tmp_path / f"m_{int(native)}.model").read_bytes() == (tmp_path / "o.model").read_bytes()
+  assert (tmp_path / f"m_{int(native)}.vocab").read_bytes() == (tmp_path / "o.vocab").read_bytes()
