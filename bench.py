@@ -131,7 +131,7 @@ def run_cpu_once(sample_path: str, nbytes: int, workdir: str) -> dict:
 
 
 # ----------------------------------------------------------------------------- workload
-def make_corpus(spec: synth.CorpusSpec, pinned: bool):
+def make_corpus(spec: synth.CorpusSpec, pinned: bool, first_chunk: int = 0):
   """The workload corpus as a uint8 numpy array (backed by pinned host memory when possible)."""
   import torch
   t0 = time.perf_counter()
@@ -141,7 +141,7 @@ def make_corpus(spec: synth.CorpusSpec, pinned: bool):
     host = torch.empty(spec.nbytes, dtype=torch.uint8)
   arr = host.numpy()
   pos = 0
-  for chunk in synth.generate(spec):
+  for chunk in synth.generate(spec, first_chunk=first_chunk):
     arr[pos: pos + chunk.size] = chunk
     pos += chunk.size
   assert pos == spec.nbytes
@@ -168,7 +168,10 @@ def main():
                         f"{spec.alphabet} corpus ({spec.n_types} word types, s={spec.zipf_s}, seed {spec.seed}), "
                         f"min_pair_freq {TRAIN_KW['min_pair_freq']}, unk_id 0, coverage 0.995",
             "corpus_bytes": spec.nbytes, "l2": "input (1 GB) and the first-pass word table are larger than L2; no flush between steps",
-            "parallelism": "1 GPU" if world == 1 else f"unique words sharded over {world} GPUs, replicated heap"}
+            "parallelism": "1 GPU" if world == 1 else
+                           f"weak scaling: {world} GPUs x one {spec.nbytes / 1e9:g} GB piece each (same word types, disjoint sampling streams) = one "
+                           f"{world * spec.nbytes / 1e9:g} GB corpus; range-split tokenising + NCCL word-table exchange, unique words sharded "
+                           f"over the ranks, per-merge NCCL all-gather of delta records, replicated frequency table + heap"}
 
   # ------------------------------------------------------------------ reference arm
   if args.impl == "reference":
@@ -188,7 +191,7 @@ def main():
     cb = dict(runs[-1]); cb["value"] = value
     print(json.dumps({
       "impl": "reference", "metric": "train_corpus_GB_per_s", "value": value, "unit": "GB/s", "n_gpus": args.gpus,
-      "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong",
+      "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "int32 symbols, uint64 counts", "data": "synthetic", "config": config,
       "cpu_baseline": cb, "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "extra": {"merges_per_s": runs[-1]["merges_per_s"], "note": "reference is single-threaded; each step = full train on the bounded sample"},
@@ -211,9 +214,11 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     from shredword_b200.distributed import DistributedBPETrainer
 
-  host, arr = make_corpus(spec, pinned=True)
+  # N > 1: rank r holds piece r of an N x 1 GB corpus (bytes [r, r+1) GB of the whole)
+  host, arr = make_corpus(spec, pinned=True, first_chunk=rank * synth.PIECE_STRIDE)
   d_corpus = host.to(dev, non_blocking=False)
   nbytes = spec.nbytes
+  total_bytes = nbytes * world
 
   def new_trainer():
     if world > 1:
@@ -235,7 +240,9 @@ def main():
     w1 = time.perf_counter()
     t = new_trainer()
     t.set_kernel_timing(timing)
-    if resident:
+    if world > 1:
+      t.load_shard(d_corpus if resident else arr, rank * nbytes)
+    elif resident:
       t.load_device(d_corpus.data_ptr(), nbytes)
     else:
       t.load_buffer(arr)
@@ -282,8 +289,8 @@ def main():
   ms_tim, _, st_tim = timed(True, args.steps, timing=True)
 
   merges = st_res[-1]["merges"]
-  value = nbytes / 1e9 / (ms_res / 1e3)
-  e2e_value = nbytes / 1e9 / (ms_e2e / 1e3)
+  value = total_bytes / 1e9 / (ms_res / 1e3)
+  e2e_value = total_bytes / 1e9 / (ms_e2e / 1e3)
   launches = int(sum(s["kernel_launches"] for s in st_res) + sum(s["kernel_launches"] for s in st_e2e))
 
   peaks = {}
@@ -307,9 +314,9 @@ def main():
 
   out = {
     "metric": "train_corpus_GB_per_s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-    "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+    "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
     "dtype": "int32 symbols, uint64 counts", "data": "synthetic", "config": config, "clocks": clocks,
-    "e2e": {"value": e2e_value, "unit": "GB/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(nbytes),
+    "e2e": {"value": e2e_value, "unit": "GB/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(total_bytes),
             "d2h_bytes_per_step": int(st_e2e[-1]["merge_bytes"])},
     "gpu_launches": launches, "roofline": roofline,
     "extra": {"merges": merges, "merges_per_s": merges / (st_res[-1]["merge_ms"] / 1e3) if st_res[-1]["merge_ms"] else None,
@@ -317,7 +324,8 @@ def main():
               "phase_ms": {k: st_res[-1][k] for k in ("load_ms", "count_ms", "merge_ms")},
               "e2e_phase_ms": {k: st_e2e[-1][k] for k in ("load_ms", "count_ms", "merge_ms")},
               "wall_ms": st_res[-1]["wall_ms"], "e2e_wall_ms": st_e2e[-1]["wall_ms"],
-              "unique_words": st_res[-1]["words"], "rows": st_res[-1]["rows"], "wall_ms_per_step": wall_res,
+              "unique_words": st_res[-1]["words"], "rows": st_res[-1]["rows"],
+              "collectives_per_step": st_res[-1].get("collectives"), "exchange_bytes_per_step": st_res[-1].get("exchange_bytes"), "wall_ms_per_step": wall_res,
               "ms_per_step_with_kernel_timing": ms_tim},
   }
 
@@ -361,6 +369,8 @@ def main():
   if rank == 0:
     print(json.dumps(out))
   if world > 1:
+    last.pop("trainer").destroy()
+    lib.swb_dist_shutdown()
     dist.destroy_process_group()
 
 

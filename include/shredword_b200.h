@@ -184,6 +184,16 @@ void swb_dist_apply(Trainer *trainer, const int64_t *recs, size_t n);
  * the same calls). 0 on success, -1 on error. */
 int swb_dist_unique_id(void *out128);
 int swb_dist_init(Trainer *trainer, int rank, int nranks, const void *unique_id128);
+/* Range-split load: `data` (host pointer, or device pointer when on_device != 0) is only THIS rank's
+ * byte range of the corpus, starting at byte `global_offset` of the whole; ranges must be cut on
+ * delimiters. Every rank tokenises its range, the unique-word tables are exchanged over NCCL and merged,
+ * so all ranks end with the same global word table in reference order. Needs swb_dist_init. */
+int swb_load_corpus_shard(Trainer *trainer, const void *data, size_t nbytes, uint64_t global_offset, int on_device);
+/* The NCCL communicator is process-wide and shared by all handles with the same (rank, nranks): when
+ * swb_dist_has_comm() is 1, swb_dist_init may be called with unique_id128 == NULL (no id exchange needed).
+ * swb_dist_shutdown destroys it (call once, after the last handle is gone). */
+int swb_dist_has_comm(int rank, int nranks);
+void swb_dist_shutdown(void);
 /* This rank's kernels: local pair count / local merge of (a,b)->new_id. Return the record count
  * (-1 on error); records are written to recs (capacity cap records). */
 int64_t swb_shard_count(Trainer *trainer, int64_t *recs, size_t cap);

@@ -346,13 +346,27 @@ int swb_dist_unique_id(void *out128) {
   SWB_CATCH(-1)
 }
 int swb_dist_init(Trainer *trainer, int rank, int nranks, const void *unique_id128) {
-  if (!trainer || !unique_id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_err("swb_dist_init: bad arguments"); return -1; }
+  if (!trainer || nranks < 1 || rank < 0 || rank >= nranks) { set_err("swb_dist_init: bad arguments"); return -1; }
   SWB_TRY
   swb::NcclUniqueId id;
-  memcpy(&id, unique_id128, sizeof id);
-  impl_of(trainer)->dist_init(rank, nranks, id);
+  if (unique_id128) memcpy(&id, unique_id128, sizeof id);
+  impl_of(trainer)->dist_init(rank, nranks, unique_id128 ? &id : nullptr);
   return 0;
   SWB_CATCH(-1)
+}
+int swb_load_corpus_shard(Trainer *trainer, const void *data, size_t nbytes, uint64_t global_offset, int on_device) {
+  if (!trainer || (!data && nbytes)) { set_err("NULL trainer or data"); return -1; }
+  SWB_TRY
+  impl_of(trainer)->load_shard(data, nbytes, global_offset, on_device != 0);
+  return 0;
+  SWB_CATCH(-1)
+}
+int swb_dist_has_comm(int rank, int nranks) { return TrainerImpl::have_shared_comm(rank, nranks) ? 1 : 0; }
+void swb_dist_shutdown(void) {
+  SWB_TRY
+  cudaDeviceSynchronize();
+  TrainerImpl::destroy_shared_comm();
+  SWB_CATCH()
 }
 int64_t swb_shard_count(Trainer *trainer, int64_t *recs, size_t cap) {
   if (!trainer) return -1;

@@ -64,7 +64,6 @@ class TrainerImpl {
         }
       }
     }
-    if (comm_) { NcclApi::get().CommDestroy(comm_); comm_ = nullptr; }
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -150,6 +149,15 @@ class TrainerImpl {
     build_word_table(corpus, n);
     stats.load_ms += now_ms() - t0;
   }
+  void load_shard(const void *data, uint64_t n, uint64_t global_offset, bool on_device) {
+    ensure_device();
+    const double t0 = now_ms();
+    DevBuf<uint8_t> corpus(n + 64);
+    if (n) SWB_CUDA(cudaMemcpyAsync(corpus.get(), data, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
+    SWB_CUDA(cudaMemsetAsync(corpus.get() + n, ' ', 64, stream_));
+    build_word_table(corpus, n, nranks > 1, global_offset);
+    stats.load_ms += now_ms() - t0;
+  }
   void load_device(const void *d_data, uint64_t n) {
     ensure_device();
     const double t0 = now_ms();
@@ -161,8 +169,11 @@ class TrainerImpl {
   }
 
   // corpus: n bytes + >= 16 bytes of ' ' padding, 16-byte aligned (cudaMalloc)
-  void build_word_table(DevBuf<uint8_t> &corpus, uint64_t n) {
-    if (n >= (1ull << 40)) throw Error("corpus larger than 1 TiB is not supported (40-bit offsets)");
+  // split: `corpus` is only this rank's byte range of the global corpus (starting at global_offset); the
+  // per-rank tables are exchanged over NCCL and merged, so every rank ends with the global word table.
+  void build_word_table(DevBuf<uint8_t> &corpus, uint64_t n, bool split = false, uint64_t global_offset = 0) {
+    if (n >= (1ull << 40) || global_offset + n >= (1ull << 40)) throw Error("corpus larger than 1 TiB is not supported (40-bit offsets)");
+    if (split && !comm_) throw Error("a range-split load needs swb_dist_init first");
     free_corpus_state();
     unsigned int *d_nuniq = scalars_.get() + 0, *d_flags = scalars_.get() + 1, *d_cursor = scalars_.get() + 2,
                  *d_nlong = scalars_.get() + 3;
@@ -185,29 +196,105 @@ class TrainerImpl {
       cap *= 8;  // more unique words than expected: bigger table, run again
     }
     W = h_scal[0];
-    if (W >= (1ull << 31)) throw Error("more than 2^31 unique words");
-    // ---- 2. reference word order: (djb2 bucket, first occurrence)
-    DevBuf<unsigned long long> skeys(W), scnt(W), skeys2(W);
-    cnt_.alloc(W);
-    if (W) {
-      wt_compact<<<sms_ * 8, 256, 0, stream_>>>(keys.get(), counts.get(), cap, skeys.get(), scnt.get(), d_cursor); launched();
-      size_t tmp_bytes = 0;
-      cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, skeys.get(), skeys2.get(), scnt.get(), cnt_.get(), (int64_t)W, 0, 52, stream_);
-      DevBuf<uint8_t> tmp(tmp_bytes);
-      SWB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), tmp_bytes, skeys.get(), skeys2.get(), scnt.get(), cnt_.get(), (int64_t)W, 0, 52, stream_));
-      launched(8);
+    DevBuf<uint64_t> woff;
+    if (!split) {
+      if (W >= (1ull << 31)) throw Error("more than 2^31 unique words");
+      // ---- 2. reference word order: (djb2 bucket, first occurrence)
+      DevBuf<unsigned long long> skeys(W), scnt(W), skeys2(W);
+      cnt_.alloc(W);
+      woff.alloc(W);
+      if (W) {
+        wt_compact<<<sms_ * 8, 256, 0, stream_>>>(keys.get(), counts.get(), cap, skeys.get(), scnt.get(), d_cursor); launched();
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, skeys.get(), skeys2.get(), scnt.get(), cnt_.get(), (int64_t)W, 0, 52, stream_);
+        DevBuf<uint8_t> tmp(tmp_bytes);
+        SWB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), tmp_bytes, skeys.get(), skeys2.get(), scnt.get(), cnt_.get(), (int64_t)W, 0, 52, stream_));
+        launched(8);
+        wt_unpack_sorted<<<sms_ * 4, 256, 0, stream_>>>(skeys2.get(), W, woff.get()); launched();
+        sync();
+      }
+      keys.release(); counts.release();
+    } else {
+      // ---- 2'. export this rank's unique words, all-gather, merge into the global table
+      NcclApi &api = NcclApi::get();
+      const uint64_t Wl = W;
+      DevBuf<unsigned long long> skeys(Wl), scnt(Wl), len1(Wl + 1), aoff(Wl + 1);
+      unsigned long long arena_bytes = 0;
+      if (Wl) {
+        wt_compact<<<sms_ * 8, 256, 0, stream_>>>(keys.get(), counts.get(), cap, skeys.get(), scnt.get(), d_cursor); launched();
+        wt_local_lens<<<sms_ * 8, 256, 0, stream_>>>(corpus.get(), n, skeys.get(), Wl, len1.get()); launched();
+        SWB_CUDA(cudaMemsetAsync(len1.get() + Wl, 0, 8, stream_));
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, len1.get(), aoff.get(), (int64_t)(Wl + 1), stream_);
+        DevBuf<uint8_t> tmp(tb);
+        SWB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(), tb, len1.get(), aoff.get(), (int64_t)(Wl + 1), stream_));
+        launched(2);
+        SWB_CUDA(cudaMemcpyAsync(&arena_bytes, aoff.get() + Wl, 8, cudaMemcpyDeviceToHost, stream_));
+        sync();
+      }
+      keys.release(); counts.release();
+      DevBuf<unsigned long long> d_sizes(2 * (size_t)nranks);
+      const unsigned long long mine[2] = {Wl, arena_bytes};
+      SWB_CUDA(cudaMemcpyAsync(d_sizes.get() + 2 * rank, mine, 16, cudaMemcpyHostToDevice, stream_));
+      api.check(api.AllGather(d_sizes.get() + 2 * rank, d_sizes.get(), 16, NcclApi::kChar, comm_, stream_), "ncclAllGather(sizes)");
+      std::vector<unsigned long long> h_sizes(2 * (size_t)nranks);
+      SWB_CUDA(cudaMemcpyAsync(h_sizes.data(), d_sizes.get(), h_sizes.size() * 8, cudaMemcpyDeviceToHost, stream_));
       sync();
+      uint64_t maxW = 1, maxA = 16, sumW = 0;
+      for (int r = 0; r < nranks; r++) { maxW = std::max<uint64_t>(maxW, h_sizes[2 * r]); maxA = std::max<uint64_t>(maxA, h_sizes[2 * r + 1]); sumW += h_sizes[2 * r]; }
+      maxA = (maxA + 63) / 64 * 64;
+      const uint64_t base_n = maxA * (uint64_t)nranks;
+      if (base_n >= (1ull << 40)) throw Error("exchanged word arenas exceed 1 TiB");
+      DevBuf<uint8_t> arena_all(base_n + 64);
+      DevBuf<WordMeta> meta_all(maxW * (uint64_t)nranks);
+      SWB_CUDA(cudaMemsetAsync(arena_all.get(), ' ', base_n + 64, stream_));
+      if (Wl) {
+        wt_export<<<sms_ * 8, 256, 0, stream_>>>(corpus.get(), skeys.get(), scnt.get(), len1.get(), aoff.get(), Wl, global_offset,
+                                                arena_all.get() + maxA * rank, meta_all.get() + maxW * rank);
+        launched();
+      }
+      api.check(api.AllGather(arena_all.get() + maxA * rank, arena_all.get(), maxA, NcclApi::kChar, comm_, stream_), "ncclAllGather(arena)");
+      api.check(api.AllGather(meta_all.get() + maxW * rank, meta_all.get(), maxW * sizeof(WordMeta), NcclApi::kChar, comm_, stream_), "ncclAllGather(meta)");
+      stats.collectives += 3;
+      stats.exchange_bytes += (maxA + maxW * sizeof(WordMeta)) * (uint64_t)nranks;
+      skeys.release(); scnt.release(); len1.release(); aoff.release();
+      // global table
+      uint64_t gcap = std::max<uint64_t>(1ull << 16, pow2_ceil(2 * sumW + 16));
+      DevBuf<unsigned long long> gkeys(gcap), gcounts(gcap), gfirst(gcap);
+      wt_fill3<<<sms_ * 8, 256, 0, stream_>>>(gkeys.get(), gcounts.get(), gfirst.get(), gcap); launched();
+      SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
+      WordTableDev gtbl{gkeys.get(), gcounts.get(), gcap - 1, d_nuniq, d_flags, gcap};
+      wt_insert_words<<<sms_ * 8, 256, 0, stream_>>>(arena_all.get(), base_n, meta_all.get(), d_sizes.get(), nranks, maxW, maxA, gtbl, gfirst.get());
+      launched();
+      SWB_CUDA(cudaMemcpyAsync(h_scal, scalars_.get(), sizeof h_scal, cudaMemcpyDeviceToHost, stream_));
+      sync();
+      W = h_scal[0];
+      if (W >= (1ull << 31)) throw Error("more than 2^31 unique words");
+      DevBuf<unsigned long long> sk(W), sv(W), sk2(W), sv2(W);
+      cnt_.alloc(W);
+      woff.alloc(W);
+      if (W) {
+        wt_compact_dist<<<sms_ * 8, 256, 0, stream_>>>(gkeys.get(), gfirst.get(), gcap, sk.get(), sv.get(), d_cursor); launched();
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, sk.get(), sk2.get(), sv.get(), sv2.get(), (int64_t)W, 0, 52, stream_);
+        DevBuf<uint8_t> tmp(tmp_bytes);
+        SWB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), tmp_bytes, sk.get(), sk2.get(), sv.get(), sv2.get(), (int64_t)W, 0, 52, stream_));
+        launched(8);
+        wt_after_sort_dist<<<sms_ * 4, 256, 0, stream_>>>(sv2.get(), gkeys.get(), gcounts.get(), W, woff.get(), cnt_.get()); launched();
+        sync();
+      }
+      // from here on the "corpus" is the concatenation of the exchanged arenas
+      corpus = std::move(arena_all);
+      n = base_n;
     }
-    keys.release(); counts.release(); skeys.release(); scnt.release();
     // ---- 3. lengths, byte histogram, long words
-    DevBuf<uint64_t> woff(W);
     DevBuf<uint32_t> wlen(W);
     long_index_.alloc(W);
     DevBuf<unsigned long long> hist(256);
     SWB_CUDA(cudaMemsetAsync(hist.get(), 0, hist.bytes(), stream_));
     if (W) {
       wt_word_info<<<std::min<uint64_t>(sms_ * 8, (W + 255) / 256), 256, 0, stream_>>>(
-          corpus.get(), n, skeys2.get(), W, woff.get(), wlen.get(), hist.get(), d_nlong, d_u64 + 0, long_index_.get(), d_u64 + 1);
+          corpus.get(), n, woff.get(), W, wlen.get(), hist.get(), d_nlong, d_u64 + 0, long_index_.get(), d_u64 + 1);
       launched();
     }
     unsigned long long h_hist[256], h_u64[3];
@@ -215,7 +302,6 @@ class TrainerImpl {
     SWB_CUDA(cudaMemcpyAsync(h_scal, scalars_.get(), sizeof h_scal, cudaMemcpyDeviceToHost, stream_));
     SWB_CUDA(cudaMemcpyAsync(h_u64, d_u64, sizeof h_u64, cudaMemcpyDeviceToHost, stream_));
     sync();
-    skeys2.release();
     n_long_ = h_scal[3];
     const uint64_t long_total = h_u64[0];
     word_bytes_total_ = h_u64[1];
@@ -501,13 +587,36 @@ class TrainerImpl {
   }
 
   // ---------------------------------------------------------------- multi-GPU exchange (NCCL)
-  void dist_init(int rank_, int nranks_, const NcclUniqueId &id) {
+  // The communicator is process-wide (creating one costs 0.1-1 s and its first collective as much again):
+  // every handle of this process with the same (rank, nranks) shares it. `id` is only read when a new one
+  // has to be created, which all ranks do at the same point of the same program.
+  struct SharedComm { NcclComm comm = nullptr; int rank = -1, nranks = 0; };
+  static SharedComm &shared_comm() { static SharedComm c; return c; }
+  static bool have_shared_comm(int rank_, int nranks_) {
+    const SharedComm &c = shared_comm();
+    return c.comm && c.rank == rank_ && c.nranks == nranks_;
+  }
+  static void destroy_shared_comm() {
+    SharedComm &c = shared_comm();
+    if (c.comm) NcclApi::get().CommDestroy(c.comm);
+    c = SharedComm();
+  }
+  void dist_init(int rank_, int nranks_, const NcclUniqueId *id) {
     ensure_device();
     NcclApi &api = NcclApi::get();
     if (!api.ok()) throw Error("NCCL is not available: " + api.error());
-    if (comm_) { api.CommDestroy(comm_); comm_ = nullptr; }
     rank = rank_; nranks = nranks_;
-    if (nranks > 1) api.check(api.CommInitRank(&comm_, nranks, id, rank), "ncclCommInitRank");
+    comm_ = nullptr;
+    if (nranks > 1) {
+      if (!have_shared_comm(rank, nranks)) {
+        if (!id) throw Error("swb_dist_init: a unique id is needed to create the communicator");
+        destroy_shared_comm();
+        SharedComm &c = shared_comm();
+        api.check(api.CommInitRank(&c.comm, nranks, *id, rank), "ncclCommInitRank");
+        c.rank = rank; c.nranks = nranks;
+      }
+      comm_ = shared_comm().comm;
+    }
     pt_cap_ = 0;  // the pair tables are (re)built with the reduction table next time
   }
   void ensure_dist_buffers(size_t cap) {

@@ -198,8 +198,8 @@ __global__ void wt_compact(const unsigned long long *__restrict__ keys, const un
 // histogram.cpp:30-36 counts every byte of every UNIQUE word once); words longer than ROW-1
 // symbols are registered in the long-word list.
 __global__ void __launch_bounds__(256)
-wt_word_info(const uint8_t *__restrict__ corpus, uint64_t n, const unsigned long long *__restrict__ sorted_keys,
-             uint64_t W, uint64_t *__restrict__ woff, uint32_t *__restrict__ wlen,
+wt_word_info(const uint8_t *__restrict__ corpus, uint64_t n, const uint64_t *__restrict__ woff,
+             uint64_t W, uint32_t *__restrict__ wlen,
              unsigned long long *__restrict__ hist256, unsigned int *n_long, unsigned long long *long_syms,
              uint32_t *__restrict__ long_index /* [W]: index into the long list or ~0 */,
              unsigned long long *__restrict__ byte_total) {
@@ -208,7 +208,7 @@ wt_word_info(const uint8_t *__restrict__ corpus, uint64_t n, const unsigned long
   __syncthreads();
   unsigned long long my_bytes = 0;
   for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < W; w += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t off = sorted_keys[w] & ((1ull << 40) - 1);
+    const uint64_t off = woff[w];
     uint64_t i = off;
     while (i < n) {
       const uint8_t c = corpus[i];
@@ -217,7 +217,7 @@ wt_word_info(const uint8_t *__restrict__ corpus, uint64_t n, const unsigned long
       ++i;
     }
     const uint32_t len = (uint32_t)(i - off);
-    woff[w] = off; wlen[w] = len;
+    wlen[w] = len;
     my_bytes += len;
     if (len > ROW - 1) {
       const unsigned int j = atomicAdd(n_long, 1u);
@@ -231,6 +231,103 @@ wt_word_info(const uint8_t *__restrict__ corpus, uint64_t n, const unsigned long
   __syncthreads();
   for (int i = threadIdx.x; i < 256; i += blockDim.x)
     if (sh[i]) atomicAdd(&hist256[i], (unsigned long long)sh[i]);
+}
+
+// sorted (bucket << 40 | first offset) keys -> byte offsets of the words, in reference order
+__global__ void wt_unpack_sorted(const unsigned long long *__restrict__ sorted_keys, uint64_t W, uint64_t *__restrict__ woff) {
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < W; w += (uint64_t)gridDim.x * blockDim.x)
+    woff[w] = sorted_keys[w] & ((1ull << 40) - 1);
+}
+
+// ---- range-split load (multi-GPU): every rank tokenises its own byte range, the per-rank unique-word
+// tables are all-gathered (word bytes + count + GLOBAL first offset) and merged on every rank.
+struct __align__(16) WordMeta { unsigned long long aoff, count, first; unsigned int len, pad; };  // 32 bytes
+
+__global__ void wt_local_lens(const uint8_t *__restrict__ corpus, uint64_t n, const unsigned long long *__restrict__ skeys,
+                              uint64_t Wl, unsigned long long *__restrict__ len1 /* len + 1 (separator) */) {
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < Wl; w += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t off = skeys[w] & ((1ull << 40) - 1);
+    uint64_t i = off;
+    while (i < n && !is_delim(corpus[i])) ++i;
+    len1[w] = (i - off) + 1;
+  }
+}
+// local unique word j -> its bytes + ' ' at arena[aoff[j]] and its meta record
+__global__ void wt_export(const uint8_t *__restrict__ corpus, const unsigned long long *__restrict__ skeys,
+                          const unsigned long long *__restrict__ scnt, const unsigned long long *__restrict__ len1,
+                          const unsigned long long *__restrict__ aoff, uint64_t Wl, uint64_t global_offset,
+                          uint8_t *__restrict__ arena, WordMeta *__restrict__ meta) {
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < Wl; w += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t off = skeys[w] & ((1ull << 40) - 1);
+    const uint32_t len = (uint32_t)(len1[w] - 1);
+    uint8_t *dst = arena + aoff[w];
+    for (uint32_t k = 0; k < len; k++) dst[k] = corpus[off + k];
+    dst[len] = ' ';
+    WordMeta m;
+    m.aoff = aoff[w]; m.count = scnt[w]; m.first = global_offset + off; m.len = len; m.pad = 0;
+    meta[w] = m;
+  }
+}
+// every rank's exported words -> one global table. The key only references bytes (claimed once); the
+// global first offset is min-reduced in `gfirst`, the counts are summed.
+__global__ void __launch_bounds__(256)
+wt_insert_words(const uint8_t *__restrict__ base, uint64_t base_n, const WordMeta *__restrict__ meta_all,
+                const unsigned long long *__restrict__ sizes /* [2*R]: Wl, arena bytes */, int R, uint64_t maxW, uint64_t maxA,
+                WordTableDev tbl, unsigned long long *__restrict__ gfirst) {
+  for (int r = 0; r < R; r++) {
+    const uint64_t Wl = sizes[2 * r];
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < Wl; j += (uint64_t)gridDim.x * blockDim.x) {
+      const WordMeta m = meta_all[(uint64_t)r * maxW + j];
+      const uint64_t off = (uint64_t)r * maxA + m.aoff;
+      uint64_t h64; uint32_t djb;
+      const uint32_t len = wt_scan_word(base, off, base_n, h64, djb);
+      const uint64_t tag = (djb & 0xFFFu) | (((h64 >> 40) & 0xFFFu) << 12);
+      const unsigned long long key = (off << WT_TAG_BITS) | tag;
+      uint64_t slot = h64 & tbl.mask;
+      for (uint64_t probe = 0; probe <= tbl.mask; probe++) {
+        unsigned long long cur = tbl.keys[slot];
+        if (cur == WT_EMPTY) {
+          const unsigned long long prev = atomicCAS(&tbl.keys[slot], WT_EMPTY, key);
+          if (prev == WT_EMPTY) {
+            if (atomicAdd(tbl.n_unique, 1u) >= tbl.limit) atomicOr(tbl.flags, 1u);
+            cur = key;
+          } else cur = prev;
+        }
+        if (cur == key || ((cur & WT_TAG_MASK) == tag && wt_same_word(base, base_n, off, cur >> WT_TAG_BITS, len))) {
+          atomicAdd(&tbl.counts[slot], m.count);
+          atomicMin(&gfirst[slot], m.first);
+          break;
+        }
+        slot = (slot + 1) & tbl.mask;
+      }
+    }
+  }
+}
+__global__ void wt_fill3(unsigned long long *keys, unsigned long long *counts, unsigned long long *gfirst, uint64_t cap) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    keys[i] = WT_EMPTY; counts[i] = 0; gfirst[i] = ~0ull;
+  }
+}
+__global__ void wt_compact_dist(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ gfirst,
+                                uint64_t cap, unsigned long long *__restrict__ sort_keys, unsigned long long *__restrict__ slots,
+                                unsigned int *cursor) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    if (k != WT_EMPTY) {
+      const unsigned int j = atomicAdd(cursor, 1u);
+      sort_keys[j] = ((k & 0xFFFull) << 40) | gfirst[i];
+      slots[j] = i;
+    }
+  }
+}
+__global__ void wt_after_sort_dist(const unsigned long long *__restrict__ sorted_slots, const unsigned long long *__restrict__ keys,
+                                   const unsigned long long *__restrict__ counts, uint64_t W, uint64_t *__restrict__ woff,
+                                   unsigned long long *__restrict__ cnt) {
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < W; w += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long s = sorted_slots[w];
+    woff[w] = keys[s] >> WT_TAG_BITS;
+    cnt[w] = counts[s];
+  }
 }
 
 // ---- row packing. A batch of PACK_BATCH consecutive words (one warp) starts on a fresh row and is

@@ -66,12 +66,14 @@ class DistributedBPETrainer(BPETrainer):
     self.exchange_bytes = 0
     self.collectives = 0
     if self.native:
-      uid = np.zeros(128, dtype=np.uint8)
-      if self.rank == 0 and lib.swb_dist_unique_id(_ptr(uid)) != 0:
-        raise RuntimeError(last_error())
-      box = [uid.tobytes()]
-      dist.broadcast_object_list(box, src=0, group=group)
-      uid = np.frombuffer(box[0], dtype=np.uint8).copy()
+      uid = None
+      if not lib.swb_dist_has_comm(self.rank, self.world):  # the communicator is created once per process
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0 and lib.swb_dist_unique_id(_ptr(uid)) != 0:
+          raise RuntimeError(last_error())
+        box = [uid.tobytes()]
+        dist.broadcast_object_list(box, src=0, group=group)
+        uid = np.frombuffer(box[0], dtype=np.uint8).copy()
       if lib.swb_dist_init(self.trainer, self.rank, self.world, _ptr(uid)) != 0:
         raise RuntimeError(last_error())
       self.local = None
@@ -79,6 +81,18 @@ class DistributedBPETrainer(BPETrainer):
     if lib.swb_set_shard(self.trainer, self.rank, self.world) != 0:
       raise RuntimeError(last_error())
     self.local = local_ops if local_ops is not None else _CudaLocalOps(self)
+
+  def load_shard(self, data, global_offset: int) -> None:
+    """Range-split load (native mode): `data` is this rank's byte range of the corpus (cut on delimiters),
+    starting at byte `global_offset` of the whole. A host buffer/array, or a CUDA torch tensor."""
+    if isinstance(data, torch.Tensor) and data.is_cuda:
+      rc = lib.swb_load_corpus_shard(self.trainer, ctypes.c_void_p(data.data_ptr()), data.numel(), global_offset, 1)
+    else:
+      a = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+      a = np.ascontiguousarray(a, dtype=np.uint8)
+      rc = lib.swb_load_corpus_shard(self.trainer, _ptr(a), a.size, global_offset, 0)
+    if rc != 0:
+      raise IOError(f"Failed to load corpus shard: {last_error()}")
 
   # ---- the one exchange step: variable-length record lists -> every rank has all of them
   def _allgather_records(self, recs: np.ndarray) -> np.ndarray:

@@ -124,10 +124,12 @@ def _chunk(spec: CorpusSpec, mat, lens, cdf, chunk_no: int, chunk_words: int) ->
   return rows[np.arange(mat.shape[1])[None, :] <= l[:, None]]
 
 
-def generate(spec: CorpusSpec, chunk_words: int = 1_200_000, threads: int | None = None):
+def generate(spec: CorpusSpec, chunk_words: int = 1_200_000, threads: int | None = None, first_chunk: int = 0):
   """Yields consecutive uint8 chunks of the corpus; total length == spec.nbytes exactly.
 
-  The last line is cut at spec.nbytes and terminated with '\\n' (a cut word is still a word)."""
+  The last line is cut at spec.nbytes and terminated with '\n' (a cut word is still a word).
+  first_chunk > 0 starts the word stream at that chunk number: piece r of a multi-rank corpus is
+  generate(spec, first_chunk=r * PIECE_STRIDE) -- same word types, a disjoint part of the sampling stream."""
   from concurrent.futures import ThreadPoolExecutor
   assert chunk_words % WORDS_PER_LINE == 0
   rng = np.random.default_rng(spec.seed)
@@ -137,7 +139,7 @@ def generate(spec: CorpusSpec, chunk_words: int = 1_200_000, threads: int | None
   cdf /= cdf[-1]
   threads = threads or min(8, os.cpu_count() or 1)
   produced = 0
-  chunk_no = 0
+  chunk_no = first_chunk
   with ThreadPoolExecutor(threads) as pool:
     while produced < spec.nbytes:
       futs = [pool.submit(_chunk, spec, mat, lens, cdf, chunk_no + k, chunk_words) for k in range(threads)]
@@ -153,11 +155,14 @@ def generate(spec: CorpusSpec, chunk_words: int = 1_200_000, threads: int | None
         yield flat
 
 
-def corpus_bytes(spec: CorpusSpec) -> np.ndarray:
+PIECE_STRIDE = 100_000  # chunk-number distance between the pieces of a multi-rank corpus
+
+
+def corpus_bytes(spec: CorpusSpec, first_chunk: int = 0) -> np.ndarray:
   """Whole corpus as one uint8 array (use only for sizes that fit in host memory)."""
   out = np.empty(spec.nbytes, dtype=np.uint8)
   pos = 0
-  for chunk in generate(spec):
+  for chunk in generate(spec, first_chunk=first_chunk):
     out[pos: pos + chunk.size] = chunk
     pos += chunk.size
   assert pos == spec.nbytes

@@ -36,6 +36,7 @@ def _worker(rank, world, port, name, native, out_dir):
     assert st["collectives"] >= n
   dist.barrier()
   t.destroy()
+  lib.swb_dist_shutdown()
   dist.destroy_process_group()
 
 
@@ -57,3 +58,55 @@ def test_two_gpus_match_oracle(name, native, product, oracle_mod, tmp_path):
     assert np.array_equal(np.load(tmp_path / f"freq_{int(native)}_{r}.npy"), o.token_freq()), f"rank {r}"
   assert (tmp_path / f"m_{int(native)}.model").read_bytes() == (tmp_path / "o.model").read_bytes()
   assert (tmp_path / f"m_{int(native)}.vocab").read_bytes() == (tmp_path / "o.vocab").read_bytes()
+
+
+def _shard_worker(rank, world, port, out_dir):
+  sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+  import torch
+  import torch.distributed as dist
+  torch.cuda.set_device(rank)
+  from shredword_b200.cbase import lib
+  lib.swb_set_device(rank)
+  dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  from shredword_b200.distributed import DistributedBPETrainer
+  data = np.load(os.path.join(out_dir, "corpus.npy"))
+  cuts = np.load(os.path.join(out_dir, "cuts.npy"))
+  t = DistributedBPETrainer(1500, min_pair_freq=5, device=torch.device("cuda", rank))
+  piece = data[cuts[rank]:cuts[rank + 1]]
+  if rank == 0:
+    t.load_shard(piece, int(cuts[rank]))                                   # host buffer
+  else:
+    t.load_shard(torch.from_numpy(piece.copy()).cuda(), int(cuts[rank]))   # device tensor
+  boff, by, _, _, cnt = t.words()
+  np.save(os.path.join(out_dir, f"wbytes_{rank}.npy"), by); np.save(os.path.join(out_dir, f"wcnt_{rank}.npy"), cnt)
+  n = t.train_quiet()
+  np.save(os.path.join(out_dir, f"smerges_{rank}.npy"), t.merges_array())
+  np.save(os.path.join(out_dir, f"sfreq_{rank}.npy"), t.token_freq())
+  dist.barrier()
+  t.destroy()
+  lib.swb_dist_shutdown()
+  dist.destroy_process_group()
+
+
+def test_range_split_load_matches_oracle(product, oracle_mod, tmp_path):
+  """Every rank tokenises only its byte range; the exchanged + merged word table must be the global one
+  (same words, same order, summed counts, first occurrence = global minimum)."""
+  import torch
+  import torch.multiprocessing as mp
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs 2 GPUs")
+  from shredword_b200 import synth
+  data = synth.corpus_bytes(synth.small_spec(4_000_000, 60_000, 77, "multi"))
+  mid = data.size // 2
+  while data[mid] not in b" \n":
+    mid += 1
+  np.save(tmp_path / "corpus.npy", data); np.save(tmp_path / "cuts.npy", np.array([0, mid + 1, data.size]))
+  o = oracle_mod.Oracle(1500, 0, 0.995, 5); o.load_buffer(data)
+  _, oby, _, _, ocnt = o.words()
+  o.train()
+  s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+  mp.spawn(_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  for r in range(2):
+    assert np.array_equal(np.load(tmp_path / f"wbytes_{r}.npy"), oby) and np.array_equal(np.load(tmp_path / f"wcnt_{r}.npy"), ocnt), f"word table, rank {r}"
+    assert np.array_equal(np.load(tmp_path / f"smerges_{r}.npy"), o.merges), f"rank {r}"
+    assert np.array_equal(np.load(tmp_path / f"sfreq_{r}.npy"), o.token_freq()), f"rank {r}"
