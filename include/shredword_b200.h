@@ -139,6 +139,7 @@ typedef struct SwbStats {
   double host_pop_ms, host_launch_ms, host_wait_ms, host_apply_ms; /* merge loop split on the host */
   uint64_t records, heap_pushes, heap_pops, heap_peak;             /* host replica counters */
   uint64_t collectives, exchange_bytes;                            /* multi-GPU: NCCL all-gathers and their bytes */
+  uint64_t loop_runs, loop_stop_tie, loop_stop_big, loop_stop_rebuild, loop_stop_other; /* device-resident loop */
 } SwbStats;
 void swb_get_stats(const Trainer *trainer, SwbStats *out);
 /* 1: bracket every merge-scan launch with CUDA events (adds a little latency); 0: off (default). */

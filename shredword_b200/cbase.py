@@ -42,7 +42,9 @@ class SwbStats(Structure):
               ("rows", c_uint64), ("live_symbols", c_uint64), ("words", c_uint64), ("long_words", c_uint64), ("repacks", c_uint64),
               ("host_pop_ms", c_double), ("host_launch_ms", c_double), ("host_wait_ms", c_double), ("host_apply_ms", c_double),
               ("records", c_uint64), ("heap_pushes", c_uint64), ("heap_pops", c_uint64), ("heap_peak", c_uint64),
-              ("collectives", c_uint64), ("exchange_bytes", c_uint64)]
+              ("collectives", c_uint64), ("exchange_bytes", c_uint64),
+              ("loop_runs", c_uint64), ("loop_stop_tie", c_uint64), ("loop_stop_big", c_uint64), ("loop_stop_rebuild", c_uint64),
+              ("loop_stop_other", c_uint64)]
 
 # ---- the reference's eight entry points (reference cbase.py:44-59)
 lib.create_trainer.argtypes = [POINTER(BPEConfig)]

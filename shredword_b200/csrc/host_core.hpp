@@ -365,6 +365,15 @@ class HostCore {
     }
   }
 
+  // every pair the host knows with frequency >= min_pair_freq (device-table mode: that is all of them)
+  void pairs_at_or_above_min(std::vector<PairInfo> &out) const {
+    std::vector<PairInfo> all;
+    pairs_.in_creation_order(all);
+    out.clear();
+    const uint64_t minf = tr_->config.min_pair_freq;
+    for (const PairInfo &p : all) if (p.freq >= minf) out.push_back(p);
+  }
+
   const std::vector<PairKey> &merges() const { return merges_; }
   PairTable &pairs() { return pairs_; }
   bool pending() const { return pending_; }

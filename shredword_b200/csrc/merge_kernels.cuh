@@ -107,6 +107,35 @@ __global__ void gt_dump(GlobalTableDev g, unsigned long long *__restrict__ out, 
   }
 }
 
+// ---- device-resident merge loop (single GPU, device-table mode)
+// The next pair to merge is the valid heap entry with the highest frequency; when that maximum is
+// UNIQUE it is the same pair whatever the heap's internal order, so the device can pick it itself and
+// the next merge kernel (already queued) can start without a host round trip. The device keeps every
+// pair with frequency >= theta in a candidate list (theta and the list are (re)built by the host from
+// its exact table); after the deltas of a merge are applied, the last block takes the arg-max over the
+// list. A tie at the maximum, an exhausted list, an overflow or a too-long record list hands control
+// back to the host, whose exact heap replica arbitrates. The host replays every merge from the record
+// ring in any case and checks that its own pop equals the device's choice.
+constexpr int HDR_WORDS = 32;
+enum : uint32_t { LOOP_RUN = 0, LOOP_TIE = 1, LOOP_BIG_EMIT = 2, LOOP_REBUILD = 3, LOOP_STOP = 4 };
+struct LoopState {
+  int32_t a, b, new_id;
+  uint32_t status;
+  unsigned long long done;    // merges performed by the device since the host last set the state
+  unsigned long long theta;   // every pair with frequency >= theta is in the candidate list
+  uint32_t n_cand, pad;
+};
+struct __align__(16) CandEntry { unsigned long long key; uint32_t slot, pad; };
+struct LoopDev {
+  LoopState *st;              // nullptr: classic mode (the host passes the pair with every launch)
+  CandEntry *cand;
+  uint32_t cand_cap;
+  Rec *ring;                  // mapped host memory: ring_slots x slot_recs records
+  unsigned long long *ring_hdr;  // mapped host memory: ring_slots x HDR_WORDS
+  uint32_t ring_slots, slot_recs;
+  unsigned long long seq_base, op_base;
+};
+
 // parameters of an emit in device-table mode (mode 0 = host-resident table: plain records)
 struct EmitMode {
   int mode;                       // 0 host records (delta), 1 device table: merge, 2 device table: count
@@ -115,6 +144,12 @@ struct EmitMode {
   unsigned long long stamp_base;  // operation index << 10
   int32_t neg_unk_bucket;         // >= 0: a pair whose second is UNK_CODE lives in this delta-map bucket (negative unk_id)
   GlobalTableDev g;
+  // candidate list of the device-resident loop (nullptr: not in use): pairs crossing theta upwards are appended
+  LoopState *lst;
+  CandEntry *cand;
+  uint32_t cand_cap;
+  unsigned long long theta;
+  unsigned int fused_max;  // touched pairs the single-block tail takes; more -> flag 8, the host runs the full-grid pt_emit
 };
 __device__ __forceinline__ unsigned long long delta_bucket(const EmitMode &em, unsigned long long k) {
   if (em.neg_unk_bucket >= 0 && (uint32_t)k == (uint32_t)UNK_CODE) return (unsigned long long)em.neg_unk_bucket;
@@ -183,9 +218,13 @@ __host__ __device__ __forceinline__ unsigned long long hdr_check(unsigned long l
   return (seq * HDR_MAGIC) ^ (n + 0x1234567ull) ^ (flags << 48) ^ (removed * 31ull) ^ x ^ (sm << 1 | sm >> 63);
 }
 
+// `out` may be a shared-memory stage of `stage_cap` records backed by `direct` (the final destination):
+// records that do not fit the stage are written straight to their final place.
 __device__ __forceinline__ void rec_out(Rec *__restrict__ out, size_t out_cap, unsigned int j, unsigned long long k,
-                                        long long v, unsigned long long mk, unsigned long long &cx, unsigned long long &cs) {
+                                        long long v, unsigned long long mk, unsigned long long &cx, unsigned long long &cs,
+                                        Rec *__restrict__ direct = nullptr, unsigned int stage_cap = 0xFFFFFFFFu) {
   if (j >= out_cap) return;
+  if (j >= stage_cap) out = direct;
   Rec r;
   r.first = (int32_t)(k >> 32); r.second = (int32_t)(k & 0xFFFFFFFFu);
   r.delta = v; r.key = (long long)mk;
@@ -203,7 +242,8 @@ __device__ __forceinline__ void rec_out(Rec *__restrict__ out, size_t out_cap, u
 __device__ __forceinline__ void pt_emit_range(const PairTableDev &t, const EmitMode &em, Rec *__restrict__ out, size_t out_cap,
                                               unsigned int n, unsigned int first, unsigned int stride,
                                               unsigned int *out_count, unsigned long long &cx, unsigned long long &cs,
-                                              unsigned int &inserted) {
+                                              unsigned int &inserted, Rec *__restrict__ direct = nullptr,
+                                              unsigned int stage_cap = 0xFFFFFFFFu) {
   for (unsigned int i = first; i < n; i += stride) {
     const uint4 tc = __ldcg(&t.touched[i]);
     const unsigned int h = tc.x;
@@ -217,7 +257,7 @@ __device__ __forceinline__ void pt_emit_range(const PairTableDev &t, const EmitM
     const long long d = (long long)__ldcg(&t.val[h]);
     const unsigned long long mk = __ldcg(&t.minkey[h]);
     t.keys[h] = PT_EMPTY; t.val[h] = 0; t.minkey[h] = ~0ull;
-    if (em.mode == 0) { rec_out(out, out_cap, i, k, d, mk, cx, cs); continue; }
+    if (em.mode == 0) { rec_out(out, out_cap, i, k, d, mk, cx, cs, direct, stage_cap); continue; }
     if (!dev) continue;  // the merged pair itself: reference bpe.cpp:494-496
     unsigned long long old;
     if (gs.x == k) old = gs.y;  // common case: the pair is already in the table, at its home slot
@@ -230,7 +270,12 @@ __device__ __forceinline__ void pt_emit_range(const PairTableDev &t, const EmitM
     if (d < 0) { const unsigned long long ad = (unsigned long long)(-d); nw = old >= ad ? old - ad : 0ull; }
     else nw = old + (unsigned long long)d;
     em.g.slots[g].freq = nw;
-    if (old >= em.min_freq || nw >= em.min_freq) rec_out(out, out_cap, atomicAdd(out_count, 1u), k, (long long)nw, mk, cx, cs);
+    if (em.cand && nw >= em.theta && old < em.theta) {
+      const unsigned int ci = atomicAdd(&em.lst->n_cand, 1u);
+      if (ci < em.cand_cap) em.cand[ci] = CandEntry{k, g, 0u};
+    }
+    if (old >= em.min_freq || nw >= em.min_freq)
+      rec_out(out, out_cap, atomicAdd(out_count, 1u), k, (long long)nw, mk, cx, cs, direct, stage_cap);
   }
 }
 // block-wide XOR / SUM of per-thread checksums (all threads of the block must call)
@@ -300,23 +345,65 @@ pt_emit(PairTableDev t, EmitMode em, Rec *__restrict__ out, size_t out_cap, unsi
   }
 }
 
-constexpr unsigned int FUSED_EMIT_MAX = 384;  // above this the records are emitted by a full-grid pt_emit
+constexpr unsigned int FUSED_EMIT_MAX = 1024;  // touched pairs the single-block tail takes (more: full-grid pt_emit)
+constexpr unsigned int STAGE_RECS = 384;        // records staged in shared memory before they cross PCIe  // above this the records are emitted by a full-grid pt_emit
 
 // Tail run by ALL threads of the last block of a kernel (blockDim.x == 256): emits the touched pairs of
 // table `t` (staged in shared memory, copied out with lane-consecutive 16-byte stores: a store to mapped
 // host memory becomes a PCIe write, and scattered per-thread writes cost ~16x more transactions than full
 // lines), applies them to the device frequency table when em.mode != 0, and publishes the header.
 struct TailSmem { Rec *stage; unsigned long long *csum; unsigned int *count; };
+// arg-max over the candidate list (all 256 threads of the block); returns the status for the next merge
+// and, for LOOP_RUN, its pair. Each thread owns up to CAND_PER_THREAD entries; their list entries and then
+// their frequencies are fetched as two batches of independent loads (two L2 round trips in total, not two
+// per entry), and the tie test at the maximum reuses the registers.
+constexpr int CAND_PER_THREAD = 16;  // x 256 threads = the largest candidate list (4096)
+__device__ __forceinline__ uint32_t loop_pick_next(const LoopDev &lp, const GlobalTableDev &g, unsigned long long *scratch /* >= 4 u64, shared */,
+                                                   unsigned long long &next_key) {
+  const uint32_t n_raw = __ldcg(&lp.st->n_cand);
+  const uint32_t n = min(n_raw, lp.cand_cap);
+  const unsigned long long theta = __ldcg(&lp.st->theta);
+  if (threadIdx.x == 0) { scratch[0] = 0; scratch[1] = ~0ull; scratch[2] = 0; }
+  __syncthreads();
+  unsigned long long key[CAND_PER_THREAD], freq[CAND_PER_THREAD];
+  uint32_t slot[CAND_PER_THREAD];
+#pragma unroll
+  for (int j = 0; j < CAND_PER_THREAD; j++) {
+    const uint32_t i = threadIdx.x + j * 256;
+    if (i < n) { const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(lp.cand) + i); key[j] = ((unsigned long long)e.y << 32) | e.x; slot[j] = e.z; }
+    else { key[j] = 0; slot[j] = 0xFFFFFFFFu; }
+  }
+  unsigned long long best = 0;
+#pragma unroll
+  for (int j = 0; j < CAND_PER_THREAD; j++) {
+    freq[j] = slot[j] != 0xFFFFFFFFu ? __ldcg(&g.slots[slot[j]].freq) : 0ull;
+    best = max(best, freq[j]);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) best = max(best, __shfl_down_sync(0xffffffffu, best, d));
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(&scratch[0], best);
+  __syncthreads();
+  const unsigned long long fmax = scratch[0];
+#pragma unroll
+  for (int j = 0; j < CAND_PER_THREAD; j++)
+    if (fmax && freq[j] == fmax) { atomicMin(&scratch[1], key[j]); atomicMax(&scratch[2], key[j]); }
+  __syncthreads();
+  next_key = scratch[1];
+  if (n_raw > lp.cand_cap || fmax < theta || fmax == 0) return LOOP_REBUILD;
+  if (scratch[1] != scratch[2]) return LOOP_TIE;
+  return LOOP_RUN;
+}
+
 __device__ __forceinline__ void fused_tail(const PairTableDev &t, const EmitMode &em, const TailSmem &ts, Rec *__restrict__ out,
                                            size_t out_cap, unsigned long long *__restrict__ out_hdr, unsigned long long *removed,
-                                           unsigned long long seq, unsigned int extra_flags) {
+                                           unsigned long long seq, unsigned int extra_flags, const LoopDev *lp = nullptr) {
   const unsigned int n = __ldcg(t.n_touched);
-  const bool small = n <= FUSED_EMIT_MAX;
+  const bool small = n <= min(em.fused_max, FUSED_EMIT_MAX);
   unsigned long long cx = 0, cs = 0;
   if (threadIdx.x == 0) *ts.count = 0;
   __syncthreads();
   unsigned int inserted = 0;
-  if (small) pt_emit_range(t, em, ts.stage, FUSED_EMIT_MAX, n, threadIdx.x, blockDim.x, ts.count, cx, cs, inserted);
+  if (small) pt_emit_range(t, em, ts.stage, min((size_t)FUSED_EMIT_MAX, out_cap), n, threadIdx.x, blockDim.x, ts.count, cx, cs, inserted, out, STAGE_RECS);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, d);
   if ((threadIdx.x & 31) == 0 && em.mode != 0) gt_account(em.g, inserted);
@@ -325,16 +412,35 @@ __device__ __forceinline__ void fused_tail(const PairTableDev &t, const EmitMode
   if (small) {
     const uint4 *src = reinterpret_cast<const uint4 *>(ts.stage);
     uint4 *dst = reinterpret_cast<uint4 *>(out);
-    const unsigned int chunks = 2u * (unsigned int)min((size_t)n_out, out_cap);
+    const unsigned int chunks = 2u * (unsigned int)min(min((size_t)n_out, out_cap), (size_t)STAGE_RECS);
     for (unsigned int i = threadIdx.x; i < chunks; i += blockDim.x) dst[i] = src[i];
   }
+  if (threadIdx.x == 0 && small && em.mode == 1) {
+    unsigned int ins = 0;
+    em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;  // bpe.cpp:523
+    gt_account(em.g, ins);
+  }
+  uint32_t next_status = LOOP_STOP;
+  unsigned long long next_key = 0;
+  if (lp) {  // device-resident loop: choose the next pair (block-wide arg-max over the candidate list)
+    __threadfence();
+    __syncthreads();  // the zeroed frequency of the merged pair and all updates of this block are visible
+    if (small) next_status = loop_pick_next(*lp, em.g, ts.csum, next_key);
+    else next_status = LOOP_BIG_EMIT;
+  }
   if (threadIdx.x == 0) {
-    if (small && em.mode == 1) {
-      unsigned int ins = 0;
-      em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;  // bpe.cpp:523
-      gt_account(em.g, ins);
-    }
     const unsigned int gflag = (em.mode != 0 && __ldcg(em.g.flags)) ? 16u : 0u;  // frequency table past 50 % load
+    if (lp) {
+      LoopState *st = lp->st;
+      if (gflag && next_status == LOOP_RUN) next_status = LOOP_STOP;  // the host must grow the table first
+      out_hdr[16] = em.merged_key;
+      out_hdr[17] = (unsigned long long)(uint32_t)st->new_id | ((unsigned long long)next_status << 32);
+      out_hdr[18] = st->n_cand;
+      out_hdr[19] = out_hdr[16] ^ (out_hdr[17] * HDR_MAGIC) ^ seq;  // check word of the loop fields (see hdr_check)
+      if (next_status == LOOP_RUN) { st->a = (int32_t)(next_key >> 32); st->b = (int32_t)(next_key & 0xFFFFFFFFu); st->new_id = st->new_id + 1; }
+      st->status = next_status;
+      st->done = st->done + 1;
+    }
 #ifdef SWB_KERNEL_TRACE
     unsigned long long tr_emit_done; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_emit_done));
     out_hdr[9] = tr_emit_done; out_hdr[10] = n;
@@ -449,12 +555,24 @@ __device__ __noinline__ uint32_t merge_row_slow(int *sm, Match *ml, unsigned int
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, unsigned long long *removed_total,
            int fused, EmitMode em, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
-           unsigned long long seq) {
+           unsigned long long seq, LoopDev lp) {
+  if (lp.st) {  // device-resident loop: the pair, the record slot and the sequence number come from the device state
+    if (__ldcg(&lp.st->status) != LOOP_RUN) return;  // control is with the host: this queued launch is a no-op
+    a = __ldcg(&lp.st->a); b = __ldcg(&lp.st->b); new_id = __ldcg(&lp.st->new_id);
+    const unsigned long long done = __ldcg(&lp.st->done);
+    const uint32_t slot = (uint32_t)((lp.seq_base + done) % lp.ring_slots);
+    out = lp.ring + (size_t)slot * lp.slot_recs;
+    out_cap = lp.slot_recs;
+    out_hdr = lp.ring_hdr + (size_t)slot * HDR_WORDS;
+    seq = lp.seq_base + done + 1;
+    em.merged_key = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
+    em.stamp_base = (lp.op_base + done) << 10;
+  }
   __shared__ __align__(16) int sm[MERGE_WARPS][ROW];
   __shared__ Match ml[MERGE_WARPS][MATCH_CAP];
   __shared__ unsigned int n_match[MERGE_WARPS];
   __shared__ unsigned long long csum_sh[64];
-  __shared__ __align__(16) Rec stage[FUSED_EMIT_MAX];  // 32 KB: the fused tail's records before they cross PCIe
+  __shared__ __align__(16) Rec stage[STAGE_RECS];  // 12 KB: the fused tail's records before they cross PCIe
   __shared__ unsigned int tail_count;
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -532,7 +650,17 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
 #ifdef SWB_KERNEL_TRACE
   out_hdr[8] = tr_scan_done;
 #endif
-  fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u);
+  fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u, lp.st ? &lp : nullptr);
+}
+
+// candidate keys -> frequency-table slots (after the host rebuilt the list)
+__global__ void cand_resolve(GlobalTableDev g, CandEntry *cand, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long k = cand[i].key;
+    uint32_t h = gt_home(g, k);
+    while (g.slots[h].key != k && g.slots[h].key != PT_EMPTY) h = (h + 1) & g.mask;
+    cand[i].slot = h;  // the key exists: the host only lists pairs it received from this table
+  }
 }
 
 // long words: lanes stride over the word to detect; the rare word with a match is rewritten by lane 0
@@ -699,7 +827,7 @@ __global__ void __launch_bounds__(256)
 dist_reduce(const unsigned long long *__restrict__ slots, int nranks, size_t slot_words, PairTableDev local, PairTableDev t,
             EmitMode em, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
             unsigned long long *removed, unsigned long long seq) {
-  __shared__ __align__(16) Rec stage[FUSED_EMIT_MAX];
+  __shared__ __align__(16) Rec stage[STAGE_RECS];
   __shared__ unsigned long long csum_sh[64];
   __shared__ unsigned int tail_count;
   __shared__ bool is_last;

@@ -95,8 +95,8 @@ class TrainerImpl {
     SWB_CUDA(cudaEventCreate(&ev1_));
     scalars_.alloc(16);
     SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
-    hdr_.alloc(16);
-    memset(hdr_.host(), 0, 16 * sizeof(unsigned long long));
+    hdr_.alloc(HDR_WORDS);
+    memset(hdr_.host(), 0, HDR_WORDS * sizeof(unsigned long long));
     SWB_CUDA(cudaFuncSetAttribute(wt_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
   }
   void sync() { SWB_CUDA(cudaStreamSynchronize(stream_)); }
@@ -448,10 +448,12 @@ class TrainerImpl {
     if (gt_cap_) { gt_rehash<<<sms_ * 8, 256, 0, stream_>>>(gt_, ng); launched(); }
     sync();
     gt_slots_ = std::move(k); gt_scal_ = std::move(scal);
+    cand_valid_ = false;  // the candidate list holds slot indices of the old table
     gt_ = ng;
     gt_cap_ = cap;
   }
   void reset_global_table() {
+    cand_valid_ = false;
     if (!gt_cap_) return;
     gt_clear<<<sms_ * 8, 256, 0, stream_>>>(gt_); launched();
   }
@@ -471,6 +473,8 @@ class TrainerImpl {
     em.stamp_base = op_index_ << 10;
     em.neg_unk_bucket = tr_->config.unk_id < 0 ? (int32_t)((uint32_t)tr_->config.unk_id & 1023u) : -1;
     em.g = gt_;
+    em.fused_max = 384;  // measured: beyond this a 32-block pt_emit (one more launch) beats the single-block tail
+    if (device_tables_ && cand_valid_) { em.lst = loop_state_.get(); em.cand = cand_.get(); em.cand_cap = CAND_CAP; em.theta = theta_; }
     return em;
   }
   // caller id -> device code (negative ids: unk_id travels as UNK_CODE, the -1 of a sign-extended key as NEG1_CODE)
@@ -525,8 +529,8 @@ class TrainerImpl {
   // memory, and until the n records it announces have all arrived (XOR/SUM check, see pt_emit_range).
   // Polling is cheaper than cudaStreamSynchronize on a loop that runs once per merge; the stream is
   // queried from time to time so that a failed launch cannot hang the host.
-  void wait_seq(unsigned long long seq) {
-    volatile unsigned long long *h = hdr_.host();
+  void wait_seq(unsigned long long seq) { wait_seq_at(seq, hdr_.host(), recs_.host(), recs_.size()); }
+  void wait_seq_at(unsigned long long seq, volatile unsigned long long *h, const Rec *recs, size_t recs_cap) {
     uint64_t spin = 0;
     auto check_stream = [&]() {
       if ((++spin & 0x3FFF) != 0) return;
@@ -540,9 +544,9 @@ class TrainerImpl {
         const unsigned long long n = h[1], fl = h[2], rem = h[3], cx = h[4], cs = h[5];
         if (h[6] == hdr_check(seq, n, fl, rem, cx, cs)) {
           if (fl & 8u) return;  // records were not emitted by this kernel
-          const size_t m = (size_t)std::min<unsigned long long>(n, recs_.size());
+          const size_t m = (size_t)std::min<unsigned long long>(n, recs_cap);
           for (;;) {
-            const volatile long long *r = reinterpret_cast<const volatile long long *>(recs_.host());
+            const volatile long long *r = reinterpret_cast<const volatile long long *>(recs);
             unsigned long long x = 0, sm = 0;
             for (size_t i = 0; i < m; i++) {
               const unsigned long long a = (unsigned long long)r[4 * i], b = (unsigned long long)r[4 * i + 1],
@@ -759,8 +763,10 @@ class TrainerImpl {
       const uint64_t warps_needed = (n_rows_ + 31) / 32;  // one warp tests 32 row signatures per iteration
       const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 4, (warps_needed + MERGE_WARPS - 1) / MERGE_WARPS);
       if (fused) seq = ++seq_;
+      LoopDev no_loop;
+      memset(&no_loop, 0, sizeof no_loop);
       merge_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, da, db, new_id, removed_.get(), fused ? 1 : 0, em, recs_.dev(),
-                                                      recs_.size(), hdr_.dev(), seq);
+                                                      recs_.size(), hdr_.dev(), seq, no_loop);
       launched();
       stats.merge_launches++;
     }
@@ -854,9 +860,173 @@ class TrainerImpl {
     reset_tables();
     count_bigrams();
   }
+  // ---------------------------------------------------------------- device-resident merge loop
+  static constexpr uint32_t CAND_CAP = 4096, RING_SLOTS = 32;
+  uint32_t max_ahead_ = getenv("SWB_MAX_AHEAD") ? (uint32_t)atoi(getenv("SWB_MAX_AHEAD")) : 4;
+  bool use_device_loop() const {
+    // Experimental, off by default (SWB_DEVICE_LOOP=1): correct (the host validates every choice) but on the
+    // bench corpus a quarter of the merges tie at the maximum and hand control back, and the arg-max tail
+    // lengthens every kernel, so it does not beat the synchronous loop yet.
+    static const bool on = getenv("SWB_DEVICE_LOOP") && atoi(getenv("SWB_DEVICE_LOOP")) > 0;
+    return on && device_tables_ && !comm_ && !timing && loaded_ && n_rows_ > 0 && n_long_ == 0;
+  }
+  void ensure_loop_buffers() {
+    if (loop_state_.size()) return;
+    loop_state_.alloc(1); cand_.alloc(CAND_CAP);
+    ring_.alloc((size_t)RING_SLOTS * FUSED_EMIT_MAX);  // a slot takes every record a single-block tail can produce
+    ring_hdr_.alloc((size_t)RING_SLOTS * HDR_WORDS);
+    memset(ring_hdr_.host(), 0, (size_t)RING_SLOTS * HDR_WORDS * 8);
+  }
+  // Candidate list = every pair with frequency >= theta, taken from the host's exact table (which holds
+  // every pair >= min_pair_freq in device-table mode). theta is chosen so that about half the list is used.
+  void rebuild_candidates() {
+    std::vector<PairInfo> v;
+    core.pairs_at_or_above_min(v);
+    std::sort(v.begin(), v.end(), [](const PairInfo &x, const PairInfo &y) { return x.freq > y.freq; });
+    size_t k = std::min<size_t>(v.size(), CAND_CAP / 2);
+    theta_ = tr_->config.min_pair_freq;
+    if (k < v.size()) {  // cut where the frequency changes, so that every pair >= theta is inside
+      uint64_t f = v[k - 1].freq;
+      size_t hi = k;
+      while (hi < v.size() && v[hi].freq == f) hi++;
+      if (hi <= CAND_CAP - 512) { k = hi; theta_ = f; }
+      else { while (k > 0 && v[k - 1].freq == f) k--; theta_ = f + 1; }
+    }
+    std::vector<CandEntry> h(k);
+    for (size_t i = 0; i < k; i++) {
+      const int32_t a = to_dev(v[i].first), b = to_dev(v[i].second);
+      h[i] = CandEntry{((unsigned long long)(uint32_t)a << 32) | (uint32_t)b, 0u, 0u};
+    }
+    n_cand_host_ = (uint32_t)k;
+    if (k) {
+      SWB_CUDA(cudaMemcpyAsync(cand_.get(), h.data(), k * sizeof(CandEntry), cudaMemcpyHostToDevice, stream_));
+      cand_resolve<<<std::min<uint32_t>(sms_, (uint32_t)(k + 255) / 256), 256, 0, stream_>>>(gt_, cand_.get(), (uint32_t)k); launched();
+      sync();  // h goes out of scope
+    }
+    cand_valid_ = true;
+    stats.repacks++;  // (counter reused: candidate-list rebuilds)
+  }
+  // Runs merges on the device starting with (a, b) -- already popped from the host heap and pending in
+  // `core` -- for as long as the device can choose the next pair itself (at most max_merges).
+  // Every merge is replayed on the host from the record ring. Returns the number of merges performed.
+  int run_device_loop(int32_t a, int32_t b, int32_t new_id, int max_merges) {
+    ensure_loop_buffers();
+    stats.loop_runs++;
+    ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
+    maybe_grow_global_table(gt_flagged_);
+    gt_flagged_ = false;
+    if (!cand_valid_) rebuild_candidates();
+    const int32_t unk = tr_->config.unk_id;
+    LoopState st;
+    memset(&st, 0, sizeof st);
+    st.a = to_dev(a); st.b = to_dev(b); st.new_id = new_id; st.status = LOOP_RUN; st.done = 0; st.theta = theta_; st.n_cand = n_cand_host_;
+    SWB_CUDA(cudaMemcpyAsync(loop_state_.get(), &st, sizeof st, cudaMemcpyHostToDevice, stream_));
+    LoopDev lp;
+    lp.st = loop_state_.get(); lp.cand = cand_.get(); lp.cand_cap = CAND_CAP;
+    lp.ring = ring_.dev(); lp.ring_hdr = ring_hdr_.dev(); lp.ring_slots = RING_SLOTS; lp.slot_recs = FUSED_EMIT_MAX;
+    lp.seq_base = seq_; lp.op_base = op_index_ + 1;
+    EmitMode em = emit_mode(1, 0, 0);
+    em.fused_max = FUSED_EMIT_MAX;  // here a stop costs a relaunch: let the tail take everything a ring slot holds
+    pt_.canon_on = unk < 0 ? 1 : 0;
+    pt_.canon_first = unk == -1 ? UNK_CODE : NEG1_CODE;
+    pt_.gpf.slots = (void *)gt_.slots; pt_.gpf.mask = gt_.mask;
+    StreamDev s = stream_dev();
+    const uint64_t warps_needed = (n_rows_ + 31) / 32;
+    const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 4, (warps_needed + MERGE_WARPS - 1) / MERGE_WARPS);
+    const unsigned long long seq_base = seq_;
+    int launched_n = 0, consumed = 0;
+    bool stopped = false;
+    while (!stopped) {
+      while (launched_n < max_merges && launched_n - consumed < (int)max_ahead_) {
+        merge_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, 0, 0, 0, removed_.get(), 1, em, nullptr, 0, nullptr, 0ull, lp);
+        launched(); stats.merge_launches++;
+        launched_n++;
+      }
+      if (consumed == launched_n) break;
+      const uint32_t slot = (uint32_t)((seq_base + consumed) % RING_SLOTS);
+      volatile unsigned long long *h = ring_hdr_.host() + (size_t)slot * HDR_WORDS;
+      Rec *recs = ring_.host() + (size_t)slot * FUSED_EMIT_MAX;
+      const double tw0 = now_ms();
+      wait_seq_at(seq_base + consumed + 1, h, recs, FUSED_EMIT_MAX);
+      stats.host_wait_ms += now_ms() - tw0;
+      for (uint64_t spin = 0; h[19] != (h[16] ^ (h[17] * HDR_MAGIC) ^ (seq_base + consumed + 1)); spin++)  // loop fields still in flight
+        if (spin > (1ull << 28)) throw Error("device-resident loop: header never became consistent");
+      const unsigned long long n = h[1], flags = h[2], removed = h[3], pair = h[16];
+      const uint32_t status_after = (uint32_t)(h[17] >> 32);
+      if (consumed > 0) {  // the device chose this pair itself: the exact heap must agree
+        int32_t ha, hb, hn;
+        const double tp0 = now_ms();
+        if (!core.next_merge(&ha, &hb, &hn)) throw Error("device-resident loop ran a merge the host heap does not have");
+        stats.host_pop_ms += now_ms() - tp0;
+        const unsigned long long hk = ((unsigned long long)(uint32_t)to_dev(ha) << 32) | (uint32_t)to_dev(hb);
+        if (hk != pair || (uint32_t)hn != (uint32_t)(h[17] & 0xFFFFFFFFu))
+          throw Error("device-resident loop and host heap disagree on the next pair (internal error)");
+      }
+      // (flag 4 together with 8 only says that the list did not fit the ring slot: handled below)
+      if ((flags & 1u) || ((flags & 4u) && !(flags & 8u))) throw Error("pair table overflow during a merge (internal sizing error)");
+      op_index_++;
+      seq_ = seq_base + consumed + 1;
+      stats.merge_scan_bytes += n_rows_ * ROW * 4;
+      stats.merge_alg_bytes += 4 * live_symbols_ + 8 * W;
+      const double ta0 = now_ms();
+      if (flags & 8u) {  // too many records for the ring slot: finish this merge with the full-grid emit
+        // (the launches still queued are no-ops -- the device set its status before publishing -- and the
+        //  stream orders them before everything issued from here on: no need to wait for them)
+        unsigned int fl2 = 0;
+        uint64_t rem2 = 0;
+        EmitMode em2 = emit_mode(1, (int32_t)(pair >> 32), (int32_t)(pair & 0xFFFFFFFFu));
+        t_launch0_ = now_ms();
+        const size_t n2 = emit_and_wait(em2, &fl2, &rem2);
+        if (fl2 & 5u) throw Error("pair table overflow during a merge (internal sizing error)");
+        if (fl2 & 16u) gt_flagged_ = true;
+        live_symbols_ -= rem2;
+        translate_out(recs_.host(), n2);
+        core.apply_absolute(recs_.host(), n2);
+        stopped = true;
+        stats.loop_stop_big++;
+      } else {
+        live_symbols_ -= removed;
+        translate_out(recs, (size_t)n);
+        core.apply_absolute(recs, (size_t)n);
+        if (flags & 16u) gt_flagged_ = true;
+        if (status_after != LOOP_RUN) {
+          stopped = true;
+          if (status_after == LOOP_REBUILD) { cand_valid_ = false; stats.loop_stop_rebuild++; }
+          else if (status_after == LOOP_TIE) stats.loop_stop_tie++;
+          else stats.loop_stop_other++;
+        }
+      }
+      stats.host_apply_ms += now_ms() - ta0;
+      stats.live_symbols = live_symbols_;
+      consumed++;
+      if (consumed == max_merges) break;
+    }
+    // after a stop the device counts its candidates itself; keep the host's idea of the list length in step
+    if (consumed) {
+      LoopState back;
+      SWB_CUDA(cudaMemcpyAsync(&back, loop_state_.get(), sizeof back, cudaMemcpyDeviceToHost, stream_));
+      sync();
+      n_cand_host_ = std::min<uint32_t>(back.n_cand, CAND_CAP);
+      if (back.n_cand > CAND_CAP) cand_valid_ = false;
+    }
+    return consumed;
+  }
+
   int merge_batch(int batch) {  // reference bpe_merge_batch
     const double t0 = now_ms();
     int done = 0;
+    if (use_device_loop()) {
+      while (done < batch && !core.heap_empty()) {
+        int32_t a, b, nid;
+        const double tp0 = now_ms();
+        if (!core.next_merge(&a, &b, &nid)) break;
+        stats.host_pop_ms += now_ms() - tp0;
+        tables_fresh_ = false;
+        done += run_device_loop(a, b, nid, batch - done);
+      }
+      stats.merge_ms += now_ms() - t0;
+      return done;
+    }
     while (done < batch && !core.heap_empty()) {
       int32_t a, b, nid;
       const double tp0 = now_ms();
@@ -966,6 +1136,14 @@ class TrainerImpl {
   int idle_polls_ = 0;
   uint64_t gt_used_estimate_ = 0;
   bool gt_flagged_ = false;
+  // device-resident loop
+  DevBuf<LoopState> loop_state_;
+  DevBuf<CandEntry> cand_;
+  PinnedBuf<Rec> ring_;
+  PinnedBuf<unsigned long long> ring_hdr_;
+  bool cand_valid_ = false;
+  unsigned long long theta_ = 0;
+  uint32_t n_cand_host_ = 0;
   bool trace_wait_ = getenv("SWB_TRACE_WAIT") != nullptr;
   std::vector<float> wait_trace_;
   std::vector<uint32_t> trace_removed_, trace_nrec_;
