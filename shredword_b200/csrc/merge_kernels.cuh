@@ -398,12 +398,12 @@ __device__ __forceinline__ void fused_tail(const PairTableDev &t, const EmitMode
                                            size_t out_cap, unsigned long long *__restrict__ out_hdr, unsigned long long *removed,
                                            unsigned long long seq, unsigned int extra_flags, const LoopDev *lp = nullptr) {
   const unsigned int n = __ldcg(t.n_touched);
-  const bool small = n <= min(em.fused_max, FUSED_EMIT_MAX);
+  const bool small = n <= em.fused_max;
   unsigned long long cx = 0, cs = 0;
   if (threadIdx.x == 0) *ts.count = 0;
   __syncthreads();
   unsigned int inserted = 0;
-  if (small) pt_emit_range(t, em, ts.stage, min((size_t)FUSED_EMIT_MAX, out_cap), n, threadIdx.x, blockDim.x, ts.count, cx, cs, inserted, out, STAGE_RECS);
+  if (small) pt_emit_range(t, em, ts.stage, out_cap, n, threadIdx.x, blockDim.x, ts.count, cx, cs, inserted, out, STAGE_RECS);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, d);
   if ((threadIdx.x & 31) == 0 && em.mode != 0) gt_account(em.g, inserted);
@@ -550,37 +550,13 @@ __device__ __noinline__ uint32_t merge_row_slow(int *sm, Match *ml, unsigned int
   return removed;
 }
 
-// fused != 0: the last block to finish also emits the records and publishes the header (one launch per
-// merge); used when there are no long words to process after this kernel.
-__global__ void __launch_bounds__(MERGE_THREADS)
-merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, unsigned long long *removed_total,
-           int fused, EmitMode em, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
-           unsigned long long seq, LoopDev lp) {
-  if (lp.st) {  // device-resident loop: the pair, the record slot and the sequence number come from the device state
-    if (__ldcg(&lp.st->status) != LOOP_RUN) return;  // control is with the host: this queued launch is a no-op
-    a = __ldcg(&lp.st->a); b = __ldcg(&lp.st->b); new_id = __ldcg(&lp.st->new_id);
-    const unsigned long long done = __ldcg(&lp.st->done);
-    const uint32_t slot = (uint32_t)((lp.seq_base + done) % lp.ring_slots);
-    out = lp.ring + (size_t)slot * lp.slot_recs;
-    out_cap = lp.slot_recs;
-    out_hdr = lp.ring_hdr + (size_t)slot * HDR_WORDS;
-    seq = lp.seq_base + done + 1;
-    em.merged_key = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
-    em.stamp_base = (lp.op_base + done) << 10;
-  }
-  __shared__ __align__(16) int sm[MERGE_WARPS][ROW];
-  __shared__ Match ml[MERGE_WARPS][MATCH_CAP];
-  __shared__ unsigned int n_match[MERGE_WARPS];
-  __shared__ unsigned long long csum_sh[64];
-  __shared__ __align__(16) Rec stage[STAGE_RECS];  // 12 KB: the fused tail's records before they cross PCIe
-  __shared__ unsigned int tail_count;
-  __shared__ bool is_last;
+// The scan of one merge: every warp tests 32 row signatures per iteration, loads the candidate rows (four
+// in flight), rewrites those with a match and emits their deltas. Returns this thread's removed-symbol count.
+__device__ __forceinline__ uint32_t scan_rows(const StreamDev &s, const PairTableDev &t, int32_t a, int32_t b, int32_t new_id,
+                                              int (*sm)[ROW], Match (*ml)[MATCH_CAP], unsigned int *n_match) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint64_t warp = (blockIdx.x * (uint64_t)MERGE_THREADS + threadIdx.x) >> 5;
   const uint64_t n_warps = ((uint64_t)gridDim.x * MERGE_THREADS) >> 5;
-#ifdef SWB_KERNEL_TRACE
-  if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0)); out_hdr[11] = t0; }
-#endif
   const uint32_t ha = sig_hash(a), hb = sig_hash(b);
   const uint32_t wa = ha >> 5, ba = 1u << (ha & 31), wb = hb >> 5, bb = 1u << (hb & 31);
   uint32_t removed = 0;
@@ -595,9 +571,6 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
     uint32_t cmask = __ballot_sync(0xffffffffu, cand);
     if (lane == 0) n_match[wib] = 0;
     __syncwarp();
-#ifdef SWB_KERNEL_TRACE
-    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt)); out_hdr[12] = tt; out_hdr[15] = __popc(cmask); }
-#endif
     while (cmask) {  // candidate rows, four loads in flight at a time
       uint64_t rr[4];
       int4 vv[4];
@@ -628,6 +601,39 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
     if (n_match[wib]) emit_matches(ml[wib], n_match[wib], lane, t, a, b, new_id);
     __syncwarp();
   }
+  return removed;
+}
+
+// fused != 0: the last block to finish also emits the records and publishes the header (one launch per
+// merge); used when there are no long words to process after this kernel.
+__global__ void __launch_bounds__(MERGE_THREADS)
+merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, unsigned long long *removed_total,
+           int fused, EmitMode em, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
+           unsigned long long seq, LoopDev lp) {
+  if (lp.st) {  // device-resident loop: the pair, the record slot and the sequence number come from the device state
+    if (__ldcg(&lp.st->status) != LOOP_RUN) return;  // control is with the host: this queued launch is a no-op
+    a = __ldcg(&lp.st->a); b = __ldcg(&lp.st->b); new_id = __ldcg(&lp.st->new_id);
+    const unsigned long long done = __ldcg(&lp.st->done);
+    const uint32_t slot = (uint32_t)((lp.seq_base + done) % lp.ring_slots);
+    out = lp.ring + (size_t)slot * lp.slot_recs;
+    out_cap = lp.slot_recs;
+    out_hdr = lp.ring_hdr + (size_t)slot * HDR_WORDS;
+    seq = lp.seq_base + done + 1;
+    em.merged_key = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
+    em.stamp_base = (lp.op_base + done) << 10;
+  }
+  __shared__ __align__(16) int sm[MERGE_WARPS][ROW];
+  __shared__ Match ml[MERGE_WARPS][MATCH_CAP];
+  __shared__ unsigned int n_match[MERGE_WARPS];
+  __shared__ unsigned long long csum_sh[64];
+  __shared__ __align__(16) Rec stage[STAGE_RECS];  // 12 KB: the fused tail's records before they cross PCIe
+  __shared__ unsigned int tail_count;
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31;
+#ifdef SWB_KERNEL_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0)); out_hdr[11] = t0; }
+#endif
+  uint32_t removed = scan_rows(s, t, a, b, new_id, sm, ml, n_match);
 #ifdef SWB_KERNEL_TRACE
   if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt)); out_hdr[13] = tt; }
 #endif
@@ -651,6 +657,85 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
   out_hdr[8] = tr_scan_done;
 #endif
   fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u, lp.st ? &lp : nullptr);
+}
+
+// ---------------------------------------------------------------- persistent merge kernel
+// One cooperative launch serves a whole batch of merges: the grid stays resident, the host sends the
+// next pair through a mapped-memory mailbox and gets the records back the same way, so a merge costs one
+// PCIe round trip (~5 us on this box) instead of a kernel launch + completion (~9 us). Per merge: all
+// blocks scan; the last block to finish runs the tail (emit + publish), then polls the mailbox for the
+// next command and releases the other blocks through a device-memory epoch. Every spin has a time-out:
+// if the host goes away the kernel exits instead of hanging the GPU.
+struct HostCmd { unsigned long long seq, pair, new_id_op, check; };      // mapped host memory; op (bit 32 of new_id_op): 1 = stop
+struct DevCmd { unsigned long long epoch, pair, new_id_op, pad; };       // device memory
+__host__ __device__ __forceinline__ unsigned long long cmd_check(unsigned long long seq, unsigned long long pair,
+                                                                 unsigned long long nio) {
+  return (seq * HDR_MAGIC) ^ pair ^ (nio << 7 | nio >> 57);
+}
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+__global__ void __launch_bounds__(MERGE_THREADS)
+merge_persistent(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *removed_total, Rec *__restrict__ out, size_t out_cap,
+                 unsigned long long *__restrict__ out_hdr, unsigned long long seq_base, unsigned long long op_base,
+                 volatile HostCmd *hcmd, DevCmd *dcmd, int32_t a, int32_t b, int32_t new_id, unsigned long long timeout_ns) {
+  __shared__ __align__(16) int sm[MERGE_WARPS][ROW];
+  __shared__ Match ml[MERGE_WARPS][MATCH_CAP];
+  __shared__ unsigned int n_match[MERGE_WARPS];
+  __shared__ unsigned long long csum_sh[64];
+  __shared__ __align__(16) Rec stage[STAGE_RECS];
+  __shared__ unsigned int tail_count;
+  __shared__ bool is_last;
+  __shared__ unsigned long long s_pair, s_nio;
+  const int lane = threadIdx.x & 31;
+  for (unsigned long long k = 0;; k++) {
+    uint32_t removed = scan_rows(s, t, a, b, new_id, sm, ml, n_match);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) removed += __shfl_down_sync(0xffffffffu, removed, d);
+    if (lane == 0 && removed) atomicAdd(removed_total, (unsigned long long)removed);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last) {
+      em.merged_key = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
+      em.stamp_base = (op_base + k) << 10;
+      TailSmem ts{stage, csum_sh, &tail_count};
+      fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq_base + k + 1, 0u, nullptr);
+      if (threadIdx.x == 0) {  // next command from the host
+        const unsigned long long want = seq_base + k + 2;
+        const unsigned long long t0 = gtime_ns();
+        unsigned long long pair = 0, nio = 1ull << 32;
+        for (unsigned long long spin = 0;; spin++) {
+          if (hcmd->seq == want) {
+            pair = hcmd->pair; nio = hcmd->new_id_op;
+            if (hcmd->check == cmd_check(want, pair, nio)) break;
+          }
+          if ((spin & 255) == 255 && gtime_ns() - t0 > timeout_ns) { pair = 0; nio = 3ull << 32; break; }  // abort
+        }
+        dcmd->pair = pair; dcmd->new_id_op = nio;
+        __threadfence();
+        *(volatile unsigned long long *)&dcmd->epoch = seq_base + k + 2;
+      }
+    }
+    if (threadIdx.x == 0) {  // every block: wait for the release of merge k+1
+      const unsigned long long want = seq_base + k + 2;
+      const unsigned long long t0 = gtime_ns();
+      unsigned long long nio = 0, pair = 0;
+      for (unsigned long long spin = 0;; spin++) {
+        if (*(volatile unsigned long long *)&dcmd->epoch >= want) {
+          __threadfence();
+          pair = *(volatile unsigned long long *)&dcmd->pair; nio = *(volatile unsigned long long *)&dcmd->new_id_op;
+          break;
+        }
+        if ((spin & 255) == 255 && gtime_ns() - t0 > 2 * timeout_ns) { nio = 3ull << 32; break; }
+      }
+      s_pair = pair; s_nio = nio;
+    }
+    __syncthreads();
+    if (s_nio >> 32) return;  // stop (1) or abort (3)
+    a = (int32_t)(s_pair >> 32); b = (int32_t)(s_pair & 0xFFFFFFFFu); new_id = (int32_t)(s_nio & 0xFFFFFFFFu);
+    __syncthreads();
+  }
 }
 
 // candidate keys -> frequency-table slots (after the host rebuilt the list)

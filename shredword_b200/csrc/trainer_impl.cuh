@@ -98,6 +98,11 @@ class TrainerImpl {
     hdr_.alloc(HDR_WORDS);
     memset(hdr_.host(), 0, HDR_WORDS * sizeof(unsigned long long));
     SWB_CUDA(cudaFuncSetAttribute(wt_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
+    int coop = 0;
+    SWB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
+    SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks_per_sm_, merge_persistent, MERGE_THREADS, 0));
+    coop_ok_ = coop != 0 && coop_blocks_per_sm_ >= 1;
+    coop_blocks_per_sm_ = std::min(coop_blocks_per_sm_, 4);
   }
   void sync() { SWB_CUDA(cudaStreamSynchronize(stream_)); }
   void launched(uint64_t n = 1) { stats.kernel_launches += n; }
@@ -1012,9 +1017,106 @@ class TrainerImpl {
     return consumed;
   }
 
+  // ---------------------------------------------------------------- persistent merge kernel (default single-GPU path)
+  bool use_persistent() const {
+    static const bool off = getenv("SWB_NO_PERSISTENT") && atoi(getenv("SWB_NO_PERSISTENT")) > 0;
+    return !off && device_tables_ && !comm_ && !timing && loaded_ && n_rows_ > 0 && n_long_ == 0 && coop_ok_;
+  }
+  struct HostCmdSender {  // makes sure the resident kernel is always told to stop, also when an exception unwinds
+    volatile HostCmd *c = nullptr;
+    unsigned long long next_seq = 0;
+    bool running = false;
+    void send(unsigned long long pair, unsigned long long nio) {
+      c->pair = pair; c->new_id_op = nio; c->check = cmd_check(next_seq, pair, nio);
+      __atomic_thread_fence(__ATOMIC_RELEASE);
+      c->seq = next_seq;
+      __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    }
+    ~HostCmdSender() { if (running) send(0, 1ull << 32); }
+  };
+  // Runs up to max_merges merges starting with (a, b) (already popped, pending in `core`) inside ONE
+  // cooperative launch. Returns the number performed; stops early when the heap is exhausted or a table
+  // has to grow.
+  int run_persistent(int32_t a, int32_t b, int32_t new_id, int max_merges) {
+    ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
+    maybe_grow_global_table(gt_flagged_);
+    gt_flagged_ = false;
+    if (!hcmd_.size()) { hcmd_.alloc(1); dcmd_.alloc(1); }
+    memset((void *)hcmd_.host(), 0, sizeof(HostCmd));
+    SWB_CUDA(cudaMemsetAsync(dcmd_.get(), 0, sizeof(DevCmd), stream_));
+    const int32_t unk = tr_->config.unk_id;
+    EmitMode em = emit_mode(1, 0, 0);
+    em.fused_max = 0xFFFFFFFFu;  // the resident kernel's tail takes every merge, whatever its size
+    pt_.canon_on = unk < 0 ? 1 : 0;
+    pt_.canon_first = unk == -1 ? UNK_CODE : NEG1_CODE;
+    pt_.gpf.slots = (void *)gt_.slots; pt_.gpf.mask = gt_.mask;
+    StreamDev s = stream_dev();
+    const uint64_t warps_needed = (n_rows_ + 31) / 32;
+    int grid = (int)std::min<uint64_t>((uint64_t)sms_ * coop_blocks_per_sm_, (warps_needed + MERGE_WARPS - 1) / MERGE_WARPS);
+    grid = std::max(grid, 1);
+    const unsigned long long seq_base = seq_, op_base = op_index_ + 1;
+    unsigned long long *removed_p = removed_.get();
+    Rec *out = recs_.dev();
+    size_t out_cap = recs_.size();
+    unsigned long long *out_hdr = hdr_.dev();
+    volatile HostCmd *hc = hcmd_.dev();
+    DevCmd *dc = dcmd_.get();
+    int32_t da = to_dev(a), db = to_dev(b);
+    unsigned long long timeout_ns = 2000000000ull;
+    void *args[] = {&s, &pt_, &em, &removed_p, &out, &out_cap, &out_hdr, (void *)&seq_base, (void *)&op_base, &hc, &dc, &da, &db, &new_id, &timeout_ns};
+    SWB_CUDA(cudaLaunchCooperativeKernel((const void *)merge_persistent, dim3(grid), dim3(MERGE_THREADS), args, 0, stream_));
+    launched(); stats.merge_launches++;
+    HostCmdSender sender;
+    sender.c = hcmd_.host(); sender.running = true;
+    sender.next_seq = seq_base + 2;  // the command that follows the first merge
+    int done = 0;
+    for (;;) {
+      const double tw0 = now_ms();
+      wait_seq_at(seq_base + done + 1, hdr_.host(), recs_.host(), recs_.size());
+      const double tw1 = now_ms();
+      stats.host_wait_ms += tw1 - tw0;
+      const size_t n = (size_t)hdr_.host()[1];
+      const unsigned int flags = (unsigned int)hdr_.host()[2];
+      const uint64_t removed = hdr_.host()[3];
+      if (flags & 5u) throw Error("pair table overflow during a merge (internal sizing error)");
+      if (flags & 16u) gt_flagged_ = true;
+      op_index_++;
+      seq_ = seq_base + done + 1;
+      stats.merge_scan_bytes += n_rows_ * ROW * 4;
+      stats.merge_alg_bytes += 4 * live_symbols_ + 8 * W;
+      live_symbols_ -= removed;
+      stats.live_symbols = live_symbols_;
+      translate_out(recs_.host(), n);
+      core.apply_absolute(recs_.host(), n);
+      const double ta1 = now_ms();
+      stats.host_apply_ms += ta1 - tw1;
+      done++;
+      bool go = done < max_merges && !gt_flagged_;
+      int32_t na = 0, nb = 0, nn = 0;
+      if (go) { go = core.next_merge(&na, &nb, &nn); stats.host_pop_ms += now_ms() - ta1; }
+      sender.next_seq = seq_base + done + 1;
+      if (!go) { sender.send(0, 1ull << 32); sender.running = false; break; }
+      sender.send(((unsigned long long)(uint32_t)to_dev(na) << 32) | (uint32_t)to_dev(nb), (unsigned long long)(uint32_t)nn);
+    }
+    sync();
+    return done;
+  }
+
   int merge_batch(int batch) {  // reference bpe_merge_batch
     const double t0 = now_ms();
     int done = 0;
+    if (use_persistent()) {
+      while (done < batch && !core.heap_empty()) {
+        int32_t a, b, nid;
+        const double tp0 = now_ms();
+        if (!core.next_merge(&a, &b, &nid)) break;
+        stats.host_pop_ms += now_ms() - tp0;
+        tables_fresh_ = false;
+        done += run_persistent(a, b, nid, batch - done);
+      }
+      stats.merge_ms += now_ms() - t0;
+      return done;
+    }
     if (use_device_loop()) {
       while (done < batch && !core.heap_empty()) {
         int32_t a, b, nid;
@@ -1136,6 +1238,11 @@ class TrainerImpl {
   int idle_polls_ = 0;
   uint64_t gt_used_estimate_ = 0;
   bool gt_flagged_ = false;
+  // persistent merge kernel
+  bool coop_ok_ = false;
+  int coop_blocks_per_sm_ = 0;
+  PinnedBuf<HostCmd> hcmd_;
+  DevBuf<DevCmd> dcmd_;
   // device-resident loop
   DevBuf<LoopState> loop_state_;
   DevBuf<CandEntry> cand_;
