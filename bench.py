@@ -274,13 +274,15 @@ def main():
       ms = float(tt.item())
     return ms / k, wall_ms / k, stats
 
+  # the sampler is started before the warm-up: spawning nvidia-smi and its first NVML queries stall the
+  # driver for tens of ms, which must not land inside the timed region; it keeps sampling through it
+  sampler = ClockSampler(local_rank)
+  sampler.start()
   for i in range(args.warmup):
     s = step(True, False)
     log(f"[bench] warmup {i}: merges={s['merges']} load={s['load_ms']:.1f}ms count={s['count_ms']:.1f}ms merge={s['merge_ms']:.1f}ms")
   step(False, False)  # e2e warm-up (pinned registration, first H2D)
 
-  sampler = ClockSampler(local_rank)
-  sampler.start()
   ms_res, wall_res, st_res = timed(True, args.steps, timing=False)
   ms_e2e, wall_e2e, st_e2e = timed(False, args.steps, timing=False)
   clocks = sampler.stop()
@@ -323,7 +325,7 @@ def main():
               "us_per_merge": st_res[-1]["merge_ms"] * 1e3 / max(merges, 1),
               "phase_ms": {k: st_res[-1][k] for k in ("load_ms", "count_ms", "merge_ms")},
               "e2e_phase_ms": {k: st_e2e[-1][k] for k in ("load_ms", "count_ms", "merge_ms")},
-              "wall_ms": st_res[-1]["wall_ms"], "e2e_wall_ms": st_e2e[-1]["wall_ms"],
+              "wall_ms": [s_["wall_ms"] for s_ in st_res], "e2e_wall_ms": [s_["wall_ms"] for s_ in st_e2e],
               "unique_words": st_res[-1]["words"], "rows": st_res[-1]["rows"],
               "collectives_per_step": st_res[-1].get("collectives"), "exchange_bytes_per_step": st_res[-1].get("exchange_bytes"), "wall_ms_per_step": wall_res,
               "ms_per_step_with_kernel_timing": ms_tim},

@@ -32,6 +32,21 @@ constexpr int ENC_TILE = ENC_THREADS * 16;  // bytes per block iteration
 constexpr int ENC_SHORT = 64;               // words up to this many bytes are encoded in shared memory
 constexpr uint32_t RANK_NONE = 0xFFFFFFFFu;
 
+// Word memo: text is Zipfian, so most word occurrences repeat a word that was already encoded. A 64-byte
+// slot caches word bytes -> tokens; it is filled by whoever encodes the word first (one CAS on the tag) and
+// read with L2-coherent loads. No busy state and no ordering between the tag and the payload: a reader
+// accepts a slot only if tag, length, BYTES and the token check word all match, and encodes the word
+// itself otherwise (torn or foreign slots are simply misses).
+constexpr int MEMO_MAX_LEN = 14, MEMO_MAX_TOK = 9;
+struct __align__(16) MemoSlot {
+  unsigned long long tag;             // word hash (never 0); 0 = free
+  uint8_t len, ntok, bytes[MEMO_MAX_LEN];
+  int32_t tok[MEMO_MAX_TOK];
+  uint32_t check;                     // tag ^ ntok ^ xor of the tokens, folded to 32 bits
+};
+static_assert(sizeof(MemoSlot) == 64, "memo slot is one 64-byte block");
+struct MemoDev { MemoSlot *slots; uint32_t mask; };
+
 struct RankSlot { unsigned long long key; unsigned long long val; };  // val = rank << 32 | new_id
 struct RankTableDev { const RankSlot *slots; uint32_t mask; };
 
@@ -78,6 +93,21 @@ __device__ __forceinline__ uint32_t enc_starts(const uint8_t *__restrict__ text,
   const uint32_t prev_delim = (seg == 0) ? 1u : (is_delim(text[seg * 16 - 1]) ? 1u : 0u);
   return ~dm & ((dm << 1) | prev_delim) & 0xFFFFu;
 }
+// 16 bytes starting at an arbitrary byte offset (two aligned 16-byte loads + a funnel shift); the buffers
+// are padded, so reading past the end of a word or of the text is safe
+__device__ __forceinline__ uint4 enc_load16(const uint8_t *__restrict__ text, uint64_t off) {
+  const uint4 *p = reinterpret_cast<const uint4 *>(text + (off & ~15ull));
+  const uint4 a = p[0], b = p[1];
+  const uint32_t sh = (uint32_t)(off & 15), bs = (sh & 3) * 8;
+  uint32_t v0, v1, v2, v3, v4;
+  switch (sh >> 2) {
+    case 0: v0 = a.x; v1 = a.y; v2 = a.z; v3 = a.w; v4 = b.x; break;
+    case 1: v0 = a.y; v1 = a.z; v2 = a.w; v3 = b.x; v4 = b.y; break;
+    case 2: v0 = a.z; v1 = a.w; v2 = b.x; v3 = b.y; v4 = b.z; break;
+    default: v0 = a.w; v1 = b.x; v2 = b.y; v3 = b.z; v4 = b.w; break;
+  }
+  return make_uint4(__funnelshift_r(v0, v1, bs), __funnelshift_r(v1, v2, bs), __funnelshift_r(v2, v3, bs), __funnelshift_r(v3, v4, bs));
+}
 __device__ __forceinline__ uint32_t enc_word_len(const uint8_t *__restrict__ text, uint64_t off, uint64_t n) {
   uint64_t i = off;
   while (i < n && !is_delim(text[i])) ++i;
@@ -86,7 +116,7 @@ __device__ __forceinline__ uint32_t enc_word_len(const uint8_t *__restrict__ tex
 
 // text: n bytes, 16-byte aligned, followed by >= 16 bytes of ' '. One tile per block iteration.
 __global__ void __launch_bounds__(ENC_THREADS)
-enc_words(const uint8_t *__restrict__ text, uint64_t n, RankTableDev tbl, const int32_t *__restrict__ byte_map,
+enc_words(const uint8_t *__restrict__ text, uint64_t n, RankTableDev tbl, MemoDev memo, const int32_t *__restrict__ byte_map,
           int32_t *__restrict__ tmp, uint32_t *__restrict__ tile_ntok, uint32_t *__restrict__ tile_nwords) {
   __shared__ int stok[ENC_TILE + ENC_SHORT];
   __shared__ uint16_t wstart[ENC_TILE / 2];
@@ -117,9 +147,68 @@ enc_words(const uint8_t *__restrict__ text, uint64_t n, RankTableDev tbl, const 
     for (unsigned int j = threadIdx.x; j < nw; j += ENC_THREADS) {
       const uint32_t rel = wstart[j];
       const uint64_t off = tile * ENC_TILE + rel;
-      const uint32_t L = enc_word_len(text, off, n);
+      // the word's first 16 bytes in registers: its length comes from the delimiter mask, not from a byte loop
+      const uint4 wv = enc_load16(text, off);
+      const uint32_t dmask = enc_delim_bits(wv.x) | (enc_delim_bits(wv.y) << 4) | (enc_delim_bits(wv.z) << 8) | (enc_delim_bits(wv.w) << 12);
+      uint32_t L = dmask ? (uint32_t)(__ffs(dmask) - 1) : 16u;
+      if (off + L > n) L = (uint32_t)(n - off);
+      if (L >= 15) L = enc_word_len(text, off, n);
       uint32_t nt;
-      if (L <= ENC_SHORT) {
+      if (L <= MEMO_MAX_LEN) {  // memoizable word
+        uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};  // zero the bytes from L on
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int keep = (int)L - 4 * k;  // bytes of this word to keep
+          w4[k] = keep >= 4 ? w4[k] : (keep <= 0 ? 0u : (w4[k] & (0xFFFFFFFFu >> (8 * (4 - keep)))));
+        }
+        unsigned long long h = dmix64(((unsigned long long)w4[1] << 32 | w4[0]) ^ 0x9E3779B97F4A7C15ull) ^
+                               dmix64(((unsigned long long)w4[3] << 32 | w4[2]) + ((unsigned long long)L << 56) + 0x632BE59BD9B4E019ull);
+        h = dmix64(h) | 1ull;
+        MemoSlot *slot = memo.slots + ((uint32_t)(h >> 20) & memo.mask);
+        const uint4 q0 = __ldcg(reinterpret_cast<const uint4 *>(slot));       // tag, len, ntok, bytes[0..5]
+        const uint4 q1 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 1);   // bytes[6..13], tok[0..1]
+        const uint4 q2 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 2);   // tok[2..5]
+        const uint4 q3 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 3);   // tok[6..8], check
+        const unsigned long long tag = ((unsigned long long)q0.y << 32) | q0.x;
+        // expected image of {len, ntok, bytes}: len | ntok << 8 | bytes << 16 over q0.z, q0.w, q1.x, q1.y
+        const uint32_t e0 = L | (w4[0] << 16), m0 = 0xFFFF00FFu;          // ntok byte masked out
+        const uint32_t e1 = (w4[0] >> 16) | (w4[1] << 16);
+        const uint32_t e2 = (w4[1] >> 16) | (w4[2] << 16);
+        const uint32_t e3 = (w4[2] >> 16) | (w4[3] << 16);
+        bool hit = false;
+        if (tag == h && (q0.z & m0) == e0 && q0.w == e1 && q1.x == e2 && q1.y == e3) {
+          const uint32_t mt = (q0.z >> 8) & 0xFFu;
+          const int tk[MEMO_MAX_TOK] = {(int)q1.z, (int)q1.w, (int)q2.x, (int)q2.y, (int)q2.z, (int)q2.w, (int)q3.x, (int)q3.y, (int)q3.z};
+          uint32_t ck = (uint32_t)h ^ (uint32_t)(h >> 32) ^ mt;
+#pragma unroll
+          for (int k = 0; k < MEMO_MAX_TOK; k++) ck ^= (uint32_t)tk[k] * (2u * k + 3u);
+          if (ck == q3.w && mt >= 1 && mt <= MEMO_MAX_TOK && mt <= L) {
+            hit = true;
+            nt = mt;
+#pragma unroll
+            for (int k = 0; k < MEMO_MAX_TOK; k++) if (k < (int)mt) tmp[off + k] = tk[k];
+          }
+        }
+        if (!hit) {
+          int *ids = stok + rel;
+          for (uint32_t k = 0; k < L; k++) ids[k] = bmap[(w4[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+          nt = enc_word(ids, L, tbl);
+          for (uint32_t k = 0; k < nt; k++) tmp[off + k] = ids[k];
+          if (tag == 0ull && nt <= MEMO_MAX_TOK && atomicCAS(&slot->tag, 0ull, h) == 0ull) {  // first encoder fills the slot
+            int tk[MEMO_MAX_TOK];
+            uint32_t ck = (uint32_t)h ^ (uint32_t)(h >> 32) ^ nt;
+#pragma unroll
+            for (int k = 0; k < MEMO_MAX_TOK; k++) { tk[k] = k < (int)nt ? ids[k] : 0; ck ^= (uint32_t)tk[k] * (2u * k + 3u); }
+            uint4 *dst = reinterpret_cast<uint4 *>(slot);
+            // (the tag, in q0.x/q0.y, is already there: written by the CAS)
+            reinterpret_cast<uint32_t *>(slot)[2] = e0 | (nt << 8);
+            reinterpret_cast<uint32_t *>(slot)[3] = e1;
+            dst[1] = make_uint4(e2, e3, (uint32_t)tk[0], (uint32_t)tk[1]);
+            dst[2] = make_uint4((uint32_t)tk[2], (uint32_t)tk[3], (uint32_t)tk[4], (uint32_t)tk[5]);
+            dst[3] = make_uint4((uint32_t)tk[6], (uint32_t)tk[7], (uint32_t)tk[8], ck);
+          }
+        }
+      } else if (L <= ENC_SHORT) {
         int *ids = stok + rel;
         for (uint32_t k = 0; k < L; k++) ids[k] = bmap[text[off + k]];
         nt = enc_word(ids, L, tbl);
@@ -262,6 +351,11 @@ class EncoderImpl {
     SWB_CUDA(cudaMemcpyAsync(d_bmap_.get(), dev_bmap_, sizeof dev_bmap_, cudaMemcpyHostToDevice, stream_));
     SWB_CUDA(cudaStreamSynchronize(stream_));
     tbl_ = RankTableDev{slots_.get(), (uint32_t)(cap - 1)};
+    const uint64_t memo_cap = 1ull << 20;  // 64 MB: the hot words of Zipfian text stay L2 resident
+    memo_slots_.alloc(memo_cap);
+    SWB_CUDA(cudaMemsetAsync(memo_slots_.get(), 0, memo_cap * sizeof(MemoSlot), stream_));
+    SWB_CUDA(cudaStreamSynchronize(stream_));
+    memo_ = MemoDev{memo_slots_.get(), (uint32_t)(memo_cap - 1)};
   }
 
   // Encodes one device-resident piece [d_text, d_text+n) that is 16-byte aligned and padded with 16 ' '.
@@ -279,7 +373,7 @@ class EncoderImpl {
     SWB_CUDA(cudaMemsetAsync(tile_tok_.get() + n_tiles, 0, 4, stream_));
     SWB_CUDA(cudaMemsetAsync(tile_words_.get() + n_tiles, 0, 4, stream_));
     const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)sms_ * 4);
-    enc_words<<<grid, ENC_THREADS, 0, stream_>>>(d_text, n, tbl_, d_bmap_.get(), tmp_.get(), tile_tok_.get(), tile_words_.get());
+    enc_words<<<grid, ENC_THREADS, 0, stream_>>>(d_text, n, tbl_, memo_, d_bmap_.get(), tmp_.get(), tile_tok_.get(), tile_words_.get());
     launches++;
     SWB_CUDA(cudaGetLastError());
     scan(tile_tok_.get(), tile_tok_off_.get(), n_tiles + 1);
@@ -377,6 +471,8 @@ class EncoderImpl {
   cudaStream_t stream_ = nullptr;
   int sms_ = 148;
   DevBuf<RankSlot> slots_;
+  DevBuf<MemoSlot> memo_slots_;
+  MemoDev memo_{};
   DevBuf<int32_t> d_bmap_;
   RankTableDev tbl_{};
   DevBuf<int32_t> tmp_;
