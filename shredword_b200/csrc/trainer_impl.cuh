@@ -13,6 +13,8 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include <chrono>
+#include <map>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <vector>
@@ -79,17 +81,36 @@ class TrainerImpl {
   std::vector<uint64_t> h_counts;  // host mirror of the word counts (Corpus.word_counts)
 
   // ---------------------------------------------------------------- device bring-up
+  // Per-process, per-device facts (cudaGetDeviceProperties, occupancy and attribute calls take the driver's
+  // global lock and cost from 1 to 100+ ms each while other work is in flight): queried once, not per handle.
+  struct DeviceFacts { int sms = 0, coop_blocks_per_sm = 0; bool coop_ok = false; };
+  static const DeviceFacts &device_facts(int device) {
+    static std::mutex mu;
+    static std::map<int, DeviceFacts> facts;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = facts.find(device);
+    if (it != facts.end()) return it->second;
+    DeviceFacts f;
+    SWB_CUDA(cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, device));
+    SWB_CUDA(cudaFuncSetAttribute(wt_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
+    int coop = 0;
+    SWB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f.coop_blocks_per_sm, merge_persistent, MERGE_THREADS, 0));
+    f.coop_ok = coop != 0 && f.coop_blocks_per_sm >= 1;
+    f.coop_blocks_per_sm = std::min(f.coop_blocks_per_sm, 4);
+    return facts.emplace(device, f).first->second;
+  }
   void ensure_device() {
     if (stream_) return;
+    const double t_init0 = now_ms();
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
       throw Error(std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
                   " (this library has no CPU fallback)");
     SWB_CUDA(cudaGetDevice(&device_));
-    cudaDeviceProp prop;
-    SWB_CUDA(cudaGetDeviceProperties(&prop, device_));
-    sms_ = prop.multiProcessorCount;
+    const DeviceFacts &f = device_facts(device_);
+    sms_ = f.sms; coop_ok_ = f.coop_ok; coop_blocks_per_sm_ = f.coop_blocks_per_sm;
     SWB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     SWB_CUDA(cudaEventCreate(&ev0_));
     SWB_CUDA(cudaEventCreate(&ev1_));
@@ -97,12 +118,7 @@ class TrainerImpl {
     SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
     hdr_.alloc(HDR_WORDS);
     memset(hdr_.host(), 0, HDR_WORDS * sizeof(unsigned long long));
-    SWB_CUDA(cudaFuncSetAttribute(wt_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
-    int coop = 0;
-    SWB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
-    SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks_per_sm_, merge_persistent, MERGE_THREADS, 0));
-    coop_ok_ = coop != 0 && coop_blocks_per_sm_ >= 1;
-    coop_blocks_per_sm_ = std::min(coop_blocks_per_sm_, 4);
+    if (getenv("SWB_TRACE_INIT")) fprintf(stderr, "[trace] ensure_device %.3f ms\n", now_ms() - t_init0);
   }
   void sync() { SWB_CUDA(cudaStreamSynchronize(stream_)); }
   void launched(uint64_t n = 1) { stats.kernel_launches += n; }
