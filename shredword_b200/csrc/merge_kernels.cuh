@@ -136,6 +136,37 @@ struct LoopDev {
   unsigned long long seq_base, op_base;
 };
 
+// ---- birth log: pair -> words that can contain it
+// An adjacent pair (x, y) with max(x, y) >= 256 comes into existence only while the NEWER of its two
+// tokens is being created: as (L, new) or (new, R) of a match of that merge (reference bpe.cpp:459-470).
+// Every merge therefore appends, for each positive delta it emits, one entry {other symbol, side, word,
+// location of the word's header} to its own contiguous log -- once per (pair, word). A later merge of
+// (a, b) reads the log of the merge that created max(a, b), keeps the entries with the right neighbour
+// and side, and visits exactly those words, one THREAD per word (a superset of the words that still hold
+// the pair: occurrences are only ever destroyed afterwards, and a word never moves).
+// Pairs of two initial symbols (< 256) have no log and use the row-signature scan.
+struct BirthLogDev {
+  uint4 *ent;            // {other symbol, side << 31 | word index, header location lo, hi}; side 0: (other, new), 1: (new, other)
+  unsigned int *cursor;  // entries appended so far
+  unsigned int *start;   // start[m] .. start[m+1]: the log of merge m (token 256 + m)
+  unsigned int *flags;   // bit 0: capacity exceeded (internal sizing error)
+  uint32_t cap;
+  uint32_t m_cur;        // index of the merge being performed; logs 0 .. m_cur-1 are complete
+};
+__device__ __forceinline__ uint4 log_entry(uint32_t other, bool right_side, uint32_t wi, uint64_t hloc) {
+  return make_uint4(other, (right_side ? 0x80000000u : 0u) | wi, (uint32_t)hloc, (uint32_t)(hloc >> 32));
+}
+// which log, neighbour and side hold the births of pair (a, b); false: no log (two initial symbols, or ids
+// that are not tokens of this stream)
+__device__ __forceinline__ bool log_lookup(const BirthLogDev &lg, int32_t a, int32_t b, uint32_t &merge, uint32_t &other, uint32_t &side) {
+  const int32_t newer = a > b ? a : b;
+  if (lg.ent == nullptr || newer < 256 || (uint32_t)(newer - 256) >= lg.m_cur) return false;
+  merge = (uint32_t)(newer - 256);
+  if (b == newer) { other = (uint32_t)a; side = 0u; }     // (a, b) was born as (L, new)
+  else { other = (uint32_t)b; side = 0x80000000u; }       // ... or as (new, R)
+  return true;
+}
+
 // parameters of an emit in device-table mode (mode 0 = host-resident table: plain records)
 struct EmitMode {
   int mode;                       // 0 host records (delta), 1 device table: merge, 2 device table: count
@@ -150,6 +181,7 @@ struct EmitMode {
   uint32_t cand_cap;
   unsigned long long theta;
   unsigned int fused_max;  // touched pairs the single-block tail takes; more -> flag 8, the host runs the full-grid pt_emit
+  BirthLogDev log;         // ent == nullptr: no birth log
 };
 __device__ __forceinline__ unsigned long long delta_bucket(const EmitMode &em, unsigned long long k) {
   if (em.neg_unk_bucket >= 0 && (uint32_t)k == (uint32_t)UNK_CODE) return (unsigned long long)em.neg_unk_bucket;
@@ -294,9 +326,13 @@ __device__ __forceinline__ void block_checksum(unsigned long long &cx, unsigned 
 __device__ __forceinline__ void pt_publish(const PairTableDev &t, unsigned int n, size_t out_cap, unsigned int extra_flags,
                                            volatile unsigned long long *out_hdr, unsigned long long *removed,
                                            unsigned long long seq, unsigned long long cx, unsigned long long cs,
-                                           bool keep_state = false) {
-  const unsigned long long flags = __ldcg(t.flags) | (n > out_cap ? 4u : 0u) | extra_flags;
+                                           const BirthLogDev *lg = nullptr, bool keep_state = false) {
+  unsigned long long flags = __ldcg(t.flags) | (n > out_cap ? 4u : 0u) | extra_flags;
   const unsigned long long rem = removed ? __ldcg(removed) : 0ull;
+  if (lg && lg->ent) {  // this merge's birth log ends here
+    lg->start[lg->m_cur + 1] = __ldcg(lg->cursor);
+    if (__ldcg(lg->flags)) flags |= 32u;
+  }
   out_hdr[1] = n; out_hdr[2] = flags; out_hdr[3] = rem; out_hdr[4] = cx; out_hdr[5] = cs;
   out_hdr[6] = hdr_check(seq, n, flags, rem, cx, cs);
   out_hdr[0] = seq; out_hdr[7] = seq;
@@ -341,7 +377,7 @@ pt_emit(PairTableDev t, EmitMode em, Rec *__restrict__ out, size_t out_cap, unsi
       }
     }
     const unsigned int gflag = (em.mode != 0 && __ldcg(em.g.flags)) ? 16u : 0u;  // frequency table past 50 % load
-    pt_publish(t, n_out, out_cap, gflag, out_hdr, removed, seq, x, sm);
+    pt_publish(t, n_out, out_cap, gflag, out_hdr, removed, seq, x, sm, &em.log);
   }
 }
 
@@ -396,30 +432,37 @@ __device__ __forceinline__ uint32_t loop_pick_next(const LoopDev &lp, const Glob
 
 __device__ __forceinline__ void fused_tail(const PairTableDev &t, const EmitMode &em, const TailSmem &ts, Rec *__restrict__ out,
                                            size_t out_cap, unsigned long long *__restrict__ out_hdr, unsigned long long *removed,
-                                           unsigned long long seq, unsigned int extra_flags, const LoopDev *lp = nullptr) {
+                                           unsigned long long seq, unsigned int extra_flags, const LoopDev *lp = nullptr,
+                                           unsigned long long *trace = nullptr) {
+  const long long tc0 = clock64();
   const unsigned int n = __ldcg(t.n_touched);
   const bool small = n <= em.fused_max;
   unsigned long long cx = 0, cs = 0;
   if (threadIdx.x == 0) *ts.count = 0;
   __syncthreads();
   unsigned int inserted = 0;
+  const long long tc1 = clock64();
   if (small) pt_emit_range(t, em, ts.stage, out_cap, n, threadIdx.x, blockDim.x, ts.count, cx, cs, inserted, out, STAGE_RECS);
+  const long long tc2 = clock64();
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, d);
   if ((threadIdx.x & 31) == 0 && em.mode != 0) gt_account(em.g, inserted);
   block_checksum(cx, cs, ts.csum);  // (contains a __syncthreads: the stage is complete after it)
   const unsigned int n_out = !small ? n : (em.mode == 0 ? n : *ts.count);
+  const long long tc3 = clock64();
   if (small) {
     const uint4 *src = reinterpret_cast<const uint4 *>(ts.stage);
     uint4 *dst = reinterpret_cast<uint4 *>(out);
     const unsigned int chunks = 2u * (unsigned int)min(min((size_t)n_out, out_cap), (size_t)STAGE_RECS);
     for (unsigned int i = threadIdx.x; i < chunks; i += blockDim.x) dst[i] = src[i];
   }
+  const long long tc4 = clock64();
   if (threadIdx.x == 0 && small && em.mode == 1) {
     unsigned int ins = 0;
     em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;  // bpe.cpp:523
     gt_account(em.g, ins);
   }
+  const long long tc5 = clock64();
   uint32_t next_status = LOOP_STOP;
   unsigned long long next_key = 0;
   if (lp) {  // device-resident loop: choose the next pair (block-wide arg-max over the candidate list)
@@ -444,8 +487,19 @@ __device__ __forceinline__ void fused_tail(const PairTableDev &t, const EmitMode
 #ifdef SWB_KERNEL_TRACE
     unsigned long long tr_emit_done; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_emit_done));
     out_hdr[9] = tr_emit_done; out_hdr[10] = n;
+    if (em.log.ent) {
+      out_hdr[20] = em.log.flags[1]; out_hdr[22] = em.log.flags[2]; em.log.flags[1] = 0; em.log.flags[2] = 0;
+      const int32_t ka = (int32_t)(em.merged_key >> 32), kb = (int32_t)(em.merged_key & 0xFFFFFFFFu), nw_ = ka > kb ? ka : kb;
+      out_hdr[21] = (nw_ >= 256 && (uint32_t)(nw_ - 256) < em.log.m_cur) ? em.log.start[nw_ - 256 + 1] - em.log.start[nw_ - 256] : ~0ull;
+    }
 #endif
-    pt_publish(t, n_out, out_cap, (small ? 0u : 8u) | gflag | extra_flags, out_hdr, removed, seq, cx, cs);
+    pt_publish(t, n_out, out_cap, (small ? 0u : 8u) | gflag | extra_flags, out_hdr, removed, seq, cx, cs, &em.log);
+    if (trace) {
+      const long long tc6 = clock64();
+      trace[9] += (unsigned long long)(tc1 - tc0); trace[10] += (unsigned long long)(tc2 - tc1); trace[11] += (unsigned long long)(tc3 - tc2);
+      trace[12] += (unsigned long long)(tc4 - tc3); trace[13] += (unsigned long long)(tc5 - tc4); trace[14] += (unsigned long long)(tc6 - tc5);
+      trace[15] += n;
+    }
   }
 }
 
@@ -467,16 +521,16 @@ __device__ __forceinline__ uint64_t word_gwi(const StreamDev &, uint32_t wi) { r
 // ---------------------------------------------------------------- merge (a, b) -> new_id
 constexpr int MERGE_THREADS = 256;
 constexpr int MERGE_WARPS = MERGE_THREADS / 32;
-constexpr int MATCH_CAP = ROW;  // matches of one warp iteration awaiting emission (a row holds at most 64)
+constexpr int MATCH_CAP = 96;  // matches of one warp iteration awaiting emission (a row holds at most 64)
 
 // One match of the pair inside a row, recorded by the lane that rewrites the word; the four signed
 // deltas it stands for (reference bpe.cpp:453-470) are emitted afterwards, one lane per delta.
-struct Match { int32_t L, R; uint32_t wi; uint32_t pos; unsigned long long cnt; };  // L / R = -1: no such neighbour
+struct Match { int32_t L, R; uint32_t wi; uint32_t pos; unsigned long long cnt; uint32_t row, hpos; };  // L / R = -1: no such neighbour
 
 // Sequential rewrite of one word living in shared memory at sm[p+1 ...]; p = header position.
 __device__ __forceinline__ uint32_t merge_word_smem(int *sm, int p, Match *ml, unsigned int *n_match,
                                                     const unsigned long long *__restrict__ cnt, int32_t a, int32_t b,
-                                                    int32_t new_id) {
+                                                    int32_t new_id, uint32_t row) {
   const uint32_t wi = (uint32_t)(~sm[p]);
   unsigned long long c = 0;
   int r = p + 1, w = p + 1;
@@ -488,7 +542,7 @@ __device__ __forceinline__ uint32_t merge_word_smem(int *sm, int p, Match *ml, u
       Match m;
       m.L = (w > p + 1) ? sm[w - 1] : -1;                      // left neighbour: the already rewritten symbol
       m.R = (r + 2 < ROW && sm[r + 2] >= 0) ? sm[r + 2] : -1;  // right neighbour: not yet rewritten
-      m.wi = wi; m.pos = (uint32_t)r;
+      m.wi = wi; m.pos = (uint32_t)r; m.row = row; m.hpos = (uint32_t)p;
       if (nmatch == 0) c = __ldg(&cnt[wi]);  // issued here so that its latency hides behind the rest of the rewrite
       m.cnt = c;
       ml[atomicAdd(n_match, 1u)] = m;
@@ -505,31 +559,57 @@ __device__ __forceinline__ uint32_t merge_word_smem(int *sm, int p, Match *ml, u
 }
 
 // Emits the four signed deltas of every recorded match, one lane per delta (reference bpe.cpp:453-470):
-// the chain of dependent global atomics is paid once per warp, not once per matched row.
-__device__ __forceinline__ void emit_matches(const Match *ml, unsigned int nm, int lane, const PairTableDev &t, int32_t a,
-                                             int32_t b, int32_t new_id) {
-  for (unsigned int i = lane; i < 4 * nm; i += 32) {
-    const Match m = ml[i >> 2];
-    const int slot = i & 3;
-    const int nb = slot < 2 ? m.L : m.R;
-    if (nb < 0) continue;
-    const long long c = (long long)m.cnt;
-    const uint64_t key = touch_key(m.wi, m.pos, slot);
-    if (slot == 0) pt_add(t, nb, a, -c, key);
-    else if (slot == 1) pt_add(t, nb, new_id, c, key);
-    else if (slot == 2) pt_add(t, b, nb, -c, key);
-    else pt_add(t, new_id, nb, c, key);
+// the chain of dependent global atomics is paid once per warp, not once per matched row. The positive
+// deltas -- the pairs that come into existence here -- also go to the birth log, once per (pair, row).
+__device__ __forceinline__ void emit_matches(const Match *ml, unsigned int nm, int lane, const PairTableDev &t,
+                                             const BirthLogDev &lg, int32_t a, int32_t b, int32_t new_id) {
+  for (unsigned int i0 = 0; i0 < 4 * nm; i0 += 32) {  // (warp-uniform bounds: the log append below votes)
+    const unsigned int i = i0 + lane;
+    bool born = false;
+    int nb = -1;
+    uint32_t row = 0, slot = i & 3, wi = 0;
+    uint64_t hloc = 0;
+    if (i < 4 * nm) {
+      const Match m = ml[i >> 2];
+      nb = slot < 2 ? m.L : m.R;
+      row = m.row; wi = m.wi; hloc = (uint64_t)m.row * ROW + m.hpos;
+      if (nb >= 0) {
+        const long long c = (long long)m.cnt;
+        const uint64_t key = touch_key(m.wi, m.pos, slot);
+        if (slot == 0) pt_add(t, nb, a, -c, key);
+        else if (slot == 1) pt_add(t, nb, new_id, c, key);
+        else if (slot == 2) pt_add(t, b, nb, -c, key);
+        else pt_add(t, new_id, nb, c, key);
+        if (lg.ent && (slot & 1)) {
+          born = true;  // unless an earlier match of the same word already logged this neighbour on this side
+          for (int j = (int)(i >> 2) - 1; j >= 0 && ml[j].row == row; j--)
+            if (ml[j].wi == m.wi && (slot == 1 ? ml[j].L : ml[j].R) == nb) { born = false; break; }
+        }
+      }
+    }
+    const unsigned int bm = __ballot_sync(0xffffffffu, born);
+    if (bm) {
+      unsigned int base = 0;
+      const int leader = __ffs(bm) - 1;
+      if (lane == leader) base = atomicAdd(lg.cursor, (unsigned int)__popc(bm));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (born) {
+        const unsigned int idx = base + __popc(bm & ((1u << lane) - 1u));
+        if (idx < lg.cap) lg.ent[idx] = log_entry((uint32_t)nb, slot == 3, wi, hloc);
+        else atomicOr(lg.flags, 1u);
+      }
+    }
   }
 }
 
 // Slow path of one row (warp-uniform): stage in shared memory, rewrite word by word (the lane that holds
 // a header rewrites that word) and store back. The matches are appended to the warp's list `ml`; their
 // deltas are emitted later for all rows of this warp iteration together (emit_matches).
-__device__ __noinline__ uint32_t merge_row_slow(int *sm, Match *ml, unsigned int *n_match, int4 v, int lane, int4 *row_gmem,
-                                                uint32_t *row_sig, const StreamDev &s, const PairTableDev &t, int32_t a,
+__device__ __noinline__ uint32_t merge_row_slow(int *sm, Match *ml, unsigned int *n_match, int4 v, int lane, uint64_t row,
+                                                const StreamDev &s, const PairTableDev &t, const BirthLogDev &lg, int32_t a,
                                                 int32_t b, int32_t new_id) {
   if (*n_match > MATCH_CAP - ROW / 2) {  // not enough room left for a full row of matches: flush first
-    emit_matches(ml, *n_match, lane, t, a, b, new_id);
+    emit_matches(ml, *n_match, lane, t, lg, a, b, new_id);
     __syncwarp();
     if (lane == 0) *n_match = 0;
   }
@@ -539,34 +619,35 @@ __device__ __noinline__ uint32_t merge_row_slow(int *sm, Match *ml, unsigned int
   const int h[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int k = 0; k < 4; k++)
-    if (h[k] < 0 && h[k] != PAD) removed += merge_word_smem(sm, lane * 4 + k, ml, n_match, s.cnt, a, b, new_id);
+    if (h[k] < 0 && h[k] != PAD) removed += merge_word_smem(sm, lane * 4 + k, ml, n_match, s.cnt, a, b, new_id, (uint32_t)row);
   __syncwarp();
-  row_gmem[lane] = *reinterpret_cast<const int4 *>(&sm[lane * 4]);
+  s.rows[row * (ROW / 4) + lane] = *reinterpret_cast<const int4 *>(&sm[lane * 4]);
   if (lane == 0) {  // the row now contains new_id
     const uint32_t hh = sig_hash(new_id);
-    row_sig[hh >> 5] |= 1u << (hh & 31);
+    atomicOr(&s.sig[row * SIG_WORDS + (hh >> 5)], 1u << (hh & 31));
   }
   __syncwarp();
   return removed;
 }
 
-// The scan of one merge: every warp tests 32 row signatures per iteration, loads the candidate rows (four
-// in flight), rewrites those with a match and emits their deltas. Returns this thread's removed-symbol count.
-__device__ __forceinline__ uint32_t scan_rows(const StreamDev &s, const PairTableDev &t, int32_t a, int32_t b, int32_t new_id,
-                                              int (*sm)[ROW], Match (*ml)[MATCH_CAP], unsigned int *n_match) {
+// The row scan of one merge (pairs without a birth log): every warp tests 32 row signatures per iteration,
+// loads the candidate rows (four in flight), rewrites those with a match and emits their deltas. Loads of
+// mutable data bypass L1: the word-granular path rewrites rows behind the back of the warp that scans them
+// here, and the resident kernel keeps its L1 across merges. Returns this thread's removed-symbol count.
+__device__ __forceinline__ uint32_t scan_rows(const StreamDev &s, const PairTableDev &t, const BirthLogDev &lg, int32_t a, int32_t b,
+                                              int32_t new_id, int (*sm)[ROW], Match (*ml)[MATCH_CAP], unsigned int *n_match) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint64_t warp = (blockIdx.x * (uint64_t)MERGE_THREADS + threadIdx.x) >> 5;
-  const uint64_t n_warps = ((uint64_t)gridDim.x * MERGE_THREADS) >> 5;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const uint32_t ha = sig_hash(a), hb = sig_hash(b);
   const uint32_t wa = ha >> 5, ba = 1u << (ha & 31), wb = hb >> 5, bb = 1u << (hb & 31);
   uint32_t removed = 0;
-  // 32 rows per warp iteration: lane l tests the signature of row base+l (8 bytes of a 32-byte signature)
   for (uint64_t base = warp * 32; base < s.n_rows; base += n_warps * 32) {
     const uint64_t row = base + lane;
     bool cand = false;
     if (row < s.n_rows) {
       const uint32_t *sg = s.sig + row * SIG_WORDS;
-      cand = (sg[wa] & ba) && (sg[wb] & bb);
+      cand = (__ldcg(&sg[wa]) & ba) && (__ldcg(&sg[wb]) & bb);
     }
     uint32_t cmask = __ballot_sync(0xffffffffu, cand);
     if (lane == 0) n_match[wib] = 0;
@@ -580,7 +661,7 @@ __device__ __forceinline__ uint32_t scan_rows(const StreamDev &s, const PairTabl
         if (cmask) {
           rr[u] = base + (__ffs(cmask) - 1);
           cmask &= cmask - 1;
-          vv[u] = s.rows[rr[u] * (ROW / 4) + lane];
+          vv[u] = __ldcg(&s.rows[rr[u] * (ROW / 4) + lane]);
           nc = u + 1;
         }
       }
@@ -592,16 +673,139 @@ __device__ __forceinline__ uint32_t scan_rows(const StreamDev &s, const PairTabl
           if (lane == 31) nxt = PAD;
           const bool m = (v.x == a && v.y == b) || (v.y == a && v.z == b) || (v.z == a && v.w == b) || (v.w == a && nxt == b);
           if (__any_sync(0xffffffffu, m))
-            removed += merge_row_slow(sm[wib], ml[wib], &n_match[wib], v, lane, s.rows + rr[u] * (ROW / 4),
-                                      s.sig + rr[u] * SIG_WORDS, s, t, a, b, new_id);
+            removed += merge_row_slow(sm[wib], ml[wib], &n_match[wib], v, lane, rr[u], s, t, lg, a, b, new_id);
         }
       }
     }
     __syncwarp();
-    if (n_match[wib]) emit_matches(ml[wib], n_match[wib], lane, t, a, b, new_id);
+    if (n_match[wib]) emit_matches(ml[wib], n_match[wib], lane, t, lg, a, b, new_id);
     __syncwarp();
   }
   return removed;
+}
+
+// ---------------------------------------------------------------- word-granular merge (pairs with a birth log)
+// One thread rewrites one word: the symbols are copied to thread-local memory, rewritten left to right with
+// the reference's sequential semantics (already-merged left neighbour, not-yet-merged right neighbour:
+// reference bpe.cpp:437-483), and the changed tail is stored back. Every match hands its four signed deltas
+// to `sink.add`, every newly born pair (once per word) to `sink.birth`.
+// hloc = flat index of the word's header in the row stream. Returns the number of matches.
+template <typename Sink>
+__device__ __forceinline__ uint32_t merge_one_word(const StreamDev &s, uint64_t hloc, uint32_t wi, int32_t a, int32_t b, int32_t new_id,
+                                                   Sink &sink) {
+  int32_t *flat = reinterpret_cast<int32_t *>(s.rows);
+  const int hpos = (int)(hloc & (ROW - 1));
+  const uint64_t row_base = hloc - hpos;
+  const unsigned long long c = __ldg(&s.cnt[wi]);  // in flight while the symbols arrive
+  int buf[ROW];
+  int n = 0;
+  {  // symbols hpos+1 .. end of word, 16 bytes at a time
+    bool open = true;
+    for (int q = (hpos + 1) >> 2; q < ROW / 4 && open; q++) {
+      const int4 v = __ldcg(reinterpret_cast<const int4 *>(flat + row_base) + q);
+      const int x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int p = 4 * q + k;
+        if (p <= hpos || !open) continue;
+        if (x[k] < 0) { open = false; continue; }
+        buf[n++] = x[k];
+      }
+    }
+  }
+  int w = 0, r = 0, first_changed = -1;
+  uint32_t nmatch = 0;
+  const long long cc = (long long)c;
+  while (r < n) {
+    const int x = buf[r];
+    if (x == a && r + 1 < n && buf[r + 1] == b) {
+      const int L = w > 0 ? buf[w - 1] : -1;       // already rewritten
+      const int R = r + 2 < n ? buf[r + 2] : -1;   // not yet rewritten
+      const uint32_t pos = (uint32_t)(hpos + 1 + r);
+      if (L >= 0) { sink.add(L, a, -cc, touch_key(wi, pos, 0)); sink.add(L, new_id, cc, touch_key(wi, pos, 1)); }
+      if (R >= 0) { sink.add(b, R, -cc, touch_key(wi, pos, 2)); sink.add(new_id, R, cc, touch_key(wi, pos, 3)); }
+      if (first_changed < 0) first_changed = w;
+      buf[w++] = new_id;
+      r += 2;
+      nmatch++;
+    } else {
+      buf[w++] = x;
+      r++;
+    }
+  }
+  if (!nmatch) return 0;
+  for (int i = first_changed; i < n; i++) flat[row_base + hpos + 1 + i] = i < w ? buf[i] : PAD;
+  {  // the row now contains new_id
+    const uint32_t hh = sig_hash(new_id);
+    atomicOr(&s.sig[(row_base / ROW) * SIG_WORDS + (hh >> 5)], 1u << (hh & 31));
+  }
+  // births: the pairs around every new_id of the rewritten word, each (side, neighbour) once per word
+  for (int i = first_changed; i < w; i++) {
+    if (buf[i] != new_id) continue;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const int j = side ? i + 1 : i - 1;
+      if (j < 0 || j >= w) continue;
+      const int nb = buf[j];
+      if (side == 1 && nb == new_id) continue;  // (new, new) is looked up through its left-side entry
+      bool dup = false;
+      for (int q = first_changed; q < i && !dup; q++) {
+        if (buf[q] != new_id) continue;
+        const int jq = side ? q + 1 : q - 1;
+        dup = jq >= 0 && jq < w && buf[jq] == nb;
+      }
+      if (!dup) sink.birth((uint32_t)nb, side == 1, wi, hloc);
+    }
+  }
+  return nmatch;
+}
+
+// warp-aggregated append to the birth log from divergent code
+__device__ __forceinline__ void log_append(const BirthLogDev &lg, uint4 e) {
+  const unsigned int conv = __activemask();
+  const int lane_id = threadIdx.x & 31;
+  const int leader = __ffs(conv) - 1;
+  unsigned int base = 0;
+  if (lane_id == leader) base = atomicAdd(lg.cursor, (unsigned int)__popc(conv));
+  base = __shfl_sync(conv, base, leader);
+  const unsigned int idx = base + __popc(conv & ((1u << lane_id) - 1u));
+  if (idx < lg.cap) lg.ent[idx] = e;
+  else atomicOr(lg.flags, 1u);
+}
+
+// deltas -> the global per-merge pair table, births -> the global log
+struct GlobalSink {
+  const PairTableDev &t;
+  const BirthLogDev &lg;
+  __device__ __forceinline__ void add(int32_t x, int32_t y, long long delta, uint64_t key) { pt_add(t, x, y, delta, key); }
+  __device__ __forceinline__ void birth(uint32_t other, bool right_side, uint32_t wi, uint64_t hloc) {
+    log_append(lg, log_entry(other, right_side, wi, hloc));
+  }
+};
+
+// The indexed scan of one merge over the whole grid: one thread per log entry of the merge that created
+// max(a, b); the entries with the wanted neighbour and side name the words to rewrite.
+// Returns this thread's removed-symbol count.
+__device__ __forceinline__ uint32_t scan_log_words(const StreamDev &s, const PairTableDev &t, const BirthLogDev &lg, uint32_t merge,
+                                                   uint32_t want_other, uint32_t want_side, int32_t a, int32_t b, int32_t new_id) {
+  const uint64_t lo = __ldcg(&lg.start[merge]);
+  const uint64_t n = __ldcg(&lg.start[merge + 1]) - lo;
+  GlobalSink sink{t, lg};
+  uint32_t removed = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 e = __ldcg(&lg.ent[lo + i]);
+    if (e.x == want_other && (e.y & 0x80000000u) == want_side)
+      removed += merge_one_word(s, ((uint64_t)e.w << 32) | e.z, e.y & 0x7FFFFFFFu, a, b, new_id, sink);
+  }
+  return removed;
+}
+
+// One merge over the whole grid: the indexed word scan when the pair has a birth log, the row-signature scan otherwise.
+__device__ __forceinline__ uint32_t scan_merge(const StreamDev &s, const PairTableDev &t, const BirthLogDev &lg, int32_t a, int32_t b,
+                                               int32_t new_id, int (*sm)[ROW], Match (*ml)[MATCH_CAP], unsigned int *n_match) {
+  uint32_t merge, other, side;
+  if (log_lookup(lg, a, b, merge, other, side)) return scan_log_words(s, t, lg, merge, other, side, a, b, new_id);
+  return scan_rows(s, t, lg, a, b, new_id, sm, ml, n_match);
 }
 
 // fused != 0: the last block to finish also emits the records and publishes the header (one launch per
@@ -621,6 +825,7 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
     seq = lp.seq_base + done + 1;
     em.merged_key = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
     em.stamp_base = (lp.op_base + done) << 10;
+    em.log.m_cur += (uint32_t)done;
   }
   __shared__ __align__(16) int sm[MERGE_WARPS][ROW];
   __shared__ Match ml[MERGE_WARPS][MATCH_CAP];
@@ -633,7 +838,7 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
 #ifdef SWB_KERNEL_TRACE
   if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0)); out_hdr[11] = t0; }
 #endif
-  uint32_t removed = scan_rows(s, t, a, b, new_id, sm, ml, n_match);
+  uint32_t removed = scan_merge(s, t, em.log, a, b, new_id, sm, ml, n_match);
 #ifdef SWB_KERNEL_TRACE
   if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt)); out_hdr[13] = tt; }
 #endif
@@ -641,14 +846,17 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
   for (int d = 16; d > 0; d >>= 1) removed += __shfl_down_sync(0xffffffffu, removed, d);
   if (lane == 0 && removed) atomicAdd(removed_total, (unsigned long long)removed);
   if (!fused) return;
-  __threadfence();
   __syncthreads();
 #ifdef SWB_KERNEL_TRACE
   if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt)); out_hdr[14] = tt; }
 #endif
-  if (threadIdx.x == 0) is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) {  // (a release by one thread after the barrier covers the whole block's writes)
+    __threadfence();
+    is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (!is_last) return;
+  __threadfence();
 #ifdef SWB_KERNEL_TRACE
   unsigned long long tr_scan_done; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_scan_done));
 #endif
@@ -677,7 +885,8 @@ __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t;
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_persistent(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *removed_total, Rec *__restrict__ out, size_t out_cap,
                  unsigned long long *__restrict__ out_hdr, unsigned long long seq_base, unsigned long long op_base,
-                 volatile HostCmd *hcmd, DevCmd *dcmd, int32_t a, int32_t b, int32_t new_id, unsigned long long timeout_ns) {
+                 volatile HostCmd *hcmd, DevCmd *dcmd, int32_t a, int32_t b, int32_t new_id, unsigned long long timeout_ns,
+                 unsigned long long *trace /* nullptr or [16] accumulators (development aid) */) {
   __shared__ __align__(16) int sm[MERGE_WARPS][ROW];
   __shared__ Match ml[MERGE_WARPS][MATCH_CAP];
   __shared__ unsigned int n_match[MERGE_WARPS];
@@ -687,21 +896,31 @@ merge_persistent(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *r
   __shared__ bool is_last;
   __shared__ unsigned long long s_pair, s_nio;
   const int lane = threadIdx.x & 31;
+  const uint32_t log_m_base = em.log.m_cur;
+  unsigned long long tr_released = gtime_ns();  // (thread 0 only) when this block learnt about the current merge
+  long long tr_c0 = clock64();
   for (unsigned long long k = 0;; k++) {
-    uint32_t removed = scan_rows(s, t, a, b, new_id, sm, ml, n_match);
+    em.log.m_cur = log_m_base + (uint32_t)k;
+    uint32_t removed = scan_merge(s, t, em.log, a, b, new_id, sm, ml, n_match);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) removed += __shfl_down_sync(0xffffffffu, removed, d);
     if (lane == 0 && removed) atomicAdd(removed_total, (unsigned long long)removed);
-    __threadfence();
+    const long long tr_c1 = clock64();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) {  // (a release by one thread after the barrier covers the whole block's writes)
+      __threadfence();
+      is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (is_last) {
+      __threadfence();
+      const long long tr_c2 = clock64();
       em.merged_key = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
       em.stamp_base = (op_base + k) << 10;
       TailSmem ts{stage, csum_sh, &tail_count};
-      fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq_base + k + 1, 0u, nullptr);
+      fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq_base + k + 1, 0u, nullptr, trace);
       if (threadIdx.x == 0) {  // next command from the host
+        const long long tr_c3 = clock64();
         const unsigned long long want = seq_base + k + 2;
         const unsigned long long t0 = gtime_ns();
         unsigned long long pair = 0, nio = 1ull << 32;
@@ -711,6 +930,13 @@ merge_persistent(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *r
             if (hcmd->check == cmd_check(want, pair, nio)) break;
           }
           if ((spin & 255) == 255 && gtime_ns() - t0 > timeout_ns) { pair = 0; nio = 3ull << 32; break; }  // abort
+        }
+        const unsigned long long t1 = gtime_ns();
+        if (trace) {
+          // [0] merges, [1] cycles scan (this block), [2] cycles sync+fence+count, [3] cycles tail, [4] ns host turnaround
+          // as seen here (publish -> next command), [5] ns from this block's release to its tail's end
+          trace[0] += 1; trace[1] += (unsigned long long)(tr_c1 - tr_c0); trace[2] += (unsigned long long)(tr_c2 - tr_c1);
+          trace[3] += (unsigned long long)(tr_c3 - tr_c2); trace[4] += t1 - t0; trace[5] += t0 - tr_released;
         }
         dcmd->pair = pair; dcmd->new_id_op = nio;
         __threadfence();
@@ -730,8 +956,10 @@ merge_persistent(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *r
         if ((spin & 255) == 255 && gtime_ns() - t0 > 2 * timeout_ns) { nio = 3ull << 32; break; }
       }
       s_pair = pair; s_nio = nio;
+      tr_released = gtime_ns();
     }
     __syncthreads();
+    tr_c0 = clock64();
     if (s_nio >> 32) return;  // stop (1) or abort (3)
     a = (int32_t)(s_pair >> 32); b = (int32_t)(s_pair & 0xFFFFFFFFu); new_id = (int32_t)(s_nio & 0xFFFFFFFFu);
     __syncthreads();

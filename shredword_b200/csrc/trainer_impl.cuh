@@ -54,6 +54,17 @@ class TrainerImpl {
       double sh = 0, st = 0; for (size_t i = 0; i < n; i++) (i < 200 ? sh : st) += wait_trace_[i];
       fprintf(stderr, " | sum first200=%.1f ms rest=%.1f ms\n", sh / 1e3, st / 1e3);
       if (tw_n_) fprintf(stderr, "[trace]   block0/warp0 on quiet merges: sig %.2f us, candidate rows %.2f us (%.1f candidates of 32), fence+sync %.2f us\n", tw_sig_ / tw_n_, tw_rows_ / tw_n_, tw_cand_ / tw_n_, tw_fence_ / tw_n_);
+      if (trace_cand_.size() == n) {  // birth-log statistics: candidates per merge
+        const uint32_t ce[] = {0, 1, 9, 33, 129, 513, 2049, 8193, 0xFFFFFFFFu};
+        size_t base_pairs = 0;
+        for (size_t i = 0; i < n; i++) base_pairs += trace_logn_[i] == ~0ull;
+        fprintf(stderr, "[trace]   merges without a birth log (two initial symbols): %zu\n", base_pairs);
+        for (int b = 0; b + 1 < 9; b++) {
+          size_t c = 0; double lat = 0, logn = 0, mr = 0, sc = 0;
+          for (size_t i = 0; i < n; i++) if (trace_logn_[i] != ~0ull && trace_cand_[i] >= ce[b] && trace_cand_[i] < ce[b + 1]) { c++; lat += wait_trace_[i]; logn += (double)trace_logn_[i]; mr += trace_mrows_[i]; sc += trace_scan_[i]; }
+          if (c) fprintf(stderr, "[trace]   candidates in [%u, %u): %zu merges, mean log entries %.0f, matched rows %.1f, latency %.1f us (scan %.1f)\n", ce[b], ce[b + 1], c, logn / c, mr / c, lat / c, sc / c);
+        }
+      }
       if (trace_removed_.size() == n) {
         const uint32_t edges[] = {0, 10, 30, 100, 300, 1000, 3000, 10000, 100000, 0xFFFFFFFFu};
         for (int b = 0; b + 1 < 10; b++) {
@@ -393,6 +404,7 @@ class TrainerImpl {
     }
     corpus.release();
     SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
+    setup_birth_log();
     // public mirror fields (reference Corpus)
     tr_->corpus.vocab_size = W;
     tr_->corpus.word_counts = h_counts.data();
@@ -423,6 +435,45 @@ class TrainerImpl {
     for (size_t i = 0; i < nkeep && i < c; i++) keep[order[i]] = 1;
     for (int i = 0; i < 256; i++) byte_map[i] = keep[i] ? i : tr_->config.unk_id;
     if (core.log_level > 0) printf("[DEBUG]\t Character histogram built with %zu unique characters.\n", c);
+  }
+
+  // ---------------------------------------------------------------- birth log
+  // A match removes one symbol and logs at most two entries; a word of L symbols can match at most L-1
+  // times over a whole training run, so 2 * (symbols - words) entries can never overflow.
+  void setup_birth_log() {
+    static const bool off = getenv("SWB_NO_BIRTH_LOG") && atoi(getenv("SWB_NO_BIRTH_LOG")) > 0;
+    log_ok_ = false; stream_merges_ = 0; log_cap_ = 0;
+    if (off || !n_rows_) return;
+    const uint64_t cap = 2 * live_symbols_ + 64;
+    if (cap >= (1ull << 31)) return;  // (entries are indexed with 32 bits; such a table falls back to the signature scan)
+    log_ent_.alloc(cap);
+    log_cap_ = (uint32_t)cap;
+    log_scal_.alloc(4);
+    SWB_CUDA(cudaMemsetAsync(log_scal_.get(), 0, log_scal_.bytes(), stream_));
+    log_merge_cap_ = 0;
+    ensure_log_merges(tr_->config.target_vocab_size > 256 ? (uint32_t)(tr_->config.target_vocab_size - 256) : 1024u);
+    log_ok_ = true;
+  }
+  void ensure_log_merges(uint32_t merges) {  // room for start[0 .. merges]
+    if (merges + 2 <= log_merge_cap_) return;
+    const uint32_t cap = (uint32_t)pow2_ceil((uint64_t)merges + 2);
+    DevBuf<unsigned int> ns(cap);
+    SWB_CUDA(cudaMemsetAsync(ns.get(), 0, ns.bytes(), stream_));
+    if (log_merge_cap_) SWB_CUDA(cudaMemcpyAsync(ns.get(), log_start_.get(), (size_t)log_merge_cap_ * 4, cudaMemcpyDeviceToDevice, stream_));
+    sync();
+    log_start_ = std::move(ns);
+    log_merge_cap_ = cap;
+  }
+  // the log as the next merge (which creates new_id) sees it; tokens must be numbered 256 + merges done on this stream
+  BirthLogDev birth_log(int32_t new_id, uint32_t merges_ahead) {
+    BirthLogDev lg;
+    memset(&lg, 0, sizeof lg);
+    if (log_ok_ && (int64_t)new_id != 256 + (int64_t)stream_merges_) log_ok_ = false;
+    if (!log_ok_) return lg;
+    ensure_log_merges(stream_merges_ + merges_ahead);
+    lg.ent = log_ent_.get(); lg.cursor = log_scal_.get(); lg.flags = log_scal_.get() + 1; lg.start = log_start_.get();
+    lg.cap = log_cap_; lg.m_cur = stream_merges_;
+    return lg;
   }
 
   // ---------------------------------------------------------------- pair table plumbing
@@ -766,11 +817,12 @@ class TrainerImpl {
     if (!loaded_) return recs_.host();
     const int32_t unk = tr_->config.unk_id;
     const bool absent = (a < 0 && a != unk) || (b < 0 && b != unk);  // such ids exist in no word
-    if (absent && !device_tables_) return recs_.host();
+    if (absent && !device_tables_) { log_ok_ = false; return recs_.host(); }  // (the token numbering moves on without this stream)
     const int32_t da = to_dev(a), db = to_dev(b);
     if (device_tables_) { maybe_grow_global_table(gt_flagged_); gt_flagged_ = false; }
     op_index_++;
     EmitMode em = emit_mode(1, da, db);
+    em.log = birth_log(new_id, 1);
     pt_.canon_on = (device_tables_ && unk < 0) ? 1 : 0;
     pt_.canon_first = unk == -1 ? UNK_CODE : NEG1_CODE;
     pt_.gpf.slots = device_tables_ ? (void *)gt_.slots : nullptr;
@@ -810,6 +862,7 @@ class TrainerImpl {
         trace_scan_.push_back((float)((double)(hh[8] - hh[11]) * 1e-3));
         trace_tail_.push_back((float)((double)(hh[9] - hh[8]) * 1e-3));
         trace_nrec_.push_back((uint32_t)hh[10]);
+        trace_cand_.push_back((uint32_t)hh[20]); trace_logn_.push_back((uint64_t)hh[21]); trace_mrows_.push_back((uint32_t)hh[22]);
         if (trace_removed_.size() > 200 && hh[10] < 10) { tw_sig_ += (double)(hh[12] - hh[11]) * 1e-3; tw_rows_ += (double)(hh[13] - hh[12]) * 1e-3; tw_fence_ += (double)(hh[14] - hh[13]) * 1e-3; tw_cand_ += (double)hh[15]; tw_n_++; }
 #endif
       }
@@ -827,6 +880,8 @@ class TrainerImpl {
     }
     if (flags & 16u) gt_flagged_ = true;
     if (flags & 5u) throw Error("pair table overflow during a merge (internal sizing error)");
+    if (flags & 32u) throw Error("birth log overflow (internal sizing error)");
+    stream_merges_++;
     if (timing) {
       float ms = 0;
       SWB_CUDA(cudaEventSynchronize(ev1_));
@@ -947,6 +1002,7 @@ class TrainerImpl {
     lp.ring = ring_.dev(); lp.ring_hdr = ring_hdr_.dev(); lp.ring_slots = RING_SLOTS; lp.slot_recs = FUSED_EMIT_MAX;
     lp.seq_base = seq_; lp.op_base = op_index_ + 1;
     EmitMode em = emit_mode(1, 0, 0);
+    em.log = birth_log(new_id, (uint32_t)max_merges + 1);
     em.fused_max = FUSED_EMIT_MAX;  // here a stop costs a relaunch: let the tail take everything a ring slot holds
     pt_.canon_on = unk < 0 ? 1 : 0;
     pt_.canon_first = unk == -1 ? UNK_CODE : NEG1_CODE;
@@ -996,6 +1052,7 @@ class TrainerImpl {
         unsigned int fl2 = 0;
         uint64_t rem2 = 0;
         EmitMode em2 = emit_mode(1, (int32_t)(pair >> 32), (int32_t)(pair & 0xFFFFFFFFu));
+        em2.log = em.log; em2.log.m_cur = stream_merges_;
         t_launch0_ = now_ms();
         const size_t n2 = emit_and_wait(em2, &fl2, &rem2);
         if (fl2 & 5u) throw Error("pair table overflow during a merge (internal sizing error)");
@@ -1019,6 +1076,8 @@ class TrainerImpl {
       }
       stats.host_apply_ms += now_ms() - ta0;
       stats.live_symbols = live_symbols_;
+      if ((flags & 32u)) throw Error("birth log overflow (internal sizing error)");
+      stream_merges_++;
       consumed++;
       if (consumed == max_merges) break;
     }
@@ -1062,6 +1121,7 @@ class TrainerImpl {
     SWB_CUDA(cudaMemsetAsync(dcmd_.get(), 0, sizeof(DevCmd), stream_));
     const int32_t unk = tr_->config.unk_id;
     EmitMode em = emit_mode(1, 0, 0);
+    em.log = birth_log(new_id, (uint32_t)max_merges + 1);
     em.fused_max = 0xFFFFFFFFu;  // the resident kernel's tail takes every merge, whatever its size
     pt_.canon_on = unk < 0 ? 1 : 0;
     pt_.canon_first = unk == -1 ? UNK_CODE : NEG1_CODE;
@@ -1079,7 +1139,12 @@ class TrainerImpl {
     DevCmd *dc = dcmd_.get();
     int32_t da = to_dev(a), db = to_dev(b);
     unsigned long long timeout_ns = 2000000000ull;
-    void *args[] = {&s, &pt_, &em, &removed_p, &out, &out_cap, &out_hdr, (void *)&seq_base, (void *)&op_base, &hc, &dc, &da, &db, &new_id, &timeout_ns};
+    unsigned long long *trace_p = nullptr;
+    if (trace_wait_) {
+      if (!ptrace_.size()) { ptrace_.alloc(16); SWB_CUDA(cudaMemsetAsync(ptrace_.get(), 0, ptrace_.bytes(), stream_)); }
+      trace_p = ptrace_.get();
+    }
+    void *args[] = {&s, &pt_, &em, &removed_p, &out, &out_cap, &out_hdr, (void *)&seq_base, (void *)&op_base, &hc, &dc, &da, &db, &new_id, &timeout_ns, &trace_p};
     SWB_CUDA(cudaLaunchCooperativeKernel((const void *)merge_persistent, dim3(grid), dim3(MERGE_THREADS), args, 0, stream_));
     launched(); stats.merge_launches++;
     HostCmdSender sender;
@@ -1095,8 +1160,10 @@ class TrainerImpl {
       const unsigned int flags = (unsigned int)hdr_.host()[2];
       const uint64_t removed = hdr_.host()[3];
       if (flags & 5u) throw Error("pair table overflow during a merge (internal sizing error)");
+      if (flags & 32u) throw Error("birth log overflow (internal sizing error)");
       if (flags & 16u) gt_flagged_ = true;
       op_index_++;
+      stream_merges_++;
       seq_ = seq_base + done + 1;
       stats.merge_scan_bytes += n_rows_ * ROW * 4;
       stats.merge_alg_bytes += 4 * live_symbols_ + 8 * W;
@@ -1115,6 +1182,16 @@ class TrainerImpl {
       sender.send(((unsigned long long)(uint32_t)to_dev(na) << 32) | (uint32_t)to_dev(nb), (unsigned long long)(uint32_t)nn);
     }
     sync();
+    if (trace_p) {
+      unsigned long long h[16];
+      SWB_CUDA(cudaMemcpy(h, trace_p, sizeof h, cudaMemcpyDeviceToHost));
+      const double n = (double)std::max<unsigned long long>(h[0], 1), ghz = 1.965;
+      fprintf(stderr, "[trace] resident kernel, per merge (%llu merges): scan %.2f us, sync+fence+count %.2f us, tail %.2f us | release->tail end %.2f us, "
+              "host turnaround seen by the GPU %.2f us\n", h[0], h[1] / n / ghz / 1e3, h[2] / n / ghz / 1e3, h[3] / n / ghz / 1e3,
+              h[5] / n / 1e3, h[4] / n / 1e3);
+      fprintf(stderr, "[trace]   tail split (us): read count %.2f, emit range %.2f, checksum+sync %.2f, copy to host %.2f, merged-pair upsert %.2f, publish %.2f; touched pairs %.1f\n",
+              h[9] / n / ghz / 1e3, h[10] / n / ghz / 1e3, h[11] / n / ghz / 1e3, h[12] / n / ghz / 1e3, h[13] / n / ghz / 1e3, h[14] / n / ghz / 1e3, h[15] / n);
+    }
     return done;
   }
 
@@ -1220,6 +1297,7 @@ class TrainerImpl {
   void free_corpus_state() {
     rows_.release(); sig_.release(); cnt_.release(); wloc_.release(); long_index_.release(); long_syms_.release(); long_off_.release();
     long_len_.release(); long_word_.release(); word_bytes_.release(); word_boff_.release();
+    log_ent_.release(); log_ok_ = false; stream_merges_ = 0; log_cap_ = 0;
     n_rows_ = 0; n_long_ = 0; W = 0; live_symbols_ = 0; word_bytes_total_ = 0; loaded_ = false;
     h_counts.clear();
   }
@@ -1247,6 +1325,11 @@ class TrainerImpl {
   uint64_t live_symbols_ = 0, word_bytes_total_ = 0;
   DevBuf<uint8_t> word_bytes_;
   DevBuf<uint64_t> word_boff_;
+  // birth log (pair -> candidate rows), see BirthLogDev
+  DevBuf<uint4> log_ent_;
+  DevBuf<unsigned int> log_scal_, log_start_;
+  uint32_t log_cap_ = 0, log_merge_cap_ = 0, stream_merges_ = 0;
+  bool log_ok_ = false;
   // pair table
   uint64_t pt_cap_ = 0;
   PairTableDev pt_{};
@@ -1259,6 +1342,7 @@ class TrainerImpl {
   int coop_blocks_per_sm_ = 0;
   PinnedBuf<HostCmd> hcmd_;
   DevBuf<DevCmd> dcmd_;
+  DevBuf<unsigned long long> ptrace_;
   // device-resident loop
   DevBuf<LoopState> loop_state_;
   DevBuf<CandEntry> cand_;
@@ -1269,7 +1353,8 @@ class TrainerImpl {
   uint32_t n_cand_host_ = 0;
   bool trace_wait_ = getenv("SWB_TRACE_WAIT") != nullptr;
   std::vector<float> wait_trace_;
-  std::vector<uint32_t> trace_removed_, trace_nrec_;
+  std::vector<uint32_t> trace_removed_, trace_nrec_, trace_cand_, trace_mrows_;
+  std::vector<uint64_t> trace_logn_;
   std::vector<float> trace_scan_, trace_tail_;
   double tw_sig_ = 0, tw_rows_ = 0, tw_fence_ = 0, tw_cand_ = 0; size_t tw_n_ = 0;
   // device-resident frequency table (single-GPU mode)
