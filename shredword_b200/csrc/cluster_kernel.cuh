@@ -1,0 +1,416 @@
+// cluster_kernel.cuh -- the resident merge kernel (default single-GPU path of bpe_merge_batch / bpe_train).
+//
+// Replaces the scan + splice + delta bookkeeping of reference bpe_merge_batch (reference
+// csrc/bpe/bpe.cpp:437-520) for a whole batch of merges with ONE launch that stays resident:
+//
+//   grid    = thread-block clusters of CL_SIZE CTAs (one CTA per SM), CL_THREADS threads each
+//   cluster 0 ("leader") talks to the host: CTA 0 / thread 0 polls a mailbox in mapped host memory for
+//             the next pair, the results go back the same way -> one PCIe round trip per merge, no launch
+//   LOCAL   a merge whose pair has a birth log of at most CL_LOCAL_MAX entries is done by the leader
+//           cluster alone: one thread per candidate word, the signed deltas are aggregated in ONE hash
+//           table distributed over the shared memories of the cluster (DSMEM atomics; owner CTA = pair
+//           hash), cluster barriers instead of grid-wide atomics + fences, then every CTA applies its
+//           own pairs to the device frequency table and writes its records to the host
+//   GRID    every other merge (two initial symbols: row-signature scan; very long logs) runs on all
+//           clusters through the global pair table, exactly like the per-launch kernel merge_rows
+//
+// Every spin has a time-out so that a vanished host cannot hang the GPU.
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "merge_kernels.cuh"
+
+namespace swb {
+
+namespace cg = cooperative_groups;
+
+constexpr int CL_THREADS = 512;
+constexpr int CL_WARPS = CL_THREADS / 32;
+constexpr int CL_SIZE = 8;                 // CTAs per cluster (portable maximum)
+constexpr int CL_HT_SLOTS = 4096;          // slots of the distributed delta table per CTA
+constexpr int CL_BIRTH_STAGE = 1024;       // log entries staged per CTA and merge
+constexpr int CL_REC_STAGE = 512;          // records staged per CTA and merge
+constexpr unsigned int CL_LOCAL_MAX = CL_SIZE * CL_THREADS * 8;  // longest birth log the leader cluster takes alone
+constexpr int CL_MAX_PROBES = 256;
+
+// host -> device command (mapped host memory). op (new_id_op >> 32): 0 = merge, 1 = stop
+struct HostCmd2 { unsigned long long seq, pair, new_id_op, log_range /* lo << 32 | n; ~0: no log */, check, pad[3]; };
+// leader -> other clusters (device memory)
+struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, pad[2]; };
+__host__ __device__ __forceinline__ unsigned long long cmd2_check(unsigned long long seq, unsigned long long pair,
+                                                                  unsigned long long nio, unsigned long long lr) {
+  return (seq * HDR_MAGIC) ^ pair ^ (nio << 7 | nio >> 57) ^ (lr * 0xD6E8FEB86659FD93ull);
+}
+
+// per-CTA control block in shared memory
+struct ClusterCtl {
+  // the command, written into every CTA of the leader cluster by its CTA 0
+  unsigned long long pair, new_id_op, log_range, k;
+  unsigned int mode, stop;             // mode 0 = LOCAL, 1 = GRID
+  // per CTA, per merge
+  unsigned int n_births, n_recs, n_occ, rec_base, birth_base, pad0;
+  // cluster-wide, live in CTA 0 only
+  unsigned int spill, n_recs_total, removed, inserted;
+  unsigned long long part_cx[CL_SIZE], part_cs[CL_SIZE];  // per-CTA record checksums (plain remote stores; combined by CTA 0)
+};
+
+struct ClusterSmem {
+  unsigned long long *keys, *val, *mk;   // distributed delta table (this CTA's part)
+  uint4 *births;
+  Rec *recs;
+  unsigned short *occ;                   // occupied slots of this CTA's part
+  ClusterCtl *ctl;
+  unsigned long long *csum;              // [64] scratch of block_checksum
+  // GRID mode scratch (aliases the delta table, which is empty then)
+  int (*rows)[ROW];
+  Match (*ml)[MATCH_CAP];
+  unsigned int *n_match;
+  Rec *tail_stage;
+  unsigned int *tail_count;
+};
+constexpr size_t CL_SMEM_TABLE = (size_t)CL_HT_SLOTS * 24;
+constexpr size_t CL_SMEM_GRID = (size_t)CL_WARPS * ROW * 4 + (size_t)CL_WARPS * MATCH_CAP * sizeof(Match) + CL_WARPS * 4 + STAGE_RECS * sizeof(Rec) + 16;
+static_assert(CL_SMEM_GRID <= CL_SMEM_TABLE, "GRID-mode scratch must fit into the delta table's shared memory");
+constexpr size_t CL_SMEM_BYTES = CL_SMEM_TABLE + (size_t)CL_BIRTH_STAGE * 16 + (size_t)CL_REC_STAGE * sizeof(Rec) + CL_HT_SLOTS * 2 +
+                                 sizeof(ClusterCtl) + 64 * 8 + 64;
+
+__device__ __forceinline__ ClusterSmem cluster_smem(unsigned char *base) {
+  ClusterSmem m;
+  unsigned char *p = base;
+  m.keys = reinterpret_cast<unsigned long long *>(p);
+  m.val = m.keys + CL_HT_SLOTS;
+  m.mk = m.val + CL_HT_SLOTS;
+  {  // GRID-mode view of the same bytes
+    unsigned char *q = base;
+    m.rows = reinterpret_cast<int (*)[ROW]>(q); q += (size_t)CL_WARPS * ROW * 4;
+    m.ml = reinterpret_cast<Match (*)[MATCH_CAP]>(q); q += (size_t)CL_WARPS * MATCH_CAP * sizeof(Match);
+    m.tail_stage = reinterpret_cast<Rec *>(q); q += STAGE_RECS * sizeof(Rec);
+    m.n_match = reinterpret_cast<unsigned int *>(q); q += CL_WARPS * 4;
+    m.tail_count = reinterpret_cast<unsigned int *>(q);
+  }
+  p += CL_SMEM_TABLE;
+  m.births = reinterpret_cast<uint4 *>(p); p += (size_t)CL_BIRTH_STAGE * 16;
+  m.recs = reinterpret_cast<Rec *>(p); p += (size_t)CL_REC_STAGE * sizeof(Rec);
+  m.csum = reinterpret_cast<unsigned long long *>(p); p += 64 * 8;
+  m.ctl = reinterpret_cast<ClusterCtl *>(p); p += sizeof(ClusterCtl);
+  m.occ = reinterpret_cast<unsigned short *>(p);
+  return m;
+}
+
+// deltas -> the cluster's distributed shared-memory table, births -> this CTA's stage
+struct ClusterSink {
+  cg::cluster_group &cluster;
+  const ClusterSmem &m;
+  const PairTableDev &t;      // spill target + canonicalisation of a negative unk_id
+  const BirthLogDev &lg;
+  __device__ __forceinline__ void add(int32_t x, int32_t y, long long delta, uint64_t key) {
+    if (t.canon_on && y == UNK_CODE) x = t.canon_first;
+    const unsigned long long k = ((unsigned long long)(uint32_t)x << 32) | (uint32_t)y;
+    const uint64_t h = dmix64(k);
+    const unsigned int owner = (unsigned int)h & (CL_SIZE - 1);
+    unsigned long long *rk = cluster.map_shared_rank(m.keys, owner);
+    uint32_t sl = (uint32_t)(h >> 3) & (CL_HT_SLOTS - 1);
+    for (int probe = 0; probe < CL_MAX_PROBES; probe++) {
+      const unsigned long long cur = atomicCAS(&rk[sl], PT_EMPTY, k);
+      if (cur == PT_EMPTY && t.gpf.slots)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<char *>(t.gpf.slots) +
+                                                     32ull * ((uint32_t)dmix64(k + 0x632BE59BD9B4E019ull) & t.gpf.mask)));
+      if (cur == PT_EMPTY || cur == k) {
+        atomicAdd(cluster.map_shared_rank(m.val, owner) + sl, (unsigned long long)delta);
+        // 64-bit min through compare-and-swap: atomicMin / atomicXor on 64-bit words of a REMOTE shared memory
+        // returned wrong results on this toolchain (add and CAS are fine)
+        unsigned long long *pm = cluster.map_shared_rank(m.mk, owner) + sl;
+        unsigned long long seen = *(volatile unsigned long long *)pm;
+        while ((unsigned long long)key < seen) {
+          const unsigned long long prev = atomicCAS(pm, seen, (unsigned long long)key);
+          if (prev == seen) break;
+          seen = prev;
+        }
+        return;
+      }
+      sl = (sl + 1) & (CL_HT_SLOTS - 1);
+    }
+    // the owner's part is (nearly) full: this delta goes to the global table, and so will everything else
+    atomicOr(&cluster.map_shared_rank(m.ctl, 0)->spill, 1u);
+    pt_add(t, x, y, delta, key);
+  }
+  __device__ __forceinline__ void birth(uint32_t other, bool right_side, uint32_t wi, uint64_t hloc) {
+    const uint4 e = log_entry(other, right_side, wi, hloc);
+    const unsigned int i = atomicAdd(&m.ctl->n_births, 1u);
+    if (i < CL_BIRTH_STAGE) m.births[i] = e;
+    else log_append(lg, e);
+  }
+};
+
+__device__ __forceinline__ void cluster_barrier(cg::cluster_group &cluster) { cluster.sync(); }
+
+// LOCAL merge, phase 2 of one CTA: apply this CTA's pairs to the device frequency table and stage the records
+__device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const EmitMode &em, const PairTableDev &t, bool spill,
+                                                  unsigned long long &cx, unsigned long long &cs, unsigned int &inserted,
+                                                  Rec *__restrict__ out, size_t out_cap, cg::cluster_group &cluster, int32_t new_id) {
+  // pass 1: which slots are occupied
+  for (int sl = threadIdx.x; sl < CL_HT_SLOTS; sl += CL_THREADS)
+    if (m.keys[sl] != PT_EMPTY) m.occ[atomicAdd(&m.ctl->n_occ, 1u)] = (unsigned short)sl;
+  __syncthreads();
+  const unsigned int n_occ = m.ctl->n_occ;
+  ClusterCtl *c0 = cluster.map_shared_rank(m.ctl, 0);
+  for (unsigned int i = threadIdx.x; i < n_occ; i += CL_THREADS) {
+    const int sl = m.occ[i];
+    const unsigned long long k = m.keys[sl];
+    const long long d = (long long)m.val[sl];
+    const unsigned long long mk = m.mk[sl];
+    m.keys[sl] = PT_EMPTY; m.val[sl] = 0; m.mk[sl] = ~0ull;
+    if (spill) {  // some delta of this merge went to the global table: everything follows it there
+      pt_add(t, (int32_t)(k >> 32), (int32_t)(k & 0xFFFFFFFFu), d, mk);
+      continue;
+    }
+    if (k == em.merged_key) continue;  // reference bpe.cpp:494-496
+    uint32_t g = gt_home(em.g, k);
+    unsigned long long old;
+    if ((int32_t)(k >> 32) == new_id || (int32_t)(k & 0xFFFFFFFFu) == new_id) {
+      // a pair around the token this merge creates cannot be in the table yet: claim its slot straight away
+      const unsigned int before = inserted;
+      g = gt_upsert(em.g, k, em.stamp_base | delta_bucket(em, k), ~mk, inserted);
+      old = inserted != before ? 0ull : em.g.slots[g].freq;
+    } else {
+      const ulonglong2 gs = __ldcg(reinterpret_cast<const ulonglong2 *>(em.g.slots + g));
+      if (gs.x == k) old = gs.y;
+      else {
+        g = gt_upsert(em.g, k, em.stamp_base | delta_bucket(em, k), ~mk, inserted);
+        old = em.g.slots[g].freq;
+      }
+    }
+    unsigned long long nw;
+    if (d < 0) { const unsigned long long ad = (unsigned long long)(-d); nw = old >= ad ? old - ad : 0ull; }  // bpe.cpp:500-509
+    else nw = old + (unsigned long long)d;
+    em.g.slots[g].freq = nw;
+    if (old >= em.min_freq || nw >= em.min_freq) {
+      const unsigned int j = atomicAdd(&m.ctl->n_recs, 1u);
+      if (j < CL_REC_STAGE) rec_out(m.recs, CL_REC_STAGE, j, k, (long long)nw, mk, cx, cs);
+      else rec_out(out, out_cap, atomicAdd(&c0->n_recs_total, 1u), k, (long long)nw, mk, cx, cs);  // past the stage: straight to its final place
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CL_THREADS, 1)
+merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *removed_total, Rec *__restrict__ out, size_t out_cap,
+              unsigned long long *__restrict__ out_hdr, unsigned long long seq_base, unsigned long long op_base,
+              volatile HostCmd2 *hcmd, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace) {
+  extern __shared__ __align__(16) unsigned char cl_dyn_smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const ClusterSmem m = cluster_smem(cl_dyn_smem);
+  __shared__ bool is_last;
+  const unsigned int crank = cluster.block_rank();
+  const bool leader = blockIdx.x < CL_SIZE;  // cluster 0
+  const int lane = threadIdx.x & 31;
+  const uint32_t log_m_base = em.log.m_cur;
+
+  for (int sl = threadIdx.x; sl < CL_HT_SLOTS; sl += CL_THREADS) { m.keys[sl] = PT_EMPTY; m.val[sl] = 0; m.mk[sl] = ~0ull; }
+  if (threadIdx.x == 0) memset(m.ctl, 0, sizeof(ClusterCtl));
+  __syncthreads();
+  cluster_barrier(cluster);
+
+  unsigned long long grid_epoch = 0;  // GRID merges seen so far
+  long long tr_poll = 0, tr_p1 = 0, tr_p2 = 0, tr_pub = 0;
+  for (unsigned long long k = 0;; k++) {
+    // ---------------------------------------------------------------- next command
+    if (leader) {
+      if (crank == 0 && threadIdx.x == 0) {
+        const long long c0 = clock64();
+        const unsigned long long want = seq_base + k + 1;
+        const unsigned long long t0 = gtime_ns();
+        unsigned long long pair = 0, nio = 3ull << 32, lr = ~0ull;
+        for (unsigned long long spin = 0;; spin++) {
+          const unsigned long long sq = hcmd->seq, p = hcmd->pair, n = hcmd->new_id_op, l = hcmd->log_range, ck = hcmd->check;
+          if (sq == want && ck == cmd2_check(want, p, n, l)) { pair = p; nio = n; lr = l; break; }
+          if ((spin & 63) == 63 && gtime_ns() - t0 > timeout_ns) break;  // abort: the host went away
+        }
+        const unsigned int stop = (unsigned int)(nio >> 32);
+        const unsigned int mode = (lr == ~0ull || (unsigned int)(lr & 0xFFFFFFFFu) > CL_LOCAL_MAX) ? 1u : 0u;
+        for (unsigned int r = 0; r < CL_SIZE; r++) {
+          ClusterCtl *c = cluster.map_shared_rank(m.ctl, r);
+          c->pair = pair; c->new_id_op = nio; c->log_range = lr; c->k = k; c->mode = mode; c->stop = stop;
+        }
+        if (stop || mode == 1u) {  // the other clusters take part (or leave)
+          dcmd->pair = pair; dcmd->new_id_op = nio; dcmd->log_range = lr; dcmd->k = k;
+          __threadfence();
+          *(volatile unsigned long long *)&dcmd->epoch = grid_epoch + 1;
+        }
+        *(volatile unsigned long long *)&dcmd->alive_ns = gtime_ns();
+        tr_poll += clock64() - c0;
+      }
+      cluster_barrier(cluster);  // (release/acquire: the command is visible in every CTA of the leader cluster)
+    } else {
+      if (threadIdx.x == 0) {
+        unsigned long long pair = 0, nio = 3ull << 32, lr = ~0ull, kk = 0;
+        for (unsigned long long spin = 0;; spin++) {
+          if (*(volatile unsigned long long *)&dcmd->epoch > grid_epoch) {
+            __threadfence();
+            pair = *(volatile unsigned long long *)&dcmd->pair; nio = *(volatile unsigned long long *)&dcmd->new_id_op;
+            lr = *(volatile unsigned long long *)&dcmd->log_range; kk = *(volatile unsigned long long *)&dcmd->k;
+            break;
+          }
+          if ((spin & 255) == 255 && gtime_ns() - *(volatile unsigned long long *)&dcmd->alive_ns > 4 * timeout_ns) break;  // leader gone
+        }
+        m.ctl->pair = pair; m.ctl->new_id_op = nio; m.ctl->log_range = lr; m.ctl->k = kk; m.ctl->mode = 1u; m.ctl->stop = (unsigned int)(nio >> 32);
+      }
+      __syncthreads();
+    }
+    if (m.ctl->stop) return;
+    const unsigned long long pairk = m.ctl->pair;
+    const int32_t a = (int32_t)(pairk >> 32), b = (int32_t)(pairk & 0xFFFFFFFFu), new_id = (int32_t)(m.ctl->new_id_op & 0xFFFFFFFFu);
+    const unsigned int mode = m.ctl->mode;
+    em.log.m_cur = (uint32_t)(new_id - 256);  // (== log_m_base + merges done; the host only sends consistent ids while the log is on)
+    em.merged_key = pairk;
+    const unsigned long long mk_ = m.ctl->k;  // (the other clusters only iterate on GRID merges: their own counter lags)
+    em.stamp_base = (op_base + mk_) << 10;
+    const unsigned long long seq = seq_base + mk_ + 1;
+
+    if (mode == 1u) {
+      // ---------------------------------------------------------------- GRID: all clusters, global pair table
+      grid_epoch++;
+      uint32_t removed = scan_merge(s, t, em.log, a, b, new_id, m.rows, m.ml, m.n_match);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) removed += __shfl_down_sync(0xffffffffu, removed, d);
+      if (lane == 0 && removed) atomicAdd(removed_total, (unsigned long long)removed);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
+      }
+      __syncthreads();
+      if (is_last) {
+        __threadfence();
+        TailSmem ts{m.tail_stage, m.csum, m.tail_count};
+        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u, nullptr, nullptr);
+      }
+      __syncthreads();
+      // the scratch aliased the delta table: empty it again
+      for (int sl = threadIdx.x; sl < CL_HT_SLOTS; sl += CL_THREADS) { m.keys[sl] = PT_EMPTY; m.val[sl] = 0; m.mk[sl] = ~0ull; }
+      __syncthreads();
+      continue;
+    }
+
+    // ---------------------------------------------------------------- LOCAL: the leader cluster alone
+    const long long c1 = clock64();
+    {
+      const unsigned long long lr = m.ctl->log_range;
+      const uint64_t lo = lr >> 32, n = lr & 0xFFFFFFFFu;
+      uint32_t merge = 0, other = 0, side = 0;
+      const bool have_log = log_lookup(em.log, a, b, merge, other, side);  // (true: the host sent a log range)
+      ClusterSink sink{cluster, m, t, em.log};
+      uint32_t removed = 0;
+      // this thread's log entries are requested together (one round trip), then the matching words are rewritten
+      constexpr int PER_THREAD = (int)(CL_LOCAL_MAX / (CL_SIZE * CL_THREADS));
+      uint4 ev[PER_THREAD];
+#pragma unroll
+      for (int u = 0; u < PER_THREAD; u++) {
+        const uint64_t i = (uint64_t)u * (CL_SIZE * CL_THREADS) + crank * CL_THREADS + threadIdx.x;
+        ev[u] = (have_log && i < n) ? __ldcg(&em.log.ent[lo + i]) : make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+      }
+      long long cA = 0;
+      if (trace && crank == 0 && threadIdx.x == 0) { unsigned int acc = 0;
+#pragma unroll
+        for (int u = 0; u < PER_THREAD; u++) acc += ev[u].x;
+        if (acc == 0x12345u) trace[15] = 1;  // (forces the loads to complete here)
+        cA = clock64(); trace[8] += (unsigned long long)(cA - c1); }
+#pragma unroll
+      for (int u = 0; u < PER_THREAD; u++) {
+        const uint4 e = ev[u];
+        if (have_log && e.x == other && (e.y & 0x80000000u) == side && (uint64_t)u * (CL_SIZE * CL_THREADS) + crank * CL_THREADS + threadIdx.x < n)
+          removed += merge_one_word(s, ((uint64_t)e.w << 32) | e.z, e.y & 0x7FFFFFFFu, a, b, new_id, sink);
+      }
+      if (trace && crank == 0 && threadIdx.x == 0) trace[9] += (unsigned long long)(clock64() - cA);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) removed += __shfl_down_sync(0xffffffffu, removed, d);
+      if (lane == 0 && removed) atomicAdd(&cluster.map_shared_rank(m.ctl, 0)->removed, removed);
+      if (trace && crank == 0 && threadIdx.x == 0) { trace[5] += (unsigned long long)(clock64() - c1); trace[6] += n; }
+    }
+    __syncthreads();
+    if (trace && crank == 0 && threadIdx.x == 0) trace[7] += (unsigned long long)(clock64() - c1);
+    cluster_barrier(cluster);  // every delta of this merge is in the distributed table
+    const long long c2 = clock64();
+    {
+      ClusterCtl *c0 = cluster.map_shared_rank(m.ctl, 0);
+      const bool spill = c0->spill != 0;
+      unsigned long long cx = 0, cs = 0;
+      unsigned int inserted = 0;
+      if (threadIdx.x == 64) {  // this CTA's range in the birth log: requested now, needed after the records are staged
+        const unsigned int nb = min(m.ctl->n_births, (unsigned int)CL_BIRTH_STAGE);
+        m.ctl->birth_base = nb ? atomicAdd(em.log.cursor, nb) : 0u;
+      }
+      cluster_emit_part(m, em, t, spill, cx, cs, inserted, out, out_cap, cluster, new_id);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, d);
+      if (lane == 0) gt_account(em.g, inserted);
+      __syncthreads();
+      if (threadIdx.x == 0) {  // this CTA's ranges in the record buffer and in the birth log
+        const unsigned int nr = min(m.ctl->n_recs, (unsigned int)CL_REC_STAGE);
+        m.ctl->rec_base = nr ? atomicAdd(&c0->n_recs_total, nr) : 0u;
+      }
+      __syncthreads();
+      {
+        const unsigned int nr = min(m.ctl->n_recs, (unsigned int)CL_REC_STAGE), base = m.ctl->rec_base;
+        const uint4 *src = reinterpret_cast<const uint4 *>(m.recs);
+        for (unsigned int i = threadIdx.x; i < 2u * nr; i += CL_THREADS) {
+          const size_t r = (size_t)base + (i >> 1);
+          if (r < out_cap) reinterpret_cast<uint4 *>(out)[2 * r + (i & 1)] = src[i];
+        }
+        const unsigned int nb = min(m.ctl->n_births, (unsigned int)CL_BIRTH_STAGE), bbase = m.ctl->birth_base;
+        for (unsigned int i = threadIdx.x; i < nb; i += CL_THREADS) {
+          if (bbase + i < em.log.cap) em.log.ent[bbase + i] = m.births[i];
+          else atomicOr(em.log.flags, 1u);
+        }
+      }
+      block_checksum(cx, cs, m.csum);
+      if (threadIdx.x == 0) {
+        c0->part_cx[crank] = cx; c0->part_cs[crank] = cs;
+        m.ctl->n_births = 0; m.ctl->n_recs = 0; m.ctl->n_occ = 0;
+      }
+      if (crank == 0 && threadIdx.x == 32 && !spill) {  // the merged pair's frequency becomes 0 (bpe.cpp:523)
+        unsigned int ins = 0;
+        em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;
+        gt_account(em.g, ins);
+      }
+    }
+    cluster_barrier(cluster);  // all records, checksums and log entries of this merge are out
+    const long long c3 = clock64();
+    if (crank == 0) {
+      ClusterCtl *c = m.ctl;
+      if (c->spill) {  // rare: the merge did not fit the distributed table; CTA 0 finishes it from the global one
+        if (threadIdx.x == 0 && c->removed) atomicAdd(removed_total, (unsigned long long)c->removed);
+        __threadfence();
+        __syncthreads();
+        TailSmem ts{m.tail_stage, m.csum, m.tail_count};
+        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u, nullptr, nullptr);
+        __syncthreads();
+        for (int sl = threadIdx.x; sl < CL_HT_SLOTS; sl += CL_THREADS) { m.keys[sl] = PT_EMPTY; m.val[sl] = 0; m.mk[sl] = ~0ull; }
+        if (threadIdx.x == 0) { c->spill = 0; c->n_recs_total = 0; c->removed = 0; }
+        __syncthreads();
+      } else if (threadIdx.x == 0) {
+        const unsigned int n = c->n_recs_total;
+        unsigned long long flags = (n > out_cap ? 4u : 0u) | (__ldcg(em.g.flags) ? 16u : 0u);
+        const unsigned int cur = __ldcg(em.log.cursor);
+        em.log.start[em.log.m_cur + 1] = cur;
+        if (__ldcg(em.log.flags)) flags |= 32u;
+        flags |= (unsigned long long)cur << 32;  // the host keeps the log ranges
+        unsigned long long x = 0, sm = 0;
+#pragma unroll
+        for (int r = 0; r < CL_SIZE; r++) { x ^= c->part_cx[r]; sm += c->part_cs[r]; }
+        volatile unsigned long long *h = out_hdr;
+        h[1] = n; h[2] = flags; h[3] = c->removed; h[4] = x; h[5] = sm;
+        h[6] = hdr_check(seq, n, flags, c->removed, x, sm);
+        h[0] = seq; h[7] = seq;
+        c->n_recs_total = 0; c->removed = 0;
+        if (trace) {
+          trace[0] += 1; trace[1] += (unsigned long long)(c2 - c1); trace[2] += (unsigned long long)(c3 - c2);
+          trace[3] += (unsigned long long)(clock64() - c3); trace[4] += (unsigned long long)tr_poll; tr_poll = 0;
+        }
+      }
+    }
+    (void)tr_p1; (void)tr_p2; (void)tr_pub; (void)log_m_base;
+  }
+}
+
+}  // namespace swb

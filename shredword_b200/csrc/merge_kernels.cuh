@@ -247,7 +247,7 @@ constexpr unsigned long long HDR_MAGIC = 0x9E3779B97F4A7C15ull;
 __host__ __device__ __forceinline__ unsigned long long hdr_check(unsigned long long seq, unsigned long long n,
                                                                  unsigned long long flags, unsigned long long removed,
                                                                  unsigned long long x, unsigned long long sm) {
-  return (seq * HDR_MAGIC) ^ (n + 0x1234567ull) ^ (flags << 48) ^ (removed * 31ull) ^ x ^ (sm << 1 | sm >> 63);
+  return (seq * HDR_MAGIC) ^ (n + 0x1234567ull) ^ (flags << 48) ^ ((flags >> 32) * 0x9E3779B1ull) ^ (removed * 31ull) ^ x ^ (sm << 1 | sm >> 63);
 }
 
 // `out` may be a shared-memory stage of `stage_cap` records backed by `direct` (the final destination):
@@ -329,9 +329,11 @@ __device__ __forceinline__ void pt_publish(const PairTableDev &t, unsigned int n
                                            const BirthLogDev *lg = nullptr, bool keep_state = false) {
   unsigned long long flags = __ldcg(t.flags) | (n > out_cap ? 4u : 0u) | extra_flags;
   const unsigned long long rem = removed ? __ldcg(removed) : 0ull;
-  if (lg && lg->ent) {  // this merge's birth log ends here
-    lg->start[lg->m_cur + 1] = __ldcg(lg->cursor);
+  if (lg && lg->ent) {  // this merge's birth log ends here; the host keeps the ranges too (high half of the flags word)
+    const unsigned int cur = __ldcg(lg->cursor);
+    lg->start[lg->m_cur + 1] = cur;
     if (__ldcg(lg->flags)) flags |= 32u;
+    flags |= (unsigned long long)cur << 32;
   }
   out_hdr[1] = n; out_hdr[2] = flags; out_hdr[3] = rem; out_hdr[4] = cx; out_hdr[5] = cs;
   out_hdr[6] = hdr_check(seq, n, flags, rem, cx, cs);
@@ -699,15 +701,32 @@ __device__ __forceinline__ uint32_t merge_one_word(const StreamDev &s, uint64_t 
   const unsigned long long c = __ldg(&s.cnt[wi]);  // in flight while the symbols arrive
   int buf[ROW];
   int n = 0;
-  {  // symbols hpos+1 .. end of word, 16 bytes at a time
+  {  // symbols hpos+1 .. end of word, 16 bytes at a time; the first three chunks (most words end there) are
+     // requested together, so that a typical word costs ONE memory round trip
+    const int4 *rowv = reinterpret_cast<const int4 *>(flat + row_base);
+    const int q0 = (hpos + 1) >> 2;
+    const int4 pad4 = make_int4(PAD, PAD, PAD, PAD);
+    int4 pre[3];
+#pragma unroll
+    for (int u = 0; u < 3; u++) pre[u] = q0 + u < ROW / 4 ? __ldcg(rowv + q0 + u) : pad4;
     bool open = true;
-    for (int q = (hpos + 1) >> 2; q < ROW / 4 && open; q++) {
-      const int4 v = __ldcg(reinterpret_cast<const int4 *>(flat + row_base) + q);
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      const int x[4] = {pre[u].x, pre[u].y, pre[u].z, pre[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int p = 4 * (q0 + u) + k;
+        if (p <= hpos || !open) continue;
+        if (x[k] < 0) { open = false; continue; }
+        buf[n++] = x[k];
+      }
+    }
+    for (int q = q0 + 3; q < ROW / 4 && open; q++) {
+      const int4 v = __ldcg(rowv + q);
       const int x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const int p = 4 * q + k;
-        if (p <= hpos || !open) continue;
+        if (!open) continue;
         if (x[k] < 0) { open = false; continue; }
         buf[n++] = x[k];
       }

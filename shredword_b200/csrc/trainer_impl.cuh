@@ -22,6 +22,7 @@
 #include "device_util.cuh"
 #include "host_core.hpp"
 #include "merge_kernels.cuh"
+#include "cluster_kernel.cuh"
 #include "nccl_dyn.hpp"
 #include "word_table.cuh"
 
@@ -443,6 +444,7 @@ class TrainerImpl {
   void setup_birth_log() {
     static const bool off = getenv("SWB_NO_BIRTH_LOG") && atoi(getenv("SWB_NO_BIRTH_LOG")) > 0;
     log_ok_ = false; stream_merges_ = 0; log_cap_ = 0;
+    log_start_h_.assign(1, 0u);
     if (off || !n_rows_) return;
     const uint64_t cap = 2 * live_symbols_ + 64;
     if (cap >= (1ull << 31)) return;  // (entries are indexed with 32 bits; such a table falls back to the signature scan)
@@ -463,6 +465,17 @@ class TrainerImpl {
     sync();
     log_start_ = std::move(ns);
     log_merge_cap_ = cap;
+  }
+  void merge_done_on_stream(unsigned long long hdr_flags) {
+    stream_merges_++;
+    if (log_ok_) log_start_h_.push_back((uint32_t)(hdr_flags >> 32));
+  }
+  // lo << 32 | n of the log that holds the births of (a, b) (device ids), ~0 when the pair has none
+  unsigned long long log_range_of(int32_t da, int32_t db) const {
+    const int32_t newer = da > db ? da : db;
+    if (!log_ok_ || newer < 256 || (uint32_t)(newer - 256) >= stream_merges_ || (size_t)(newer - 256) + 1 >= log_start_h_.size()) return ~0ull;
+    const uint32_t lo = log_start_h_[newer - 256], hi = log_start_h_[newer - 256 + 1];
+    return ((unsigned long long)lo << 32) | (unsigned long long)(hi - lo);
   }
   // the log as the next merge (which creates new_id) sees it; tokens must be numbered 256 + merges done on this stream
   BirthLogDev birth_log(int32_t new_id, uint32_t merges_ahead) {
@@ -607,7 +620,22 @@ class TrainerImpl {
     auto check_stream = [&]() {
       if ((++spin & 0x3FFF) != 0) return;
       cudaError_t e = cudaStreamQuery(stream_);
-      if (e == cudaSuccess) { if (++idle_polls_ > 64) throw Error("merge kernels finished without publishing a valid result"); }
+      if (e == cudaSuccess) {
+        if (++idle_polls_ > 64) {
+          char msg[512];
+          const unsigned long long n = h[1], fl = h[2], rem = h[3], cx = h[4], cs = h[5];
+          unsigned long long x = 0, sm = 0;
+          const volatile long long *r = reinterpret_cast<const volatile long long *>(recs);
+          for (size_t i = 0; i < (size_t)std::min<unsigned long long>(n, recs_cap); i++) {
+            const unsigned long long a = (unsigned long long)r[4 * i], b = (unsigned long long)r[4 * i + 1], c = (unsigned long long)r[4 * i + 2], d = (unsigned long long)r[4 * i + 3];
+            x ^= a ^ b ^ c ^ d; sm += a + 3ull * b + 5ull * c + 7ull * d;
+          }
+          snprintf(msg, sizeof msg, "merge kernels finished without publishing a valid result (want seq %llu; header seq %llu/%llu n %llu flags %llx removed %llu; "
+                   "header check %s; records xor %llx vs %llx, sum %llx vs %llx)", seq, (unsigned long long)h[0], (unsigned long long)h[7], n, fl, rem,
+                   h[6] == hdr_check(h[0], n, fl, rem, cx, cs) ? "ok" : "BAD", x, cx, sm, cs);
+          throw Error(msg);
+        }
+      }
       else if (e != cudaErrorNotReady) SWB_CUDA(e);
     };
     idle_polls_ = 0;
@@ -881,7 +909,7 @@ class TrainerImpl {
     if (flags & 16u) gt_flagged_ = true;
     if (flags & 5u) throw Error("pair table overflow during a merge (internal sizing error)");
     if (flags & 32u) throw Error("birth log overflow (internal sizing error)");
-    stream_merges_++;
+    merge_done_on_stream(hdr_.host()[2]);
     if (timing) {
       float ms = 0;
       SWB_CUDA(cudaEventSynchronize(ev1_));
@@ -1077,7 +1105,7 @@ class TrainerImpl {
       stats.host_apply_ms += now_ms() - ta0;
       stats.live_symbols = live_symbols_;
       if ((flags & 32u)) throw Error("birth log overflow (internal sizing error)");
-      stream_merges_++;
+      merge_done_on_stream((flags & 8u) ? hdr_.host()[2] : flags);
       consumed++;
       if (consumed == max_merges) break;
     }
@@ -1163,7 +1191,7 @@ class TrainerImpl {
       if (flags & 32u) throw Error("birth log overflow (internal sizing error)");
       if (flags & 16u) gt_flagged_ = true;
       op_index_++;
-      stream_merges_++;
+      merge_done_on_stream(hdr_.host()[2]);
       seq_ = seq_base + done + 1;
       stats.merge_scan_bytes += n_rows_ * ROW * 4;
       stats.merge_alg_bytes += 4 * live_symbols_ + 8 * W;
@@ -1195,9 +1223,158 @@ class TrainerImpl {
     return done;
   }
 
+  // ---------------------------------------------------------------- resident cluster kernel (default single-GPU path)
+  struct ClusterFacts { int clusters = 0; bool ok = false, cooperative = false; };
+  static const ClusterFacts &cluster_facts(int device) {
+    static std::mutex mu;
+    static std::map<int, ClusterFacts> facts;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = facts.find(device);
+    if (it != facts.end()) return it->second;
+    ClusterFacts f;
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (cudaFuncSetAttribute(merge_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM_BYTES) == cudaSuccess) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3(CL_SIZE * 64); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, merge_cluster, &cfg) == cudaSuccess && n >= 1) { f.clusters = n; f.ok = true; f.cooperative = coop != 0; }
+    }
+    cudaGetLastError();
+    if (getenv("SWB_TRACE_INIT")) fprintf(stderr, "[trace] cluster kernel: %d resident clusters of %d CTAs, %zu bytes of shared memory each\n", f.clusters, CL_SIZE, CL_SMEM_BYTES);
+    return facts.emplace(device, f).first->second;
+  }
+  bool use_resident() const {
+    static const bool off = getenv("SWB_NO_CLUSTER") && atoi(getenv("SWB_NO_CLUSTER")) > 0;
+    return !off && use_persistent() && cluster_facts(device_).ok;
+  }
+  struct HostCmd2Sender {  // makes sure the resident kernel is always told to stop, also when an exception unwinds
+    volatile HostCmd2 *c = nullptr;
+    unsigned long long next_seq = 0;
+    bool running = false;
+    void send(unsigned long long pair, unsigned long long nio, unsigned long long lr) {
+      c->pair = pair; c->new_id_op = nio; c->log_range = lr; c->check = cmd2_check(next_seq, pair, nio, lr);
+      __atomic_thread_fence(__ATOMIC_RELEASE);
+      c->seq = next_seq;
+      __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    }
+    ~HostCmd2Sender() { if (running) send(0, 1ull << 32, ~0ull); }
+  };
+  // Runs up to max_merges merges starting with (a, b) (already popped, pending in `core`) inside ONE launch of
+  // merge_cluster. Returns the number performed; stops early when the heap is exhausted or a table has to grow.
+  int run_resident(int32_t a, int32_t b, int32_t new_id, int max_merges) {
+    ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
+    maybe_grow_global_table(gt_flagged_);
+    gt_flagged_ = false;
+    if (!hcmd2_.size()) { hcmd2_.alloc(1); dcmd2_.alloc(1); }
+    memset((void *)hcmd2_.host(), 0, sizeof(HostCmd2));
+    SWB_CUDA(cudaMemsetAsync(dcmd2_.get(), 0, sizeof(DevCmd2), stream_));
+    const int32_t unk = tr_->config.unk_id;
+    EmitMode em = emit_mode(1, 0, 0);
+    em.log = birth_log(new_id, (uint32_t)max_merges + 1);
+    em.fused_max = 0xFFFFFFFFu;  // the resident kernel's tails take every merge, whatever its size
+    pt_.canon_on = unk < 0 ? 1 : 0;
+    pt_.canon_first = unk == -1 ? UNK_CODE : NEG1_CODE;
+    pt_.gpf.slots = (void *)gt_.slots; pt_.gpf.mask = gt_.mask;
+    StreamDev s = stream_dev();
+    const ClusterFacts &cf = cluster_facts(device_);
+    const unsigned long long seq_base = seq_, op_base = op_index_ + 1;
+    unsigned long long *removed_p = removed_.get();
+    Rec *out = recs_.dev();
+    size_t out_cap = recs_.size();
+    unsigned long long *out_hdr = hdr_.dev();
+    volatile HostCmd2 *hc = hcmd2_.dev();
+    DevCmd2 *dc = dcmd2_.get();
+    unsigned long long timeout_ns = 2000000000ull;
+    unsigned long long *trace_p = nullptr;
+    if (trace_wait_) {
+      if (!ptrace_.size()) { ptrace_.alloc(16); SWB_CUDA(cudaMemsetAsync(ptrace_.get(), 0, ptrace_.bytes(), stream_)); }
+      trace_p = ptrace_.get();
+    }
+    HostCmd2Sender sender;
+    sender.c = hcmd2_.host();
+    sender.next_seq = seq_base + 1;  // the first merge travels through the mailbox like all the others
+    int32_t da = to_dev(a), db = to_dev(b);
+    sender.send(((unsigned long long)(uint32_t)da << 32) | (uint32_t)db, (unsigned long long)(uint32_t)new_id, log_range_of(da, db));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(cf.clusters * CL_SIZE)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES; cfg.stream = stream_;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = cf.cooperative ? 2 : 1;
+    SWB_CUDA(cudaLaunchKernelEx(&cfg, merge_cluster, s, pt_, em, removed_p, out, out_cap, out_hdr, seq_base, op_base, hc, dc, timeout_ns, trace_p));
+    SWB_CUDA(cudaGetLastError());
+    launched(); stats.merge_launches++;
+    sender.running = true;
+    int done = 0;
+    for (;;) {
+      const double tw0 = now_ms();
+      wait_seq_at(seq_base + done + 1, hdr_.host(), recs_.host(), recs_.size());
+      const double tw1 = now_ms();
+      stats.host_wait_ms += tw1 - tw0;
+      const size_t n = (size_t)hdr_.host()[1];
+      const unsigned long long hflags = hdr_.host()[2];
+      const unsigned int flags = (unsigned int)hflags;
+      const uint64_t removed = hdr_.host()[3];
+      if (flags & 5u) throw Error("pair table overflow during a merge (internal sizing error)");
+      if (flags & 32u) throw Error("birth log overflow (internal sizing error)");
+      if (flags & 16u) gt_flagged_ = true;
+      op_index_++;
+      merge_done_on_stream(hflags);
+      seq_ = seq_base + done + 1;
+      stats.merge_scan_bytes += n_rows_ * ROW * 4;
+      stats.merge_alg_bytes += 4 * live_symbols_ + 8 * W;
+      live_symbols_ -= removed;
+      stats.live_symbols = live_symbols_;
+      translate_out(recs_.host(), n);
+      core.apply_absolute(recs_.host(), n);
+      const double ta1 = now_ms();
+      stats.host_apply_ms += ta1 - tw1;
+      done++;
+      bool go = done < max_merges && !gt_flagged_;
+      int32_t na = 0, nb = 0, nn = 0;
+      if (go) { go = core.next_merge(&na, &nb, &nn); stats.host_pop_ms += now_ms() - ta1; }
+      sender.next_seq = seq_base + done + 1;
+      if (!go) { sender.send(0, 1ull << 32, ~0ull); sender.running = false; break; }
+      da = to_dev(na); db = to_dev(nb);
+      sender.send(((unsigned long long)(uint32_t)da << 32) | (uint32_t)db, (unsigned long long)(uint32_t)nn, log_range_of(da, db));
+    }
+    sync();
+    if (trace_p) {
+      unsigned long long h[16];
+      SWB_CUDA(cudaMemcpy(h, trace_p, sizeof h, cudaMemcpyDeviceToHost));
+      const double n = (double)std::max<unsigned long long>(h[0], 1), ghz = 1.965;
+      fprintf(stderr, "[trace] cluster kernel, per LOCAL merge (%llu of %d merges): words+deltas %.2f us, apply+records %.2f us, publish %.2f us, "
+              "waiting for the host %.2f us | words+deltas: thread 0 alone %.2f us, its CTA %.2f us; log entries %.0f\n", h[0], done, h[1] / n / ghz / 1e3, h[2] / n / ghz / 1e3, h[3] / n / ghz / 1e3, h[4] / n / ghz / 1e3,
+              h[5] / n / ghz / 1e3, h[7] / n / ghz / 1e3, h[6] / n);
+      fprintf(stderr, "[trace]   thread 0: entries arrived after %.2f us, own words %.2f us\n", h[8] / n / ghz / 1e3, h[9] / n / ghz / 1e3);
+    }
+    return done;
+  }
+
   int merge_batch(int batch) {  // reference bpe_merge_batch
     const double t0 = now_ms();
     int done = 0;
+    if (use_resident()) {
+      while (done < batch && !core.heap_empty()) {
+        int32_t a, b, nid;
+        const double tp0 = now_ms();
+        if (!core.next_merge(&a, &b, &nid)) break;
+        stats.host_pop_ms += now_ms() - tp0;
+        tables_fresh_ = false;
+        done += run_resident(a, b, nid, batch - done);
+      }
+      stats.merge_ms += now_ms() - t0;
+      return done;
+    }
     if (use_persistent()) {
       while (done < batch && !core.heap_empty()) {
         int32_t a, b, nid;
@@ -1330,6 +1507,7 @@ class TrainerImpl {
   DevBuf<unsigned int> log_scal_, log_start_;
   uint32_t log_cap_ = 0, log_merge_cap_ = 0, stream_merges_ = 0;
   bool log_ok_ = false;
+  std::vector<uint32_t> log_start_h_;  // host copy of the log ranges: [m] .. [m+1] = log of merge m (from the result headers)
   // pair table
   uint64_t pt_cap_ = 0;
   PairTableDev pt_{};
@@ -1342,6 +1520,8 @@ class TrainerImpl {
   int coop_blocks_per_sm_ = 0;
   PinnedBuf<HostCmd> hcmd_;
   DevBuf<DevCmd> dcmd_;
+  PinnedBuf<HostCmd2> hcmd2_;
+  DevBuf<DevCmd2> dcmd2_;
   DevBuf<unsigned long long> ptrace_;
   // device-resident loop
   DevBuf<LoopState> loop_state_;
