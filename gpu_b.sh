@@ -1,3 +1,10 @@
 cd $GRAFT_REPO_ROOT
-SWB_TRACE_WAIT=1 timeout 120 python scripts/profile_step.py config2_1GB 1 > gpurun_out/trace0.log 2>&1
-grep "trace\|rror" gpurun_out/trace0.log | tail -3 | cut -c1-500
+for nc in 0 1; do
+SWB_NO_CLUSTER=$nc SWB_TRACE_WAIT=1 timeout 60 python scripts/profile_step.py config2_1GB 2 > gpurun_out/trace$nc.log 2>&1
+grep "trace\] cluster\|trace\] resident" gpurun_out/trace$nc.log | tail -1 | cut -c1-330
+tail -1 gpurun_out/trace$nc.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); s=d['stats']
+print('no_cluster=$nc', 'merge', round(d['merge'],4), 'us/merge', round(d['us_per_merge'],2), {k:round(s[k],1) for k in ('host_pop_ms','host_wait_ms','host_apply_ms')})
+"
+done

@@ -28,19 +28,33 @@ namespace cg = cooperative_groups;
 constexpr int CL_THREADS = 512;
 constexpr int CL_WARPS = CL_THREADS / 32;
 constexpr int CL_SIZE = 8;                 // CTAs per cluster (portable maximum)
-constexpr int CL_HT_SLOTS = 4096;          // slots of the distributed delta table per CTA
+constexpr int CL_HT_SLOTS = 2048;          // slots per CTA of each delta table (T1: this CTA's partial sums, T2: the pairs this CTA owns)
+constexpr int CL_INBOX = 1024;             // partial sums a CTA can receive per merge
 constexpr int CL_BIRTH_STAGE = 1024;       // log entries staged per CTA and merge
 constexpr int CL_REC_STAGE = 512;          // records staged per CTA and merge
-constexpr unsigned int CL_LOCAL_MAX = CL_SIZE * CL_THREADS * 8;  // longest birth log the leader cluster takes alone
+constexpr unsigned int CL_LOCAL_MAX = CL_SIZE * CL_THREADS * 64;  // longest birth log the leader cluster takes alone (entries)
+constexpr int CL_CAND_CAP = 1024;          // candidate words listed per CTA and merge (more: rewritten where they are found)
 constexpr int CL_MAX_PROBES = 256;
 
-// host -> device command (mapped host memory). op (new_id_op >> 32): 0 = merge, 1 = stop
-struct HostCmd2 { unsigned long long seq, pair, new_id_op, log_range /* lo << 32 | n; ~0: no log */, check, pad[3]; };
+// host -> device command: ONE 16-byte word in mapped host memory, written with a single 16-byte store and read with a
+// single 16-byte load (one PCIe read per poll, no second trip for a payload):
+//   x, y = the pair (second, first);  z = new_id | op << 28 (op 0 = merge, 1 = stop);  w = seq (24 bits) << 8 | check (8 bits)
+struct __align__(16) HostCmd2 { unsigned int x, y, z, w; };
+__host__ __device__ __forceinline__ unsigned int cmd3_word(unsigned long long seq, unsigned int x, unsigned int y, unsigned int z) {
+  const unsigned int s24 = (unsigned int)seq & 0xFFFFFFu;
+  unsigned int f = x ^ (y * 0x9E3779B1u) ^ (z * 0x85EBCA6Bu) ^ (s24 * 0xC2B2AE35u);
+  f ^= f >> 16; f ^= f >> 8;
+  return (s24 << 8) | (f & 0xFFu);
+}
 // leader -> other clusters (device memory)
 struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, pad[2]; };
 __host__ __device__ __forceinline__ unsigned long long cmd2_check(unsigned long long seq, unsigned long long pair,
                                                                   unsigned long long nio, unsigned long long lr) {
   return (seq * HDR_MAGIC) ^ pair ^ (nio << 7 | nio >> 57) ^ (lr * 0xD6E8FEB86659FD93ull);
+}
+__host__ __device__ __forceinline__ unsigned long long cmd2_check(unsigned long long seq, unsigned long long pair, unsigned long long nio,
+                                                                  unsigned long long lr, unsigned long long cursor) {
+  return cmd2_check(seq, pair, nio, lr) ^ (cursor * 0xA24BAED4963EE407ull);
 }
 
 // per-CTA control block in shared memory
@@ -48,18 +62,23 @@ struct ClusterCtl {
   // the command, written into every CTA of the leader cluster by its CTA 0
   unsigned long long pair, new_id_op, log_range, k;
   unsigned int mode, stop;             // mode 0 = LOCAL, 1 = GRID
+  unsigned int log_cursor, births_total;  // CTA 0: log entries before this merge (from the host) / appended by this merge so far
   // per CTA, per merge
-  unsigned int n_births, n_recs, n_occ, rec_base, birth_base, pad0;
+  unsigned int n_births, n_recs, n_occ, rec_base, birth_base, n_cand, n_occ1, inbox_n, n_ovf, pad1;
   // cluster-wide, live in CTA 0 only
   unsigned int spill, n_recs_total, removed, inserted;
   unsigned long long part_cx[CL_SIZE], part_cs[CL_SIZE];  // per-CTA record checksums (plain remote stores; combined by CTA 0)
 };
 
 struct ClusterSmem {
-  unsigned long long *keys, *val, *mk;   // distributed delta table (this CTA's part)
+  unsigned long long *keys, *val, *mk;   // T2: the pairs this CTA owns (owner = pair hash), filled from the inbox
+  unsigned long long *k1, *v1, *m1;      // T1: partial sums of the deltas produced by this CTA's own threads
+  uint4 *inbox;                          // 2 x uint4 per message: {key, val}, {min key, -}
+  unsigned short *occ1;
   uint4 *births;
   Rec *recs;
   unsigned short *occ;                   // occupied slots of this CTA's part
+  uint4 *cand;                           // candidate words of this CTA: {word index, header location lo, hi, -}
   ClusterCtl *ctl;
   unsigned long long *csum;              // [64] scratch of block_checksum
   // GRID mode scratch (aliases the delta table, which is empty then)
@@ -69,10 +88,10 @@ struct ClusterSmem {
   Rec *tail_stage;
   unsigned int *tail_count;
 };
-constexpr size_t CL_SMEM_TABLE = (size_t)CL_HT_SLOTS * 24;
+constexpr size_t CL_SMEM_TABLE = (size_t)CL_HT_SLOTS * 24 * 2;
 constexpr size_t CL_SMEM_GRID = (size_t)CL_WARPS * ROW * 4 + (size_t)CL_WARPS * MATCH_CAP * sizeof(Match) + CL_WARPS * 4 + STAGE_RECS * sizeof(Rec) + 16;
 static_assert(CL_SMEM_GRID <= CL_SMEM_TABLE, "GRID-mode scratch must fit into the delta table's shared memory");
-constexpr size_t CL_SMEM_BYTES = CL_SMEM_TABLE + (size_t)CL_BIRTH_STAGE * 16 + (size_t)CL_REC_STAGE * sizeof(Rec) + CL_HT_SLOTS * 2 +
+constexpr size_t CL_SMEM_BYTES = CL_SMEM_TABLE + (size_t)CL_BIRTH_STAGE * 16 + (size_t)CL_REC_STAGE * sizeof(Rec) + CL_HT_SLOTS * 4 + (size_t)CL_CAND_CAP * 16 + (size_t)CL_INBOX * 32 +
                                  sizeof(ClusterCtl) + 64 * 8 + 64;
 
 __device__ __forceinline__ ClusterSmem cluster_smem(unsigned char *base) {
@@ -81,6 +100,9 @@ __device__ __forceinline__ ClusterSmem cluster_smem(unsigned char *base) {
   m.keys = reinterpret_cast<unsigned long long *>(p);
   m.val = m.keys + CL_HT_SLOTS;
   m.mk = m.val + CL_HT_SLOTS;
+  m.k1 = m.mk + CL_HT_SLOTS;
+  m.v1 = m.k1 + CL_HT_SLOTS;
+  m.m1 = m.v1 + CL_HT_SLOTS;
   {  // GRID-mode view of the same bytes
     unsigned char *q = base;
     m.rows = reinterpret_cast<int (*)[ROW]>(q); q += (size_t)CL_WARPS * ROW * 4;
@@ -92,69 +114,141 @@ __device__ __forceinline__ ClusterSmem cluster_smem(unsigned char *base) {
   p += CL_SMEM_TABLE;
   m.births = reinterpret_cast<uint4 *>(p); p += (size_t)CL_BIRTH_STAGE * 16;
   m.recs = reinterpret_cast<Rec *>(p); p += (size_t)CL_REC_STAGE * sizeof(Rec);
+  m.cand = reinterpret_cast<uint4 *>(p); p += (size_t)CL_CAND_CAP * 16;
+  m.inbox = reinterpret_cast<uint4 *>(p); p += (size_t)CL_INBOX * 32;
   m.csum = reinterpret_cast<unsigned long long *>(p); p += 64 * 8;
   m.ctl = reinterpret_cast<ClusterCtl *>(p); p += sizeof(ClusterCtl);
-  m.occ = reinterpret_cast<unsigned short *>(p);
+  m.occ = reinterpret_cast<unsigned short *>(p); p += CL_HT_SLOTS * 2;
+  m.occ1 = reinterpret_cast<unsigned short *>(p);
   return m;
 }
 
-// deltas -> the cluster's distributed shared-memory table, births -> this CTA's stage
+// (key, delta, first-touch key) -> a table in THIS CTA's shared memory. false: no room within the probe limit.
+__device__ __forceinline__ bool smem_table_add(unsigned long long *keys, unsigned long long *val, unsigned long long *mk,
+                                               unsigned long long k, long long delta, unsigned long long key,
+                                               unsigned short *occ, unsigned int *n_occ,
+                                               const PairTableDev::GSlotRef pf = PairTableDev::GSlotRef{nullptr, 0}) {
+  uint32_t sl = (uint32_t)(dmix64(k) >> 3) & (CL_HT_SLOTS - 1);
+#pragma unroll 1
+  for (int probe = 0; probe < CL_MAX_PROBES; probe++) {
+    const unsigned long long cur = atomicCAS(&keys[sl], PT_EMPTY, k);
+    if (cur == PT_EMPTY) occ[atomicAdd(n_occ, 1u)] = (unsigned short)sl;  // the list of occupied slots, for whoever empties the table
+    if (cur == PT_EMPTY && pf.slots)  // first touch: pull the pair's frequency-table slot into L2 for the emit phase
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<char *>(pf.slots) + 32ull * ((uint32_t)dmix64(k + 0x632BE59BD9B4E019ull) & pf.mask)));
+    if (cur == PT_EMPTY || cur == k) {
+      {  // 64-bit add as two native 32-bit shared-memory atomics (a 64-bit atomicAdd on shared memory is a compare-and-swap
+         // loop, which crawls when many threads hit one hot pair): every add carries its own overflow into the high half
+        unsigned int *v32 = reinterpret_cast<unsigned int *>(&val[sl]);
+        const unsigned int dlo = (unsigned int)(unsigned long long)delta, dhi = (unsigned int)((unsigned long long)delta >> 32);
+        const unsigned int old = atomicAdd(&v32[0], dlo);
+        const unsigned int carry = (old + dlo) < old ? 1u : 0u;
+        if (dhi + carry) atomicAdd(&v32[1], dhi + carry);
+      }
+      unsigned long long sn = *(volatile unsigned long long *)&mk[sl];  // 64-bit min by compare-and-swap
+#pragma unroll 1
+      while (key < sn) {
+        const unsigned long long prev = atomicCAS(&mk[sl], sn, key);
+        if (prev == sn) break;
+        sn = prev;
+      }
+      return true;
+    }
+    sl = (sl + 1) & (CL_HT_SLOTS - 1);
+  }
+  return false;
+}
+
+// deltas -> T1 (this CTA's shared memory: fast local atomics), births -> this CTA's stage
 struct ClusterSink {
   cg::cluster_group &cluster;
   const ClusterSmem &m;
   const PairTableDev &t;      // spill target + canonicalisation of a negative unk_id
   const BirthLogDev &lg;
-  __device__ __forceinline__ void add(int32_t x, int32_t y, long long delta, uint64_t key) {
-    if (t.canon_on && y == UNK_CODE) x = t.canon_first;
-    const unsigned long long k = ((unsigned long long)(uint32_t)x << 32) | (uint32_t)y;
-    const uint64_t h = dmix64(k);
-    const unsigned int owner = (unsigned int)h & (CL_SIZE - 1);
-    unsigned long long *rk = cluster.map_shared_rank(m.keys, owner);
-    uint32_t sl = (uint32_t)(h >> 3) & (CL_HT_SLOTS - 1);
-    for (int probe = 0; probe < CL_MAX_PROBES; probe++) {
-      const unsigned long long cur = atomicCAS(&rk[sl], PT_EMPTY, k);
-      if (cur == PT_EMPTY && t.gpf.slots)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<char *>(t.gpf.slots) +
-                                                     32ull * ((uint32_t)dmix64(k + 0x632BE59BD9B4E019ull) & t.gpf.mask)));
-      if (cur == PT_EMPTY || cur == k) {
-        atomicAdd(cluster.map_shared_rank(m.val, owner) + sl, (unsigned long long)delta);
-        // 64-bit min through compare-and-swap: atomicMin / atomicXor on 64-bit words of a REMOTE shared memory
-        // returned wrong results on this toolchain (add and CAS are fine)
-        unsigned long long *pm = cluster.map_shared_rank(m.mk, owner) + sl;
-        unsigned long long seen = *(volatile unsigned long long *)pm;
-        while ((unsigned long long)key < seen) {
-          const unsigned long long prev = atomicCAS(pm, seen, (unsigned long long)key);
-          if (prev == seen) break;
-          seen = prev;
-        }
-        return;
+  __device__ __forceinline__ void add_batch(int n, const int32_t *x, const int32_t *y, const long long *delta, const uint64_t *key) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+      int32_t xx = x[i];
+      if (t.canon_on && y[i] == UNK_CODE) xx = t.canon_first;
+      const unsigned long long k = ((unsigned long long)(uint32_t)xx << 32) | (uint32_t)y[i];
+      if (!smem_table_add(m.k1, m.v1, m.m1, k, delta[i], (unsigned long long)key[i], m.occ1, &m.ctl->n_occ1, t.gpf)) {
+        // T1 is (nearly) full: this delta goes to the global table, and so will everything else of this merge
+        atomicOr(&cluster.map_shared_rank(m.ctl, 0)->spill, 1u);
+        pt_add(t, xx, y[i], delta[i], key[i]);
       }
-      sl = (sl + 1) & (CL_HT_SLOTS - 1);
     }
-    // the owner's part is (nearly) full: this delta goes to the global table, and so will everything else
-    atomicOr(&cluster.map_shared_rank(m.ctl, 0)->spill, 1u);
-    pt_add(t, x, y, delta, key);
   }
   __device__ __forceinline__ void birth(uint32_t other, bool right_side, uint32_t wi, uint64_t hloc) {
     const uint4 e = log_entry(other, right_side, wi, hloc);
     const unsigned int i = atomicAdd(&m.ctl->n_births, 1u);
     if (i < CL_BIRTH_STAGE) m.births[i] = e;
-    else log_append(lg, e);
+    else {  // past the stage: straight to its final place
+      ClusterCtl *c0 = cluster.map_shared_rank(m.ctl, 0);
+      const unsigned int idx = c0->log_cursor + atomicAdd(&c0->births_total, 1u);
+      if (idx < lg.cap) lg.ent[idx] = e;
+      else atomicOr(lg.flags, 1u);
+    }
   }
 };
 
 __device__ __forceinline__ void cluster_barrier(cg::cluster_group &cluster) { cluster.sync(); }
+__device__ __forceinline__ void cluster_clear_tables(const ClusterSmem &m) {
+  for (int sl = threadIdx.x; sl < CL_HT_SLOTS; sl += CL_THREADS) {
+    m.keys[sl] = PT_EMPTY; m.val[sl] = 0; m.mk[sl] = ~0ull;
+    m.k1[sl] = PT_EMPTY; m.v1[sl] = 0; m.m1[sl] = ~0ull;
+  }
+}
+
+// LOCAL merge, exchange: every partial sum of T1 goes to the CTA that owns its pair -- straight into T2 when that is
+// this CTA, otherwise as one message into the owner's inbox (one remote 32-bit atomic for the place, two remote
+// 16-byte stores). Remote 64-bit min/xor atomics are avoided altogether (wrong results on this toolchain).
+__device__ __forceinline__ void cluster_exchange(const ClusterSmem &m, const PairTableDev &t, cg::cluster_group &cluster, unsigned int crank) {
+  const unsigned int n1 = m.ctl->n_occ1;  // (listed while the deltas were added; the caller has synchronised the block)
+#pragma unroll 1
+  for (unsigned int i = threadIdx.x; i < n1; i += CL_THREADS) {
+    const int sl = m.occ1[i];
+    const unsigned long long k = m.k1[sl], d = m.v1[sl], mk = m.m1[sl];
+    m.k1[sl] = PT_EMPTY; m.v1[sl] = 0; m.m1[sl] = ~0ull;
+    const unsigned int owner = (unsigned int)dmix64(k) & (CL_SIZE - 1);
+    bool ok;
+    if (owner == crank) ok = smem_table_add(m.keys, m.val, m.mk, k, (long long)d, mk, m.occ, &m.ctl->n_occ);
+    else {
+      ClusterCtl *oc = cluster.map_shared_rank(m.ctl, owner);
+      const unsigned int j = atomicAdd(&oc->inbox_n, 1u);
+      ok = j < CL_INBOX;
+      if (ok) {
+        uint4 *ob = cluster.map_shared_rank(m.inbox, owner);
+        ob[2 * j] = make_uint4((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)d, (uint32_t)(d >> 32));
+        ob[2 * j + 1] = make_uint4((uint32_t)mk, (uint32_t)(mk >> 32), 0u, 0u);
+      }
+    }
+    if (!ok) {
+      atomicOr(&cluster.map_shared_rank(m.ctl, 0)->spill, 1u);
+      pt_add(t, (int32_t)(k >> 32), (int32_t)(k & 0xFFFFFFFFu), (long long)d, mk);
+    }
+  }
+}
+// ... and after the cluster barrier the owner folds its inbox into T2
+__device__ __forceinline__ void cluster_fold_inbox(const ClusterSmem &m, const PairTableDev &t, cg::cluster_group &cluster) {
+  const unsigned int nin = min(m.ctl->inbox_n, (unsigned int)CL_INBOX);
+#pragma unroll 1
+  for (unsigned int i = threadIdx.x; i < nin; i += CL_THREADS) {
+    const uint4 q0 = m.inbox[2 * i], q1 = m.inbox[2 * i + 1];
+    const unsigned long long k = ((unsigned long long)q0.y << 32) | q0.x, d = ((unsigned long long)q0.w << 32) | q0.z,
+                             mk = ((unsigned long long)q1.y << 32) | q1.x;
+    if (!smem_table_add(m.keys, m.val, m.mk, k, (long long)d, mk, m.occ, &m.ctl->n_occ)) {
+      atomicOr(t.flags, 1u);  // cannot happen (T2 is at most 2/3 full with a whole inbox): reported as an internal sizing error
+    }
+  }
+  __syncthreads();
+}
 
 // LOCAL merge, phase 2 of one CTA: apply this CTA's pairs to the device frequency table and stage the records
 __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const EmitMode &em, const PairTableDev &t, bool spill,
                                                   unsigned long long &cx, unsigned long long &cs, unsigned int &inserted,
                                                   Rec *__restrict__ out, size_t out_cap, cg::cluster_group &cluster, int32_t new_id) {
-  // pass 1: which slots are occupied
-  for (int sl = threadIdx.x; sl < CL_HT_SLOTS; sl += CL_THREADS)
-    if (m.keys[sl] != PT_EMPTY) m.occ[atomicAdd(&m.ctl->n_occ, 1u)] = (unsigned short)sl;
-  __syncthreads();
-  const unsigned int n_occ = m.ctl->n_occ;
+  const unsigned int n_occ = m.ctl->n_occ;  // (listed while T2 was filled; the caller has synchronised the block)
   ClusterCtl *c0 = cluster.map_shared_rank(m.ctl, 0);
+#pragma unroll 1
   for (unsigned int i = threadIdx.x; i < n_occ; i += CL_THREADS) {
     const int sl = m.occ[i];
     const unsigned long long k = m.keys[sl];
@@ -196,7 +290,8 @@ __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const Em
 __global__ void __launch_bounds__(CL_THREADS, 1)
 merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *removed_total, Rec *__restrict__ out, size_t out_cap,
               unsigned long long *__restrict__ out_hdr, unsigned long long seq_base, unsigned long long op_base,
-              volatile HostCmd2 *hcmd, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace) {
+              volatile HostCmd2 *hcmd, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace,
+              uint4 *ovf /* [CL_LOCAL_MAX]: candidate words that did not fit a CTA's shared-memory list */) {
   extern __shared__ __align__(16) unsigned char cl_dyn_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const ClusterSmem m = cluster_smem(cl_dyn_smem);
@@ -206,12 +301,14 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
   const int lane = threadIdx.x & 31;
   const uint32_t log_m_base = em.log.m_cur;
 
-  for (int sl = threadIdx.x; sl < CL_HT_SLOTS; sl += CL_THREADS) { m.keys[sl] = PT_EMPTY; m.val[sl] = 0; m.mk[sl] = ~0ull; }
+  cluster_clear_tables(m);
   if (threadIdx.x == 0) memset(m.ctl, 0, sizeof(ClusterCtl));
   __syncthreads();
   cluster_barrier(cluster);
 
   unsigned long long grid_epoch = 0;  // GRID merges seen so far
+  unsigned int pre_flags = 0;
+  bool cursor_stale = true;  // (CTA 0 / thread 0) the log cursor kept in shared memory is behind the global one
   long long tr_poll = 0, tr_p1 = 0, tr_p2 = 0, tr_pub = 0;
   for (unsigned long long k = 0;; k++) {
     // ---------------------------------------------------------------- next command
@@ -222,9 +319,24 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         const unsigned long long t0 = gtime_ns();
         unsigned long long pair = 0, nio = 3ull << 32, lr = ~0ull;
         for (unsigned long long spin = 0;; spin++) {
-          const unsigned long long sq = hcmd->seq, p = hcmd->pair, n = hcmd->new_id_op, l = hcmd->log_range, ck = hcmd->check;
-          if (sq == want && ck == cmd2_check(want, p, n, l)) { pair = p; nio = n; lr = l; break; }
+          uint4 v;  // one 16-byte load from mapped host memory = one PCIe read
+          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(hcmd) : "memory");
+          if (v.w == cmd3_word(want, v.x, v.y, v.z)) {
+            pair = ((unsigned long long)v.y << 32) | v.x;
+            nio = (unsigned long long)(v.z & 0x0FFFFFFFu) | ((unsigned long long)(v.z >> 28) << 32);
+            break;
+          }
           if ((spin & 63) == 63 && gtime_ns() - t0 > timeout_ns) break;  // abort: the host went away
+        }
+        if (!(nio >> 32)) {  // the birth log of the newer token of the pair (device-side bookkeeping: cheaper than a second PCIe trip)
+          const int32_t pa = (int32_t)(pair >> 32), pb = (int32_t)(pair & 0xFFFFFFFFu), newer = pa > pb ? pa : pb;
+          const uint32_t mcur = (uint32_t)((uint32_t)(nio & 0xFFFFFFFFu) - 256u);
+          if (em.log.ent != nullptr && newer >= 256 && (uint32_t)(newer - 256) < mcur) {
+            const unsigned int lo = __ldcg(&em.log.start[newer - 256]), hi = __ldcg(&em.log.start[newer - 256 + 1]);
+            lr = ((unsigned long long)lo << 32) | (unsigned long long)(hi - lo);
+          }
+          if (cursor_stale && em.log.ent != nullptr) { m.ctl->log_cursor = __ldcg(em.log.cursor); cursor_stale = false; }
+          m.ctl->births_total = 0;
         }
         const unsigned int stop = (unsigned int)(nio >> 32);
         const unsigned int mode = (lr == ~0ull || (unsigned int)(lr & 0xFFFFFFFFu) > CL_LOCAL_MAX) ? 1u : 0u;
@@ -232,6 +344,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           ClusterCtl *c = cluster.map_shared_rank(m.ctl, r);
           c->pair = pair; c->new_id_op = nio; c->log_range = lr; c->k = k; c->mode = mode; c->stop = stop;
         }
+        if (mode == 1u) cursor_stale = true;  // a GRID merge appends through the global cursor
         if (stop || mode == 1u) {  // the other clusters take part (or leave)
           dcmd->pair = pair; dcmd->new_id_op = nio; dcmd->log_range = lr; dcmd->k = k;
           __threadfence();
@@ -286,8 +399,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u, nullptr, nullptr);
       }
       __syncthreads();
-      // the scratch aliased the delta table: empty it again
-      for (int sl = threadIdx.x; sl < CL_HT_SLOTS; sl += CL_THREADS) { m.keys[sl] = PT_EMPTY; m.val[sl] = 0; m.mk[sl] = ~0ull; }
+      // the scratch aliased the delta tables: empty them again
+      cluster_clear_tables(m);
       __syncthreads();
       continue;
     }
@@ -301,25 +414,43 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       const bool have_log = log_lookup(em.log, a, b, merge, other, side);  // (true: the host sent a log range)
       ClusterSink sink{cluster, m, t, em.log};
       uint32_t removed = 0;
-      // this thread's log entries are requested together (one round trip), then the matching words are rewritten
-      constexpr int PER_THREAD = (int)(CL_LOCAL_MAX / (CL_SIZE * CL_THREADS));
-      uint4 ev[PER_THREAD];
-#pragma unroll
-      for (int u = 0; u < PER_THREAD; u++) {
-        const uint64_t i = (uint64_t)u * (CL_SIZE * CL_THREADS) + crank * CL_THREADS + threadIdx.x;
-        ev[u] = (have_log && i < n) ? __ldcg(&em.log.ent[lo + i]) : make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
-      }
+      // Eight log entries per thread are requested together (one round trip); the matching ones are listed in
+      // shared memory and then dealt out evenly, so that no thread rewrites more words than its neighbours.
       long long cA = 0;
-      if (trace && crank == 0 && threadIdx.x == 0) { unsigned int acc = 0;
+      for (uint64_t base = 0; have_log && base < n; base += 8ull * CL_SIZE * CL_THREADS) {
+        uint4 ev[8];
 #pragma unroll
-        for (int u = 0; u < PER_THREAD; u++) acc += ev[u].x;
-        if (acc == 0x12345u) trace[15] = 1;  // (forces the loads to complete here)
-        cA = clock64(); trace[8] += (unsigned long long)(cA - c1); }
+        for (int u = 0; u < 8; u++) {
+          const uint64_t i = base + (uint64_t)u * (CL_SIZE * CL_THREADS) + crank * CL_THREADS + threadIdx.x;
+          ev[u] = i < n ? __ldcg(&em.log.ent[lo + i]) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+        }
 #pragma unroll
-      for (int u = 0; u < PER_THREAD; u++) {
-        const uint4 e = ev[u];
-        if (have_log && e.x == other && (e.y & 0x80000000u) == side && (uint64_t)u * (CL_SIZE * CL_THREADS) + crank * CL_THREADS + threadIdx.x < n)
-          removed += merge_one_word(s, ((uint64_t)e.w << 32) | e.z, e.y & 0x7FFFFFFFu, a, b, new_id, sink);
+        for (int u = 0; u < 8; u++) {
+          const uint4 e = ev[u];
+          if (e.x == other && (e.y & 0x80000000u) == side && !(e.x == 0xFFFFFFFFu && e.y == 0xFFFFFFFFu)) {
+            const unsigned int ci = atomicAdd(&m.ctl->n_cand, 1u);
+            {  // the word and its count are on their way while the candidates are dealt out
+              const uint64_t hl = ((uint64_t)e.w << 32) | e.z;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const int32_t *>(s.rows) + hl));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(s.cnt + (e.y & 0x7FFFFFFFu)));
+            }
+            if (ci < CL_CAND_CAP) m.cand[ci] = make_uint4(e.y & 0x7FFFFFFFu, e.z, e.w, 0u);
+            else ovf[(size_t)crank * (CL_LOCAL_MAX / CL_SIZE) + atomicAdd(&m.ctl->n_ovf, 1u)] = make_uint4(e.y & 0x7FFFFFFFu, e.z, e.w, 0u);  // rare: listed in global memory
+          }
+        }
+      }
+      __syncthreads();
+      if (trace && crank == 0 && threadIdx.x == 0) { cA = clock64(); trace[8] += (unsigned long long)(cA - c1); }
+      {
+        // candidate i goes to warp i % 16, lane i / 16: the work is spread over all warps (and schedulers) of the CTA;
+        // candidates past the shared-memory list (rare) follow from this CTA's part of the global overflow list
+        const unsigned int nc = min(m.ctl->n_cand, (unsigned int)CL_CAND_CAP), nall = nc + m.ctl->n_ovf;
+        const uint4 *ovf_mine = ovf + (size_t)crank * (CL_LOCAL_MAX / CL_SIZE);
+#pragma unroll 1
+        for (unsigned int i = (threadIdx.x >> 5) + (unsigned int)CL_WARPS * (threadIdx.x & 31); i < nall; i += CL_THREADS) {
+          const uint4 cnd = i < nc ? m.cand[i] : __ldcg(&ovf_mine[i - nc]);
+          removed += merge_one_word(s, ((uint64_t)cnd.z << 32) | cnd.y, cnd.x, a, b, new_id, sink);
+        }
       }
       if (trace && crank == 0 && threadIdx.x == 0) trace[9] += (unsigned long long)(clock64() - cA);
 #pragma unroll
@@ -329,21 +460,34 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
     }
     __syncthreads();
     if (trace && crank == 0 && threadIdx.x == 0) trace[7] += (unsigned long long)(clock64() - c1);
-    cluster_barrier(cluster);  // every delta of this merge is in the distributed table
+    cluster_exchange(m, t, cluster, crank);
+    cluster_barrier(cluster);  // every partial sum of this merge has reached the CTA that owns its pair
     const long long c2 = clock64();
     {
       ClusterCtl *c0 = cluster.map_shared_rank(m.ctl, 0);
       const bool spill = c0->spill != 0;
+      if (crank == 0 && threadIdx.x == 0) {
+        // rarely set conditions, requested now and looked at when the header is written (a flag raised later in this
+        // merge is seen one merge later: the thresholds leave that much room, the others are fatal either way)
+        pre_flags = (__ldcg(t.flags) & 1u) | (__ldcg(em.log.flags) ? 2u : 0u) |
+                    ((__ldcg(em.g.flags) || __ldcg(em.g.n_used) >= (em.g.mask >> 1)) ? 4u : 0u);
+      }
+      if (crank == 0 && threadIdx.x == 32 && !spill) {  // the merged pair's frequency becomes 0 (bpe.cpp:523)
+        unsigned int ins = 0;
+        em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;
+        if (ins) atomicAdd(em.g.n_used, ins);
+      }
+      cluster_fold_inbox(m, t, cluster);
       unsigned long long cx = 0, cs = 0;
       unsigned int inserted = 0;
       if (threadIdx.x == 64) {  // this CTA's range in the birth log: requested now, needed after the records are staged
         const unsigned int nb = min(m.ctl->n_births, (unsigned int)CL_BIRTH_STAGE);
-        m.ctl->birth_base = nb ? atomicAdd(em.log.cursor, nb) : 0u;
+        m.ctl->birth_base = c0->log_cursor + (nb ? atomicAdd(&c0->births_total, nb) : 0u);
       }
       cluster_emit_part(m, em, t, spill, cx, cs, inserted, out, out_cap, cluster, new_id);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, d);
-      if (lane == 0) gt_account(em.g, inserted);
+      if (lane == 0 && inserted) atomicAdd(em.g.n_used, inserted);  // (no result needed here: CTA 0 looks at the load once per merge)
       __syncthreads();
       if (threadIdx.x == 0) {  // this CTA's ranges in the record buffer and in the birth log
         const unsigned int nr = min(m.ctl->n_recs, (unsigned int)CL_REC_STAGE);
@@ -366,12 +510,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       block_checksum(cx, cs, m.csum);
       if (threadIdx.x == 0) {
         c0->part_cx[crank] = cx; c0->part_cs[crank] = cs;
-        m.ctl->n_births = 0; m.ctl->n_recs = 0; m.ctl->n_occ = 0;
-      }
-      if (crank == 0 && threadIdx.x == 32 && !spill) {  // the merged pair's frequency becomes 0 (bpe.cpp:523)
-        unsigned int ins = 0;
-        em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;
-        gt_account(em.g, ins);
+        m.ctl->n_births = 0; m.ctl->n_recs = 0; m.ctl->n_occ = 0; m.ctl->n_cand = 0; m.ctl->n_occ1 = 0; m.ctl->inbox_n = 0; m.ctl->n_ovf = 0;
       }
     }
     cluster_barrier(cluster);  // all records, checksums and log entries of this merge are out
@@ -379,21 +518,26 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
     if (crank == 0) {
       ClusterCtl *c = m.ctl;
       if (c->spill) {  // rare: the merge did not fit the distributed table; CTA 0 finishes it from the global one
-        if (threadIdx.x == 0 && c->removed) atomicAdd(removed_total, (unsigned long long)c->removed);
+        if (threadIdx.x == 0) {
+          if (c->removed) atomicAdd(removed_total, (unsigned long long)c->removed);
+          *em.log.cursor = c->log_cursor + c->births_total;  // (this merge's births were placed through the shared counter)
+        }
         __threadfence();
         __syncthreads();
         TailSmem ts{m.tail_stage, m.csum, m.tail_count};
         fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u, nullptr, nullptr);
         __syncthreads();
-        for (int sl = threadIdx.x; sl < CL_HT_SLOTS; sl += CL_THREADS) { m.keys[sl] = PT_EMPTY; m.val[sl] = 0; m.mk[sl] = ~0ull; }
+        cluster_clear_tables(m);
         if (threadIdx.x == 0) { c->spill = 0; c->n_recs_total = 0; c->removed = 0; }
         __syncthreads();
       } else if (threadIdx.x == 0) {
         const unsigned int n = c->n_recs_total;
-        unsigned long long flags = (n > out_cap ? 4u : 0u) | (__ldcg(em.g.flags) ? 16u : 0u);
-        const unsigned int cur = __ldcg(em.log.cursor);
+        unsigned long long flags = (n > out_cap ? 4u : 0u) | (pre_flags & 1u) | ((pre_flags & 4u) ? 16u : 0u);
+        const unsigned int cur = c->log_cursor + c->births_total;  // (GRID merges append through the global cursor: keep it current)
+        *em.log.cursor = cur;
+        c->log_cursor = cur;
         em.log.start[em.log.m_cur + 1] = cur;
-        if (__ldcg(em.log.flags)) flags |= 32u;
+        if (pre_flags & 2u) flags |= 32u;
         flags |= (unsigned long long)cur << 32;  // the host keeps the log ranges
         unsigned long long x = 0, sm = 0;
 #pragma unroll

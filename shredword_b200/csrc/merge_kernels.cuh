@@ -192,6 +192,7 @@ __device__ __forceinline__ void pt_add(const PairTableDev &t, int32_t a, int32_t
   if (t.canon_on && b == UNK_CODE) a = t.canon_first;
   const unsigned long long k = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
   uint32_t h = (uint32_t)dmix64(k) & t.mask;
+#pragma unroll 1
   for (uint32_t probe = 0; probe <= t.mask; probe++) {
     // CAS straight away (one L2 round trip): the table is empty at the start of every merge, so the
     // common case is a first touch
@@ -276,6 +277,7 @@ __device__ __forceinline__ void pt_emit_range(const PairTableDev &t, const EmitM
                                               unsigned int *out_count, unsigned long long &cx, unsigned long long &cs,
                                               unsigned int &inserted, Rec *__restrict__ direct = nullptr,
                                               unsigned int stage_cap = 0xFFFFFFFFu) {
+#pragma unroll 1
   for (unsigned int i = first; i < n; i += stride) {
     const uint4 tc = __ldcg(&t.touched[i]);
     const unsigned int h = tc.x;
@@ -578,10 +580,11 @@ __device__ __forceinline__ void emit_matches(const Match *ml, unsigned int nm, i
       if (nb >= 0) {
         const long long c = (long long)m.cnt;
         const uint64_t key = touch_key(m.wi, m.pos, slot);
-        if (slot == 0) pt_add(t, nb, a, -c, key);
-        else if (slot == 1) pt_add(t, nb, new_id, c, key);
-        else if (slot == 2) pt_add(t, b, nb, -c, key);
-        else pt_add(t, new_id, nb, c, key);
+        {  // (one call site: pt_add is large)
+          const int32_t px = slot == 0 ? nb : slot == 1 ? nb : slot == 2 ? b : new_id;
+          const int32_t py = slot == 0 ? a : slot == 1 ? new_id : nb;
+          pt_add(t, px, py, (slot & 1) ? c : -c, key);
+        }
         if (lg.ent && (slot & 1)) {
           born = true;  // unless an earlier match of the same word already logged this neighbour on this side
           for (int j = (int)(i >> 2) - 1; j >= 0 && ml[j].row == row; j--)
@@ -692,6 +695,51 @@ __device__ __forceinline__ uint32_t scan_rows(const StreamDev &s, const PairTabl
 // reference bpe.cpp:437-483), and the changed tail is stored back. Every match hands its four signed deltas
 // to `sink.add`, every newly born pair (once per word) to `sink.birth`.
 // hloc = flat index of the word's header in the row stream. Returns the number of matches.
+__device__ unsigned long long g_word_trace[8];  // development aid (SWB_KERNEL_TRACE builds): stage cycles of block 0 / thread 0
+#ifdef SWB_KERNEL_TRACE
+#define SWB_WT(i, t0) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t1_ = clock64(); g_word_trace[i] += (unsigned long long)(t1_ - t0); t0 = t1_; } } while (0)
+#else
+#define SWB_WT(i, t0) do { } while (0)
+#endif
+
+// The four signed deltas of each recorded match (reference bpe.cpp:453-470), handed to the sink together.
+// Called when the lanes of the warp have reconverged: the matches of different words sit at different
+// positions, and emitting from inside the rewrite loop would run the table updates once per lane instead of
+// once per warp.
+template <typename Sink>
+__device__ __forceinline__ void emit_word_matches(uint32_t nmatch, const int *mL, const int *mR, const unsigned char *mpos, uint32_t wi,
+                                                  long long cc, int32_t a, int32_t b, int32_t new_id, Sink &sink) {
+#pragma unroll 1
+  for (uint32_t mi = 0; mi < nmatch; mi++) {
+    const int L = mL[mi], R = mR[mi];
+    const uint32_t pos = mpos[mi];
+    int32_t bx[4], by[4];
+    long long bd[4];
+    uint64_t bk[4];
+    int nbt = 0;
+    if (L >= 0) {
+      bx[0] = L; by[0] = a; bd[0] = -cc; bk[0] = touch_key(wi, pos, 0);
+      bx[1] = L; by[1] = new_id; bd[1] = cc; bk[1] = touch_key(wi, pos, 1);
+      nbt = 2;
+    }
+    if (R >= 0) {
+      bx[nbt] = b; by[nbt] = R; bd[nbt] = -cc; bk[nbt] = touch_key(wi, pos, 2);
+      bx[nbt + 1] = new_id; by[nbt + 1] = R; bd[nbt + 1] = cc; bk[nbt + 1] = touch_key(wi, pos, 3);
+      nbt += 2;
+    }
+    sink.add_batch(nbt, bx, by, bd, bk);
+  }
+}
+
+// One thread rewrites one word (reference bpe.cpp:437-483: already-merged left neighbour, not-yet-merged right
+// neighbour). Every match hands its four signed deltas to the sink, every newly born pair (once per word) to
+// `sink.birth`. hloc = flat index of the word's header in the row stream. Returns the number of matches.
+//
+// Words of up to WORD_FAST symbols (nearly all of them) never leave the registers: the three 16-byte chunks that
+// hold them are requested together (one memory round trip), realigned, and rewritten by fully unrolled code whose
+// only memory traffic are the stores of the changed symbols. Longer words take the general path through
+// thread-local memory.
+constexpr int WORD_FAST = 8;
 template <typename Sink>
 __device__ __forceinline__ uint32_t merge_one_word(const StreamDev &s, uint64_t hloc, uint32_t wi, int32_t a, int32_t b, int32_t new_id,
                                                    Sink &sink) {
@@ -699,30 +747,112 @@ __device__ __forceinline__ uint32_t merge_one_word(const StreamDev &s, uint64_t 
   const int hpos = (int)(hloc & (ROW - 1));
   const uint64_t row_base = hloc - hpos;
   const unsigned long long c = __ldg(&s.cnt[wi]);  // in flight while the symbols arrive
-  int buf[ROW];
-  int n = 0;
-  {  // symbols hpos+1 .. end of word, 16 bytes at a time; the first three chunks (most words end there) are
-     // requested together, so that a typical word costs ONE memory round trip
-    const int4 *rowv = reinterpret_cast<const int4 *>(flat + row_base);
-    const int q0 = (hpos + 1) >> 2;
-    const int4 pad4 = make_int4(PAD, PAD, PAD, PAD);
-    int4 pre[3];
+  long long wt0 = clock64(); (void)wt0;
+  const unsigned int entered = __activemask();
+  const int4 *rowv = reinterpret_cast<const int4 *>(flat + row_base);
+  const int q0 = (hpos + 1) >> 2;
+  const int4 pad4 = make_int4(PAD, PAD, PAD, PAD);
+  int4 pre[3];
 #pragma unroll
-    for (int u = 0; u < 3; u++) pre[u] = q0 + u < ROW / 4 ? __ldcg(rowv + q0 + u) : pad4;
-    bool open = true;
+  for (int u = 0; u < 3; u++) pre[u] = q0 + u < ROW / 4 ? __ldcg(rowv + q0 + u) : pad4;
+  const long long cc = (long long)c;
+  int32_t *wsym = flat + row_base + hpos + 1;  // the word's first symbol
+  int mL[ROW / 2], mR[ROW / 2];
+  unsigned char mpos[ROW / 2];
+  uint32_t nmatch = 0;
+
+  // ---- realign: y[j] = symbol j of the word (PAD past what was loaded)
+  int y[12];
+  {
+    const int x[12] = {pre[0].x, pre[0].y, pre[0].z, pre[0].w, pre[1].x, pre[1].y, pre[1].z, pre[1].w, pre[2].x, pre[2].y, pre[2].z, pre[2].w};
+    const int off = (hpos + 1) & 3;
 #pragma unroll
-    for (int u = 0; u < 3; u++) {
-      const int x[4] = {pre[u].x, pre[u].y, pre[u].z, pre[u].w};
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int p = 4 * (q0 + u) + k;
-        if (p <= hpos || !open) continue;
-        if (x[k] < 0) { open = false; continue; }
-        buf[n++] = x[k];
-      }
+    for (int j = 0; j < 12; j++) {
+      int v = PAD;
+      if (off == 0) v = x[j];
+      else if (off == 1) v = j + 1 < 12 ? x[j + 1] : PAD;
+      else if (off == 2) v = j + 2 < 12 ? x[j + 2] : PAD;
+      else v = j + 3 < 12 ? x[j + 3] : PAD;
+      y[j] = v;
     }
-    for (int q = q0 + 3; q < ROW / 4 && open; q++) {
-      const int4 v = __ldcg(rowv + q);
+  }
+  int n = 0;  // length, if the word ends inside the first WORD_FAST + 1 slots
+  bool fast = false;
+#pragma unroll
+  for (int j = WORD_FAST; j >= 0; j--)
+    if (y[j] < 0) { n = j; fast = true; }
+  SWB_WT(0, wt0);
+  if (fast) {
+    // ---- registers only. `out` = symbol written at position w; births are read off consecutive outputs.
+    int w = 0, prev = -1;
+    bool skip = false;
+    uint32_t lb[4], rb[4];  // neighbours already logged on the left / right side of a new_id of this word
+    int nlb = 0, nrb = 0;
+#pragma unroll
+    for (int r = 0; r < WORD_FAST; r++) {
+      if (r >= n) continue;
+      if (skip) { skip = false; continue; }
+      int out = y[r];
+      if (y[r] == a && r + 1 < n && y[r + 1] == b) {
+        mL[nmatch] = prev;
+        mR[nmatch] = r + 2 < n ? y[r + 2] : -1;
+        mpos[nmatch] = (unsigned char)(hpos + 1 + r);
+        nmatch++;
+        out = new_id;
+        skip = true;
+      }
+      if (nmatch) {
+        if (w != r || out != y[r]) wsym[w] = out;
+        // births: (prev, out) is a final adjacency; it involves new_id iff one of the two is new_id
+        if (prev >= 0) {
+          if (out == new_id) {  // left side of a new_id (also covers (new, new))
+            bool dup = false;
+            for (int q = 0; q < nlb; q++) dup |= lb[q] == (uint32_t)prev;
+            if (!dup && nlb < 4) lb[nlb++] = (uint32_t)prev;
+          } else if (prev == new_id) {  // right side of a new_id
+            bool dup = false;
+            for (int q = 0; q < nrb; q++) dup |= rb[q] == (uint32_t)out;
+            if (!dup && nrb < 4) rb[nrb++] = (uint32_t)out;
+          }
+        }
+      }
+      prev = out;
+      w++;
+    }
+    if (nmatch) {
+      for (int q = w; q < n; q++) wsym[q] = PAD;
+      const uint32_t hh = sig_hash(new_id);
+      atomicOr(&s.sig[(row_base / ROW) * SIG_WORDS + (hh >> 5)], 1u << (hh & 31));
+    }
+    SWB_WT(1, wt0);
+    __syncwarp(entered);
+    SWB_WT(2, wt0);
+    emit_word_matches(nmatch, mL, mR, mpos, wi, cc, a, b, new_id, sink);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {  // births, lanes side by side (at most 4 per side: a fast word has at most 4 matches)
+      if (q < nlb) sink.birth(lb[q], false, wi, hloc);
+      if (q < nrb) sink.birth(rb[q], true, wi, hloc);
+    }
+    SWB_WT(3, wt0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_word_trace[6] += 1;
+    return nmatch;
+  }
+
+  // ---- general path: the word goes through thread-local memory
+  int buf[ROW];
+  n = 0;
+  {
+    bool open = true;
+    const int have = 12 - ((hpos + 1) & 3);  // symbols of the word that the three chunks can hold
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+      if (!open || j >= have) continue;
+      if (y[j] < 0) { open = false; continue; }
+      buf[n++] = y[j];
+    }
+    // (a word that stops exactly at the end of the loaded chunks or of the row is closed by the loop condition)
+    for (int p = hpos + 1 + 12 - ((hpos + 1) & 3); open && p < ROW; p += 4) {
+      const int4 v = __ldcg(rowv + (p >> 2));
       const int x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -733,16 +863,12 @@ __device__ __forceinline__ uint32_t merge_one_word(const StreamDev &s, uint64_t 
     }
   }
   int w = 0, r = 0, first_changed = -1;
-  uint32_t nmatch = 0;
-  const long long cc = (long long)c;
   while (r < n) {
     const int x = buf[r];
     if (x == a && r + 1 < n && buf[r + 1] == b) {
-      const int L = w > 0 ? buf[w - 1] : -1;       // already rewritten
-      const int R = r + 2 < n ? buf[r + 2] : -1;   // not yet rewritten
-      const uint32_t pos = (uint32_t)(hpos + 1 + r);
-      if (L >= 0) { sink.add(L, a, -cc, touch_key(wi, pos, 0)); sink.add(L, new_id, cc, touch_key(wi, pos, 1)); }
-      if (R >= 0) { sink.add(b, R, -cc, touch_key(wi, pos, 2)); sink.add(new_id, R, cc, touch_key(wi, pos, 3)); }
+      mL[nmatch] = w > 0 ? buf[w - 1] : -1;       // already rewritten
+      mR[nmatch] = r + 2 < n ? buf[r + 2] : -1;   // not yet rewritten
+      mpos[nmatch] = (unsigned char)(hpos + 1 + r);
       if (first_changed < 0) first_changed = w;
       buf[w++] = new_id;
       r += 2;
@@ -752,8 +878,10 @@ __device__ __forceinline__ uint32_t merge_one_word(const StreamDev &s, uint64_t 
       r++;
     }
   }
+  __syncwarp(entered);
+  emit_word_matches(nmatch, mL, mR, mpos, wi, cc, a, b, new_id, sink);
   if (!nmatch) return 0;
-  for (int i = first_changed; i < n; i++) flat[row_base + hpos + 1 + i] = i < w ? buf[i] : PAD;
+  for (int i = first_changed; i < n; i++) wsym[i] = i < w ? buf[i] : PAD;
   {  // the row now contains new_id
     const uint32_t hh = sig_hash(new_id);
     atomicOr(&s.sig[(row_base / ROW) * SIG_WORDS + (hh >> 5)], 1u << (hh & 31));
@@ -796,7 +924,10 @@ __device__ __forceinline__ void log_append(const BirthLogDev &lg, uint4 e) {
 struct GlobalSink {
   const PairTableDev &t;
   const BirthLogDev &lg;
-  __device__ __forceinline__ void add(int32_t x, int32_t y, long long delta, uint64_t key) { pt_add(t, x, y, delta, key); }
+  __device__ __forceinline__ void add_batch(int n, const int32_t *x, const int32_t *y, const long long *delta, const uint64_t *key) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) pt_add(t, x[i], y[i], delta[i], key[i]);
+  }
   __device__ __forceinline__ void birth(uint32_t other, bool right_side, uint32_t wi, uint64_t hloc) {
     log_append(lg, log_entry(other, right_side, wi, hloc));
   }
@@ -811,6 +942,7 @@ __device__ __forceinline__ uint32_t scan_log_words(const StreamDev &s, const Pai
   const uint64_t n = __ldcg(&lg.start[merge + 1]) - lo;
   GlobalSink sink{t, lg};
   uint32_t removed = 0;
+#pragma unroll 1
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 e = __ldcg(&lg.ent[lo + i]);
     if (e.x == want_other && (e.y & 0x80000000u) == want_side)

@@ -12,6 +12,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#include <emmintrin.h>
+
 #include <chrono>
 #include <map>
 #include <mutex>
@@ -470,6 +472,7 @@ class TrainerImpl {
     stream_merges_++;
     if (log_ok_) log_start_h_.push_back((uint32_t)(hdr_flags >> 32));
   }
+  unsigned long long log_cursor_h() const { return (log_ok_ && !log_start_h_.empty()) ? log_start_h_.back() : 0ull; }
   // lo << 32 | n of the log that holds the births of (a, b) (device ids), ~0 when the pair has none
   unsigned long long log_range_of(int32_t da, int32_t db) const {
     const int32_t newer = da > db ? da : db;
@@ -1257,13 +1260,13 @@ class TrainerImpl {
     volatile HostCmd2 *c = nullptr;
     unsigned long long next_seq = 0;
     bool running = false;
-    void send(unsigned long long pair, unsigned long long nio, unsigned long long lr) {
-      c->pair = pair; c->new_id_op = nio; c->log_range = lr; c->check = cmd2_check(next_seq, pair, nio, lr);
-      __atomic_thread_fence(__ATOMIC_RELEASE);
-      c->seq = next_seq;
+    void send(unsigned long long pair, unsigned int new_id, unsigned int op) {
+      const unsigned int x = (unsigned int)pair, y = (unsigned int)(pair >> 32), z = (new_id & 0x0FFFFFFFu) | (op << 28);
+      const __m128i v = _mm_set_epi32((int)cmd3_word(next_seq, x, y, z), (int)z, (int)y, (int)x);
+      _mm_store_si128(reinterpret_cast<__m128i *>(const_cast<HostCmd2 *>(c)), v);  // one 16-byte store: the device never sees half a command
       __atomic_thread_fence(__ATOMIC_SEQ_CST);
     }
-    ~HostCmd2Sender() { if (running) send(0, 1ull << 32, ~0ull); }
+    ~HostCmd2Sender() { if (running) send(0, 0, 1); }
   };
   // Runs up to max_merges merges starting with (a, b) (already popped, pending in `core`) inside ONE launch of
   // merge_cluster. Returns the number performed; stops early when the heap is exhausted or a table has to grow.
@@ -1271,7 +1274,7 @@ class TrainerImpl {
     ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
     maybe_grow_global_table(gt_flagged_);
     gt_flagged_ = false;
-    if (!hcmd2_.size()) { hcmd2_.alloc(1); dcmd2_.alloc(1); }
+    if (!hcmd2_.size()) { hcmd2_.alloc(1); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); }
     memset((void *)hcmd2_.host(), 0, sizeof(HostCmd2));
     SWB_CUDA(cudaMemsetAsync(dcmd2_.get(), 0, sizeof(DevCmd2), stream_));
     const int32_t unk = tr_->config.unk_id;
@@ -1300,17 +1303,39 @@ class TrainerImpl {
     sender.c = hcmd2_.host();
     sender.next_seq = seq_base + 1;  // the first merge travels through the mailbox like all the others
     int32_t da = to_dev(a), db = to_dev(b);
-    sender.send(((unsigned long long)(uint32_t)da << 32) | (uint32_t)db, (unsigned long long)(uint32_t)new_id, log_range_of(da, db));
+    sender.send(((unsigned long long)(uint32_t)da << 32) | (uint32_t)db, (unsigned int)new_id, 0);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)(cf.clusters * CL_SIZE)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES; cfg.stream = stream_;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeCooperative;
-    at[1].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = cf.cooperative ? 2 : 1;
-    SWB_CUDA(cudaLaunchKernelEx(&cfg, merge_cluster, s, pt_, em, removed_p, out, out_cap, out_hdr, seq_base, op_base, hc, dc, timeout_ns, trace_p));
+    cudaLaunchAttribute at[3];
+    int n_at = 0;
+    at[n_at].id = cudaLaunchAttributeClusterDimension;
+    at[n_at].val.clusterDim.x = CL_SIZE; at[n_at].val.clusterDim.y = 1; at[n_at].val.clusterDim.z = 1;
+    n_at++;
+    if (cf.cooperative) { at[n_at].id = cudaLaunchAttributeCooperative; at[n_at].val.cooperative = 1; n_at++; }
+    {  // keep the symbol rows resident in L2 across the merges of this launch (the birth log streams through it)
+      static const bool no_persist = getenv("SWB_NO_L2_PERSIST") && atoi(getenv("SWB_NO_L2_PERSIST")) > 0;
+      int max_persist = 0, max_window = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device_);
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device_);
+      const size_t want = n_rows_ * (size_t)ROW * 4;
+      if (!no_persist && max_persist > 0 && max_window > 0 && want > 0) {
+        const size_t persist = std::min<size_t>((size_t)max_persist, want);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+          const size_t win = std::min<size_t>(want, (size_t)max_window);
+          at[n_at].id = cudaLaunchAttributeAccessPolicyWindow;
+          at[n_at].val.accessPolicyWindow.base_ptr = (void *)rows_.get();
+          at[n_at].val.accessPolicyWindow.num_bytes = win;
+          at[n_at].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)win);
+          at[n_at].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+          at[n_at].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+          n_at++;
+        }
+        cudaGetLastError();
+      }
+    }
+    cfg.attrs = at; cfg.numAttrs = n_at;
+    SWB_CUDA(cudaLaunchKernelEx(&cfg, merge_cluster, s, pt_, em, removed_p, out, out_cap, out_hdr, seq_base, op_base, hc, dc, timeout_ns, trace_p, cl_ovf_.get()));
     SWB_CUDA(cudaGetLastError());
     launched(); stats.merge_launches++;
     sender.running = true;
@@ -1343,9 +1368,9 @@ class TrainerImpl {
       int32_t na = 0, nb = 0, nn = 0;
       if (go) { go = core.next_merge(&na, &nb, &nn); stats.host_pop_ms += now_ms() - ta1; }
       sender.next_seq = seq_base + done + 1;
-      if (!go) { sender.send(0, 1ull << 32, ~0ull); sender.running = false; break; }
+      if (!go) { sender.send(0, 0, 1); sender.running = false; break; }
       da = to_dev(na); db = to_dev(nb);
-      sender.send(((unsigned long long)(uint32_t)da << 32) | (uint32_t)db, (unsigned long long)(uint32_t)nn, log_range_of(da, db));
+      sender.send(((unsigned long long)(uint32_t)da << 32) | (uint32_t)db, (unsigned int)nn, 0);
     }
     sync();
     if (trace_p) {
@@ -1356,6 +1381,12 @@ class TrainerImpl {
               "waiting for the host %.2f us | words+deltas: thread 0 alone %.2f us, its CTA %.2f us; log entries %.0f\n", h[0], done, h[1] / n / ghz / 1e3, h[2] / n / ghz / 1e3, h[3] / n / ghz / 1e3, h[4] / n / ghz / 1e3,
               h[5] / n / ghz / 1e3, h[7] / n / ghz / 1e3, h[6] / n);
       fprintf(stderr, "[trace]   thread 0: entries arrived after %.2f us, own words %.2f us\n", h[8] / n / ghz / 1e3, h[9] / n / ghz / 1e3);
+      unsigned long long wt[8];
+      if (cudaMemcpyFromSymbol(wt, g_word_trace, sizeof wt) == cudaSuccess && wt[6]) {
+        const double nw = (double)wt[6];
+        fprintf(stderr, "[trace]   one word (block 0 / thread 0, %llu words): load+parse %.2f us, rewrite %.2f us, reconverge %.2f us, deltas %.2f us, write back+births %.2f us\n",
+                wt[6], wt[0] / nw / ghz / 1e3, wt[1] / nw / ghz / 1e3, wt[2] / nw / ghz / 1e3, wt[3] / nw / ghz / 1e3, wt[4] / nw / ghz / 1e3);
+      }
     }
     return done;
   }
@@ -1522,6 +1553,7 @@ class TrainerImpl {
   DevBuf<DevCmd> dcmd_;
   PinnedBuf<HostCmd2> hcmd2_;
   DevBuf<DevCmd2> dcmd2_;
+  DevBuf<uint4> cl_ovf_;
   DevBuf<unsigned long long> ptrace_;
   // device-resident loop
   DevBuf<LoopState> loop_state_;
