@@ -169,6 +169,10 @@ class HostCore {
     size_t i = 0;
     for (;;) {  // left child if strictly larger, then right if strictly larger than that (heap.cpp:97-111)
       size_t l = 2 * i + 1, r = l + 1, best = i;
+      {  // the four grandchildren are contiguous (96 bytes): fetch them while the children are compared
+        const size_t g = 4 * i + 3;
+        if (g < h.size) { __builtin_prefetch(&h.data[g]); __builtin_prefetch(reinterpret_cast<const char *>(&h.data[g]) + 64); }
+      }
       if (l < h.size && h.data[l].freq > h.data[best].freq) best = l;
       if (r < h.size && h.data[r].freq > h.data[best].freq) best = r;
       if (best == i) break;
@@ -288,6 +292,22 @@ class HostCore {
   // bucket entries were prepended, so the most recently first-touched pair comes first. Counting sort by
   // bucket, then each bucket by key descending ((L, new_id) for every L share one bucket: runs can be long).
   void sort_delta_order(const Rec *recs, size_t n) {
+    if (n <= 48) {  // short lists (most merges): one insertion sort by (bucket ascending, key descending) beats the 1024-bucket pass
+      order_.resize(n);
+      for (size_t i = 0; i < n; i++) {
+        const uint32_t bk = (uint32_t)recs[i].second & 1023u;
+        const uint64_t key = (uint64_t)recs[i].key;
+        size_t y = i;
+        while (y > 0) {
+          const uint32_t pb = (uint32_t)recs[order_[y - 1].idx].second & 1023u;
+          if (pb < bk || (pb == bk && order_[y - 1].key >= key)) break;
+          order_[y] = order_[y - 1];
+          y--;
+        }
+        order_[y] = KeyIdx{key, (uint32_t)i};
+      }
+      return;
+    }
     uint32_t start[1025];
     memset(start, 0, sizeof start);
     for (size_t i = 0; i < n; i++) start[((uint32_t)recs[i].second & 1023u) + 1]++;

@@ -781,62 +781,43 @@ __device__ __forceinline__ uint32_t merge_one_word(const StreamDev &s, uint64_t 
 #pragma unroll
   for (int j = WORD_FAST; j >= 0; j--)
     if (y[j] < 0) { n = j; fast = true; }
-  SWB_WT(0, wt0);
-  if (fast) {
-    // ---- registers only. `out` = symbol written at position w; births are read off consecutive outputs.
-    int w = 0, prev = -1;
-    bool skip = false;
-    uint32_t lb[4], rb[4];  // neighbours already logged on the left / right side of a new_id of this word
-    int nlb = 0, nrb = 0;
+  // where the pair sits (bit r: symbols r, r+1). The register path takes the words with exactly ONE match -- nearly all
+  // candidates; overlapping or repeated matches go through the general path below.
+  unsigned int mm = 0;
 #pragma unroll
-    for (int r = 0; r < WORD_FAST; r++) {
-      if (r >= n) continue;
-      if (skip) { skip = false; continue; }
-      int out = y[r];
-      if (y[r] == a && r + 1 < n && y[r + 1] == b) {
-        mL[nmatch] = prev;
-        mR[nmatch] = r + 2 < n ? y[r + 2] : -1;
-        mpos[nmatch] = (unsigned char)(hpos + 1 + r);
-        nmatch++;
-        out = new_id;
-        skip = true;
-      }
-      if (nmatch) {
-        if (w != r || out != y[r]) wsym[w] = out;
-        // births: (prev, out) is a final adjacency; it involves new_id iff one of the two is new_id
-        if (prev >= 0) {
-          if (out == new_id) {  // left side of a new_id (also covers (new, new))
-            bool dup = false;
-            for (int q = 0; q < nlb; q++) dup |= lb[q] == (uint32_t)prev;
-            if (!dup && nlb < 4) lb[nlb++] = (uint32_t)prev;
-          } else if (prev == new_id) {  // right side of a new_id
-            bool dup = false;
-            for (int q = 0; q < nrb; q++) dup |= rb[q] == (uint32_t)out;
-            if (!dup && nrb < 4) rb[nrb++] = (uint32_t)out;
-          }
-        }
-      }
-      prev = out;
-      w++;
+  for (int r = 0; r + 1 < WORD_FAST; r++)
+    if (y[r] == a && y[r + 1] == b && r + 1 < n) mm |= 1u << r;
+  SWB_WT(0, wt0);
+  if (fast && mm != 0 && (mm & (mm - 1)) == 0) {
+    const int r0 = __ffs(mm) - 1;
+    int L = -1, R = -1;
+#pragma unroll
+    for (int j = 0; j < WORD_FAST; j++) {
+      if (j == r0 - 1) L = y[j];
+      if (j == r0 + 2 && j < n) R = y[j];
     }
-    if (nmatch) {
-      for (int q = w; q < n; q++) wsym[q] = PAD;
+    // symbols r0 .. n-1 change: new_id, then the tail moved up by one, then PAD
+#pragma unroll
+    for (int q = 0; q < WORD_FAST; q++)
+      if (q >= r0 && q < n) wsym[q] = q == r0 ? new_id : (q + 1 < n ? y[q + 1] : PAD);
+    {
       const uint32_t hh = sig_hash(new_id);
       atomicOr(&s.sig[(row_base / ROW) * SIG_WORDS + (hh >> 5)], 1u << (hh & 31));
     }
     SWB_WT(1, wt0);
     __syncwarp(entered);
     SWB_WT(2, wt0);
-    emit_word_matches(nmatch, mL, mR, mpos, wi, cc, a, b, new_id, sink);
-#pragma unroll
-    for (int q = 0; q < 4; q++) {  // births, lanes side by side (at most 4 per side: a fast word has at most 4 matches)
-      if (q < nlb) sink.birth(lb[q], false, wi, hloc);
-      if (q < nrb) sink.birth(rb[q], true, wi, hloc);
-    }
+    mL[0] = L; mR[0] = R; mpos[0] = (unsigned char)(hpos + 1 + r0);
+    emit_word_matches(1, mL, mR, mpos, wi, cc, a, b, new_id, sink);
+    if (L >= 0) sink.birth((uint32_t)L, false, wi, hloc);  // the final neighbours of the one new_id
+    if (R >= 0) sink.birth((uint32_t)R, true, wi, hloc);
     SWB_WT(3, wt0);
+#ifdef SWB_KERNEL_TRACE
     if (blockIdx.x == 0 && threadIdx.x == 0) g_word_trace[6] += 1;
-    return nmatch;
+#endif
+    return 1;
   }
+  if (fast && mm == 0) { __syncwarp(entered); return 0; }  // a candidate that no longer holds the pair
 
   // ---- general path: the word goes through thread-local memory
   int buf[ROW];
