@@ -140,6 +140,10 @@ typedef struct SwbStats {
   uint64_t records, heap_pushes, heap_pops, heap_peak;             /* host replica counters */
   uint64_t collectives, exchange_bytes;                            /* multi-GPU: NCCL all-gathers and their bytes */
   uint64_t loop_runs, loop_stop_tie, loop_stop_big, loop_stop_rebuild, loop_stop_other; /* device-resident loop */
+  /* resident cluster kernel: merges done by the leader cluster alone / by the whole grid, and the device time
+   * they took (command seen -> result published, %globaltimer; also added to merge_kernel_ms) */
+  uint64_t resident_local_merges, resident_grid_merges;
+  double resident_local_ms, resident_grid_ms;
 } SwbStats;
 void swb_get_stats(const Trainer *trainer, SwbStats *out);
 /* 1: bracket every merge-scan launch with CUDA events (adds a little latency); 0: off (default). */

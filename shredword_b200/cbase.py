@@ -44,7 +44,9 @@ class SwbStats(Structure):
               ("records", c_uint64), ("heap_pushes", c_uint64), ("heap_pops", c_uint64), ("heap_peak", c_uint64),
               ("collectives", c_uint64), ("exchange_bytes", c_uint64),
               ("loop_runs", c_uint64), ("loop_stop_tie", c_uint64), ("loop_stop_big", c_uint64), ("loop_stop_rebuild", c_uint64),
-              ("loop_stop_other", c_uint64)]
+              ("loop_stop_other", c_uint64),
+              ("resident_local_merges", c_uint64), ("resident_grid_merges", c_uint64),
+              ("resident_local_ms", c_double), ("resident_grid_ms", c_double)]
 
 # ---- the reference's eight entry points (reference cbase.py:44-59)
 lib.create_trainer.argtypes = [POINTER(BPEConfig)]

@@ -47,7 +47,7 @@ __host__ __device__ __forceinline__ unsigned int cmd3_word(unsigned long long se
   return (s24 << 8) | (f & 0xFFu);
 }
 // leader -> other clusters (device memory)
-struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, pad[2]; };
+struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, t_cmd /* %globaltimer when the command arrived */, pad; };
 __host__ __device__ __forceinline__ unsigned long long cmd2_check(unsigned long long seq, unsigned long long pair,
                                                                   unsigned long long nio, unsigned long long lr) {
   return (seq * HDR_MAGIC) ^ pair ^ (nio << 7 | nio >> 57) ^ (lr * 0xD6E8FEB86659FD93ull);
@@ -62,7 +62,8 @@ struct ClusterCtl {
   // the command, written into every CTA of the leader cluster by its CTA 0
   unsigned long long pair, new_id_op, log_range, k;
   unsigned int mode, stop;             // mode 0 = LOCAL, 1 = GRID
-  unsigned int log_cursor, births_total;  // CTA 0: log entries before this merge (from the host) / appended by this merge so far
+  unsigned int log_cursor, births_total;  // CTA 0: log entries before this merge / appended by this merge so far
+  unsigned long long t_cmd;               // %globaltimer when the command of this merge arrived
   // per CTA, per merge
   unsigned int n_births, n_recs, n_occ, rec_base, birth_base, n_cand, n_occ1, inbox_n, n_ovf, pad1;
   // cluster-wide, live in CTA 0 only
@@ -291,7 +292,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
 merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *removed_total, Rec *__restrict__ out, size_t out_cap,
               unsigned long long *__restrict__ out_hdr, unsigned long long seq_base, unsigned long long op_base,
               volatile HostCmd2 *hcmd, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace,
-              uint4 *ovf /* [CL_LOCAL_MAX]: candidate words that did not fit a CTA's shared-memory list */) {
+              uint4 *ovf /* [CL_LOCAL_MAX]: candidate words that did not fit a CTA's shared-memory list */,
+              unsigned long long *acct /* [4]: LOCAL merges, their device ns, GRID merges, their device ns */) {
   extern __shared__ __align__(16) unsigned char cl_dyn_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const ClusterSmem m = cluster_smem(cl_dyn_smem);
@@ -338,15 +340,16 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           if (cursor_stale && em.log.ent != nullptr) { m.ctl->log_cursor = __ldcg(em.log.cursor); cursor_stale = false; }
           m.ctl->births_total = 0;
         }
+        const unsigned long long t_cmd = gtime_ns();
         const unsigned int stop = (unsigned int)(nio >> 32);
         const unsigned int mode = (lr == ~0ull || (unsigned int)(lr & 0xFFFFFFFFu) > CL_LOCAL_MAX) ? 1u : 0u;
         for (unsigned int r = 0; r < CL_SIZE; r++) {
           ClusterCtl *c = cluster.map_shared_rank(m.ctl, r);
-          c->pair = pair; c->new_id_op = nio; c->log_range = lr; c->k = k; c->mode = mode; c->stop = stop;
+          c->pair = pair; c->new_id_op = nio; c->log_range = lr; c->k = k; c->mode = mode; c->stop = stop; c->t_cmd = t_cmd;
         }
         if (mode == 1u) cursor_stale = true;  // a GRID merge appends through the global cursor
         if (stop || mode == 1u) {  // the other clusters take part (or leave)
-          dcmd->pair = pair; dcmd->new_id_op = nio; dcmd->log_range = lr; dcmd->k = k;
+          dcmd->pair = pair; dcmd->new_id_op = nio; dcmd->log_range = lr; dcmd->k = k; dcmd->t_cmd = t_cmd;
           __threadfence();
           *(volatile unsigned long long *)&dcmd->epoch = grid_epoch + 1;
         }
@@ -362,6 +365,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
             __threadfence();
             pair = *(volatile unsigned long long *)&dcmd->pair; nio = *(volatile unsigned long long *)&dcmd->new_id_op;
             lr = *(volatile unsigned long long *)&dcmd->log_range; kk = *(volatile unsigned long long *)&dcmd->k;
+            m.ctl->t_cmd = *(volatile unsigned long long *)&dcmd->t_cmd;
             break;
           }
           if ((spin & 255) == 255 && gtime_ns() - *(volatile unsigned long long *)&dcmd->alive_ns > 4 * timeout_ns) break;  // leader gone
@@ -397,6 +401,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         __threadfence();
         TailSmem ts{m.tail_stage, m.csum, m.tail_count};
         fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u, nullptr, nullptr);
+        if (threadIdx.x == 0) { acct[2] += 1; acct[3] += gtime_ns() - m.ctl->t_cmd; }  // (one publisher at a time)
       }
       __syncthreads();
       // the scratch aliased the delta tables: empty them again
@@ -528,6 +533,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u, nullptr, nullptr);
         __syncthreads();
         cluster_clear_tables(m);
+        if (threadIdx.x == 0) { acct[0] += 1; acct[1] += gtime_ns() - c->t_cmd; }
         if (threadIdx.x == 0) { c->spill = 0; c->n_recs_total = 0; c->removed = 0; }
         __syncthreads();
       } else if (threadIdx.x == 0) {
@@ -548,6 +554,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(out_hdr + 4), "l"(x), "l"(sm) : "memory");
           asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(out_hdr + 0), "l"(seq), "l"((unsigned long long)n) : "memory");
           asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(out_hdr + 6), "l"(chk), "l"(seq) : "memory");
+          acct[0] += 1; acct[1] += gtime_ns() - c->t_cmd;
         }
         c->n_recs_total = 0; c->removed = 0;
         if (trace) {

@@ -1274,7 +1274,8 @@ class TrainerImpl {
     ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
     maybe_grow_global_table(gt_flagged_);
     gt_flagged_ = false;
-    if (!hcmd2_.size()) { hcmd2_.alloc(1); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); }
+    if (!hcmd2_.size()) { hcmd2_.alloc(1); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(4); }
+    SWB_CUDA(cudaMemsetAsync(cl_acct_.get(), 0, cl_acct_.bytes(), stream_));
     memset((void *)hcmd2_.host(), 0, sizeof(HostCmd2));
     SWB_CUDA(cudaMemsetAsync(dcmd2_.get(), 0, sizeof(DevCmd2), stream_));
     const int32_t unk = tr_->config.unk_id;
@@ -1335,7 +1336,7 @@ class TrainerImpl {
       }
     }
     cfg.attrs = at; cfg.numAttrs = n_at;
-    SWB_CUDA(cudaLaunchKernelEx(&cfg, merge_cluster, s, pt_, em, removed_p, out, out_cap, out_hdr, seq_base, op_base, hc, dc, timeout_ns, trace_p, cl_ovf_.get()));
+    SWB_CUDA(cudaLaunchKernelEx(&cfg, merge_cluster, s, pt_, em, removed_p, out, out_cap, out_hdr, seq_base, op_base, hc, dc, timeout_ns, trace_p, cl_ovf_.get(), cl_acct_.get()));
     SWB_CUDA(cudaGetLastError());
     launched(); stats.merge_launches++;
     sender.running = true;
@@ -1373,6 +1374,13 @@ class TrainerImpl {
       sender.send(((unsigned long long)(uint32_t)da << 32) | (uint32_t)db, (unsigned int)nn, 0);
     }
     sync();
+    {  // device time of this launch's merges (command seen -> result published), per mode
+      unsigned long long ac[4];
+      SWB_CUDA(cudaMemcpy(ac, cl_acct_.get(), sizeof ac, cudaMemcpyDeviceToHost));
+      stats.resident_local_merges += ac[0]; stats.resident_local_ms += (double)ac[1] * 1e-6;
+      stats.resident_grid_merges += ac[2]; stats.resident_grid_ms += (double)ac[3] * 1e-6;
+      stats.merge_kernel_ms += (double)(ac[1] + ac[3]) * 1e-6;
+    }
     if (trace_p) {
       unsigned long long h[16];
       SWB_CUDA(cudaMemcpy(h, trace_p, sizeof h, cudaMemcpyDeviceToHost));
@@ -1554,6 +1562,7 @@ class TrainerImpl {
   PinnedBuf<HostCmd2> hcmd2_;
   DevBuf<DevCmd2> dcmd2_;
   DevBuf<uint4> cl_ovf_;
+  DevBuf<unsigned long long> cl_acct_;
   DevBuf<unsigned long long> ptrace_;
   // device-resident loop
   DevBuf<LoopState> loop_state_;
