@@ -144,6 +144,10 @@ typedef struct SwbStats {
    * they took (command seen -> result published, %globaltimer; also added to merge_kernel_ms) */
   uint64_t resident_local_merges, resident_grid_merges;
   double resident_local_ms, resident_grid_ms;
+  /* look-ahead of the resident kernel: hints the host sent (HostCore::peek_next), merges the device started
+   * from one without waiting for the command, hints it turned down; host time spent looking ahead */
+  uint64_t hints_sent, hints_taken, hints_rejected;
+  double host_peek_ms;
 } SwbStats;
 void swb_get_stats(const Trainer *trainer, SwbStats *out);
 /* 1: bracket every merge-scan launch with CUDA events (adds a little latency); 0: off (default). */
@@ -182,6 +186,16 @@ void swb_dist_seed(Trainer *trainer, const int64_t *recs, size_t n);
 int swb_dist_next_merge(Trainer *trainer, int32_t *a, int32_t *b, int32_t *new_id);
 /* Replica step 3: apply the reduced delta records of the merge returned by step 2. */
 void swb_dist_apply(Trainer *trainer, const int64_t *recs, size_t n);
+/* Look-ahead between steps 2 and 3 (what the resident merge kernel's hints are made of): 1 = the pair step 2
+ * will return NEXT is (a, b), currently at frequency *freq, PROVIDED the pending merge pushes no entry with a
+ * frequency >= *freq and leaves (a, b)'s frequency unchanged; 0 = no statement. The heap (reference
+ * heap.cpp:53-114 array) is left bit for bit as it was. */
+int swb_dist_peek_next(Trainer *trainer, int32_t *a, int32_t *b, uint64_t *freq);
+/* The same for the next `want` pairs: out[3*i .. 3*i+2] = {a, b, freq} of the pair that step 2 returns i calls
+ * after the next one, PROVIDED no merge from the pending one up to the one before it pushes an entry with a
+ * frequency >= that freq, and the pair's frequency is still that freq when its turn comes. Returns the
+ * number of entries filled (0 .. want). */
+size_t swb_dist_peek_list(Trainer *trainer, int64_t *out, size_t want);
 /* In-library multi-GPU training (one process per GPU): NCCL is loaded with dlopen and the per-merge
  * all-gather is issued from C++ on the handle's stream. Rank 0 calls swb_dist_unique_id, the caller
  * ships the 128 bytes to every rank (any transport), every rank calls swb_dist_init before loading the

@@ -46,7 +46,8 @@ class SwbStats(Structure):
               ("loop_runs", c_uint64), ("loop_stop_tie", c_uint64), ("loop_stop_big", c_uint64), ("loop_stop_rebuild", c_uint64),
               ("loop_stop_other", c_uint64),
               ("resident_local_merges", c_uint64), ("resident_grid_merges", c_uint64),
-              ("resident_local_ms", c_double), ("resident_grid_ms", c_double)]
+              ("resident_local_ms", c_double), ("resident_grid_ms", c_double),
+              ("hints_sent", c_uint64), ("hints_taken", c_uint64), ("hints_rejected", c_uint64), ("host_peek_ms", c_double)]
 
 # ---- the reference's eight entry points (reference cbase.py:44-59)
 lib.create_trainer.argtypes = [POINTER(BPEConfig)]
@@ -99,6 +100,8 @@ _sigs = {
   "swb_dist_seed": ([T, c_void_p, c_size_t], None),
   "swb_dist_next_merge": ([T, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)], c_int),
   "swb_dist_apply": ([T, c_void_p, c_size_t], None),
+  "swb_dist_peek_next": ([T, POINTER(c_int32), POINTER(c_int32), POINTER(c_uint64)], c_int),
+  "swb_dist_peek_list": ([T, c_void_p, c_size_t], c_size_t),
   "swb_shard_count": ([T, c_void_p, c_size_t], c_int64),
   "swb_shard_merge": ([T, c_int32, c_int32, c_int32, c_void_p, c_size_t], c_int64),
   "swb_dist_unique_id": ([c_void_p], c_int),

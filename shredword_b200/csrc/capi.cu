@@ -330,6 +330,18 @@ int swb_dist_next_merge(Trainer *trainer, int32_t *a, int32_t *b, int32_t *new_i
   if (!trainer || !a || !b || !new_id) return 0;
   return impl_of(trainer)->core.next_merge(a, b, new_id) ? 1 : 0;
 }
+int swb_dist_peek_next(Trainer *trainer, int32_t *a, int32_t *b, uint64_t *freq) {
+  if (!trainer || !a || !b || !freq) return 0;
+  return impl_of(trainer)->core.peek_next(a, b, freq) ? 1 : 0;
+}
+size_t swb_dist_peek_list(Trainer *trainer, int64_t *out, size_t want) {
+  if (!trainer || !out) return 0;
+  swb::HostCore::Peek p[16];
+  if (want > 16) want = 16;
+  const size_t n = impl_of(trainer)->core.peek_next(p, want);
+  for (size_t i = 0; i < n; i++) { out[3 * i] = p[i].a; out[3 * i + 1] = p[i].b; out[3 * i + 2] = (int64_t)p[i].freq; }
+  return n;
+}
 void swb_dist_apply(Trainer *trainer, const int64_t *recs, size_t n) {
   if (!trainer) return;
   impl_of(trainer)->core.apply(reinterpret_cast<const Rec *>(recs), n);

@@ -47,7 +47,7 @@ __host__ __device__ __forceinline__ unsigned int cmd3_word(unsigned long long se
   return (s24 << 8) | (f & 0xFFu);
 }
 // leader -> other clusters (device memory)
-struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, t_cmd /* %globaltimer when the command arrived */, pad; };
+struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, t_cmd /* %globaltimer when the command arrived */, spec /* started from a hint */; };
 __host__ __device__ __forceinline__ unsigned long long cmd2_check(unsigned long long seq, unsigned long long pair,
                                                                   unsigned long long nio, unsigned long long lr) {
   return (seq * HDR_MAGIC) ^ pair ^ (nio << 7 | nio >> 57) ^ (lr * 0xD6E8FEB86659FD93ull);
@@ -65,10 +65,12 @@ struct ClusterCtl {
   unsigned int log_cursor, births_total;  // CTA 0: log entries before this merge / appended by this merge so far
   unsigned long long t_cmd;               // %globaltimer when the command of this merge arrived
   // per CTA, per merge
-  unsigned int n_births, n_recs, n_occ, rec_base, birth_base, n_cand, n_occ1, inbox_n, n_ovf, pad1;
+  unsigned int n_births, n_recs, n_occ, rec_base, birth_base, n_cand, n_occ1, inbox_n, n_ovf, spec /* this merge was started from a hint */;
+  unsigned long long maxpush;          // per CTA, per merge: largest new frequency >= min_freq among this CTA's records (what the host will push)
   // cluster-wide, live in CTA 0 only
   unsigned int spill, n_recs_total, removed, inserted;
   unsigned long long part_cx[CL_SIZE], part_cs[CL_SIZE];  // per-CTA record checksums (plain remote stores; combined by CTA 0)
+  unsigned long long part_max[CL_SIZE];                    // per-CTA maxpush
 };
 
 struct ClusterSmem {
@@ -246,7 +248,7 @@ __device__ __forceinline__ void cluster_fold_inbox(const ClusterSmem &m, const P
 // LOCAL merge, phase 2 of one CTA: apply this CTA's pairs to the device frequency table and stage the records
 __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const EmitMode &em, const PairTableDev &t, bool spill,
                                                   unsigned long long &cx, unsigned long long &cs, unsigned int &inserted,
-                                                  Rec *__restrict__ out, size_t out_cap, cg::cluster_group &cluster, int32_t new_id) {
+                                                  unsigned long long &maxpush, Rec *__restrict__ out, size_t out_cap, cg::cluster_group &cluster, int32_t new_id) {
   const unsigned int n_occ = m.ctl->n_occ;  // (listed while T2 was filled; the caller has synchronised the block)
   ClusterCtl *c0 = cluster.map_shared_rank(m.ctl, 0);
 #pragma unroll 1
@@ -281,6 +283,7 @@ __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const Em
     else nw = old + (unsigned long long)d;
     em.g.slots[g].freq = nw;
     if (old >= em.min_freq || nw >= em.min_freq) {
+      if (nw >= em.min_freq && nw > maxpush) maxpush = nw;  // the host pushes this pair (reference bpe.cpp:512-515)
       const unsigned int j = atomicAdd(&m.ctl->n_recs, 1u);
       if (j < CL_REC_STAGE) rec_out(m.recs, CL_REC_STAGE, j, k, (long long)nw, mk, cx, cs);
       else rec_out(out, out_cap, atomicAdd(&c0->n_recs_total, 1u), k, (long long)nw, mk, cx, cs);  // past the stage: straight to its final place
@@ -289,11 +292,11 @@ __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const Em
 }
 
 __global__ void __launch_bounds__(CL_THREADS, 1)
-merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *removed_total, Rec *__restrict__ out, size_t out_cap,
-              unsigned long long *__restrict__ out_hdr, unsigned long long seq_base, unsigned long long op_base,
-              volatile HostCmd2 *hcmd, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace,
+merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *removed_total, Rec *__restrict__ out0, Rec *__restrict__ out1, size_t out_cap,
+              unsigned long long *__restrict__ out_hdr0, unsigned long long *__restrict__ out_hdr1, unsigned long long seq_base, unsigned long long op_base,
+              volatile HostCmd2 *hcmd /* [3] in mapped host memory: the command, the hints for even / odd sequence numbers */, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace,
               uint4 *ovf /* [CL_LOCAL_MAX]: candidate words that did not fit a CTA's shared-memory list */,
-              unsigned long long *acct /* [4]: LOCAL merges, their device ns, GRID merges, their device ns */) {
+              unsigned long long *acct /* [8]: LOCAL merges, their device ns, GRID merges, their device ns, hints accepted, hints rejected, hints accepted without a PCIe trip, - */) {
   extern __shared__ __align__(16) unsigned char cl_dyn_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const ClusterSmem m = cluster_smem(cl_dyn_smem);
@@ -311,6 +314,11 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
   unsigned long long grid_epoch = 0;  // GRID merges seen so far
   unsigned int pre_flags = 0;
   bool cursor_stale = true;  // (CTA 0 / thread 0) the log cursor kept in shared memory is behind the global one
+  // (CTA 0 / thread 0) hints: the previous merge was LOCAL and clean, the largest frequency it makes the host push, its token
+  bool hint_ok = false;
+  unsigned long long prev_maxpush = 0;
+  unsigned int prev_new_id = 0;
+  uint4 pre_hv = make_uint4(0u, 0u, 0u, 0u);  // the hint word for the NEXT merge, requested while this one runs (a read of mapped host memory takes microseconds)
   long long tr_poll = 0, tr_p1 = 0, tr_p2 = 0, tr_pub = 0;
   for (unsigned long long k = 0;; k++) {
     // ---------------------------------------------------------------- next command
@@ -320,16 +328,41 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         const unsigned long long want = seq_base + k + 1;
         const unsigned long long t0 = gtime_ns();
         unsigned long long pair = 0, nio = 3ull << 32, lr = ~0ull;
+        unsigned int spec = 0;
         for (unsigned long long spin = 0;; spin++) {
-          uint4 v;  // one 16-byte load from mapped host memory = one PCIe read
-          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(hcmd) : "memory");
-          if (v.w == cmd3_word(want, v.x, v.y, v.z)) {
+          uint4 v = make_uint4(0u, 0u, 0u, 0u), hv = make_uint4(0u, 0u, 0u, 0u);  // one 16-byte load from mapped host memory = one PCIe read (the two are in flight together)
+          bool have_v = true;
+          if (spin == 0 && hint_ok && pre_hv.z != 0u && pre_hv.w == cmd3_word(want, pre_hv.x, pre_hv.y, pre_hv.z)) { hv = pre_hv; have_v = false; }  // already here: no trip at all
+          else {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(hcmd) : "memory");
+            if (hint_ok) asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hv.x), "=r"(hv.y), "=r"(hv.z), "=r"(hv.w) : "l"(hcmd + 1 + (want & 1ull)) : "memory");
+          }
+          if (have_v && v.w == cmd3_word(want, v.x, v.y, v.z)) {
             pair = ((unsigned long long)v.y << 32) | v.x;
             nio = (unsigned long long)(v.z & 0x0FFFFFFFu) | ((unsigned long long)(v.z >> 28) << 32);
             break;
           }
+          if (have_v && (v.z >> 28) == 1u && v.w == cmd3_word(want - 1, v.x, v.y, v.z)) {  // a stop addressed to the merge this kernel started from a hint
+            nio = 1ull << 32;
+            break;
+          }
+          // Hint {second, first, frequency F}: "the next pair is (first, second) if the merge before it pushes nothing >= F and
+          // leaves that pair's frequency at F" (the host derived it from its exact heap, see HostCore::peek_next). Both conditions
+          // are checked here, against the device frequency table; a rejected hint is ignored and the command awaited.
+          if (hint_ok && hv.z != 0u && hv.w == cmd3_word(want, hv.x, hv.y, hv.z)) {
+            const unsigned long long hk = ((unsigned long long)hv.y << 32) | hv.x, F = hv.z;
+            if (prev_maxpush < F && gt_find_freq(em.g, hk) == F) {
+              pair = hk; nio = (unsigned long long)((prev_new_id + 1u) & 0x0FFFFFFFu); spec = 1u;
+              acct[4] += 1;
+              if (!have_v) acct[6] += 1;  // ... and it was already here when the merge before finished
+              break;
+            }
+            acct[5] += 1;
+            hint_ok = false;
+          }
           if ((spin & 63) == 63 && gtime_ns() - t0 > timeout_ns) break;  // abort: the host went away
         }
+        hint_ok = false;
         if (!(nio >> 32)) {  // the birth log of the newer token of the pair (device-side bookkeeping: cheaper than a second PCIe trip)
           const int32_t pa = (int32_t)(pair >> 32), pb = (int32_t)(pair & 0xFFFFFFFFu), newer = pa > pb ? pa : pb;
           const uint32_t mcur = (uint32_t)((uint32_t)(nio & 0xFFFFFFFFu) - 256u);
@@ -345,16 +378,19 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         const unsigned int mode = (lr == ~0ull || (unsigned int)(lr & 0xFFFFFFFFu) > CL_LOCAL_MAX) ? 1u : 0u;
         for (unsigned int r = 0; r < CL_SIZE; r++) {
           ClusterCtl *c = cluster.map_shared_rank(m.ctl, r);
-          c->pair = pair; c->new_id_op = nio; c->log_range = lr; c->k = k; c->mode = mode; c->stop = stop; c->t_cmd = t_cmd;
+          c->pair = pair; c->new_id_op = nio; c->log_range = lr; c->k = k; c->mode = mode; c->stop = stop; c->t_cmd = t_cmd; c->spec = spec;
         }
         if (mode == 1u) cursor_stale = true;  // a GRID merge appends through the global cursor
         if (stop || mode == 1u) {  // the other clusters take part (or leave)
-          dcmd->pair = pair; dcmd->new_id_op = nio; dcmd->log_range = lr; dcmd->k = k; dcmd->t_cmd = t_cmd;
+          dcmd->pair = pair; dcmd->new_id_op = nio; dcmd->log_range = lr; dcmd->k = k; dcmd->t_cmd = t_cmd; dcmd->spec = spec;
           __threadfence();
           *(volatile unsigned long long *)&dcmd->epoch = grid_epoch + 1;
         }
         *(volatile unsigned long long *)&dcmd->alive_ns = gtime_ns();
         tr_poll += clock64() - c0;
+        // the hint for the merge after this one may already be in the mailbox (the host sends it a merge ahead when it can):
+        // ask for it now, look at it when this merge is done
+        if (!stop) asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pre_hv.x), "=r"(pre_hv.y), "=r"(pre_hv.z), "=r"(pre_hv.w) : "l"(hcmd + 1 + ((want + 1) & 1ull)) : "memory");
       }
       cluster_barrier(cluster);  // (release/acquire: the command is visible in every CTA of the leader cluster)
     } else {
@@ -366,6 +402,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
             pair = *(volatile unsigned long long *)&dcmd->pair; nio = *(volatile unsigned long long *)&dcmd->new_id_op;
             lr = *(volatile unsigned long long *)&dcmd->log_range; kk = *(volatile unsigned long long *)&dcmd->k;
             m.ctl->t_cmd = *(volatile unsigned long long *)&dcmd->t_cmd;
+            m.ctl->spec = (unsigned int)*(volatile unsigned long long *)&dcmd->spec;
             break;
           }
           if ((spin & 255) == 255 && gtime_ns() - *(volatile unsigned long long *)&dcmd->alive_ns > 4 * timeout_ns) break;  // leader gone
@@ -383,6 +420,11 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
     const unsigned long long mk_ = m.ctl->k;  // (the other clusters only iterate on GRID merges: their own counter lags)
     em.stamp_base = (op_base + mk_) << 10;
     const unsigned long long seq = seq_base + mk_ + 1;
+    // two record buffers / headers, used in turn: a merge started from a hint writes its results while the host still reads
+    // those of the merge before it
+    Rec *__restrict__ out = (seq & 1ull) ? out1 : out0;
+    unsigned long long *__restrict__ out_hdr = (seq & 1ull) ? out_hdr1 : out_hdr0;
+    const unsigned int spec_flag = m.ctl->spec ? 64u : 0u;
 
     if (mode == 1u) {
       // ---------------------------------------------------------------- GRID: all clusters, global pair table
@@ -400,7 +442,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       if (is_last) {
         __threadfence();
         TailSmem ts{m.tail_stage, m.csum, m.tail_count};
-        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u, nullptr, nullptr);
+        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag, nullptr, nullptr);
         if (threadIdx.x == 0) { acct[2] += 1; acct[3] += gtime_ns() - m.ctl->t_cmd; }  // (one publisher at a time)
       }
       __syncthreads();
@@ -476,6 +518,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         // merge is seen one merge later: the thresholds leave that much room, the others are fatal either way)
         pre_flags = (__ldcg(t.flags) & 1u) | (__ldcg(em.log.flags) ? 2u : 0u) |
                     ((__ldcg(em.g.flags) || __ldcg(em.g.n_used) >= (em.g.mask >> 1)) ? 4u : 0u);
+        if (pre_hv.z != 0u && pre_hv.w == cmd3_word(seq + 1, pre_hv.x, pre_hv.y, pre_hv.z))  // the hinted pair's slot: looked at when this merge is done
+          gt_prefetch(em.g, ((unsigned long long)pre_hv.y << 32) | pre_hv.x);
       }
       if (crank == 0 && threadIdx.x == 32 && !spill) {  // the merged pair's frequency becomes 0 (bpe.cpp:523)
         unsigned int ins = 0;
@@ -489,10 +533,16 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         const unsigned int nb = min(m.ctl->n_births, (unsigned int)CL_BIRTH_STAGE);
         m.ctl->birth_base = c0->log_cursor + (nb ? atomicAdd(&c0->births_total, nb) : 0u);
       }
-      cluster_emit_part(m, em, t, spill, cx, cs, inserted, out, out_cap, cluster, new_id);
+      unsigned long long maxpush = 0;
+      cluster_emit_part(m, em, t, spill, cx, cs, inserted, maxpush, out, out_cap, cluster, new_id);
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, d);
+      for (int d = 16; d > 0; d >>= 1) {
+        inserted += __shfl_down_sync(0xffffffffu, inserted, d);
+        const unsigned long long o = __shfl_down_sync(0xffffffffu, maxpush, d);
+        maxpush = o > maxpush ? o : maxpush;
+      }
       if (lane == 0 && inserted) atomicAdd(em.g.n_used, inserted);  // (no result needed here: CTA 0 looks at the load once per merge)
+      if (lane == 0 && maxpush) atomicMax(&m.ctl->maxpush, maxpush);
       __syncthreads();
       if (threadIdx.x == 0) {  // this CTA's ranges in the record buffer and in the birth log
         const unsigned int nr = min(m.ctl->n_recs, (unsigned int)CL_REC_STAGE);
@@ -514,7 +564,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       }
       block_checksum(cx, cs, m.csum);
       if (threadIdx.x == 0) {
-        c0->part_cx[crank] = cx; c0->part_cs[crank] = cs;
+        c0->part_cx[crank] = cx; c0->part_cs[crank] = cs; c0->part_max[crank] = m.ctl->maxpush;
+        m.ctl->maxpush = 0;
         m.ctl->n_births = 0; m.ctl->n_recs = 0; m.ctl->n_occ = 0; m.ctl->n_cand = 0; m.ctl->n_occ1 = 0; m.ctl->inbox_n = 0; m.ctl->n_ovf = 0;
       }
     }
@@ -530,7 +581,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         __threadfence();
         __syncthreads();
         TailSmem ts{m.tail_stage, m.csum, m.tail_count};
-        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u, nullptr, nullptr);
+        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag, nullptr, nullptr);
         __syncthreads();
         cluster_clear_tables(m);
         if (threadIdx.x == 0) { acct[0] += 1; acct[1] += gtime_ns() - c->t_cmd; }
@@ -538,7 +589,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         __syncthreads();
       } else if (threadIdx.x == 0) {
         const unsigned int n = c->n_recs_total;
-        unsigned long long flags = (n > out_cap ? 4u : 0u) | (pre_flags & 1u) | ((pre_flags & 4u) ? 16u : 0u);
+        unsigned long long flags = (n > out_cap ? 4u : 0u) | (pre_flags & 1u) | ((pre_flags & 4u) ? 16u : 0u) | spec_flag;
         const unsigned int cur = c->log_cursor + c->births_total;  // (GRID merges append through the global cursor: keep it current)
         *em.log.cursor = cur;
         c->log_cursor = cur;
@@ -546,8 +597,12 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         if (pre_flags & 2u) flags |= 32u;
         flags |= (unsigned long long)cur << 32;  // the host keeps the log ranges
         unsigned long long x = 0, sm = 0;
+        unsigned long long mxp = 0;
 #pragma unroll
-        for (int r = 0; r < CL_SIZE; r++) { x ^= c->part_cx[r]; sm += c->part_cs[r]; }
+        for (int r = 0; r < CL_SIZE; r++) { x ^= c->part_cx[r]; sm += c->part_cs[r]; mxp = c->part_max[r] > mxp ? c->part_max[r] : mxp; }
+        // the next merge may start from a hint: this one was LOCAL, complete and raised no flag
+        hint_ok = pre_flags == 0u && n <= out_cap;
+        prev_maxpush = mxp; prev_new_id = (unsigned int)new_id;
         {  // the 64-byte header as four 16-byte stores (fewer PCIe writes than eight 8-byte ones; it validates itself)
           const unsigned long long rem = c->removed, chk = hdr_check(seq, n, flags, rem, x, sm);
           asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(out_hdr + 2), "l"(flags), "l"(rem) : "memory");

@@ -14,7 +14,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <vector>
+
+#include <sys/mman.h>
 
 #include "../../include/shredword_b200.h"
 
@@ -22,6 +25,32 @@ namespace swb {
 
 struct Rec { int64_t first, second, delta, key; };  // wire format of a record: 4 x int64
 static_assert(sizeof(Rec) == 32, "record must be 4 x int64");
+
+// The heap array and the pair table are tens of MB that every merge probes at random: on 4 KB pages nearly every
+// probe also misses the TLB. Large blocks are 2 MB-aligned and offered to the kernel as transparent huge pages
+// (a hint: without THP this is a plain allocation). Memory comes from / goes back to malloc's free().
+static inline void *huge_alloc(size_t bytes) {
+  constexpr size_t HP = 2u << 20;
+  if (bytes < HP) return malloc(bytes ? bytes : 1);
+  const size_t rounded = (bytes + HP - 1) / HP * HP;
+  void *p = aligned_alloc(HP, rounded);
+  if (p) madvise(p, rounded, MADV_HUGEPAGE);
+  return p;
+}
+template <class T>
+struct HugeAllocator {
+  using value_type = T;
+  HugeAllocator() = default;
+  template <class U> HugeAllocator(const HugeAllocator<U> &) {}
+  T *allocate(size_t n) {
+    void *p = huge_alloc(n * sizeof(T));
+    if (!p) throw std::bad_alloc();
+    return static_cast<T *>(p);
+  }
+  void deallocate(T *p, size_t) { free(p); }
+  template <class U> bool operator==(const HugeAllocator<U> &) const { return true; }
+  template <class U> bool operator!=(const HugeAllocator<U> &) const { return false; }
+};
 
 static inline uint64_t mix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
@@ -72,6 +101,16 @@ class PairTable {
       h = (h + 1) & mask;
     }
   }
+  const PairInfo *find(int32_t a, int32_t b) const {
+    const size_t mask = slots_.size() - 1;
+    size_t h = home(a, b);
+    for (;;) {
+      const PairInfo &p = slots_[h];
+      if (!p.order) return nullptr;
+      if (p.first == a && p.second == b) return &p;
+      h = (h + 1) & mask;
+    }
+  }
   // all entries in creation order
   void in_creation_order(std::vector<PairInfo> &out) const {
     out.resize(n_);
@@ -81,7 +120,7 @@ class PairTable {
 
  private:
   void rehash(size_t n) {
-    std::vector<PairInfo> old;
+    std::vector<PairInfo, HugeAllocator<PairInfo>> old;
     old.swap(slots_);
     slots_.assign(n, PairInfo{0, 0, 0, 0, 0});
     for (const PairInfo &p : old) {
@@ -91,7 +130,7 @@ class PairTable {
       slots_[h] = p;
     }
   }
-  std::vector<PairInfo> slots_;
+  std::vector<PairInfo, HugeAllocator<PairInfo>> slots_;
   size_t n_ = 0;
 };
 
@@ -139,7 +178,7 @@ class HostCore {
   // ---- heap: the exact array heap of reference heap.cpp:53-114, stored in the public Trainer fields
   void heap_reset() {  // heap_free + heap_init(4096), reference bpe.cpp:182-183
     MaxHeap &h = tr_->heap;
-    if (!h.data) { h.cap = 4096; h.data = (HeapEntry *)malloc(h.cap * sizeof(HeapEntry)); }
+    if (!h.data) { h.cap = 4096; h.data = (HeapEntry *)huge_alloc(h.cap * sizeof(HeapEntry)); }
     h.size = 0;
   }
   void heap_push(int32_t a, int32_t b, uint64_t freq, uint32_t version) {
@@ -147,8 +186,11 @@ class HostCore {
     if (!h.data) heap_reset();
     if (h.size == h.cap) {
       h.cap *= 2;
-      h.data = (HeapEntry *)realloc(h.data, h.cap * sizeof(HeapEntry));
-      if (!h.data) { fprintf(stderr, "[ERROR]\t heap reallocation failed\n"); abort(); }
+      HeapEntry *bigger = (HeapEntry *)huge_alloc(h.cap * sizeof(HeapEntry));
+      if (!bigger) { fprintf(stderr, "[ERROR]\t heap reallocation failed\n"); abort(); }
+      memcpy(bigger, h.data, h.size * sizeof(HeapEntry));
+      free(h.data);
+      h.data = bigger;
     }
     size_t i = h.size++;
     n_pushes++;
@@ -165,20 +207,24 @@ class HostCore {
     MaxHeap &h = tr_->heap;
     HeapEntry top = h.data[0];
     n_pops++;
-    h.data[0] = h.data[--h.size];
+    const HeapEntry last = h.data[--h.size];
+    // the moved element sinks from the root: the hole moves down, only the entries that move up are written
     size_t i = 0;
     for (;;) {  // left child if strictly larger, then right if strictly larger than that (heap.cpp:97-111)
-      size_t l = 2 * i + 1, r = l + 1, best = i;
+      const size_t l = 2 * i + 1, r = l + 1;
       {  // the four grandchildren are contiguous (96 bytes): fetch them while the children are compared
         const size_t g = 4 * i + 3;
         if (g < h.size) { __builtin_prefetch(&h.data[g]); __builtin_prefetch(reinterpret_cast<const char *>(&h.data[g]) + 64); }
       }
-      if (l < h.size && h.data[l].freq > h.data[best].freq) best = l;
-      if (r < h.size && h.data[r].freq > h.data[best].freq) best = r;
+      size_t best = i;
+      uint64_t bf = last.freq;
+      if (l < h.size && h.data[l].freq > bf) { best = l; bf = h.data[l].freq; }
+      if (r < h.size && h.data[r].freq > bf) best = r;
       if (best == i) break;
-      std::swap(h.data[i], h.data[best]);
+      h.data[i] = h.data[best];
       i = best;
     }
+    if (h.size > 0) h.data[i] = last;
     return top;
   }
   bool heap_empty() const { return tr_->heap.size == 0; }
@@ -231,6 +277,10 @@ class HostCore {
   bool next_merge(int32_t *a, int32_t *b, int32_t *new_id) {
     const uint64_t minf = tr_->config.min_pair_freq;
     while (!heap_empty()) {
+      {  // the entries that can reach the root next: start the misses of their table slots while this pop sifts down
+        const MaxHeap &h = tr_->heap;
+        for (size_t c = 1; c < 7 && c < h.size; c++) pairs_.prefetch(h.data[c].key.first, h.data[c].key.second);
+      }
       HeapEntry top = heap_pop();
       PairInfo &info = pairs_.get(top.key.first, top.key.second);
       if (top.version != info.version) continue;  // stale (bpe.cpp:412-415)
@@ -247,6 +297,58 @@ class HostCore {
       return true;
     }
     return false;
+  }
+
+  // ---- look-ahead for the resident kernel: which pairs will the next calls of next_merge() return?
+  // Called between next_merge() and the apply of that merge (the "pending" merge, number j), i.e. before the
+  // pushes of merge j are known. Fills up to `want` entries: entry i = (pair, F_i) is the (i+1)-th LIVE entry in
+  // the order in which the heap would pop (reference heap.cpp:88-114) if nothing were pushed. Statement made
+  // for entry i:  merge j+1+i is that pair, PROVIDED that when its turn comes
+  //   (1) every entry pushed by the merges j .. j+i had a frequency < F_i, and
+  //   (2) the pair's frequency is (still) F_i.
+  // Why this is exact, ties included: entries with frequency >= F_i form a top-closed region of the heap. A push
+  // below F_i sifts up only past entries smaller than itself, so it never moves an entry of the region; a
+  // sift-down prefers any entry of the region over any entry outside it (strict comparisons, heap.cpp:97-111),
+  // so the order in which the entries of the region reach the root depends on the region alone -- provided the
+  // elements moved from the tail to the root are outside it (checked here). Entries popped before entry i are
+  // stale (for ever: versions only grow) or earlier entries of the list; one of those that loses its place
+  // (touched by a merge in between) makes the later ones move up, and then (2) fails for them once they have
+  // been merged (frequency 0). So an accepted entry is always the true next pair; a wrong guess is only ever
+  // turned down. The heap is not modified: the pops are simulated on a sparse overlay of the top of the array,
+  // where a removed root leaves a hole that is filled lazily by its larger child (left on ties) -- the rest of
+  // the sift-down of the real algorithm happens below the region and cannot influence it.
+  struct Peek { int32_t a, b; uint64_t freq; };
+  size_t peek_next(Peek *out, size_t want) {
+    const MaxHeap &h = tr_->heap;
+    const uint64_t minf = tr_->config.min_pair_freq;
+    constexpr size_t MAX_POPS = 96, TAIL_GUARD = 128;
+    if (h.size < 4 * TAIL_GUARD) return 0;  // small heaps: the top region may reach the tail of the array
+    const size_t n_eff = h.size - TAIL_GUARD;
+    ov_reset();
+    size_t got = 0, pops = 0;
+    uint64_t tail_max = 0;  // largest frequency among the tail elements the real pops would have moved to the root
+    bool ok = true;
+    while (got < want && pops < MAX_POPS && ok) {
+      const HeapEntry *top = ov_get(0, n_eff, ok);
+      if (!ok || !top) break;
+      const HeapEntry e = *top;
+      ov_set_hole(0);
+      const uint64_t tf = h.data[h.size - 1 - pops].freq;
+      if (tf > tail_max) tail_max = tf;
+      pops++;
+      const PairInfo *info = pairs_.find(e.key.first, e.key.second);
+      if (info && info->version == e.version && info->freq >= minf) {
+        if (info->freq != e.freq || tail_max >= e.freq) break;
+        out[got++] = Peek{e.key.first, e.key.second, e.freq};
+      }
+    }
+    return got;
+  }
+  bool peek_next(int32_t *a, int32_t *b, uint64_t *freq) {  // the first entry only
+    Peek p;
+    if (peek_next(&p, 1) != 1) return false;
+    *a = p.a; *b = p.b; *freq = p.freq;
+    return true;
   }
 
   // ---- reference bpe_merge_batch, bookkeeping part (bpe.cpp:486-526) for the pending merge.
@@ -404,6 +506,69 @@ class HostCore {
   std::vector<PairKey> merges_;
   std::vector<Rec> scratch_;
   struct KeyIdx { uint64_t key; uint32_t idx; };
+  // sparse overlay of the heap array used by peek_next: position -> {entry | hole | empty}
+  struct OvNode { size_t pos; HeapEntry e; int state; /* 1 entry, 2 hole, 3 empty (no entry left below) */ };
+  static constexpr size_t OV_SLOTS = 1024;  // open addressing over at most OV_MAX nodes
+  static constexpr size_t OV_MAX = 384;
+  std::vector<OvNode> ov_;
+  uint16_t ov_map_[OV_SLOTS] = {};
+  void ov_reset() {
+    for (const OvNode &n : ov_) {  // clear only what was used
+      size_t s = (n.pos * 0x9E3779B97F4A7C15ull) >> 54;
+      while (ov_map_[s]) { ov_map_[s] = 0; s = (s + 1) & (OV_SLOTS - 1); }
+    }
+    ov_.clear();
+    if (ov_.capacity() < OV_MAX + 8) ov_.reserve(OV_MAX + 8);  // (pointers into ov_ stay valid during a look-ahead)
+  }
+  OvNode *ov_find(size_t pos, bool create, bool &ok) {
+    size_t s = (pos * 0x9E3779B97F4A7C15ull) >> 54;
+    while (ov_map_[s]) {
+      if (ov_[ov_map_[s] - 1].pos == pos) return &ov_[ov_map_[s] - 1];
+      s = (s + 1) & (OV_SLOTS - 1);
+    }
+    if (!create) return nullptr;
+    if (ov_.size() >= OV_MAX) { ok = false; return nullptr; }
+    ov_.push_back(OvNode{pos, HeapEntry{}, 0});
+    ov_map_[s] = (uint16_t)ov_.size();
+    return &ov_.back();
+  }
+  void ov_set_hole(size_t pos) {
+    bool ok = true;
+    OvNode *n = ov_find(pos, true, ok);
+    if (n) n->state = 2;
+  }
+  // the entry at `pos` of the simulated heap (nullptr: none); holes are filled on demand by the larger child
+  const HeapEntry *ov_get(size_t pos, size_t n_eff, bool &ok) {
+    const MaxHeap &h = tr_->heap;
+    if (pos >= h.size) return nullptr;
+    if (pos >= n_eff) { ok = false; return nullptr; }  // too close to the tail of the array: no statement
+    OvNode *n = ov_find(pos, false, ok);
+    if (!n) {  // an untouched entry of the real array; its pair is looked up if it ever reaches the root: start that miss now
+      pairs_.prefetch(h.data[pos].key.first, h.data[pos].key.second);
+      return &h.data[pos];
+    }
+    if (n->state == 1) return &n->e;
+    if (n->state == 3) return nullptr;
+    // hole: pull up the larger child (left unless the right one is strictly larger, heap.cpp:97-111)
+    const size_t l = 2 * pos + 1, r = l + 1;
+    const HeapEntry *el = ov_get(l, n_eff, ok);
+    if (!ok) return nullptr;
+    HeapEntry lv{}; if (el) lv = *el;  // (ov_ may reallocate below: copy)
+    const HeapEntry *er = ov_get(r, n_eff, ok);
+    if (!ok) return nullptr;
+    HeapEntry rv{}; if (er) rv = *er;
+    const bool has_l = el != nullptr, has_r = er != nullptr;
+    n = ov_find(pos, false, ok);  // (re-find: the vector may have grown)
+    if (!has_l && !has_r) { n->state = 3; return nullptr; }
+    const bool take_r = has_r && (!has_l || rv.freq > lv.freq);
+    n->e = take_r ? rv : lv;
+    n->state = 1;
+    const size_t idx = (size_t)(n - ov_.data());
+    OvNode *c = ov_find(take_r ? r : l, true, ok);
+    if (!c) return nullptr;
+    c->state = 2;
+    return &ov_[idx].e;
+  }
   std::vector<KeyIdx> order_;
   int32_t cur_a_ = 0, cur_b_ = 0, cur_new_ = 0;
   bool pending_ = false;

@@ -74,6 +74,19 @@ __device__ __forceinline__ uint32_t gt_upsert(const GlobalTableDev &g, unsigned 
   }
 }
 
+// frequency of pair k, ~0 when the pair is not in the table (read through L2: other SMs update the table)
+__device__ __forceinline__ unsigned long long gt_find_freq(const GlobalTableDev &g, unsigned long long k) {
+  uint32_t h = gt_home(g, k);
+#pragma unroll 1
+  for (uint32_t probe = 0; probe <= g.mask; probe++) {
+    const ulonglong2 gs = __ldcg(reinterpret_cast<const ulonglong2 *>(g.slots + h));
+    if (gs.x == k) return gs.y;
+    if (gs.x == PT_EMPTY) break;
+    h = (h + 1) & g.mask;
+  }
+  return ~0ull;
+}
+
 __device__ __forceinline__ void gt_account(const GlobalTableDev &g, unsigned int inserted) {
   if (inserted && atomicAdd(g.n_used, inserted) + inserted >= (g.mask >> 1)) atomicOr(g.flags, 1u);
 }

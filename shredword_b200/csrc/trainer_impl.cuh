@@ -1266,6 +1266,14 @@ class TrainerImpl {
       _mm_store_si128(reinterpret_cast<__m128i *>(const_cast<HostCmd2 *>(c)), v);  // one 16-byte store: the device never sees half a command
       __atomic_thread_fence(__ATOMIC_SEQ_CST);
     }
+    // hint for the merge with sequence number `seq`: mailbox word 1 + (seq & 1) (two hint words used in turn, so that the
+    // hint for merge q+2 can be written while the device may still be reading the one for merge q+1)
+    void hint(unsigned long long seq, unsigned long long pair, unsigned int freq) {
+      const unsigned int x = (unsigned int)pair, y = (unsigned int)(pair >> 32), z = freq;
+      const __m128i v = _mm_set_epi32((int)cmd3_word(seq, x, y, z), (int)z, (int)y, (int)x);
+      _mm_store_si128(reinterpret_cast<__m128i *>(const_cast<HostCmd2 *>(c + 1 + (seq & 1ull))), v);
+      __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    }
     ~HostCmd2Sender() { if (running) send(0, 0, 1); }
   };
   // Runs up to max_merges merges starting with (a, b) (already popped, pending in `core`) inside ONE launch of
@@ -1274,9 +1282,12 @@ class TrainerImpl {
     ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
     maybe_grow_global_table(gt_flagged_);
     gt_flagged_ = false;
-    if (!hcmd2_.size()) { hcmd2_.alloc(1); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(4); }
+    if (!hcmd2_.size()) { hcmd2_.alloc(4); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(8); }
+    if (recs_b_.size() != recs_.size()) recs_b_.alloc(recs_.size());  // second record buffer + header: merges started from a hint
+    if (!hdr_b_.size()) hdr_b_.alloc(HDR_WORDS);
+    memset(hdr_b_.host(), 0, HDR_WORDS * sizeof(unsigned long long));
     SWB_CUDA(cudaMemsetAsync(cl_acct_.get(), 0, cl_acct_.bytes(), stream_));
-    memset((void *)hcmd2_.host(), 0, sizeof(HostCmd2));
+    memset((void *)hcmd2_.host(), 0, 4 * sizeof(HostCmd2));
     SWB_CUDA(cudaMemsetAsync(dcmd2_.get(), 0, sizeof(DevCmd2), stream_));
     const int32_t unk = tr_->config.unk_id;
     EmitMode em = emit_mode(1, 0, 0);
@@ -1289,12 +1300,44 @@ class TrainerImpl {
     const ClusterFacts &cf = cluster_facts(device_);
     const unsigned long long seq_base = seq_, op_base = op_index_ + 1;
     unsigned long long *removed_p = removed_.get();
-    Rec *out = recs_.dev();
+    // results of the merge with sequence number q travel through buffer q & 1
+    Rec *out0 = recs_.dev(), *out1 = recs_b_.dev();
     size_t out_cap = recs_.size();
-    unsigned long long *out_hdr = hdr_.dev();
+    unsigned long long *out_hdr0 = hdr_.dev(), *out_hdr1 = hdr_b_.dev();
     volatile HostCmd2 *hc = hcmd2_.dev();
     DevCmd2 *dc = dcmd2_.get();
     unsigned long long timeout_ns = 2000000000ull;
+    static const bool no_hints = getenv("SWB_NO_HINTS") && atoi(getenv("SWB_NO_HINTS")) > 0;
+    const bool hints = !no_hints && unk >= 0;  // (a negative unk_id canonicalises pairs on the device: no look-ahead there)
+    constexpr unsigned long long NO_HINT = ~0ull;
+    // Look-ahead (HostCore::peek_next): while merge q is pending, the exact heap names the pairs of merges q+1 and q+2,
+    // each under the condition that the merges before it push nothing at or above its frequency F and leave its own
+    // frequency at F. The device checks that against its frequency table when the merge before has finished and then
+    // starts without waiting for the command (which still follows, and which the host checks against: flag 64).
+    //   late hint  for q+1: sent right after the look-ahead (the device checks merge q)
+    //   early hint for q+2: sent as soon as the records of merge q have arrived and show that q pushed nothing >= F
+    //                       (the device checks merge q+1) -- it is on its way a whole merge before it is needed
+    HostCore::Peek pk[2];
+    size_t npk = 0;
+    unsigned long long n_early = 0;
+    static const bool no_early = getenv("SWB_NO_EARLY_HINTS") && atoi(getenv("SWB_NO_EARLY_HINTS")) > 0;
+    unsigned long long hint_ring[4][2];  // what was sent for sequence number q: [q & 3] = {early, late}
+    for (auto &h2 : hint_ring) h2[0] = h2[1] = NO_HINT;
+    auto send_hint = [&](unsigned long long hint_seq, const HostCore::Peek &e, int which, HostCmd2Sender &sd) {
+      if (e.freq == 0 || e.freq >= (1ull << 32)) return;
+      const unsigned long long key = ((unsigned long long)(uint32_t)to_dev(e.a) << 32) | (uint32_t)to_dev(e.b);
+      if (which == 1 && hint_ring[hint_seq & 3][0] == key) return;  // the early hint already said so
+      sd.hint(hint_seq, key, (unsigned int)e.freq);
+      hint_ring[hint_seq & 3][which] = key;
+      stats.hints_sent++;
+    };
+    auto look_ahead = [&]() {
+      npk = 0;
+      if (!hints) return;
+      const double th0 = now_ms();
+      npk = core.peek_next(pk, 2);
+      stats.host_peek_ms += now_ms() - th0;
+    };
     unsigned long long *trace_p = nullptr;
     if (trace_wait_) {
       if (!ptrace_.size()) { ptrace_.alloc(16); SWB_CUDA(cudaMemsetAsync(ptrace_.get(), 0, ptrace_.bytes(), stream_)); }
@@ -1336,20 +1379,45 @@ class TrainerImpl {
       }
     }
     cfg.attrs = at; cfg.numAttrs = n_at;
-    SWB_CUDA(cudaLaunchKernelEx(&cfg, merge_cluster, s, pt_, em, removed_p, out, out_cap, out_hdr, seq_base, op_base, hc, dc, timeout_ns, trace_p, cl_ovf_.get(), cl_acct_.get()));
+    SWB_CUDA(cudaLaunchKernelEx(&cfg, merge_cluster, s, pt_, em, removed_p, out0, out1, out_cap, out_hdr0, out_hdr1, seq_base, op_base, hc, dc, timeout_ns, trace_p, cl_ovf_.get(), cl_acct_.get()));
     SWB_CUDA(cudaGetLastError());
     launched(); stats.merge_launches++;
     sender.running = true;
     int done = 0;
+    unsigned long long cur_key = ((unsigned long long)(uint32_t)da << 32) | (uint32_t)db;
+    const uint64_t minf = tr_->config.min_pair_freq;
+    look_ahead();
+    if (npk >= 1 && max_merges > 1) send_hint(seq_base + 2, pk[0], 1, sender);
     for (;;) {
       const double tw0 = now_ms();
-      wait_seq_at(seq_base + done + 1, hdr_.host(), recs_.host(), recs_.size());
+      const unsigned long long q = seq_base + done + 1;
+      unsigned long long *hh = (q & 1ull) ? hdr_b_.host() : hdr_.host();
+      Rec *hr = (q & 1ull) ? recs_b_.host() : recs_.host();
+      wait_seq_at(q, hh, hr, recs_.size());
       const double tw1 = now_ms();
       stats.host_wait_ms += tw1 - tw0;
-      const size_t n = (size_t)hdr_.host()[1];
-      const unsigned long long hflags = hdr_.host()[2];
+      const size_t n = (size_t)hh[1];
+      const unsigned long long hflags = hh[2];
       const unsigned int flags = (unsigned int)hflags;
-      const uint64_t removed = hdr_.host()[3];
+      const uint64_t removed = hh[3];
+      if (flags & 64u) {  // the device started this merge from a hint: it must be the pair the exact heap chose
+        if (hint_ring[q & 3][0] != cur_key && hint_ring[q & 3][1] != cur_key)
+          throw Error("resident kernel followed a hint the heap replica did not confirm (internal error)");
+        stats.hints_taken++;
+      }
+      hint_ring[(q + 2) & 3][0] = hint_ring[(q + 2) & 3][1] = NO_HINT;
+      if (npk >= 2 && done + 2 < max_merges && !(flags & ~64u) && n <= recs_.size()) {  // early hint for merge q+2
+        uint64_t mp = 0;
+        for (size_t i = 0; i < n; i++) { const uint64_t f = (uint64_t)hr[i].delta; if (f >= minf && f > mp) mp = f; }
+        if (mp < pk[1].freq && !no_early) {
+          // With this hint the device may start merge q+2 -- whose results go into THIS record buffer -- before the records of
+          // merge q have been applied below: they move to private memory first.
+          rec_copy_.assign(hr, hr + n);
+          hr = rec_copy_.data();
+          send_hint(q + 2, pk[1], 0, sender);
+          n_early++;
+        }
+      }
       if (flags & 5u) throw Error("pair table overflow during a merge (internal sizing error)");
       if (flags & 32u) throw Error("birth log overflow (internal sizing error)");
       if (flags & 16u) gt_flagged_ = true;
@@ -1360,8 +1428,8 @@ class TrainerImpl {
       stats.merge_alg_bytes += 4 * live_symbols_ + 8 * W;
       live_symbols_ -= removed;
       stats.live_symbols = live_symbols_;
-      translate_out(recs_.host(), n);
-      core.apply_absolute(recs_.host(), n);
+      translate_out(hr, n);
+      core.apply_absolute(hr, n);
       const double ta1 = now_ms();
       stats.host_apply_ms += ta1 - tw1;
       done++;
@@ -1371,15 +1439,24 @@ class TrainerImpl {
       sender.next_seq = seq_base + done + 1;
       if (!go) { sender.send(0, 0, 1); sender.running = false; break; }
       da = to_dev(na); db = to_dev(nb);
-      sender.send(((unsigned long long)(uint32_t)da << 32) | (uint32_t)db, (unsigned int)nn, 0);
+      cur_key = ((unsigned long long)(uint32_t)da << 32) | (uint32_t)db;
+      sender.send(cur_key, (unsigned int)nn, 0);
+      look_ahead();
+      if (npk >= 1 && done + 1 < max_merges) send_hint(seq_base + done + 2, pk[0], 1, sender);  // late hint for the merge after this command's
     }
     sync();
     {  // device time of this launch's merges (command seen -> result published), per mode
-      unsigned long long ac[4];
+      unsigned long long ac[8];
       SWB_CUDA(cudaMemcpy(ac, cl_acct_.get(), sizeof ac, cudaMemcpyDeviceToHost));
+      stats.hints_rejected += ac[5];
       stats.resident_local_merges += ac[0]; stats.resident_local_ms += (double)ac[1] * 1e-6;
       stats.resident_grid_merges += ac[2]; stats.resident_grid_ms += (double)ac[3] * 1e-6;
       stats.merge_kernel_ms += (double)(ac[1] + ac[3]) * 1e-6;
+    }
+    if (trace_p) {
+      unsigned long long ac[8];
+      SWB_CUDA(cudaMemcpy(ac, cl_acct_.get(), sizeof ac, cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[trace] hints: %llu sent a merge ahead; device accepted %llu (%llu of them already loaded when needed), rejected %llu\n", n_early, ac[4], ac[6], ac[5]);
     }
     if (trace_p) {
       unsigned long long h[16];
@@ -1526,7 +1603,7 @@ class TrainerImpl {
   double t_launch0_ = 0;
   unsigned long long seq_ = 0;
   DevBuf<unsigned int> scalars_;
-  PinnedBuf<unsigned long long> hdr_;
+  PinnedBuf<unsigned long long> hdr_, hdr_b_;
   // symbol stream
   DevBuf<int4> rows_;
   DevBuf<uint32_t> sig_;
@@ -1595,7 +1672,8 @@ class TrainerImpl {
   DevBuf<unsigned int> pt2_scal_;
   DevBuf<unsigned long long> d_all_;
   size_t dist_cap_ = 0, dist_slot_words_ = 0;
-  PinnedBuf<Rec> recs_;
+  PinnedBuf<Rec> recs_, recs_b_;
+  std::vector<Rec> rec_copy_;
 };
 
 }  // namespace swb

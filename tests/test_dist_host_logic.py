@@ -83,3 +83,81 @@ def test_gloo_world2_matches_oracle(name, product, oracle_mod, tmp_path):
   mp.spawn(_worker, args=(2, port, name, str(tmp_path)), nprocs=2, join=True)
   for r in range(2):
     assert np.array_equal(np.load(tmp_path / f"merges_{r}.npy"), full.merges), f"rank {r}"
+
+
+@pytest.mark.parametrize("name", ["ascii_ties", "multi_ties", "self_pairs", "ref_fixture_f5"])
+def test_look_ahead_is_exact_and_leaves_the_heap_alone(name, product, oracle_mod):
+  """HostCore::peek_next (what the resident kernel's hints are made of): entry i of the look-ahead taken while merge
+  j is pending names merge j+1+i. Whenever the merges j .. j+i then push nothing at or above the quoted frequency and
+  the pair still has that frequency when its turn comes, the heap must pop exactly that pair -- ties included.
+  The heap array must be bit-identical before and after the look-ahead."""
+  import ctypes
+  from shredword_b200.cbase import lib
+  from shredword_b200.trainer import _ptr
+  kw = cases.kwargs(name)
+  minf = kw["min_pair_freq"]
+  DEPTH = 3
+  sh = oracle_mod.Oracle(kw["target_vocab_size"], kw.get("unk_id", 0), kw.get("character_coverage", 0.995), minf)
+  sh.load_buffer(cases.corpus(name))
+  t = product.BPETrainer(**kw)
+  recs = np.ascontiguousarray(sh.shard_count(0, 1))
+  n = lib.swb_dist_reduce_records(_ptr(recs), recs.shape[0])
+  lib.swb_dist_seed(t.trainer, _ptr(recs), n)
+  freq = {(int(r[0]), int(r[1])): int(r[2]) for r in recs[:n]}  # the test's own frequency table
+
+  def heap_bytes():
+    h = t.trainer.contents.heap
+    raw = np.frombuffer(ctypes.string_at(h.data, h.size * 24), dtype=np.uint8).reshape(-1, 24)
+    return raw[:, :20].tobytes()  # {first, second, freq, version}; bytes 20..23 are struct padding
+
+  a, b, nid = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+  out = np.zeros(3 * DEPTH, dtype=np.int64)
+  claims = []      # (merge number it names, pair, frequency, number of the merge that was pending)
+  maxpush = {}     # merge number -> largest frequency it made the heap push
+  expect = {}      # merge number -> pair, for claims whose conditions held
+  made = [0] * DEPTH
+  confirmed = [0] * DEPTH
+  tie_claims = 0
+  j = 0
+  target = 2 * (kw["target_vocab_size"] - 256)
+  while j < target and lib.swb_dist_next_merge(t.trainer, ctypes.byref(a), ctypes.byref(b), ctypes.byref(nid)):
+    j += 1  # merge j is pending
+    if j in expect:
+      for depth, pair in expect[j]:
+        assert (a.value, b.value) == pair, f"{name}: look-ahead (depth {depth}) said {pair} for merge {j}, the heap popped {(a.value, b.value)}"
+        confirmed[depth] += 1
+    check_heap = j % 8 == 0  # (copying the whole heap out every merge would dominate the test)
+    before = heap_bytes() if check_heap else None
+    got = lib.swb_dist_peek_list(t.trainer, _ptr(out), DEPTH)
+    assert not check_heap or heap_bytes() == before, "look-ahead changed the heap"
+    fs = [int(out[3 * i + 2]) for i in range(got)]
+    assert fs == sorted(fs, reverse=True)
+    tie_claims += len(set(fs)) < len(fs)
+    for i in range(got):
+      claims.append((j + 1 + i, (int(out[3 * i]), int(out[3 * i + 1])), fs[i], j, i))
+      made[i] += 1
+    recs = np.ascontiguousarray(sh.shard_merge(0, 1, a.value, b.value, nid.value))
+    n = lib.swb_dist_reduce_records(_ptr(recs), recs.shape[0]) if recs.shape[0] else 0
+    mp = 0
+    for r in recs[:n]:
+      k = (int(r[0]), int(r[1]))
+      if k == (a.value, b.value):
+        continue
+      nw = max(freq.get(k, 0) + int(r[2]), 0)
+      freq[k] = nw
+      if nw >= minf:
+        mp = max(mp, nw)
+    freq[(a.value, b.value)] = 0
+    maxpush[j] = mp
+    rest = []
+    for c in claims:
+      tgt, pair, f, base, depth = c
+      if tgt != j + 1:
+        rest.append(c)
+      elif max(maxpush[m] for m in range(base, j + 1)) < f and freq.get(pair, 0) == f:
+        expect.setdefault(tgt, []).append((depth, pair))
+    claims = rest
+    lib.swb_dist_apply(t.trainer, _ptr(recs), n)
+  print(f"\n[{name}] merges={j} claims per depth={made} confirmed per depth={confirmed} look-aheads with equal frequencies={tie_claims}")
+  if name in ("ascii_ties", "multi_ties"):  # (the small cases have heaps too small for a look-ahead: nothing may be claimed wrongly, that is all)
+    assert confirmed[0] > 1000 and confirmed[1] > 500 and confirmed[2] > 250 and tie_claims > 100, (made, confirmed, tie_claims)
