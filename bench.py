@@ -38,6 +38,7 @@ from shredword_b200 import synth  # noqa: E402
 
 TRAIN_KW = dict(target_vocab_size=8192, unk_id=0, character_coverage=0.995, min_pair_freq=2000)
 CPU_SAMPLE_BYTES = 32 * 1000 * 1000
+SHARDED_MERGE = bool(int(os.environ.get("SWB_BENCH_SHARDED_MERGE", "0")))  # N > 1: shard the merge loop too (slower: one collective per merge)
 
 
 def log(*a):
@@ -150,6 +151,14 @@ def make_corpus(spec: synth.CorpusSpec, pinned: bool, first_chunk: int = 0):
 
 
 def main():
+  # fd 1 carries exactly one JSON line: whatever libraries print there (NCCL's version banner) goes to stderr
+  real_stdout = os.dup(1)
+  os.dup2(2, 1)
+
+  def emit(obj):
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
   ap.add_argument("--steps", type=int, default=3)
@@ -170,8 +179,10 @@ def main():
             "corpus_bytes": spec.nbytes, "l2": "input (1 GB) and the first-pass word table are larger than L2; no flush between steps",
             "parallelism": "1 GPU" if world == 1 else
                            f"weak scaling: {world} GPUs x one {spec.nbytes / 1e9:g} GB piece each (same word types, disjoint sampling streams) = one "
-                           f"{world * spec.nbytes / 1e9:g} GB corpus; range-split tokenising + NCCL word-table exchange, unique words sharded "
-                           f"over the ranks, per-merge NCCL all-gather of delta records, replicated frequency table + heap"}
+                           f"{world * spec.nbytes / 1e9:g} GB corpus; range-split tokenising + NCCL word-table exchange (the part that scales with "
+                           f"the corpus), then " + ("unique words sharded over the ranks, per-merge NCCL all-gather of delta records, replicated "
+                           "frequency table + heap" if SHARDED_MERGE else "every rank runs the latency-bound merge loop on all unique words "
+                           "(replicated, no per-merge collective)")}
 
   # ------------------------------------------------------------------ reference arm
   if args.impl == "reference":
@@ -189,7 +200,7 @@ def main():
     secs = float(np.mean([r["seconds"] for r in runs]))
     value = nbytes / 1e9 / secs
     cb = dict(runs[-1]); cb["value"] = value
-    print(json.dumps({
+    emit(({
       "impl": "reference", "metric": "train_corpus_GB_per_s", "value": value, "unit": "GB/s", "n_gpus": args.gpus,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "int32 symbols, uint64 counts", "data": "synthetic", "config": config,
@@ -222,7 +233,7 @@ def main():
 
   def new_trainer():
     if world > 1:
-      return DistributedBPETrainer(**TRAIN_KW, device=dev)
+      return DistributedBPETrainer(**TRAIN_KW, device=dev, sharded_merge=SHARDED_MERGE)
     return BPETrainer(**TRAIN_KW)
 
   def barrier():
@@ -353,6 +364,8 @@ def main():
               "e2e_phase_ms": {k: st_e2e[-1][k] for k in ("load_ms", "count_ms", "merge_ms")},
               "wall_ms": [s_["wall_ms"] for s_ in st_res], "e2e_wall_ms": [s_["wall_ms"] for s_ in st_e2e],
               "unique_words": st_res[-1]["words"], "rows": st_res[-1]["rows"],
+              "look_ahead": {k: st_res[-1].get(k) for k in ("hints_sent", "hints_taken", "hints_rejected", "host_peek_ms")},
+              "host_split_ms": {k: st_res[-1].get(k) for k in ("host_pop_ms", "host_wait_ms", "host_apply_ms")},
               "collectives_per_step": st_res[-1].get("collectives"), "exchange_bytes_per_step": st_res[-1].get("exchange_bytes"), "wall_ms_per_step": wall_res,
               "ms_per_step_with_kernel_timing": ms_tim},
   }
@@ -395,7 +408,7 @@ def main():
     out["cpu_baseline"] = cb
 
   if rank == 0:
-    print(json.dumps(out))
+    emit(out)
   if world > 1:
     last.pop("trainer").destroy()
     lib.swb_dist_shutdown()

@@ -1,4 +1,5 @@
 cd $GRAFT_REPO_ROOT
 ( timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 )
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_s4.json 2> gpurun_out/bench_s4.log; echo "bench rc=$?"
-tail -c 3000 gpurun_out/bench_s4.json
+python -c "
+import json; d=json.load(open('gpurun_out/bench_s4.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['extra']['phase_ms'], d['extra']['e2e_phase_ms'], d['extra']['us_per_merge']); r=d['roofline']; print(r['kernel'], r['achieved'], r['frac'], r['avg_launch_us'], r['resident_split']); print(d['extra']['encode']); print(d['extra']['look_ahead'], d['cpu_baseline']['value'], d['gpu_launches'])"

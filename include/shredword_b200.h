@@ -203,6 +203,15 @@ size_t swb_dist_peek_list(Trainer *trainer, int64_t *out, size_t want);
  * the same calls). 0 on success, -1 on error. */
 int swb_dist_unique_id(void *out128);
 int swb_dist_init(Trainer *trainer, int rank, int nranks, const void *unique_id128);
+/* How the merge loop runs on more than one GPU (call after swb_dist_init, before loading):
+ *   sharded == 0 (default): REPLICATED. The load is range-split and the unique-word tables are exchanged
+ *     (swb_load_corpus_shard: the part of the path that scales with the corpus), then every rank holds all
+ *     unique words and runs the single-GPU merge loop; no collective per merge. The merge loop touches only
+ *     the words that hold the pair and is latency-bound, so splitting it buys nothing and costs one NCCL
+ *     exchange per merge.
+ *   sharded != 0: word wi lives on rank wi % nranks, every merge all-gathers the delta records (NCCL) and
+ *     every rank applies them to its replica of the pair table + heap. */
+int swb_dist_set_sharded(Trainer *trainer, int sharded);
 /* Range-split load: `data` (host pointer, or device pointer when on_device != 0) is only THIS rank's
  * byte range of the corpus, starting at byte `global_offset` of the whole; ranges must be cut on
  * delimiters. Every rank tokenises its range, the unique-word tables are exchanged over NCCL and merged,

@@ -106,6 +106,7 @@ _sigs = {
   "swb_shard_merge": ([T, c_int32, c_int32, c_int32, c_void_p, c_size_t], c_int64),
   "swb_dist_unique_id": ([c_void_p], c_int),
   "swb_dist_init": ([T, c_int, c_int, c_void_p], c_int),
+  "swb_dist_set_sharded": ([T, c_int], c_int),
   "swb_load_corpus_shard": ([T, c_void_p, c_size_t, c_uint64, c_int], c_int),
   "swb_dist_has_comm": ([c_int, c_int], c_int),
   "swb_dist_shutdown": ([], None),

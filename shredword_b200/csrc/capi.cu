@@ -316,6 +316,12 @@ int swb_set_shard(Trainer *trainer, int rank, int nranks) {
   if (!trainer || nranks < 1 || rank < 0 || rank >= nranks) { set_err("swb_set_shard: bad arguments"); return -1; }
   impl_of(trainer)->rank = rank;
   impl_of(trainer)->nranks = nranks;
+  impl_of(trainer)->replicated_ = false;  // the caller drives the per-merge exchange itself: this rank keeps only its words
+  return 0;
+}
+int swb_dist_set_sharded(Trainer *trainer, int sharded) {
+  if (!trainer) { set_err("swb_dist_set_sharded: NULL trainer"); return -1; }
+  impl_of(trainer)->replicated_ = sharded == 0;
   return 0;
 }
 size_t swb_dist_reduce_records(int64_t *recs, size_t n) { return swb::reduce_records(reinterpret_cast<Rec *>(recs), n); }

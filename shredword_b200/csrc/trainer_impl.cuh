@@ -82,6 +82,7 @@ class TrainerImpl {
     }
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
     if (stream_) cudaStreamDestroy(stream_);
   }
 
@@ -90,6 +91,15 @@ class TrainerImpl {
   int32_t byte_map[256];  // byte -> initial id as the caller sees it (unk_id for dropped bytes)
   uint8_t keep[256];
   int rank = 0, nranks = 1;
+  // Multi-GPU, replicated merge loop (default): the load is range-split and the word tables are exchanged (NCCL), then every
+  // rank holds ALL unique words and runs the single-GPU resident merge loop on them -- no per-merge collective. The merge
+  // loop is index-driven and latency-bound (~25 us per merge on one GPU); sharding it adds one NCCL all-gather per merge
+  // (measured 62 us per merge at 2 GPUs) and shortens nothing. replicated_ = false keeps the sharded loop (word wi on rank
+  // wi % nranks, per-merge all-gather of the delta records).
+  bool replicated_ = true;
+  int mrank() const { return replicated_ ? 0 : rank; }
+  int mnranks() const { return replicated_ ? 1 : nranks; }
+  NcclComm mcomm() const { return replicated_ ? nullptr : comm_; }
   bool timing = false;
   uint64_t W = 0;  // unique words (global)
   std::vector<uint64_t> h_counts;  // host mirror of the word counts (Corpus.word_counts)
@@ -179,10 +189,22 @@ class TrainerImpl {
     ensure_device();
     const double t0 = now_ms();
     DevBuf<uint8_t> corpus(n + 64);
-    if (n) SWB_CUDA(cudaMemcpyAsync(corpus.get(), data, n, cudaMemcpyHostToDevice, stream_));
-    SWB_CUDA(cudaMemsetAsync(corpus.get() + n, ' ', 64, stream_));
-    build_word_table(corpus, n);
+    // (development / test switches, read per load: SWB_NO_LOAD_PIPELINE=1, SWB_LOAD_PIECE=<bytes per piece>)
+    const bool no_pipe = getenv("SWB_NO_LOAD_PIPELINE") && atoi(getenv("SWB_NO_LOAD_PIPELINE")) > 0;
+    if (no_pipe || n < 4 * load_piece_bytes()) {
+      if (n) SWB_CUDA(cudaMemcpyAsync(corpus.get(), data, n, cudaMemcpyHostToDevice, stream_));
+      SWB_CUDA(cudaMemsetAsync(corpus.get() + n, ' ', 64, stream_));
+      build_word_table(corpus, n);
+    } else {  // large host buffers: the tokeniser follows the copy piece by piece (see build_word_table)
+      SWB_CUDA(cudaMemsetAsync(corpus.get() + n, ' ', 64, stream_));
+      build_word_table(corpus, n, false, 0, static_cast<const uint8_t *>(data));
+    }
     stats.load_ms += now_ms() - t0;
+  }
+  static uint64_t load_piece_bytes() {
+    const char *e = getenv("SWB_LOAD_PIECE");
+    const uint64_t v = e ? strtoull(e, nullptr, 10) : 0;
+    return v >= 4096 ? v / 16 * 16 : (64ull << 20);
   }
   void load_shard(const void *data, uint64_t n, uint64_t global_offset, bool on_device) {
     ensure_device();
@@ -206,7 +228,11 @@ class TrainerImpl {
   // corpus: n bytes + >= 16 bytes of ' ' padding, 16-byte aligned (cudaMalloc)
   // split: `corpus` is only this rank's byte range of the global corpus (starting at global_offset); the
   // per-rank tables are exchanged over NCCL and merged, so every rank ends with the global word table.
-  void build_word_table(DevBuf<uint8_t> &corpus, uint64_t n, bool split = false, uint64_t global_offset = 0) {
+  // host_src != nullptr: the n corpus bytes are still in host memory; they are copied in pieces on a second stream and
+  // every piece is tokenised as soon as it has landed (PCIe and the tokeniser run at about the same rate: overlapped,
+  // the load takes the longer of the two instead of their sum).
+  void build_word_table(DevBuf<uint8_t> &corpus, uint64_t n, bool split = false, uint64_t global_offset = 0,
+                        const uint8_t *host_src = nullptr) {
     if (n >= (1ull << 40) || global_offset + n >= (1ull << 40)) throw Error("corpus larger than 1 TiB is not supported (40-bit offsets)");
     if (split && !comm_) throw Error("a range-split load needs swb_dist_init first");
     free_corpus_state();
@@ -222,7 +248,37 @@ class TrainerImpl {
       wt_fill<<<sms_ * 8, 256, 0, stream_>>>(keys.get(), counts.get(), cap); launched();
       SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
       WordTableDev tbl{keys.get(), counts.get(), cap - 1, d_nuniq, d_flags, (uint64_t)(cap * 0.6)};
-      if (n) { wt_tokenize<<<sms_ * 4, WT_THREADS, WT_SMEM_BYTES, stream_>>>(corpus.get(), n, tbl); launched(); }
+      if (n && host_src) {
+        const uint64_t PIECE = load_piece_bytes();  // (a multiple of 16: see wt_tokenize)
+        if (!copy_stream_) SWB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+        cudaEvent_t fill_done;
+        SWB_CUDA(cudaEventCreateWithFlags(&fill_done, cudaEventDisableTiming));
+        SWB_CUDA(cudaEventRecord(fill_done, stream_));
+        SWB_CUDA(cudaStreamWaitEvent(copy_stream_, fill_done, 0));  // (also orders the copies after the allocation's previous users)
+        std::vector<cudaEvent_t> landed;
+        uint64_t tok_lo = 0;
+        for (uint64_t c0 = 0; c0 < n; c0 += PIECE) {
+          const uint64_t c1 = std::min(n, c0 + PIECE);
+          SWB_CUDA(cudaMemcpyAsync(corpus.get() + c0, host_src + c0, c1 - c0, cudaMemcpyHostToDevice, copy_stream_));
+          cudaEvent_t ev;
+          SWB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+          SWB_CUDA(cudaEventRecord(ev, copy_stream_));
+          landed.push_back(ev);
+          // words starting before tok_hi end before it: cut after the last delimiter of what has been copied
+          uint64_t tok_hi = c1;
+          if (c1 < n) while (tok_hi > tok_lo && !is_delim(host_src[tok_hi - 1])) tok_hi--;
+          SWB_CUDA(cudaStreamWaitEvent(stream_, ev, 0));
+          if (tok_hi > tok_lo) {
+            wt_tokenize<<<sms_ * 4, WT_THREADS, WT_SMEM_BYTES, stream_>>>(corpus.get(), n, tbl, tok_lo, tok_hi); launched();
+            tok_lo = tok_hi;
+          }
+        }
+        SWB_CUDA(cudaGetLastError());
+        sync();
+        for (cudaEvent_t ev : landed) cudaEventDestroy(ev);
+        cudaEventDestroy(fill_done);
+        host_src = nullptr;  // (a rerun with a larger table finds the corpus on the device)
+      } else if (n) { wt_tokenize<<<sms_ * 4, WT_THREADS, WT_SMEM_BYTES, stream_>>>(corpus.get(), n, tbl, 0, n); launched(); }
       SWB_CUDA(cudaGetLastError());
       SWB_CUDA(cudaMemcpyAsync(h_scal, scalars_.get(), sizeof h_scal, cudaMemcpyDeviceToHost, stream_));
       sync();
@@ -353,7 +409,7 @@ class TrainerImpl {
     if (W) {
       DevBuf<uint32_t> batch_rows(n_batches);
       const int pgrid = (int)std::min<uint64_t>(sms_ * 4, (n_batches + 7) / 8);
-      wt_pack<false><<<pgrid, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), long_index_.get(), W, rank, nranks,
+      wt_pack<false><<<pgrid, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), long_index_.get(), W, mrank(), mnranks(),
                                                  d_bmap.get(), batch_rows.get(), nullptr, nullptr, nullptr);
       launched();
       std::vector<uint32_t> h_rows(n_batches);
@@ -366,7 +422,7 @@ class TrainerImpl {
       rows_.alloc(n_rows_ * (ROW / 4));
       sig_.alloc(n_rows_ * SIG_WORDS);
       SWB_CUDA(cudaMemcpyAsync(batch_rows.get(), h_rows.data(), n_batches * 4, cudaMemcpyHostToDevice, stream_));
-      wt_pack<true><<<pgrid, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), long_index_.get(), W, rank, nranks,
+      wt_pack<true><<<pgrid, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), long_index_.get(), W, mrank(), mnranks(),
                                                 d_bmap.get(), batch_rows.get(), rows_.get(), wloc_.get(), sig_.get());
       launched();
       sync();
@@ -375,7 +431,7 @@ class TrainerImpl {
     long_off_.alloc(n_long_); long_len_.alloc(n_long_); long_word_.alloc(n_long_); long_syms_.alloc(long_total);
     if (n_long_) {
       wt_long_offsets<<<sms_ * 4, 256, 0, stream_>>>(wlen.get(), long_index_.get(), W, d_u64 + 2, long_off_.get());
-      wt_fill_long<<<sms_ * 4, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), long_index_.get(), W, rank, nranks,
+      wt_fill_long<<<sms_ * 4, 256, 0, stream_>>>(corpus.get(), woff.get(), wlen.get(), long_index_.get(), W, mrank(), mnranks(),
                                                   d_bmap.get(), long_off_.get(), long_syms_.get(), long_len_.get(), long_word_.get());
       launched(2);
     }
@@ -399,11 +455,11 @@ class TrainerImpl {
     sync();
     // live symbols of this rank
     live_symbols_ = 0;
-    if (nranks == 1) live_symbols_ = word_bytes_total_;
+    if (mnranks() == 1) live_symbols_ = word_bytes_total_;
     else {
       std::vector<uint32_t> h_len(W);
       if (W) SWB_CUDA(cudaMemcpy(h_len.data(), wlen.get(), W * 4, cudaMemcpyDeviceToHost));
-      for (uint64_t w = rank; w < W; w += nranks) live_symbols_ += h_len[w];
+      for (uint64_t w = mrank(); w < W; w += mnranks()) live_symbols_ += h_len[w];
     }
     corpus.release();
     SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
@@ -521,7 +577,7 @@ class TrainerImpl {
   // ---- device frequency table
   bool want_device_tables() const {
     static const bool forced_host = getenv("SWB_HOST_TABLE") && atoi(getenv("SWB_HOST_TABLE")) > 0;
-    return (nranks == 1 || comm_ != nullptr) && !forced_host;
+    return (mnranks() == 1 || mcomm() != nullptr) && !forced_host;
   }
   void ensure_global_table(uint64_t min_cap) {
     ensure_device();
@@ -789,7 +845,7 @@ class TrainerImpl {
       if (n_long_) { count_long<<<std::min<uint32_t>(sms_ * 4, (n_long_ + 3) / 4), 128, 0, stream_>>>(s, pt_, unk_dev()); launched(); }
       unsigned int flags = 0;
       size_t n = 0;
-      if (comm_) {
+      if (mcomm()) {
         if (mode == 2) {  // sized for the union of all ranks' pairs: at most nranks x the largest local list
           unsigned int n_pairs = 0;
           SWB_CUDA(cudaMemcpyAsync(&n_pairs, pt_.n_touched, 4, cudaMemcpyDeviceToHost, stream_));
@@ -861,7 +917,7 @@ class TrainerImpl {
     StreamDev s = stream_dev();
     t_launch0_ = now_ms();
     if (timing) SWB_CUDA(cudaEventRecord(ev0_, stream_));
-    const bool fused = n_rows_ && !n_long_ && !comm_;
+    const bool fused = n_rows_ && !n_long_ && !mcomm();
     unsigned long long seq = 0;
     if (n_rows_) {
       const uint64_t warps_needed = (n_rows_ + 31) / 32;  // one warp tests 32 row signatures per iteration
@@ -904,7 +960,7 @@ class TrainerImpl {
         t_launch0_ = now_ms();
         n = emit_and_wait(em, &flags, &removed);
       }
-    } else if (comm_) {
+    } else if (mcomm()) {
       n = exchange_and_reduce(em, &flags, &removed);
     } else {
       n = emit_and_wait(em, &flags, &removed);
@@ -920,7 +976,7 @@ class TrainerImpl {
       stats.merge_kernel_ms += ms;
     }
     stats.merge_scan_bytes += n_rows_ * ROW * 4;
-    stats.merge_alg_bytes += 4 * live_symbols_ + 8 * (nranks == 1 ? W : (W + nranks - 1 - rank) / nranks);
+    stats.merge_alg_bytes += 4 * live_symbols_ + 8 * (mnranks() == 1 ? W : (W + mnranks() - 1 - mrank()) / mnranks());
     live_symbols_ -= removed;
     stats.live_symbols = live_symbols_;
     if (trace_wait_ && !wait_trace_.empty()) trace_removed_.push_back((uint32_t)removed);
@@ -975,7 +1031,7 @@ class TrainerImpl {
     // bench corpus a quarter of the merges tie at the maximum and hand control back, and the arg-max tail
     // lengthens every kernel, so it does not beat the synchronous loop yet.
     static const bool on = getenv("SWB_DEVICE_LOOP") && atoi(getenv("SWB_DEVICE_LOOP")) > 0;
-    return on && device_tables_ && !comm_ && !timing && loaded_ && n_rows_ > 0 && n_long_ == 0;
+    return on && device_tables_ && !mcomm() && !timing && loaded_ && n_rows_ > 0 && n_long_ == 0;
   }
   void ensure_loop_buffers() {
     if (loop_state_.size()) return;
@@ -1126,7 +1182,7 @@ class TrainerImpl {
   // ---------------------------------------------------------------- persistent merge kernel (default single-GPU path)
   bool use_persistent() const {
     static const bool off = getenv("SWB_NO_PERSISTENT") && atoi(getenv("SWB_NO_PERSISTENT")) > 0;
-    return !off && device_tables_ && !comm_ && !timing && loaded_ && n_rows_ > 0 && n_long_ == 0 && coop_ok_;
+    return !off && device_tables_ && !mcomm() && !timing && loaded_ && n_rows_ > 0 && n_long_ == 0 && coop_ok_;
   }
   struct HostCmdSender {  // makes sure the resident kernel is always told to stop, also when an exception unwinds
     volatile HostCmd *c = nullptr;
@@ -1563,7 +1619,7 @@ class TrainerImpl {
     if (sym_off || syms) {
       StreamDev s = stream_dev();
       DevBuf<uint32_t> len(W);
-      words_live_len<<<sms_ * 4, 256, 0, stream_>>>(s, wloc_.get(), long_index_.get(), (uint32_t)W, rank, nranks, len.get()); launched();
+      words_live_len<<<sms_ * 4, 256, 0, stream_>>>(s, wloc_.get(), long_index_.get(), (uint32_t)W, mrank(), mnranks(), len.get()); launched();
       std::vector<uint32_t> h_len(W);
       SWB_CUDA(cudaMemcpyAsync(h_len.data(), len.get(), W * 4, cudaMemcpyDeviceToHost, stream_));
       sync();
@@ -1576,7 +1632,7 @@ class TrainerImpl {
         DevBuf<uint64_t> d_off(W + 1);
         DevBuf<int32_t> d_out(acc);
         SWB_CUDA(cudaMemcpyAsync(d_off.get(), off.data(), (W + 1) * 8, cudaMemcpyHostToDevice, stream_));
-        words_copy_syms<<<sms_ * 4, 256, 0, stream_>>>(s, wloc_.get(), long_index_.get(), (uint32_t)W, rank, nranks, d_off.get(), d_out.get()); launched();
+        words_copy_syms<<<sms_ * 4, 256, 0, stream_>>>(s, wloc_.get(), long_index_.get(), (uint32_t)W, mrank(), mnranks(), d_off.get(), d_out.get()); launched();
         SWB_CUDA(cudaMemcpyAsync(syms, d_out.get(), acc * 4, cudaMemcpyDeviceToHost, stream_));
         sync();
         if (tr_->config.unk_id < 0)
@@ -1597,7 +1653,7 @@ class TrainerImpl {
 
   Trainer *tr_;
   int device_ = 0, sms_ = 148;
-  cudaStream_t stream_ = nullptr;
+  cudaStream_t stream_ = nullptr, copy_stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   bool loaded_ = false;
   double t_launch0_ = 0;

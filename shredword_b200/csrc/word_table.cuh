@@ -97,8 +97,12 @@ __device__ __forceinline__ uint32_t wt_delim_bits(uint32_t w, uint32_t &nul) {
 }
 
 // corpus must be 16-byte aligned and padded with >= 16 delimiter bytes after n.
+// Counts the words that START in [lo, hi) (the whole corpus: lo = 0, hi = n). A range lets the host-buffer load
+// tokenise a piece of the corpus while the next piece is still crossing PCIe: `hi` is then cut right after a
+// delimiter, so every word that starts before it also ends before it, and the bytes of the 16-byte segments the
+// range touches have all arrived (the copy granularity is a multiple of 16).
 __global__ void __launch_bounds__(WT_THREADS)
-wt_tokenize(const uint8_t *__restrict__ corpus, uint64_t n, WordTableDev tbl) {
+wt_tokenize(const uint8_t *__restrict__ corpus, uint64_t n, WordTableDev tbl, uint64_t lo, uint64_t hi) {
   extern __shared__ __align__(16) unsigned long long wt_dyn_smem[];  // WT_SMEM_BYTES, opt-in above 48 KB
   unsigned long long *lkeys = wt_dyn_smem;
   unsigned int *lcnt = reinterpret_cast<unsigned int *>(wt_dyn_smem + LT_SLOTS);
@@ -107,11 +111,11 @@ wt_tokenize(const uint8_t *__restrict__ corpus, uint64_t n, WordTableDev tbl) {
   if (threadIdx.x == 0) lused = 0;
   __syncthreads();
 
-  const uint64_t nseg = (n + 15) / 16;
+  const uint64_t seg_lo = lo / 16, seg_hi = (hi + 15) / 16, nseg = seg_hi - seg_lo;
   // each block owns a contiguous span of segments so that its private table sees a long stretch of text
   const uint64_t per_block = ((nseg + gridDim.x - 1) / gridDim.x + WT_THREADS - 1) / WT_THREADS * WT_THREADS;
-  const uint64_t seg_begin = (uint64_t)blockIdx.x * per_block;
-  const uint64_t seg_end = min(nseg, seg_begin + per_block);
+  const uint64_t seg_begin = seg_lo + (uint64_t)blockIdx.x * per_block;
+  const uint64_t seg_end = min(seg_hi, seg_begin + per_block);
   uint32_t nul = 0;
 
   for (uint64_t base = seg_begin; base < seg_end; base += WT_THREADS) {
@@ -126,7 +130,8 @@ wt_tokenize(const uint8_t *__restrict__ corpus, uint64_t n, WordTableDev tbl) {
         const int s = __ffs(starts) - 1;
         starts &= starts - 1;
         const uint64_t off = seg * 16 + s;
-        if (off >= n) break;
+        if (off >= hi) break;
+        if (off < lo) continue;
         uint64_t h64; uint32_t djb;
         const uint32_t len = wt_scan_word(corpus, off, n, h64, djb);
         const uint64_t tag = (djb & 0xFFFu) | (((h64 >> 40) & 0xFFFu) << 12);

@@ -1,5 +1,10 @@
-"""Multi-GPU BPE training: unique words sharded over ranks, pair table + heap replicated.
+"""Multi-GPU BPE training.
 
+Default (replicated merge loop): the corpus is range-split over the ranks, every rank tokenises its range and the
+unique-word tables are exchanged over NCCL (load_shard); every rank then holds all unique words and runs the
+single-GPU resident merge loop -- identical results on every rank, no collective per merge.
+
+sharded_merge=True: unique words sharded over ranks, pair table + heap replicated.
 One process per GPU (torch.distributed). Word wi of the reference word order belongs to rank
 wi % world_size; each rank's kernels count / merge only its own rows. Per merge every rank emits its
 local (pair, net delta, first-touch key) records, the records are all-gathered, reduced by pair
@@ -51,10 +56,15 @@ class _CudaLocalOps:
 class DistributedBPETrainer(BPETrainer):
   """BPETrainer whose word table is sharded over the ranks of `group` (default: the world)."""
 
-  def __init__(self, *args, group=None, device: torch.device | None = None, local_ops=None, native: bool | None = None, **kw):
-    """native=True (default on CUDA devices): the per-merge exchange is NCCL issued from C++ inside the
-    library (swb_dist_init; bpe_train then runs the sharded loop itself). native=False: the exchange is
-    torch.distributed driven from Python (any backend; what the gloo tests use)."""
+  def __init__(self, *args, group=None, device: torch.device | None = None, local_ops=None, native: bool | None = None,
+               sharded_merge: bool = False, **kw):
+    """native=True (default on CUDA devices): NCCL is driven from C++ inside the library (swb_dist_init).
+    With sharded_merge=False (default) only the load is split -- range-split tokenising + NCCL word-table
+    exchange in load_shard -- and every rank then runs the single-GPU merge loop on all unique words (no
+    collective per merge: the loop is latency-bound); sharded_merge=True keeps each
+    rank's words on that rank and all-gathers the delta records of every merge.
+    native=False: the sharded loop with the exchange driven from Python through torch.distributed (any
+    backend; what the gloo tests use)."""
     super().__init__(*args, **kw)
     self.group = group
     self.rank = dist.get_rank(group)
@@ -63,6 +73,7 @@ class DistributedBPETrainer(BPETrainer):
     if native is None:
       native = local_ops is None and self.device.type == "cuda"
     self.native = bool(native)
+    self.sharded = bool(sharded_merge) or not self.native
     self.exchange_bytes = 0
     self.collectives = 0
     if self.native:
@@ -75,6 +86,8 @@ class DistributedBPETrainer(BPETrainer):
         dist.broadcast_object_list(box, src=0, group=group)
         uid = np.frombuffer(box[0], dtype=np.uint8).copy()
       if lib.swb_dist_init(self.trainer, self.rank, self.world, _ptr(uid)) != 0:
+        raise RuntimeError(last_error())
+      if lib.swb_dist_set_sharded(self.trainer, 1 if self.sharded else 0) != 0:
         raise RuntimeError(last_error())
       self.local = None
       return
@@ -159,6 +172,8 @@ class DistributedBPETrainer(BPETrainer):
 
   def token_freq(self) -> np.ndarray:
     """Global token histogram: sum of the ranks' shard histograms."""
+    if not self.sharded:  # every rank holds all words: its histogram is the global one
+      return super().token_freq()
     local = torch.from_numpy(super().token_freq().astype(np.int64)).to(self.device)
     dist.all_reduce(local, group=self.group)
     return local.cpu().numpy().astype(np.uint64)

@@ -1,5 +1,6 @@
-"""GPU, 2+ devices: the sharded merge loop with the NCCL exchange issued from inside the library (and the
-Python-driven torch.distributed exchange) must reproduce the single-GPU / oracle merge list bit for bit.
+"""GPU, 2+ devices: the multi-GPU trainer -- replicated merge loop (default), the sharded merge loop with the NCCL
+exchange issued from inside the library, and the Python-driven torch.distributed exchange -- must reproduce the
+single-GPU / oracle merge list bit for bit.
 Skipped on a single-GPU box (the round-end -m gpu run); exercised with `gpurun --gpus 2`."""
 import os
 import socket
@@ -14,7 +15,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, name, native, out_dir):
+def _worker(rank, world, port, name, mode, out_dir):
+  native = mode != "python"
   sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
   import torch
   import torch.distributed as dist
@@ -24,25 +26,29 @@ def _worker(rank, world, port, name, native, out_dir):
   dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
   from shredword_b200.distributed import DistributedBPETrainer
   kw = cases.kwargs(name)
-  t = DistributedBPETrainer(**kw, device=torch.device("cuda", rank), native=native)
+  t = DistributedBPETrainer(**kw, device=torch.device("cuda", rank), native=native, sharded_merge=(mode == "sharded"))
+  assert t.sharded == (mode != "replicated")
   t.load_buffer(cases.corpus(name))
   n = t.train_quiet()
-  np.save(os.path.join(out_dir, f"merges_{int(native)}_{rank}.npy"), t.merges_array())
-  np.save(os.path.join(out_dir, f"freq_{int(native)}_{rank}.npy"), t.token_freq())
-  t.save(os.path.join(out_dir, f"m_{int(native)}.model"), os.path.join(out_dir, f"m_{int(native)}.vocab"))
+  np.save(os.path.join(out_dir, f"merges_{mode}_{rank}.npy"), t.merges_array())
+  np.save(os.path.join(out_dir, f"freq_{mode}_{rank}.npy"), t.token_freq())
+  t.save(os.path.join(out_dir, f"m_{mode}.model"), os.path.join(out_dir, f"m_{mode}.vocab"))
   st = t.stats()
   assert n == len(t.merges_array())
-  if native:
+  if mode == "sharded":
     assert st["collectives"] >= n
+  if mode == "replicated":
+    assert st["collectives"] == 0 and (n == 0 or st["resident_local_merges"] + st["resident_grid_merges"] > 0 or st["long_words"] > 0)
   dist.barrier()
   t.destroy()
   lib.swb_dist_shutdown()
   dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("native", [True, False])
-@pytest.mark.parametrize("name", ["ascii_ties", "multi_unk97", "long_words", "negative_unk"])
-def test_two_gpus_match_oracle(name, native, product, oracle_mod, tmp_path):
+@pytest.mark.parametrize("name,mode", [("ascii_ties", "replicated"), ("long_words", "replicated"),
+                                       ("ascii_ties", "sharded"), ("multi_unk97", "sharded"), ("long_words", "sharded"), ("negative_unk", "sharded"),
+                                       ("ascii_ties", "python"), ("multi_unk97", "python")])
+def test_two_gpus_match_oracle(name, mode, product, oracle_mod, tmp_path):
   import torch
   import torch.multiprocessing as mp
   if torch.cuda.device_count() < 2:
@@ -52,15 +58,15 @@ def test_two_gpus_match_oracle(name, native, product, oracle_mod, tmp_path):
   o = oracle_mod.Oracle(kw["target_vocab_size"], kw.get("unk_id", 0), kw.get("character_coverage", 0.995), kw["min_pair_freq"])
   o.load_buffer(cases.corpus(name)); o.train()
   o.save(str(tmp_path / "o.model"), str(tmp_path / "o.vocab"))
-  mp.spawn(_worker, args=(2, port, name, native, str(tmp_path)), nprocs=2, join=True)
+  mp.spawn(_worker, args=(2, port, name, mode, str(tmp_path)), nprocs=2, join=True)
   for r in range(2):
-    assert np.array_equal(np.load(tmp_path / f"merges_{int(native)}_{r}.npy"), o.merges), f"rank {r}"
-    assert np.array_equal(np.load(tmp_path / f"freq_{int(native)}_{r}.npy"), o.token_freq()), f"rank {r}"
-  assert (tmp_path / f"m_{int(native)}.model").read_bytes() == (tmp_path / "o.model").read_bytes()
-  assert (tmp_path / f"m_{int(native)}.vocab").read_bytes() == (tmp_path / "o.vocab").read_bytes()
+    assert np.array_equal(np.load(tmp_path / f"merges_{mode}_{r}.npy"), o.merges), f"rank {r}"
+    assert np.array_equal(np.load(tmp_path / f"freq_{mode}_{r}.npy"), o.token_freq()), f"rank {r}"
+  assert (tmp_path / f"m_{mode}.model").read_bytes() == (tmp_path / "o.model").read_bytes()
+  assert (tmp_path / f"m_{mode}.vocab").read_bytes() == (tmp_path / "o.vocab").read_bytes()
 
 
-def _shard_worker(rank, world, port, out_dir):
+def _shard_worker(rank, world, port, sharded, out_dir):
   sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
   import torch
   import torch.distributed as dist
@@ -71,7 +77,7 @@ def _shard_worker(rank, world, port, out_dir):
   from shredword_b200.distributed import DistributedBPETrainer
   data = np.load(os.path.join(out_dir, "corpus.npy"))
   cuts = np.load(os.path.join(out_dir, "cuts.npy"))
-  t = DistributedBPETrainer(1500, min_pair_freq=5, device=torch.device("cuda", rank))
+  t = DistributedBPETrainer(1500, min_pair_freq=5, device=torch.device("cuda", rank), sharded_merge=sharded)
   piece = data[cuts[rank]:cuts[rank + 1]]
   if rank == 0:
     t.load_shard(piece, int(cuts[rank]))                                   # host buffer
@@ -80,6 +86,8 @@ def _shard_worker(rank, world, port, out_dir):
   boff, by, _, _, cnt = t.words()
   np.save(os.path.join(out_dir, f"wbytes_{rank}.npy"), by); np.save(os.path.join(out_dir, f"wcnt_{rank}.npy"), cnt)
   n = t.train_quiet()
+  st = t.stats()
+  assert st["collectives"] == (3 if not sharded else st["collectives"]) and st["collectives"] >= 3  # the word-table exchange
   np.save(os.path.join(out_dir, f"smerges_{rank}.npy"), t.merges_array())
   np.save(os.path.join(out_dir, f"sfreq_{rank}.npy"), t.token_freq())
   dist.barrier()
@@ -88,7 +96,8 @@ def _shard_worker(rank, world, port, out_dir):
   dist.destroy_process_group()
 
 
-def test_range_split_load_matches_oracle(product, oracle_mod, tmp_path):
+@pytest.mark.parametrize("sharded", [False, True])
+def test_range_split_load_matches_oracle(sharded, product, oracle_mod, tmp_path):
   """Every rank tokenises only its byte range; the exchanged + merged word table must be the global one
   (same words, same order, summed counts, first occurrence = global minimum)."""
   import torch
@@ -105,7 +114,7 @@ def test_range_split_load_matches_oracle(product, oracle_mod, tmp_path):
   _, oby, _, _, ocnt = o.words()
   o.train()
   s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-  mp.spawn(_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  mp.spawn(_shard_worker, args=(2, port, sharded, str(tmp_path)), nprocs=2, join=True)
   for r in range(2):
     assert np.array_equal(np.load(tmp_path / f"wbytes_{r}.npy"), oby) and np.array_equal(np.load(tmp_path / f"wcnt_{r}.npy"), ocnt), f"word table, rank {r}"
     assert np.array_equal(np.load(tmp_path / f"smerges_{r}.npy"), o.merges), f"rank {r}"

@@ -113,3 +113,27 @@ def test_vocab_and_merges_properties(product):
   for a, b, nid in m:
     assert v[nid] == v[a] + v[b]
   assert t.special_tokens[0] == ("<UNK>", 0)
+
+
+@pytest.mark.parametrize("piece", [4096, 65536, 1 << 20])
+def test_pipelined_host_load_equals_oracle(piece, product, oracle_mod, monkeypatch):
+  """swb_load_corpus_buffer on large buffers copies the corpus in pieces and tokenises each piece as it lands
+  (words that straddle a piece boundary, a word longer than a piece, pieces without any delimiter). The word
+  table, its order and the merges must not depend on the piece size."""
+  rng = np.random.default_rng(9)
+  giant = bytes(rng.choice(np.frombuffer(b"xyz", dtype=np.uint8), size=3 * 4096 + 77))  # longer than the smallest piece
+  data = cases.corpus("multi_ties")[:1_500_000]
+  data = data[: len(data) // 2] + b" " + giant + b" " + giant + b"\n" + data[len(data) // 2:]
+  kw = dict(target_vocab_size=600, min_pair_freq=5)
+  o = oracle_mod.Oracle(600, 0, 0.995, 5)
+  assert o.load_buffer(data) == 0
+  monkeypatch.setenv("SWB_LOAD_PIECE", str(piece))
+  t = product.BPETrainer(**kw)
+  t.load_buffer(data)
+  ob, oby, _, osy, oc = o.words()
+  tb, tby, _, tsy, tc = t.words()
+  assert np.array_equal(ob, tb) and np.array_equal(oby, tby), "unique words / reference word order differ"
+  assert np.array_equal(oc, tc), "word counts differ"
+  assert o.train() == t.train_quiet()
+  assert np.array_equal(o.merges, t.merges_array())
+  assert t.stats()["kernel_launches"] > len(data) // piece  # (one tokeniser launch per piece: the pipelined path ran)
