@@ -218,8 +218,10 @@ def main():
   from shredword_b200 import build as B
   B.build()
   from shredword_b200.cbase import lib
-  from shredword_b200.trainer import BPETrainer
+  from shredword_b200.trainer import BPETrainer, bind_host_thread_to_gpu
   lib.swb_set_device(local_rank)
+  cpus = None if os.environ.get("SWB_BENCH_NO_BIND") else bind_host_thread_to_gpu(local_rank)  # before any pinned allocation (first touch)
+  log(f"[bench] rank {rank}: host thread bound to {len(cpus)} CPUs of the GPU's NUMA node" if cpus else f"[bench] rank {rank}: host thread not bound")
   if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=dev)

@@ -126,6 +126,10 @@ size_t swb_word_bytes_total(const Trainer *trainer);
 int swb_get_words(const Trainer *trainer, uint64_t *byte_off /*[W+1]*/, uint8_t *bytes,
                   uint64_t *sym_off /*[W+1]*/, int32_t *syms, uint64_t *counts /*[W]*/);
 
+/* PCI bus id of CUDA device `device` ("0000:1b:00.0") into out; 0 on success. For NUMA placement of the calling
+ * thread (the merge loop is a latency chain through mapped host memory). */
+int swb_device_pci_bus_id(int device, char *out, size_t cap);
+
 /* Counters of the device work done so far by this handle. */
 typedef struct SwbStats {
   uint64_t kernel_launches;   /* kernels of this library launched */

@@ -312,6 +312,11 @@ size_t swb_decode(const SwbEncoder *enc, const int32_t *ids, size_t n, uint8_t *
 uint64_t swb_encoder_kernel_launches(const SwbEncoder *enc) { return enc ? enc->impl->launches : 0; }
 
 // ---- multi-GPU building blocks
+int swb_device_pci_bus_id(int device, char *out, size_t cap) {
+  if (!out || cap < 16) { set_err("swb_device_pci_bus_id: buffer too small"); return -1; }
+  if (cudaDeviceGetPCIBusId(out, (int)cap, device) != cudaSuccess) { cudaGetLastError(); set_err("swb_device_pci_bus_id: no such CUDA device"); return -1; }
+  return 0;
+}
 int swb_set_shard(Trainer *trainer, int rank, int nranks) {
   if (!trainer || nranks < 1 || rank < 0 || rank >= nranks) { set_err("swb_set_shard: bad arguments"); return -1; }
   impl_of(trainer)->rank = rank;

@@ -315,7 +315,13 @@ class EncoderImpl {
     }
     tok_off_[toks.size()] = tok_bytes_.size();
   }
-  ~EncoderImpl() { if (stream_) cudaStreamDestroy(stream_); }
+  ~EncoderImpl() {
+    if (s_in_) {
+      cudaStreamDestroy(s_in_); cudaStreamDestroy(s_out_);
+      for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_in_[i]); cudaEventDestroy(ev_gather_[i]); cudaEventDestroy(ev_out_[i]); }
+    }
+    if (stream_) cudaStreamDestroy(stream_);
+  }
 
   uint64_t launches = 0;
 
@@ -391,39 +397,76 @@ class EncoderImpl {
     SWB_CUDA(cudaGetLastError());
   }
 
-  // host text -> host ids, streamed through the device in pieces that end on a delimiter
+  // host text -> host ids, streamed through the device in pieces that end on a delimiter. Three streams, two
+  // buffers each way: while piece i is encoded, piece i+1 crosses PCIe inbound and the ids of piece i-1 outbound
+  // (pinned host memory makes the copies asynchronous; pageable memory still works, serialised by the driver).
   int64_t encode_host(const uint8_t *text, uint64_t n, int32_t *out, uint64_t cap_ids, uint32_t *word_ntok,
                       uint64_t cap_words, size_t *n_words) {
     ensure_device();
-    const uint64_t PIECE = 256ull << 20;
-    DevBuf<uint8_t> d_text(std::min<uint64_t>(n, PIECE + (1ull << 20)) + 64);
-    uint64_t pos = 0, tok_total = 0, word_total = 0;
-    DevBuf<int32_t> d_out;
-    DevBuf<uint32_t> d_wn;
-    while (pos < n) {
+    const char *pe = getenv("SWB_ENCODE_PIECE");  // (test switch: bytes per piece)
+    const uint64_t pv = pe ? strtoull(pe, nullptr, 10) : 0;
+    const uint64_t PIECE = pv >= 4096 ? pv : (64ull << 20);
+    if (!s_in_) {
+      SWB_CUDA(cudaStreamCreateWithFlags(&s_in_, cudaStreamNonBlocking));
+      SWB_CUDA(cudaStreamCreateWithFlags(&s_out_, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; i++) {
+        SWB_CUDA(cudaEventCreateWithFlags(&ev_in_[i], cudaEventDisableTiming));
+        SWB_CUDA(cudaEventCreateWithFlags(&ev_gather_[i], cudaEventDisableTiming));
+        SWB_CUDA(cudaEventCreateWithFlags(&ev_out_[i], cudaEventDisableTiming));
+      }
+    }
+    // piece boundaries (cut on a delimiter so that no word is split)
+    std::vector<uint64_t> cut{0};
+    uint64_t max_len = 0;
+    while (cut.back() < n) {
+      const uint64_t pos = cut.back();
       uint64_t end = std::min<uint64_t>(n, pos + PIECE);
-      if (end < n) {  // cut on a delimiter so that no word is split
+      if (end < n) {
         uint64_t e = end;
         while (e > pos && !is_delim(text[e - 1])) --e;
         if (e == pos) { e = end; while (e < n && !is_delim(text[e])) ++e; }
         end = e;
       }
-      const uint64_t len = end - pos;
-      if (d_text.size() < len + 64) d_text.alloc(len + 64);
-      if (d_out.size() < len) d_out.alloc(len);
-      if (word_ntok && d_wn.size() < len / 2 + 1) d_wn.alloc(len / 2 + 1);
-      SWB_CUDA(cudaMemcpyAsync(d_text.get(), text + pos, len, cudaMemcpyHostToDevice, stream_));
-      SWB_CUDA(cudaMemsetAsync(d_text.get() + len, ' ', 64, stream_));
-      uint64_t nt = 0, nw = 0;
-      encode_piece(d_text.get(), len, d_out.get(), len, 0, word_ntok ? d_wn.get() : nullptr, len / 2 + 1, 0, &nt, &nw);
-      if (tok_total + nt > cap_ids) throw Error("swb_encode: output capacity too small");
-      if (word_ntok && word_total + nw > cap_words) throw Error("swb_encode: word_ntok capacity too small");
-      if (nt) SWB_CUDA(cudaMemcpyAsync(out + tok_total, d_out.get(), nt * 4, cudaMemcpyDeviceToHost, stream_));
-      if (word_ntok && nw) SWB_CUDA(cudaMemcpyAsync(word_ntok + word_total, d_wn.get(), nw * 4, cudaMemcpyDeviceToHost, stream_));
-      SWB_CUDA(cudaStreamSynchronize(stream_));
-      tok_total += nt; word_total += nw;
-      pos = end;
+      max_len = std::max(max_len, end - pos);
+      cut.push_back(end);
     }
+    const size_t P = cut.size() - 1;
+    for (int b = 0; b < 2; b++) {
+      if (p_text_[b].size() < max_len + 64) p_text_[b].alloc(max_len + 64);
+      if (p_out_[b].size() < max_len) p_out_[b].alloc(std::max<uint64_t>(max_len, 1));
+      if (word_ntok && p_wn_[b].size() < max_len / 2 + 1) p_wn_[b].alloc(max_len / 2 + 1);
+    }
+    auto copy_in = [&](size_t i) {
+      const int b = (int)(i & 1);
+      const uint64_t len = cut[i + 1] - cut[i];
+      if (i >= 2) SWB_CUDA(cudaStreamWaitEvent(s_in_, ev_gather_[b], 0));  // piece i-2 has been read out of this buffer
+      SWB_CUDA(cudaMemcpyAsync(p_text_[b].get(), text + cut[i], len, cudaMemcpyHostToDevice, s_in_));
+      SWB_CUDA(cudaMemsetAsync(p_text_[b].get() + len, ' ', 64, s_in_));
+      SWB_CUDA(cudaEventRecord(ev_in_[b], s_in_));
+    };
+    uint64_t tok_total = 0, word_total = 0;
+    SWB_CUDA(cudaStreamSynchronize(stream_));  // (buffers may have been (re)allocated from memory this stream used)
+    if (P) copy_in(0);
+    for (size_t i = 0; i < P; i++) {
+      const int b = (int)(i & 1);
+      const uint64_t len = cut[i + 1] - cut[i];
+      if (i + 1 < P) copy_in(i + 1);
+      SWB_CUDA(cudaStreamWaitEvent(stream_, ev_in_[b], 0));
+      if (i >= 2) SWB_CUDA(cudaStreamWaitEvent(stream_, ev_out_[b], 0));  // the ids of piece i-2 have left this buffer
+      uint64_t nt = 0, nw = 0;
+      encode_piece(p_text_[b].get(), len, p_out_[b].get(), len, 0, word_ntok ? p_wn_[b].get() : nullptr, len / 2 + 1, 0, &nt, &nw);
+      SWB_CUDA(cudaEventRecord(ev_gather_[b], stream_));
+      if (tok_total + nt > cap_ids) { cudaDeviceSynchronize(); throw Error("swb_encode: output capacity too small"); }
+      if (word_ntok && word_total + nw > cap_words) { cudaDeviceSynchronize(); throw Error("swb_encode: word_ntok capacity too small"); }
+      SWB_CUDA(cudaStreamWaitEvent(s_out_, ev_gather_[b], 0));
+      if (nt) SWB_CUDA(cudaMemcpyAsync(out + tok_total, p_out_[b].get(), nt * 4, cudaMemcpyDeviceToHost, s_out_));
+      if (word_ntok && nw) SWB_CUDA(cudaMemcpyAsync(word_ntok + word_total, p_wn_[b].get(), nw * 4, cudaMemcpyDeviceToHost, s_out_));
+      SWB_CUDA(cudaEventRecord(ev_out_[b], s_out_));
+      tok_total += nt; word_total += nw;
+    }
+    SWB_CUDA(cudaStreamSynchronize(stream_));
+    SWB_CUDA(cudaStreamSynchronize(s_out_));
+    SWB_CUDA(cudaStreamSynchronize(s_in_));
     if (n_words) *n_words = word_total;
     return (int64_t)tok_total;
   }
@@ -469,6 +512,12 @@ class EncoderImpl {
   std::vector<uint8_t> tok_bytes_;
   std::vector<size_t> tok_off_;
   cudaStream_t stream_ = nullptr;
+  // encode_host pipeline: copy-in / copy-out streams, two device buffers per direction
+  cudaStream_t s_in_ = nullptr, s_out_ = nullptr;
+  cudaEvent_t ev_in_[2] = {}, ev_gather_[2] = {}, ev_out_[2] = {};
+  DevBuf<uint8_t> p_text_[2];
+  DevBuf<int32_t> p_out_[2];
+  DevBuf<uint32_t> p_wn_[2];
   int sms_ = 148;
   DevBuf<RankSlot> slots_;
   DevBuf<MemoSlot> memo_slots_;

@@ -210,9 +210,11 @@ class TrainerImpl {
     ensure_device();
     const double t0 = now_ms();
     DevBuf<uint8_t> corpus(n + 64);
-    if (n) SWB_CUDA(cudaMemcpyAsync(corpus.get(), data, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
+    const bool no_pipe = getenv("SWB_NO_LOAD_PIPELINE") && atoi(getenv("SWB_NO_LOAD_PIPELINE")) > 0;
+    const bool piped = !on_device && !no_pipe && n >= 4 * load_piece_bytes();  // (host buffers: copy and tokeniser overlap, see load_host)
+    if (n && !piped) SWB_CUDA(cudaMemcpyAsync(corpus.get(), data, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
     SWB_CUDA(cudaMemsetAsync(corpus.get() + n, ' ', 64, stream_));
-    build_word_table(corpus, n, nranks > 1, global_offset);
+    build_word_table(corpus, n, nranks > 1, global_offset, piped ? static_cast<const uint8_t *>(data) : nullptr);
     stats.load_ms += now_ms() - t0;
   }
   void load_device(const void *d_data, uint64_t n) {

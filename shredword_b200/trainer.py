@@ -12,6 +12,34 @@ from .cbase import lib, BPEConfig, SwbStats, last_error
 def _ptr(a):
   return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
+def bind_host_thread_to_gpu(device_index: int) -> list[int] | None:
+  """Pins the calling process to the CPUs of the NUMA node the GPU hangs off (Linux sysfs). The merge loop is a
+  latency chain through mapped host memory: a host thread (and its pinned pages, first touch) on the far socket adds a
+  hop to every PCIe round trip. Returns the CPU list, or None when the topology cannot be read."""
+  import os
+  try:
+    import ctypes as _c
+    buf = _c.create_string_buffer(64)
+    if lib.swb_device_pci_bus_id(device_index, buf, 64) != 0:
+      return None
+    bus = buf.value.decode().lower()
+    with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+      spec = f.read().strip()
+    cpus = []
+    for part in spec.split(","):
+      if "-" in part:
+        lo, hi = part.split("-"); cpus.extend(range(int(lo), int(hi) + 1))
+      elif part:
+        cpus.append(int(part))
+    allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+    if not allowed:
+      return None
+    os.sched_setaffinity(0, allowed)
+    return allowed
+  except Exception:
+    return None
+
+
 class BPETrainer:
   def __init__(self, target_vocab_size=8192, unk_id=0, character_coverage=0.995, min_pair_freq=2000):
     self.config = BPEConfig(

@@ -77,6 +77,8 @@ def _shard_worker(rank, world, port, sharded, out_dir):
   from shredword_b200.distributed import DistributedBPETrainer
   data = np.load(os.path.join(out_dir, "corpus.npy"))
   cuts = np.load(os.path.join(out_dir, "cuts.npy"))
+  if not sharded:
+    os.environ["SWB_LOAD_PIECE"] = "65536"  # rank 0's host buffer goes through the pipelined copy + tokenise path
   t = DistributedBPETrainer(1500, min_pair_freq=5, device=torch.device("cuda", rank), sharded_merge=sharded)
   piece = data[cuts[rank]:cuts[rank + 1]]
   if rank == 0:

@@ -90,3 +90,23 @@ def test_encode_capacity_error(product):
   out = np.zeros(4, dtype=np.int32)
   n = lib.swb_encode(enc.h, text.ctypes.data_as(ctypes.c_void_p), text.size, out.ctypes.data_as(ctypes.c_void_p), out.size, None, 0, None)
   assert n == -1  # too small: an error, never a truncated result
+
+
+@pytest.mark.parametrize("piece", [5000, 100_000])
+def test_encode_host_pipeline_many_pieces(piece, product, oracle_mod, monkeypatch):
+  """swb_encode streams host text through the device in pieces on three streams (copy in / encode / copy out, two
+  buffers each way). Many small pieces -- including a word longer than a piece -- must give the ids of one piece."""
+  data = cases.corpus("multi_ties")[:700_000]
+  data = data[:300_000] + b" " + b"abcdefgh" * 2000 + b" " + data[300_000:]
+  t = product.BPETrainer(target_vocab_size=700, min_pair_freq=5)
+  t.load_buffer(data)
+  t.train_quiet()
+  enc = t.encoder()
+  oids, own = oracle_mod.encode(t.merges_array(), t.byte_map(), data, with_word_counts=True)
+  monkeypatch.setenv("SWB_ENCODE_PIECE", str(piece))
+  l0 = enc.kernel_launches
+  ids, wn = enc.encode(data, with_word_counts=True)
+  assert enc.kernel_launches - l0 >= 2 * (len(data) // (piece + 16000) )  # (several pieces went through)
+  assert np.array_equal(own, wn) and np.array_equal(oids, ids)
+  out = np.empty(len(data), dtype=np.int32)
+  assert enc.encode_into(np.frombuffer(data, dtype=np.uint8), out) == len(oids) and np.array_equal(out[: len(oids)], oids)
