@@ -35,6 +35,7 @@ constexpr int CL_REC_STAGE = 512;          // records staged per CTA and merge
 constexpr unsigned int CL_LOCAL_MAX = CL_SIZE * CL_THREADS * 64;  // longest birth log the leader cluster takes alone (entries)
 constexpr int CL_CAND_CAP = 1024;          // candidate words listed per CTA and merge (more: rewritten where they are found)
 constexpr int CL_MAX_PROBES = 256;
+constexpr unsigned int CL_IP_LOCAL_MAX = 8192;  // longest occurrence list of a pair of two initial symbols the leader cluster takes alone (every entry is a candidate word: two per thread)
 
 // host -> device command: ONE 16-byte word in mapped host memory, written with a single 16-byte store and read with a
 // single 16-byte load (one PCIe read per poll, no second trip for a payload):
@@ -296,7 +297,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
               unsigned long long *__restrict__ out_hdr0, unsigned long long *__restrict__ out_hdr1, unsigned long long seq_base, unsigned long long op_base,
               volatile HostCmd2 *hcmd /* [3] in mapped host memory: the command, the hints for even / odd sequence numbers */, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace,
               uint4 *ovf /* [CL_LOCAL_MAX]: candidate words that did not fit a CTA's shared-memory list */,
-              unsigned long long *acct /* [8]: LOCAL merges, their device ns, GRID merges, their device ns, hints accepted, hints rejected, hints accepted without a PCIe trip, - */) {
+              unsigned long long *acct /* [8]: LOCAL merges, their device ns, GRID merges, their device ns, hints accepted, hints rejected, hints accepted without a PCIe trip, LOCAL merges that spilled to the global table */) {
   extern __shared__ __align__(16) unsigned char cl_dyn_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const ClusterSmem m = cluster_smem(cl_dyn_smem);
@@ -369,6 +370,10 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           if (em.log.ent != nullptr && newer >= 256 && (uint32_t)(newer - 256) < mcur) {
             const unsigned int lo = __ldcg(&em.log.start[newer - 256]), hi = __ldcg(&em.log.start[newer - 256 + 1]);
             lr = ((unsigned long long)lo << 32) | (unsigned long long)(hi - lo);
+          } else if (em.log.ent != nullptr && ip_lookup(em.log, pa, pb)) {  // two initial symbols: their occurrence index, unless the list is long (then the whole grid scans)
+            const unsigned int pk = (unsigned int)pa * 256u + (unsigned int)pb;
+            const unsigned int lo = __ldcg(&em.log.ip_start[pk]), hi = __ldcg(&em.log.ip_start[pk + 1]);
+            if (hi - lo <= em.log.ip_local_max) lr = ((unsigned long long)lo << 32) | (unsigned long long)(hi - lo);
           }
           if (cursor_stale && em.log.ent != nullptr) { m.ctl->log_cursor = __ldcg(em.log.cursor); cursor_stale = false; }
           m.ctl->births_total = 0;
@@ -443,7 +448,14 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         __threadfence();
         TailSmem ts{m.tail_stage, m.csum, m.tail_count};
         fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag, nullptr, nullptr);
-        if (threadIdx.x == 0) { acct[2] += 1; acct[3] += gtime_ns() - m.ctl->t_cmd; }  // (one publisher at a time)
+        if (threadIdx.x == 0) {  // (one publisher at a time)
+          const unsigned long long dt = gtime_ns() - m.ctl->t_cmd;
+          acct[2] += 1; acct[3] += dt;
+          if (trace) {  // development aid: how long do GRID merges take? [16..23] = counts, [24..31] = ns, by duration class
+            const int cls = dt < 16000 ? 0 : dt < 24000 ? 1 : dt < 32000 ? 2 : dt < 48000 ? 3 : dt < 64000 ? 4 : dt < 128000 ? 5 : dt < 256000 ? 6 : 7;
+            trace[16 + cls] += 1; trace[24 + cls] += dt;
+          }
+        }
       }
       __syncthreads();
       // the scratch aliased the delta tables: empty them again
@@ -458,7 +470,9 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       const unsigned long long lr = m.ctl->log_range;
       const uint64_t lo = lr >> 32, n = lr & 0xFFFFFFFFu;
       uint32_t merge = 0, other = 0, side = 0;
-      const bool have_log = log_lookup(em.log, a, b, merge, other, side);  // (true: the host sent a log range)
+      bool have_log = log_lookup(em.log, a, b, merge, other, side);  // (true: the command came with a log range)
+      const uint4 *__restrict__ ent = em.log.ent;
+      if (!have_log && ip_lookup(em.log, a, b)) { have_log = true; other = (uint32_t)a; side = 0u; ent = em.log.ip_ent; }  // the occurrence index has the same format
       ClusterSink sink{cluster, m, t, em.log};
       uint32_t removed = 0;
       // Eight log entries per thread are requested together (one round trip); the matching ones are listed in
@@ -469,7 +483,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
 #pragma unroll
         for (int u = 0; u < 8; u++) {
           const uint64_t i = base + (uint64_t)u * (CL_SIZE * CL_THREADS) + crank * CL_THREADS + threadIdx.x;
-          ev[u] = i < n ? __ldcg(&em.log.ent[lo + i]) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+          ev[u] = i < n ? __ldcg(&ent[lo + i]) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -584,7 +598,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag, nullptr, nullptr);
         __syncthreads();
         cluster_clear_tables(m);
-        if (threadIdx.x == 0) { acct[0] += 1; acct[1] += gtime_ns() - c->t_cmd; }
+        if (threadIdx.x == 0) { acct[0] += 1; acct[1] += gtime_ns() - c->t_cmd; acct[7] += 1; }
         if (threadIdx.x == 0) { c->spill = 0; c->n_recs_total = 0; c->removed = 0; }
         __syncthreads();
       } else if (threadIdx.x == 0) {

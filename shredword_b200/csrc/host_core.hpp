@@ -321,9 +321,11 @@ class HostCore {
   size_t peek_next(Peek *out, size_t want) {
     const MaxHeap &h = tr_->heap;
     const uint64_t minf = tr_->config.min_pair_freq;
-    constexpr size_t MAX_POPS = 96, TAIL_GUARD = 128;
-    if (h.size < 4 * TAIL_GUARD) return 0;  // small heaps: the top region may reach the tail of the array
-    const size_t n_eff = h.size - TAIL_GUARD;
+    // the simulated pops would move the last MAX_POPS elements of the array to the root: the look-ahead makes no statement
+    // as soon as it has to look at one of them (small heaps: the top region may reach the tail of the array)
+    const size_t MAX_POPS = std::min<size_t>(640, h.size / 8);
+    if (MAX_POPS < 4) return 0;
+    const size_t n_eff = h.size - MAX_POPS;
     ov_reset();
     size_t got = 0, pops = 0;
     uint64_t tail_max = 0;  // largest frequency among the tail elements the real pops would have moved to the root
@@ -508,20 +510,20 @@ class HostCore {
   struct KeyIdx { uint64_t key; uint32_t idx; };
   // sparse overlay of the heap array used by peek_next: position -> {entry | hole | empty}
   struct OvNode { size_t pos; HeapEntry e; int state; /* 1 entry, 2 hole, 3 empty (no entry left below) */ };
-  static constexpr size_t OV_SLOTS = 1024;  // open addressing over at most OV_MAX nodes
-  static constexpr size_t OV_MAX = 384;
+  static constexpr size_t OV_SLOTS = 8192;  // open addressing over at most OV_MAX nodes
+  static constexpr size_t OV_MAX = 3072;
   std::vector<OvNode> ov_;
   uint16_t ov_map_[OV_SLOTS] = {};
   void ov_reset() {
     for (const OvNode &n : ov_) {  // clear only what was used
-      size_t s = (n.pos * 0x9E3779B97F4A7C15ull) >> 54;
+      size_t s = (n.pos * 0x9E3779B97F4A7C15ull) >> 51;
       while (ov_map_[s]) { ov_map_[s] = 0; s = (s + 1) & (OV_SLOTS - 1); }
     }
     ov_.clear();
     if (ov_.capacity() < OV_MAX + 8) ov_.reserve(OV_MAX + 8);  // (pointers into ov_ stay valid during a look-ahead)
   }
   OvNode *ov_find(size_t pos, bool create, bool &ok) {
-    size_t s = (pos * 0x9E3779B97F4A7C15ull) >> 54;
+    size_t s = (pos * 0x9E3779B97F4A7C15ull) >> 51;
     while (ov_map_[s]) {
       if (ov_[ov_map_[s] - 1].pos == pos) return &ov_[ov_map_[s] - 1];
       s = (s + 1) & (OV_SLOTS - 1);

@@ -165,7 +165,43 @@ struct BirthLogDev {
   unsigned int *flags;   // bit 0: capacity exceeded (internal sizing error)
   uint32_t cap;
   uint32_t m_cur;        // index of the merge being performed; logs 0 .. m_cur-1 are complete
+  // Occurrence index of the pairs of two INITIAL symbols (both < 256), which have no birth log: built once after the
+  // load, same entry format, one contiguous range per pair: ip_ent[ip_start[x * 256 + y] .. ip_start[x * 256 + y + 1])
+  // lists every word that held (x, y) when it was loaded (once per word). Such a pair can only lose occurrences later
+  // (a merge creates adjacencies around its new token only), so the list stays a superset. nullptr: not built.
+  const uint4 *ip_ent;
+  const unsigned int *ip_start;
+  uint32_t ip_local_max;  // longest list the resident kernel's leader cluster takes alone (every entry is a candidate word); longer: whole-grid row scan
 };
+constexpr uint32_t IP_PAIRS = 256u * 256u;
+// true: (a, b) is a pair of two initial symbols with an occurrence index
+__device__ __forceinline__ bool ip_lookup(const BirthLogDev &lg, int32_t a, int32_t b) {
+  return lg.ip_start != nullptr && (uint32_t)a < 256u && (uint32_t)b < 256u;
+}
+// Builds the index, one thread per (row) word. FILL = false: counts per pair into cnt[]; FILL = true: cnt[] restarts
+// from zero as the per-pair cursor and the entries are written from start[] on.
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+ip_index_words(const int32_t *__restrict__ flat_rows, const uint64_t *__restrict__ wloc, const uint32_t *__restrict__ long_index,
+               uint32_t W, unsigned int *__restrict__ cnt, const unsigned int *__restrict__ start, uint4 *__restrict__ ent) {
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
+    if (long_index[w] != 0xFFFFFFFFu) continue;
+    const uint64_t hloc = wloc[w];
+    const int32_t *p = flat_rows + hloc + 1;
+    const int room = ROW - 1 - (int)(hloc & (ROW - 1));  // slots between the header and the end of the row
+    for (int i = 0; i + 1 < room; i++) {
+      const int32_t x = p[i], y = p[i + 1];
+      if (x < 0 || y < 0) break;  // next header / padding: the word ends here
+      if ((uint32_t)x >= 256u || (uint32_t)y >= 256u) continue;
+      bool seen = false;  // once per (pair, word): the visiting thread rewrites every occurrence in the word
+      for (int j = 0; j < i && !seen; j++) seen = p[j] == x && p[j + 1] == y;
+      if (seen) continue;
+      const uint32_t k = (uint32_t)x * 256u + (uint32_t)y;
+      const unsigned int at = atomicAdd(&cnt[k], 1u);
+      if (FILL) ent[start[k] + at] = make_uint4((uint32_t)x, w, (uint32_t)hloc, (uint32_t)(hloc >> 32));  // {other, side 0 | word, header location}
+    }
+  }
+}
 __device__ __forceinline__ uint4 log_entry(uint32_t other, bool right_side, uint32_t wi, uint64_t hloc) {
   return make_uint4(other, (right_side ? 0x80000000u : 0u) | wi, (uint32_t)hloc, (uint32_t)(hloc >> 32));
 }

@@ -515,6 +515,36 @@ class TrainerImpl {
     log_merge_cap_ = 0;
     ensure_log_merges(tr_->config.target_vocab_size > 256 ? (uint32_t)(tr_->config.target_vocab_size - 256) : 1024u);
     log_ok_ = true;
+    build_initial_pair_index();
+  }
+  // Occurrence index of the pairs of two initial symbols (BirthLogDev::ip_*): count per pair, prefix sum, fill. Only where
+  // the resident kernel can run (one GPU's worth of words in rows, no long words); a few ms once per load against ~30 us
+  // saved on every later merge of such a pair (the whole-grid row scan is the alternative: the row signatures cannot
+  // tell rows apart for common letters).
+  void build_initial_pair_index() {
+    ip_ent_.release(); ip_start_.release();
+    static const bool off = getenv("SWB_NO_IP_INDEX") && atoi(getenv("SWB_NO_IP_INDEX")) > 0;
+    if (off || !log_ok_ || n_long_ || mnranks() != 1 || !W || W >= (1ull << 31)) return;
+    DevBuf<unsigned int> cnt(IP_PAIRS + 1);
+    ip_start_.alloc(IP_PAIRS + 1);
+    SWB_CUDA(cudaMemsetAsync(cnt.get(), 0, cnt.bytes(), stream_));
+    const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 8, (W + 255) / 256);
+    const int32_t *flat = reinterpret_cast<const int32_t *>(rows_.get());
+    ip_index_words<false><<<grid, 256, 0, stream_>>>(flat, wloc_.get(), long_index_.get(), (uint32_t)W, cnt.get(), nullptr, nullptr); launched();
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.get(), ip_start_.get(), (int)(IP_PAIRS + 1), stream_);
+    DevBuf<uint8_t> tmp(tmp_bytes);
+    SWB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(), tmp_bytes, cnt.get(), ip_start_.get(), (int)(IP_PAIRS + 1), stream_));
+    launched(2);
+    unsigned int total = 0;
+    SWB_CUDA(cudaMemcpyAsync(&total, ip_start_.get() + IP_PAIRS, 4, cudaMemcpyDeviceToHost, stream_));
+    sync();
+    if (!total) { ip_start_.release(); return; }
+    ip_ent_.alloc(total);
+    SWB_CUDA(cudaMemsetAsync(cnt.get(), 0, cnt.bytes(), stream_));
+    ip_index_words<true><<<grid, 256, 0, stream_>>>(flat, wloc_.get(), long_index_.get(), (uint32_t)W, cnt.get(), ip_start_.get(), ip_ent_.get()); launched();
+    SWB_CUDA(cudaGetLastError());
+    sync();  // (cnt and tmp go back to the block cache here)
   }
   void ensure_log_merges(uint32_t merges) {  // room for start[0 .. merges]
     if (merges + 2 <= log_merge_cap_) return;
@@ -547,6 +577,11 @@ class TrainerImpl {
     ensure_log_merges(stream_merges_ + merges_ahead);
     lg.ent = log_ent_.get(); lg.cursor = log_scal_.get(); lg.flags = log_scal_.get() + 1; lg.start = log_start_.get();
     lg.cap = log_cap_; lg.m_cur = stream_merges_;
+    lg.ip_ent = ip_ent_.size() ? ip_ent_.get() : nullptr; lg.ip_start = ip_ent_.size() ? ip_start_.get() : nullptr;
+    {
+      const char *e = getenv("SWB_IP_LOCAL_MAX");  // (tuning switch)
+      lg.ip_local_max = e ? (uint32_t)strtoul(e, nullptr, 10) : CL_IP_LOCAL_MAX;
+    }
     return lg;
   }
 
@@ -1230,7 +1265,7 @@ class TrainerImpl {
     unsigned long long timeout_ns = 2000000000ull;
     unsigned long long *trace_p = nullptr;
     if (trace_wait_) {
-      if (!ptrace_.size()) { ptrace_.alloc(16); SWB_CUDA(cudaMemsetAsync(ptrace_.get(), 0, ptrace_.bytes(), stream_)); }
+      if (!ptrace_.size()) { ptrace_.alloc(32); SWB_CUDA(cudaMemsetAsync(ptrace_.get(), 0, ptrace_.bytes(), stream_)); }
       trace_p = ptrace_.get();
     }
     void *args[] = {&s, &pt_, &em, &removed_p, &out, &out_cap, &out_hdr, (void *)&seq_base, (void *)&op_base, &hc, &dc, &da, &db, &new_id, &timeout_ns, &trace_p};
@@ -1398,7 +1433,7 @@ class TrainerImpl {
     };
     unsigned long long *trace_p = nullptr;
     if (trace_wait_) {
-      if (!ptrace_.size()) { ptrace_.alloc(16); SWB_CUDA(cudaMemsetAsync(ptrace_.get(), 0, ptrace_.bytes(), stream_)); }
+      if (!ptrace_.size()) { ptrace_.alloc(32); SWB_CUDA(cudaMemsetAsync(ptrace_.get(), 0, ptrace_.bytes(), stream_)); }
       trace_p = ptrace_.get();
     }
     HostCmd2Sender sender;
@@ -1514,7 +1549,12 @@ class TrainerImpl {
     if (trace_p) {
       unsigned long long ac[8];
       SWB_CUDA(cudaMemcpy(ac, cl_acct_.get(), sizeof ac, cudaMemcpyDeviceToHost));
-      fprintf(stderr, "[trace] hints: %llu sent a merge ahead; device accepted %llu (%llu of them already loaded when needed), rejected %llu\n", n_early, ac[4], ac[6], ac[5]);
+      fprintf(stderr, "[trace] hints: %llu sent a merge ahead; device accepted %llu (%llu of them already loaded when needed), rejected %llu; %llu LOCAL merges spilled\n", n_early, ac[4], ac[6], ac[5], ac[7]);
+      unsigned long long h32[32];
+      SWB_CUDA(cudaMemcpy(h32, trace_p, sizeof h32, cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[trace] GRID merges by device time (<16, <24, <32, <48, <64, <128, <256, more us): count/ms");
+      for (int i = 0; i < 8; i++) fprintf(stderr, " %llu/%.1f", h32[16 + i], (double)h32[24 + i] * 1e-6);
+      fprintf(stderr, "\n");
     }
     if (trace_p) {
       unsigned long long h[16];
@@ -1649,6 +1689,7 @@ class TrainerImpl {
     rows_.release(); sig_.release(); cnt_.release(); wloc_.release(); long_index_.release(); long_syms_.release(); long_off_.release();
     long_len_.release(); long_word_.release(); word_bytes_.release(); word_boff_.release();
     log_ent_.release(); log_ok_ = false; stream_merges_ = 0; log_cap_ = 0;
+    ip_ent_.release(); ip_start_.release();
     n_rows_ = 0; n_long_ = 0; W = 0; live_symbols_ = 0; word_bytes_total_ = 0; loaded_ = false;
     h_counts.clear();
   }
@@ -1668,6 +1709,8 @@ class TrainerImpl {
   uint64_t n_rows_ = 0;
   DevBuf<unsigned long long> cnt_;
   DevBuf<uint64_t> wloc_;
+  DevBuf<uint4> ip_ent_;            // occurrence index of the pairs of two initial symbols (see BirthLogDev)
+  DevBuf<unsigned int> ip_start_;
   DevBuf<uint32_t> long_index_;
   DevBuf<int32_t> long_syms_;
   DevBuf<uint64_t> long_off_;
