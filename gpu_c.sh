@@ -1,9 +1,4 @@
 cd $GRAFT_REPO_ROOT
-for m in 0 2048 4096 8192 16384; do
-SWB_IP_LOCAL_MAX=$m SWB_TRACE_WAIT=1 timeout 120 python scripts/profile_step.py config2_1GB 3 > gpurun_out/trace_ip$m.log 2>&1
-tail -1 gpurun_out/trace_ip$m.log | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); s=d['stats']
-print('ipmax=$m load', round(d['load'],4), 'merge', round(d['merge'],4), 'us/merge', round(d['us_per_merge'],2), {k:round(s[k],1) for k in s if k.startswith('resident') or k.startswith('hints_t')})
-"
-done
+timeout 120 python scripts/profile_step.py 250000000 2 2>&1 | tail -2 | cut -c1-200
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_train_parity.py -x -q -k "ref_fixture or unk_enters or ragged or self_pairs" > gpurun_out/sanitizer.log 2>&1; echo "memcheck rc=$?"
+grep -E "ERROR SUMMARY|Invalid|passed|failed|at 0x|merge_cluster|=========     at" gpurun_out/sanitizer.log | head -20
