@@ -67,11 +67,11 @@ struct ClusterCtl {
   unsigned long long t_cmd;               // %globaltimer when the command of this merge arrived
   // per CTA, per merge
   unsigned int n_births, n_recs, n_occ, rec_base, birth_base, n_cand, n_occ1, inbox_n, n_ovf, spec /* this merge was started from a hint */;
-  unsigned long long pad2;
+  unsigned long long maxpush;          // per CTA, per merge: largest new frequency >= min_freq among this CTA's records (what the host will push)
   // cluster-wide, live in CTA 0 only
   unsigned int spill, n_recs_total, removed, inserted;
   unsigned long long part_cx[CL_SIZE], part_cs[CL_SIZE];  // per-CTA record checksums (plain remote stores; combined by CTA 0)
-  unsigned long long part_max[CL_SIZE], part_key[CL_SIZE], part_2nd[CL_SIZE];  // per-CTA: largest pushed frequency, its pair, the second largest
+  unsigned long long part_max[CL_SIZE];                    // per-CTA maxpush
 };
 
 struct ClusterSmem {
@@ -85,7 +85,6 @@ struct ClusterSmem {
   uint4 *cand;                           // candidate words of this CTA: {word index, header location lo, hi, -}
   ClusterCtl *ctl;
   unsigned long long *csum;              // [64] scratch of block_checksum
-  unsigned long long *top;               // [3 * CL_WARPS] per-warp {largest pushed frequency, its pair, second largest}
   // GRID mode scratch (aliases the delta table, which is empty then)
   int (*rows)[ROW];
   Match (*ml)[MATCH_CAP];
@@ -97,7 +96,7 @@ constexpr size_t CL_SMEM_TABLE = (size_t)CL_HT_SLOTS * 24 * 2;
 constexpr size_t CL_SMEM_GRID = (size_t)CL_WARPS * ROW * 4 + (size_t)CL_WARPS * MATCH_CAP * sizeof(Match) + CL_WARPS * 4 + STAGE_RECS * sizeof(Rec) + 16;
 static_assert(CL_SMEM_GRID <= CL_SMEM_TABLE, "GRID-mode scratch must fit into the delta table's shared memory");
 constexpr size_t CL_SMEM_BYTES = CL_SMEM_TABLE + (size_t)CL_BIRTH_STAGE * 16 + (size_t)CL_REC_STAGE * sizeof(Rec) + CL_HT_SLOTS * 4 + (size_t)CL_CAND_CAP * 16 + (size_t)CL_INBOX * 32 +
-                                 sizeof(ClusterCtl) + 64 * 8 + 3 * CL_WARPS * 8 + 64;
+                                 sizeof(ClusterCtl) + 64 * 8 + 64;
 
 __device__ __forceinline__ ClusterSmem cluster_smem(unsigned char *base) {
   ClusterSmem m;
@@ -122,7 +121,6 @@ __device__ __forceinline__ ClusterSmem cluster_smem(unsigned char *base) {
   m.cand = reinterpret_cast<uint4 *>(p); p += (size_t)CL_CAND_CAP * 16;
   m.inbox = reinterpret_cast<uint4 *>(p); p += (size_t)CL_INBOX * 32;
   m.csum = reinterpret_cast<unsigned long long *>(p); p += 64 * 8;
-  m.top = reinterpret_cast<unsigned long long *>(p); p += 3 * CL_WARPS * 8;
   m.ctl = reinterpret_cast<ClusterCtl *>(p); p += sizeof(ClusterCtl);
   m.occ = reinterpret_cast<unsigned short *>(p); p += CL_HT_SLOTS * 2;
   m.occ1 = reinterpret_cast<unsigned short *>(p);
@@ -137,9 +135,7 @@ __device__ __forceinline__ bool smem_table_add(unsigned long long *keys, unsigne
   uint32_t sl = (uint32_t)(dmix64(k) >> 3) & (CL_HT_SLOTS - 1);
 #pragma unroll 1
   for (int probe = 0; probe < CL_MAX_PROBES; probe++) {
-    // (a 64-bit compare-and-swap on shared memory is a lock loop: only an empty-looking slot pays for one; hot pairs are hit hundreds of times per merge)
-    unsigned long long cur = *(volatile unsigned long long *)&keys[sl];
-    if (cur == PT_EMPTY) cur = atomicCAS(&keys[sl], PT_EMPTY, k);
+    const unsigned long long cur = atomicCAS(&keys[sl], PT_EMPTY, k);
     if (cur == PT_EMPTY) occ[atomicAdd(n_occ, 1u)] = (unsigned short)sl;  // the list of occupied slots, for whoever empties the table
     if (cur == PT_EMPTY && pf.slots)  // first touch: pull the pair's frequency-table slot into L2 for the emit phase
       asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<char *>(pf.slots) + 32ull * ((uint32_t)dmix64(k + 0x632BE59BD9B4E019ull) & pf.mask)));
@@ -198,12 +194,6 @@ struct ClusterSink {
   }
 };
 
-// {largest, its key, second largest} of two sets of pushed frequencies (equal largest values make second == largest: a tie)
-__device__ __forceinline__ void top_combine(unsigned long long &m1, unsigned long long &k1, unsigned long long &m2,
-                                            unsigned long long om1, unsigned long long ok1, unsigned long long om2) {
-  if (om1 > m1) { m2 = m1 > om2 ? m1 : om2; m1 = om1; k1 = ok1; }
-  else { const unsigned long long c = om1 > om2 ? om1 : om2; m2 = c > m2 ? c : m2; }
-}
 __device__ __forceinline__ void cluster_barrier(cg::cluster_group &cluster) { cluster.sync(); }
 __device__ __forceinline__ void cluster_clear_tables(const ClusterSmem &m) {
   for (int sl = threadIdx.x; sl < CL_HT_SLOTS; sl += CL_THREADS) {
@@ -259,7 +249,7 @@ __device__ __forceinline__ void cluster_fold_inbox(const ClusterSmem &m, const P
 // LOCAL merge, phase 2 of one CTA: apply this CTA's pairs to the device frequency table and stage the records
 __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const EmitMode &em, const PairTableDev &t, bool spill,
                                                   unsigned long long &cx, unsigned long long &cs, unsigned int &inserted,
-                                                  unsigned long long &m1, unsigned long long &k1, unsigned long long &m2, Rec *__restrict__ out, size_t out_cap, cg::cluster_group &cluster, int32_t new_id) {
+                                                  unsigned long long &maxpush, Rec *__restrict__ out, size_t out_cap, cg::cluster_group &cluster, int32_t new_id) {
   const unsigned int n_occ = m.ctl->n_occ;  // (listed while T2 was filled; the caller has synchronised the block)
   ClusterCtl *c0 = cluster.map_shared_rank(m.ctl, 0);
 #pragma unroll 1
@@ -294,10 +284,7 @@ __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const Em
     else nw = old + (unsigned long long)d;
     em.g.slots[g].freq = nw;
     if (old >= em.min_freq || nw >= em.min_freq) {
-      if (nw >= em.min_freq) {  // the host pushes this pair (reference bpe.cpp:512-515): largest, whose, second largest
-        if (nw > m1) { m2 = m1; m1 = nw; k1 = k; }
-        else if (nw > m2) m2 = nw;
-      }
+      if (nw >= em.min_freq && nw > maxpush) maxpush = nw;  // the host pushes this pair (reference bpe.cpp:512-515)
       const unsigned int j = atomicAdd(&m.ctl->n_recs, 1u);
       if (j < CL_REC_STAGE) rec_out(m.recs, CL_REC_STAGE, j, k, (long long)nw, mk, cx, cs);
       else rec_out(out, out_cap, atomicAdd(&c0->n_recs_total, 1u), k, (long long)nw, mk, cx, cs);  // past the stage: straight to its final place
@@ -308,9 +295,9 @@ __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const Em
 __global__ void __launch_bounds__(CL_THREADS, 1)
 merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *removed_total, Rec *__restrict__ out0, Rec *__restrict__ out1, size_t out_cap,
               unsigned long long *__restrict__ out_hdr0, unsigned long long *__restrict__ out_hdr1, unsigned long long seq_base, unsigned long long op_base,
-              volatile HostCmd2 *hcmd /* [5] in mapped host memory: the command, hint words A and B for even, A and B for odd sequence numbers */, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace,
+              volatile HostCmd2 *hcmd /* [3] in mapped host memory: the command, the hints for even / odd sequence numbers */, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace,
               uint4 *ovf /* [CL_LOCAL_MAX]: candidate words that did not fit a CTA's shared-memory list */,
-              unsigned long long *acct /* [16]: [8..11] why hints were turned down / self-chained merges; [0..7]: LOCAL merges, their device ns, GRID merges, their device ns, hints accepted, hints rejected, hints accepted without a PCIe trip, LOCAL merges that spilled to the global table */) {
+              unsigned long long *acct /* [8]: LOCAL merges, their device ns, GRID merges, their device ns, hints accepted, hints rejected, hints accepted without a PCIe trip, LOCAL merges that spilled to the global table */) {
   extern __shared__ __align__(16) unsigned char cl_dyn_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const ClusterSmem m = cluster_smem(cl_dyn_smem);
@@ -330,9 +317,9 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
   bool cursor_stale = true;  // (CTA 0 / thread 0) the log cursor kept in shared memory is behind the global one
   // (CTA 0 / thread 0) hints: the previous merge was LOCAL and clean, the largest frequency it makes the host push, its token
   bool hint_ok = false;
-  unsigned long long prev_maxpush = 0, prev_topkey = 0, prev_second = 0;  // largest frequency it pushes, whose pair, the second largest
+  unsigned long long prev_maxpush = 0;
   unsigned int prev_new_id = 0;
-  uint4 pre_hv = make_uint4(0u, 0u, 0u, 0u), pre_hb = make_uint4(0u, 0u, 0u, 0u);  // the hint words for the NEXT merge, requested while this one runs (a read of mapped host memory takes microseconds)
+  uint4 pre_hv = make_uint4(0u, 0u, 0u, 0u);  // the hint word for the NEXT merge, requested while this one runs (a read of mapped host memory takes microseconds)
   long long tr_poll = 0, tr_p1 = 0, tr_p2 = 0, tr_pub = 0;
   for (unsigned long long k = 0;; k++) {
     // ---------------------------------------------------------------- next command
@@ -343,18 +330,13 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         const unsigned long long t0 = gtime_ns();
         unsigned long long pair = 0, nio = 3ull << 32, lr = ~0ull;
         unsigned int spec = 0;
-        bool turned_down = false;
-        unsigned int td_a = 0, td_b = 0;
         for (unsigned long long spin = 0;; spin++) {
-          uint4 v = make_uint4(0u, 0u, 0u, 0u), hv = make_uint4(0u, 0u, 0u, 0u), hb = make_uint4(0u, 0u, 0u, 0u);  // 16-byte loads from mapped host memory = PCIe reads (in flight together)
+          uint4 v = make_uint4(0u, 0u, 0u, 0u), hv = make_uint4(0u, 0u, 0u, 0u);  // one 16-byte load from mapped host memory = one PCIe read (the two are in flight together)
           bool have_v = true;
-          if (spin == 0 && hint_ok && pre_hv.z != 0u && pre_hv.w == cmd3_word(want, pre_hv.x, pre_hv.y, pre_hv.z)) { hv = pre_hv; hb = pre_hb; have_v = false; }  // already here: no trip at all
+          if (spin == 0 && hint_ok && pre_hv.z != 0u && pre_hv.w == cmd3_word(want, pre_hv.x, pre_hv.y, pre_hv.z)) { hv = pre_hv; have_v = false; }  // already here: no trip at all
           else {
             asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(hcmd) : "memory");
-            if (hint_ok) {
-              asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hb.x), "=r"(hb.y), "=r"(hb.z), "=r"(hb.w) : "l"(hcmd + 2 + 2 * (want & 1ull)) : "memory");
-              asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hv.x), "=r"(hv.y), "=r"(hv.z), "=r"(hv.w) : "l"(hcmd + 1 + 2 * (want & 1ull)) : "memory");
-            }
+            if (hint_ok) asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hv.x), "=r"(hv.y), "=r"(hv.z), "=r"(hv.w) : "l"(hcmd + 1 + (want & 1ull)) : "memory");
           }
           if (have_v && v.w == cmd3_word(want, v.x, v.y, v.z)) {
             pair = ((unsigned long long)v.y << 32) | v.x;
@@ -365,46 +347,19 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
             nio = 1ull << 32;
             break;
           }
-          // Hint, word A {second, first, F_a} (+ optional word B {second, first, F_b}, written first by the host): the next two live
-          // entries of the host's exact heap in pop order (HostCore::peek_next). With M1 / K1 / M2 = the largest frequency the merge
-          // before made the heap push, its pair, the second largest, all checked against the device frequency table:
-          //   1. nothing pushed reached F_a and pair A still has F_a                          -> pair A
-          //   2. pair A lost its place (frequency changed: its heap entry is dead), then
-          //      a. nothing pushed reached F_b and pair B still has F_b                       -> pair B
-          //      b. ONE pushed pair lies above F_b, which bounds every other live entry       -> that pair (K1)
-          //   3. pair A is untouched and ONE pushed pair lies above F_a                       -> that pair (the chain t+h -> th+e)
-          // Ties at the top are left to the host. A turned-down hint is ignored and the command awaited.
-          if (hint_ok && hv.z != 0u && hv.w == cmd3_word(want, hv.x, hv.y, hv.z) && !(turned_down && hv.w == td_a && hb.w == td_b)) {
-            const unsigned long long ka = ((unsigned long long)hv.y << 32) | hv.x, Fa = hv.z;
-            // (word B's check word is bound to word A's pair: a B left over from another hint for the same merge does not pass)
-            const bool have_b = hb.z != 0u && hb.w == cmd3_word(want ^ 0x800000ull, hb.x ^ hv.x, hb.y ^ hv.y, hb.z);
-            const unsigned long long kb = ((unsigned long long)hb.y << 32) | hb.x, Fb = hb.z;
-            const bool a_alive = gt_find_freq(em.g, ka) == Fa;
-            const bool one_top = prev_second < prev_maxpush;
-            unsigned long long take = 0;
-            unsigned int how = 0u;
-            if (a_alive) {
-              if (prev_maxpush < Fa) { take = ka; how = 1u; }
-              else if (prev_maxpush > Fa && one_top) { take = prev_topkey; how = 2u; }
-            } else if (have_b) {
-              if (prev_maxpush < Fb) { if (gt_find_freq(em.g, kb) == Fb) { take = kb; how = 1u; } }
-              else if (prev_maxpush > Fb && one_top) { take = prev_topkey; how = 2u; }
-            }
-            if (how) {
-              pair = take; nio = (unsigned long long)((prev_new_id + 1u) & 0x0FFFFFFFu); spec = how;
+          // Hint {second, first, frequency F}: "the next pair is (first, second) if the merge before it pushes nothing >= F and
+          // leaves that pair's frequency at F" (the host derived it from its exact heap, see HostCore::peek_next). Both conditions
+          // are checked here, against the device frequency table; a rejected hint is ignored and the command awaited.
+          if (hint_ok && hv.z != 0u && hv.w == cmd3_word(want, hv.x, hv.y, hv.z)) {
+            const unsigned long long hk = ((unsigned long long)hv.y << 32) | hv.x, F = hv.z;
+            if (prev_maxpush < F && gt_find_freq(em.g, hk) == F) {
+              pair = hk; nio = (unsigned long long)((prev_new_id + 1u) & 0x0FFFFFFFu); spec = 1u;
               acct[4] += 1;
               if (!have_v) acct[6] += 1;  // ... and it was already here when the merge before finished
-              if (how == 2u) acct[11] += 1;
-              if (take == kb && how == 1u && have_b) acct[12] += 1;
               break;
             }
             acct[5] += 1;
-            if (!a_alive) acct[8] += 1;                    // turned down: pair A lost its place and word B did not settle it
-            else if (prev_maxpush == Fa) acct[9] += 1;     // ... a pushed pair ties with pair A
-            else acct[10] += 1;                            // ... two pushed pairs tie above it
-            // the host may still replace these words (the hint sent a merge ahead has no word B, the one sent after the
-            // look-ahead has): keep reading, look again only at words that differ
-            turned_down = true; td_a = hv.w; td_b = hb.w;
+            hint_ok = false;
           }
           if ((spin & 63) == 63 && gtime_ns() - t0 > timeout_ns) break;  // abort: the host went away
         }
@@ -440,10 +395,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         tr_poll += clock64() - c0;
         // the hint for the merge after this one may already be in the mailbox (the host sends it a merge ahead when it can):
         // ask for it now, look at it when this merge is done
-        if (!stop) {
-          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pre_hb.x), "=r"(pre_hb.y), "=r"(pre_hb.z), "=r"(pre_hb.w) : "l"(hcmd + 2 + 2 * ((want + 1) & 1ull)) : "memory");
-          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pre_hv.x), "=r"(pre_hv.y), "=r"(pre_hv.z), "=r"(pre_hv.w) : "l"(hcmd + 1 + 2 * ((want + 1) & 1ull)) : "memory");
-        }
+        if (!stop) asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pre_hv.x), "=r"(pre_hv.y), "=r"(pre_hv.z), "=r"(pre_hv.w) : "l"(hcmd + 1 + ((want + 1) & 1ull)) : "memory");
       }
       cluster_barrier(cluster);  // (release/acquire: the command is visible in every CTA of the leader cluster)
     } else {
@@ -477,7 +429,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
     // those of the merge before it
     Rec *__restrict__ out = (seq & 1ull) ? out1 : out0;
     unsigned long long *__restrict__ out_hdr = (seq & 1ull) ? out_hdr1 : out_hdr0;
-    const unsigned int spec_flag = m.ctl->spec == 1u ? 64u : (m.ctl->spec == 2u ? 128u : 0u);  // started from a hint / from its own top push
+    const unsigned int spec_flag = m.ctl->spec ? 64u : 0u;
 
     if (mode == 1u) {
       // ---------------------------------------------------------------- GRID: all clusters, global pair table
@@ -580,10 +532,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         // merge is seen one merge later: the thresholds leave that much room, the others are fatal either way)
         pre_flags = (__ldcg(t.flags) & 1u) | (__ldcg(em.log.flags) ? 2u : 0u) |
                     ((__ldcg(em.g.flags) || __ldcg(em.g.n_used) >= (em.g.mask >> 1)) ? 4u : 0u);
-        if (pre_hv.z != 0u && pre_hv.w == cmd3_word(seq + 1, pre_hv.x, pre_hv.y, pre_hv.z)) {  // the hinted pairs' slots: looked at when this merge is done
+        if (pre_hv.z != 0u && pre_hv.w == cmd3_word(seq + 1, pre_hv.x, pre_hv.y, pre_hv.z))  // the hinted pair's slot: looked at when this merge is done
           gt_prefetch(em.g, ((unsigned long long)pre_hv.y << 32) | pre_hv.x);
-          if (pre_hb.z != 0u) gt_prefetch(em.g, ((unsigned long long)pre_hb.y << 32) | pre_hb.x);
-        }
       }
       if (crank == 0 && threadIdx.x == 32 && !spill) {  // the merged pair's frequency becomes 0 (bpe.cpp:523)
         unsigned int ins = 0;
@@ -597,17 +547,16 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         const unsigned int nb = min(m.ctl->n_births, (unsigned int)CL_BIRTH_STAGE);
         m.ctl->birth_base = c0->log_cursor + (nb ? atomicAdd(&c0->births_total, nb) : 0u);
       }
-      unsigned long long m1 = 0, k1 = 0, m2 = 0;
-      cluster_emit_part(m, em, t, spill, cx, cs, inserted, m1, k1, m2, out, out_cap, cluster, new_id);
+      unsigned long long maxpush = 0;
+      cluster_emit_part(m, em, t, spill, cx, cs, inserted, maxpush, out, out_cap, cluster, new_id);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) {
         inserted += __shfl_down_sync(0xffffffffu, inserted, d);
-        const unsigned long long om1 = __shfl_down_sync(0xffffffffu, m1, d), ok1 = __shfl_down_sync(0xffffffffu, k1, d),
-                                 om2 = __shfl_down_sync(0xffffffffu, m2, d);
-        top_combine(m1, k1, m2, om1, ok1, om2);
+        const unsigned long long o = __shfl_down_sync(0xffffffffu, maxpush, d);
+        maxpush = o > maxpush ? o : maxpush;
       }
       if (lane == 0 && inserted) atomicAdd(em.g.n_used, inserted);  // (no result needed here: CTA 0 looks at the load once per merge)
-      if (lane == 0) { m.top[3 * (threadIdx.x >> 5)] = m1; m.top[3 * (threadIdx.x >> 5) + 1] = k1; m.top[3 * (threadIdx.x >> 5) + 2] = m2; }
+      if (lane == 0 && maxpush) atomicMax(&m.ctl->maxpush, maxpush);
       __syncthreads();
       if (threadIdx.x == 0) {  // this CTA's ranges in the record buffer and in the birth log
         const unsigned int nr = min(m.ctl->n_recs, (unsigned int)CL_REC_STAGE);
@@ -629,10 +578,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       }
       block_checksum(cx, cs, m.csum);
       if (threadIdx.x == 0) {
-        c0->part_cx[crank] = cx; c0->part_cs[crank] = cs;
-        unsigned long long a1 = 0, ak = 0, a2 = 0;
-        for (int w = 0; w < CL_WARPS; w++) top_combine(a1, ak, a2, m.top[3 * w], m.top[3 * w + 1], m.top[3 * w + 2]);
-        c0->part_max[crank] = a1; c0->part_key[crank] = ak; c0->part_2nd[crank] = a2;
+        c0->part_cx[crank] = cx; c0->part_cs[crank] = cs; c0->part_max[crank] = m.ctl->maxpush;
+        m.ctl->maxpush = 0;
         m.ctl->n_births = 0; m.ctl->n_recs = 0; m.ctl->n_occ = 0; m.ctl->n_cand = 0; m.ctl->n_occ1 = 0; m.ctl->inbox_n = 0; m.ctl->n_ovf = 0;
       }
     }
@@ -664,12 +611,12 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         if (pre_flags & 2u) flags |= 32u;
         flags |= (unsigned long long)cur << 32;  // the host keeps the log ranges
         unsigned long long x = 0, sm = 0;
-        unsigned long long mxp = 0, mxk = 0, mx2 = 0;
+        unsigned long long mxp = 0;
 #pragma unroll
-        for (int r = 0; r < CL_SIZE; r++) { x ^= c->part_cx[r]; sm += c->part_cs[r]; top_combine(mxp, mxk, mx2, c->part_max[r], c->part_key[r], c->part_2nd[r]); }
+        for (int r = 0; r < CL_SIZE; r++) { x ^= c->part_cx[r]; sm += c->part_cs[r]; mxp = c->part_max[r] > mxp ? c->part_max[r] : mxp; }
         // the next merge may start from a hint: this one was LOCAL, complete and raised no flag
         hint_ok = pre_flags == 0u && n <= out_cap;
-        prev_maxpush = mxp; prev_topkey = mxk; prev_second = mx2; prev_new_id = (unsigned int)new_id;
+        prev_maxpush = mxp; prev_new_id = (unsigned int)new_id;
         {  // the 64-byte header as four 16-byte stores (fewer PCIe writes than eight 8-byte ones; it validates itself)
           const unsigned long long rem = c->removed, chk = hdr_check(seq, n, flags, rem, x, sm);
           asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(out_hdr + 2), "l"(flags), "l"(rem) : "memory");

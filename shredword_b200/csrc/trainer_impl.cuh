@@ -1359,23 +1359,12 @@ class TrainerImpl {
       _mm_store_si128(reinterpret_cast<__m128i *>(const_cast<HostCmd2 *>(c)), v);  // one 16-byte store: the device never sees half a command
       __atomic_thread_fence(__ATOMIC_SEQ_CST);
     }
-    // hint for the merge with sequence number `seq`: mailbox words 1 + 2 * (seq & 1) (A) and 2 + 2 * (seq & 1) (B); two sets used
-    // in turn, so that the hint for merge q+2 can be written while the device may still be reading the one for merge q+1.
-    // B (optional, freq_b == 0: none) is written first: a device that sees the new A sees the new B or a B of another sequence number.
-    void hint(unsigned long long seq, unsigned long long pair_a, unsigned int freq_a, unsigned long long pair_b, unsigned int freq_b) {
-      HostCmd2 *base = const_cast<HostCmd2 *>(c) + 1 + 2 * (seq & 1ull);
-      {
-        const unsigned int x = (unsigned int)pair_b, y = (unsigned int)(pair_b >> 32), z = freq_b;
-        // (the check word covers A's pair as well: the device accepts B only together with the A it was sent with)
-        const __m128i v = _mm_set_epi32((int)cmd3_word(seq ^ 0x800000ull, x ^ (unsigned int)pair_a, y ^ (unsigned int)(pair_a >> 32), z), (int)z, (int)y, (int)x);
-        _mm_store_si128(reinterpret_cast<__m128i *>(base + 1), v);
-      }
-      __atomic_thread_fence(__ATOMIC_SEQ_CST);
-      {
-        const unsigned int x = (unsigned int)pair_a, y = (unsigned int)(pair_a >> 32), z = freq_a;
-        const __m128i v = _mm_set_epi32((int)cmd3_word(seq, x, y, z), (int)z, (int)y, (int)x);
-        _mm_store_si128(reinterpret_cast<__m128i *>(base), v);
-      }
+    // hint for the merge with sequence number `seq`: mailbox word 1 + (seq & 1) (two hint words used in turn, so that the
+    // hint for merge q+2 can be written while the device may still be reading the one for merge q+1)
+    void hint(unsigned long long seq, unsigned long long pair, unsigned int freq) {
+      const unsigned int x = (unsigned int)pair, y = (unsigned int)(pair >> 32), z = freq;
+      const __m128i v = _mm_set_epi32((int)cmd3_word(seq, x, y, z), (int)z, (int)y, (int)x);
+      _mm_store_si128(reinterpret_cast<__m128i *>(const_cast<HostCmd2 *>(c + 1 + (seq & 1ull))), v);
       __atomic_thread_fence(__ATOMIC_SEQ_CST);
     }
     ~HostCmd2Sender() { if (running) send(0, 0, 1); }
@@ -1386,12 +1375,12 @@ class TrainerImpl {
     ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
     maybe_grow_global_table(gt_flagged_);
     gt_flagged_ = false;
-    if (!hcmd2_.size()) { hcmd2_.alloc(8); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(16); }
+    if (!hcmd2_.size()) { hcmd2_.alloc(4); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(8); }
     if (recs_b_.size() != recs_.size()) recs_b_.alloc(recs_.size());  // second record buffer + header: merges started from a hint
     if (!hdr_b_.size()) hdr_b_.alloc(HDR_WORDS);
     memset(hdr_b_.host(), 0, HDR_WORDS * sizeof(unsigned long long));
     SWB_CUDA(cudaMemsetAsync(cl_acct_.get(), 0, cl_acct_.bytes(), stream_));
-    memset((void *)hcmd2_.host(), 0, 8 * sizeof(HostCmd2));
+    memset((void *)hcmd2_.host(), 0, 4 * sizeof(HostCmd2));
     SWB_CUDA(cudaMemsetAsync(dcmd2_.get(), 0, sizeof(DevCmd2), stream_));
     const int32_t unk = tr_->config.unk_id;
     EmitMode em = emit_mode(1, 0, 0);
@@ -1421,29 +1410,25 @@ class TrainerImpl {
     //   late hint  for q+1: sent right after the look-ahead (the device checks merge q)
     //   early hint for q+2: sent as soon as the records of merge q have arrived and show that q pushed nothing >= F
     //                       (the device checks merge q+1) -- it is on its way a whole merge before it is needed
-    HostCore::Peek pk[3];
+    HostCore::Peek pk[2];
     size_t npk = 0;
     unsigned long long n_early = 0;
     static const bool no_early = getenv("SWB_NO_EARLY_HINTS") && atoi(getenv("SWB_NO_EARLY_HINTS")) > 0;
-    unsigned long long hint_ring[4][4];  // what was sent for sequence number q: [q & 3] = {early A, early B, late A, late B}
-    for (auto &h4 : hint_ring) h4[0] = h4[1] = h4[2] = h4[3] = NO_HINT;
-    // A = the next live entry of the heap in pop order, B = the one after it (nullptr: none); see merge_cluster for what the device does with them
-    auto send_hint = [&](unsigned long long hint_seq, const HostCore::Peek &ea, const HostCore::Peek *eb, int which, HostCmd2Sender &sd) {
-      if (ea.freq == 0 || ea.freq >= (1ull << 32)) return;
-      const unsigned long long ka = ((unsigned long long)(uint32_t)to_dev(ea.a) << 32) | (uint32_t)to_dev(ea.b);
-      unsigned long long kb = NO_HINT;
-      unsigned int fb = 0;
-      if (eb && eb->freq > 0 && eb->freq < (1ull << 32)) { kb = ((unsigned long long)(uint32_t)to_dev(eb->a) << 32) | (uint32_t)to_dev(eb->b); fb = (unsigned int)eb->freq; }
-      sd.hint(hint_seq, ka, (unsigned int)ea.freq, fb ? kb : 0ull, fb);
-      hint_ring[hint_seq & 3][2 * which] = ka;
-      hint_ring[hint_seq & 3][2 * which + 1] = kb;
+    unsigned long long hint_ring[4][2];  // what was sent for sequence number q: [q & 3] = {early, late}
+    for (auto &h2 : hint_ring) h2[0] = h2[1] = NO_HINT;
+    auto send_hint = [&](unsigned long long hint_seq, const HostCore::Peek &e, int which, HostCmd2Sender &sd) {
+      if (e.freq == 0 || e.freq >= (1ull << 32)) return;
+      const unsigned long long key = ((unsigned long long)(uint32_t)to_dev(e.a) << 32) | (uint32_t)to_dev(e.b);
+      if (which == 1 && hint_ring[hint_seq & 3][0] == key) return;  // the early hint already said so
+      sd.hint(hint_seq, key, (unsigned int)e.freq);
+      hint_ring[hint_seq & 3][which] = key;
       stats.hints_sent++;
     };
     auto look_ahead = [&]() {
       npk = 0;
       if (!hints) return;
       const double th0 = now_ms();
-      npk = core.peek_next(pk, 2);  // (a third entry would give the early hint its word B too, but costs the host more than it saves)
+      npk = core.peek_next(pk, 2);
       stats.host_peek_ms += now_ms() - th0;
     };
     unsigned long long *trace_p = nullptr;
@@ -1493,11 +1478,9 @@ class TrainerImpl {
     sender.running = true;
     int done = 0;
     unsigned long long cur_key = ((unsigned long long)(uint32_t)da << 32) | (uint32_t)db;
-    unsigned long long prev_top_key = NO_HINT;
-    bool prev_top_unique = false;
     const uint64_t minf = tr_->config.min_pair_freq;
     look_ahead();
-    if (npk >= 1 && max_merges > 1) send_hint(seq_base + 2, pk[0], npk >= 2 ? &pk[1] : nullptr, 1, sender);
+    if (npk >= 1 && max_merges > 1) send_hint(seq_base + 2, pk[0], 1, sender);
     for (;;) {
       const double tw0 = now_ms();
       const unsigned long long q = seq_base + done + 1;
@@ -1511,33 +1494,20 @@ class TrainerImpl {
       const unsigned int flags = (unsigned int)hflags;
       const uint64_t removed = hh[3];
       if (flags & 64u) {  // the device started this merge from a hint: it must be the pair the exact heap chose
-        if (hint_ring[q & 3][0] != cur_key && hint_ring[q & 3][1] != cur_key && hint_ring[q & 3][2] != cur_key && hint_ring[q & 3][3] != cur_key)
+        if (hint_ring[q & 3][0] != cur_key && hint_ring[q & 3][1] != cur_key)
           throw Error("resident kernel followed a hint the heap replica did not confirm (internal error)");
         stats.hints_taken++;
       }
-      if (flags & 128u) {  // ... or from the single pair the merge before pushed above everything else: same check
-        if (!prev_top_unique || prev_top_key != cur_key)
-          throw Error("resident kernel chained a merge the heap replica did not confirm (internal error)");
-        stats.hints_taken++;
-      }
-      for (int i = 0; i < 4; i++) hint_ring[(q + 2) & 3][i] = NO_HINT;
-      // what this merge makes the heap push: largest frequency, its pair, is it alone at the top
-      uint64_t mp = 0, mp2 = 0;
-      prev_top_key = NO_HINT;
-      for (size_t i = 0; i < n && i < recs_.size(); i++) {
-        const uint64_t f = (uint64_t)hr[i].delta;
-        if (f < minf) continue;
-        if (f > mp) { mp2 = mp; mp = f; prev_top_key = ((unsigned long long)(uint32_t)hr[i].first << 32) | (uint32_t)hr[i].second; }
-        else if (f > mp2) mp2 = f;
-      }
-      prev_top_unique = mp > mp2;
-      if (npk >= 2 && done + 2 < max_merges && !(flags & ~(64u | 128u)) && n <= recs_.size()) {  // early hint for merge q+2
+      hint_ring[(q + 2) & 3][0] = hint_ring[(q + 2) & 3][1] = NO_HINT;
+      if (npk >= 2 && done + 2 < max_merges && !(flags & ~64u) && n <= recs_.size()) {  // early hint for merge q+2
+        uint64_t mp = 0;
+        for (size_t i = 0; i < n; i++) { const uint64_t f = (uint64_t)hr[i].delta; if (f >= minf && f > mp) mp = f; }
         if (mp < pk[1].freq && !no_early) {
           // With this hint the device may start merge q+2 -- whose results go into THIS record buffer -- before the records of
           // merge q have been applied below: they move to private memory first.
           rec_copy_.assign(hr, hr + n);
           hr = rec_copy_.data();
-          send_hint(q + 2, pk[1], (npk >= 3 && mp < pk[2].freq) ? &pk[2] : nullptr, 0, sender);
+          send_hint(q + 2, pk[1], 0, sender);
           n_early++;
         }
       }
@@ -1565,7 +1535,7 @@ class TrainerImpl {
       cur_key = ((unsigned long long)(uint32_t)da << 32) | (uint32_t)db;
       sender.send(cur_key, (unsigned int)nn, 0);
       look_ahead();
-      if (npk >= 1 && done + 1 < max_merges) send_hint(seq_base + done + 2, pk[0], npk >= 2 ? &pk[1] : nullptr, 1, sender);  // late hint for the merge after this command's
+      if (npk >= 1 && done + 1 < max_merges) send_hint(seq_base + done + 2, pk[0], 1, sender);  // late hint for the merge after this command's
     }
     sync();
     {  // device time of this launch's merges (command seen -> result published), per mode
@@ -1577,11 +1547,9 @@ class TrainerImpl {
       stats.merge_kernel_ms += (double)(ac[1] + ac[3]) * 1e-6;
     }
     if (trace_p) {
-      unsigned long long ac[16];
+      unsigned long long ac[8];
       SWB_CUDA(cudaMemcpy(ac, cl_acct_.get(), sizeof ac, cudaMemcpyDeviceToHost));
-      fprintf(stderr, "[trace] hints: %llu sent a merge ahead; device accepted %llu (%llu of them already loaded when needed, %llu chained from its own top push), rejected %llu "
-              "(%llu: the pair's frequency changed, %llu: a pushed pair ties with it, %llu: pushed pairs tie above it); %llu took pair B; %llu LOCAL merges spilled\n",
-              n_early, ac[4], ac[6], ac[11], ac[5], ac[8], ac[9], ac[10], ac[12], ac[7]);
+      fprintf(stderr, "[trace] hints: %llu sent a merge ahead; device accepted %llu (%llu of them already loaded when needed), rejected %llu; %llu LOCAL merges spilled\n", n_early, ac[4], ac[6], ac[5], ac[7]);
       unsigned long long h32[32];
       SWB_CUDA(cudaMemcpy(h32, trace_p, sizeof h32, cudaMemcpyDeviceToHost));
       fprintf(stderr, "[trace] GRID merges by device time (<16, <24, <32, <48, <64, <128, <256, more us): count/ms");
