@@ -514,8 +514,11 @@ class HostCore {
   static constexpr size_t OV_MAX = 3072;
   std::vector<OvNode> ov_;
   uint16_t ov_map_[OV_SLOTS] = {};
+  static constexpr size_t OV_DIRECT = 16384;  // the top 14 levels of the heap (where nearly all of the look-ahead happens) are indexed directly
+  uint16_t ov_direct_[OV_DIRECT] = {};
   void ov_reset() {
     for (const OvNode &n : ov_) {  // clear only what was used
+      if (n.pos < OV_DIRECT) { ov_direct_[n.pos] = 0; continue; }
       size_t s = (n.pos * 0x9E3779B97F4A7C15ull) >> 51;
       while (ov_map_[s]) { ov_map_[s] = 0; s = (s + 1) & (OV_SLOTS - 1); }
     }
@@ -523,6 +526,14 @@ class HostCore {
     if (ov_.capacity() < OV_MAX + 8) ov_.reserve(OV_MAX + 8);  // (pointers into ov_ stay valid during a look-ahead)
   }
   OvNode *ov_find(size_t pos, bool create, bool &ok) {
+    if (pos < OV_DIRECT) {
+      if (ov_direct_[pos]) return &ov_[ov_direct_[pos] - 1];
+      if (!create) return nullptr;
+      if (ov_.size() >= OV_MAX) { ok = false; return nullptr; }
+      ov_.push_back(OvNode{pos, HeapEntry{}, 0});
+      ov_direct_[pos] = (uint16_t)ov_.size();
+      return &ov_.back();
+    }
     size_t s = (pos * 0x9E3779B97F4A7C15ull) >> 51;
     while (ov_map_[s]) {
       if (ov_[ov_map_[s] - 1].pos == pos) return &ov_[ov_map_[s] - 1];
