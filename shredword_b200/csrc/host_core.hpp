@@ -314,27 +314,38 @@ class HostCore {
   // stale (for ever: versions only grow) or earlier entries of the list; one of those that loses its place
   // (touched by a merge in between) makes the later ones move up, and then (2) fails for them once they have
   // been merged (frequency 0). So an accepted entry is always the true next pair; a wrong guess is only ever
-  // turned down. The heap is not modified: the pops are simulated on a sparse overlay of the top of the array,
-  // where a removed root leaves a hole that is filled lazily by its larger child (left on ties) -- the rest of
-  // the sift-down of the real algorithm happens below the region and cannot influence it.
+  // turned down. The heap is not modified and no pop is simulated: inside that region a removed root is replaced by its
+  // larger child, the LEFT one on ties (the element the real algorithm moves in from the tail is smaller than both and
+  // sinks out of the region), and so on down -- i.e. the entries of a subtree reach the root as "the subtree's root, then
+  // the two child streams merged, left first on ties". That makes the pop order a total order: frequency descending, and
+  // among equal frequencies the PRE-ORDER position in the tree (an ancestor before its descendants, a left subtree before
+  // the right one). A child never precedes its parent in that order, so a best-first walk from the root with a small
+  // priority queue over the frontier produces exactly the pop order, visiting every entry once.
   struct Peek { int32_t a, b; uint64_t freq; };
   size_t peek_next(Peek *out, size_t want) {
     const MaxHeap &h = tr_->heap;
     const uint64_t minf = tr_->config.min_pair_freq;
-    // the simulated pops would move the last MAX_POPS elements of the array to the root: the look-ahead makes no statement
+    // the real pops would move the last MAX_POPS elements of the array to the root: the look-ahead makes no statement
     // as soon as it has to look at one of them (small heaps: the top region may reach the tail of the array)
     const size_t MAX_POPS = std::min<size_t>(640, h.size / 8);
     if (MAX_POPS < 4) return 0;
     const size_t n_eff = h.size - MAX_POPS;
-    ov_reset();
+    front_.clear();
+    front_.push_back(Front{h.data[0].freq, 0});
+    pairs_.prefetch(h.data[0].key.first, h.data[0].key.second);
     size_t got = 0, pops = 0;
     uint64_t tail_max = 0;  // largest frequency among the tail elements the real pops would have moved to the root
-    bool ok = true;
-    while (got < want && pops < MAX_POPS && ok) {
-      const HeapEntry *top = ov_get(0, n_eff, ok);
-      if (!ok || !top) break;
-      const HeapEntry e = *top;
-      ov_set_hole(0);
+    while (got < want && pops < MAX_POPS && !front_.empty()) {
+      std::pop_heap(front_.begin(), front_.end(), front_after);
+      const size_t pos = front_.back().pos;
+      front_.pop_back();
+      if (pos >= n_eff) break;  // too close to the tail of the array: no statement
+      const HeapEntry &e = h.data[pos];
+      for (size_t c = 2 * pos + 1; c <= 2 * pos + 2 && c < h.size; c++) {
+        pairs_.prefetch(h.data[c].key.first, h.data[c].key.second);  // (looked up when it leaves the queue: start the miss now)
+        front_.push_back(Front{h.data[c].freq, c});
+        std::push_heap(front_.begin(), front_.end(), front_after);
+      }
       const uint64_t tf = h.data[h.size - 1 - pops].freq;
       if (tf > tail_max) tail_max = tf;
       pops++;
@@ -508,80 +519,22 @@ class HostCore {
   std::vector<PairKey> merges_;
   std::vector<Rec> scratch_;
   struct KeyIdx { uint64_t key; uint32_t idx; };
-  // sparse overlay of the heap array used by peek_next: position -> {entry | hole | empty}
-  struct OvNode { size_t pos; HeapEntry e; int state; /* 1 entry, 2 hole, 3 empty (no entry left below) */ };
-  static constexpr size_t OV_SLOTS = 8192;  // open addressing over at most OV_MAX nodes
-  static constexpr size_t OV_MAX = 3072;
-  std::vector<OvNode> ov_;
-  uint16_t ov_map_[OV_SLOTS] = {};
-  static constexpr size_t OV_DIRECT = 16384;  // the top 14 levels of the heap (where nearly all of the look-ahead happens) are indexed directly
-  uint16_t ov_direct_[OV_DIRECT] = {};
-  void ov_reset() {
-    for (const OvNode &n : ov_) {  // clear only what was used
-      if (n.pos < OV_DIRECT) { ov_direct_[n.pos] = 0; continue; }
-      size_t s = (n.pos * 0x9E3779B97F4A7C15ull) >> 51;
-      while (ov_map_[s]) { ov_map_[s] = 0; s = (s + 1) & (OV_SLOTS - 1); }
-    }
-    ov_.clear();
-    if (ov_.capacity() < OV_MAX + 8) ov_.reserve(OV_MAX + 8);  // (pointers into ov_ stay valid during a look-ahead)
+  // frontier of the look-ahead walk, ordered like the heap's pops: frequency descending, then pre-order position
+  struct Front { uint64_t freq; size_t pos; };
+  // true iff position p comes before position q in a pre-order walk of the implicit binary tree (0-based array indices)
+  static bool preorder_before(size_t p, size_t q) {
+    const size_t i = p + 1, j = q + 1;  // 1-based: the bits after the leading one are the path from the root, 0 = left
+    const int di = 63 - __builtin_clzll((unsigned long long)i), dj = 63 - __builtin_clzll((unsigned long long)j);
+    if (di <= dj) { const size_t ja = j >> (dj - di); return ja == i ? di < dj : i < ja; }  // i is an ancestor of j (or further left)
+    const size_t ia = i >> (di - dj);
+    return ia == j ? false : ia < j;  // j is an ancestor of i: j first
   }
-  OvNode *ov_find(size_t pos, bool create, bool &ok) {
-    if (pos < OV_DIRECT) {
-      if (ov_direct_[pos]) return &ov_[ov_direct_[pos] - 1];
-      if (!create) return nullptr;
-      if (ov_.size() >= OV_MAX) { ok = false; return nullptr; }
-      ov_.push_back(OvNode{pos, HeapEntry{}, 0});
-      ov_direct_[pos] = (uint16_t)ov_.size();
-      return &ov_.back();
-    }
-    size_t s = (pos * 0x9E3779B97F4A7C15ull) >> 51;
-    while (ov_map_[s]) {
-      if (ov_[ov_map_[s] - 1].pos == pos) return &ov_[ov_map_[s] - 1];
-      s = (s + 1) & (OV_SLOTS - 1);
-    }
-    if (!create) return nullptr;
-    if (ov_.size() >= OV_MAX) { ok = false; return nullptr; }
-    ov_.push_back(OvNode{pos, HeapEntry{}, 0});
-    ov_map_[s] = (uint16_t)ov_.size();
-    return &ov_.back();
+  // std heap comparator ("less" = comes later): the top of the queue is the entry the real heap would pop next
+  static bool front_after(const Front &x, const Front &y) {
+    if (x.freq != y.freq) return x.freq < y.freq;
+    return preorder_before(y.pos, x.pos);
   }
-  void ov_set_hole(size_t pos) {
-    bool ok = true;
-    OvNode *n = ov_find(pos, true, ok);
-    if (n) n->state = 2;
-  }
-  // the entry at `pos` of the simulated heap (nullptr: none); holes are filled on demand by the larger child
-  const HeapEntry *ov_get(size_t pos, size_t n_eff, bool &ok) {
-    const MaxHeap &h = tr_->heap;
-    if (pos >= h.size) return nullptr;
-    if (pos >= n_eff) { ok = false; return nullptr; }  // too close to the tail of the array: no statement
-    OvNode *n = ov_find(pos, false, ok);
-    if (!n) {  // an untouched entry of the real array; its pair is looked up if it ever reaches the root: start that miss now
-      pairs_.prefetch(h.data[pos].key.first, h.data[pos].key.second);
-      return &h.data[pos];
-    }
-    if (n->state == 1) return &n->e;
-    if (n->state == 3) return nullptr;
-    // hole: pull up the larger child (left unless the right one is strictly larger, heap.cpp:97-111)
-    const size_t l = 2 * pos + 1, r = l + 1;
-    const HeapEntry *el = ov_get(l, n_eff, ok);
-    if (!ok) return nullptr;
-    HeapEntry lv{}; if (el) lv = *el;  // (ov_ may reallocate below: copy)
-    const HeapEntry *er = ov_get(r, n_eff, ok);
-    if (!ok) return nullptr;
-    HeapEntry rv{}; if (er) rv = *er;
-    const bool has_l = el != nullptr, has_r = er != nullptr;
-    n = ov_find(pos, false, ok);  // (re-find: the vector may have grown)
-    if (!has_l && !has_r) { n->state = 3; return nullptr; }
-    const bool take_r = has_r && (!has_l || rv.freq > lv.freq);
-    n->e = take_r ? rv : lv;
-    n->state = 1;
-    const size_t idx = (size_t)(n - ov_.data());
-    OvNode *c = ov_find(take_r ? r : l, true, ok);
-    if (!c) return nullptr;
-    c->state = 2;
-    return &ov_[idx].e;
-  }
+  std::vector<Front> front_;
   std::vector<KeyIdx> order_;
   int32_t cur_a_ = 0, cur_b_ = 0, cur_new_ = 0;
   bool pending_ = false;
