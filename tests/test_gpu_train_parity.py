@@ -137,3 +137,18 @@ def test_pipelined_host_load_equals_oracle(piece, product, oracle_mod, monkeypat
   assert o.train() == t.train_quiet()
   assert np.array_equal(o.merges, t.merges_array())
   assert t.stats()["kernel_launches"] > len(data) // piece  # (one tokeniser launch per piece: the pipelined path ran)
+
+
+def test_resident_loop_uses_hints_and_the_initial_pair_index(product, oracle_mod):
+  """The single-GPU product path is the resident cluster kernel: on a tie-heavy corpus most merges must start from a
+  look-ahead hint (checked by the device, cross-checked by the host) and pairs of two initial symbols must run on the
+  leader cluster through their occurrence index -- with the merge list still equal to the oracle's."""
+  data = cases.corpus("ascii_ties")
+  kw = cases.kwargs("ascii_ties")
+  o = oracle_mod.Oracle(kw["target_vocab_size"], 0, 0.995, kw["min_pair_freq"]); o.load_buffer(data); n_o = o.train()
+  t = product.BPETrainer(**kw); t.load_buffer(data); n_t = t.train_quiet()
+  assert n_o == n_t and np.array_equal(o.merges, t.merges_array())
+  st = t.stats()
+  assert st["resident_local_merges"] + st["resident_grid_merges"] == n_t, "the resident kernel did not serve every merge"
+  assert st["hints_sent"] > n_t // 2 and st["hints_taken"] > n_t // 4, (st["hints_sent"], st["hints_taken"], n_t)
+  assert st["resident_local_merges"] > st["resident_grid_merges"], "initial-symbol pairs should mostly run on the leader cluster"
