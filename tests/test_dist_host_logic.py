@@ -161,3 +161,48 @@ def test_look_ahead_is_exact_and_leaves_the_heap_alone(name, product, oracle_mod
   print(f"\n[{name}] merges={j} claims per depth={made} confirmed per depth={confirmed} look-aheads with equal frequencies={tie_claims}")
   if name in ("ascii_ties", "multi_ties"):  # (the small cases have heaps too small for a look-ahead: nothing may be claimed wrongly, that is all)
     assert confirmed[0] > 1000 and confirmed[1] > 500 and confirmed[2] > 250 and tie_claims > 100, (made, confirmed, tie_claims)
+
+
+@pytest.mark.parametrize("seed,span", [(1, 3), (2, 8), (3, 40), (4, 1000)])
+def test_look_ahead_equals_pop_order_on_random_heaps(seed, span, product):
+  """The claim behind the look-ahead, tested on its own: the reference heap's pop order is "frequency descending, then
+  pre-order position in the tree". Random heaps with few distinct frequencies (span) and many dead entries; with nothing
+  pushed in between, the next 8 pairs named by the look-ahead must be exactly the next 8 pops that survive the version test."""
+  import ctypes
+  from shredword_b200.cbase import lib
+  from shredword_b200.trainer import _ptr
+  rng = np.random.default_rng(seed)
+  minf = 10
+  P = 6000
+  t = product.BPETrainer(target_vocab_size=100000, min_pair_freq=minf)
+  # count records: pair (i, j) with frequency minf + random small offset; key = first-touch order
+  first = rng.integers(0, 200, size=P).astype(np.int64)
+  second = np.arange(P, dtype=np.int64) + 300  # distinct pairs
+  freq = (minf + 1 + rng.integers(0, span, size=P)).astype(np.int64)
+  freq[rng.random(P) < 0.7] = minf  # filler at the bottom, so that the tail of the array is usually below the entries at the top
+  recs = np.ascontiguousarray(np.stack([first, second, freq, rng.permutation(P).astype(np.int64)], axis=1))
+  lib.swb_dist_seed(t.trainer, _ptr(recs), P)
+  a, b, nid = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+  empty = np.zeros((1, 4), dtype=np.int64)
+  # phase B: kill entries -- a zero net delta re-pushes the pair with a new version (reference bpe.cpp:512-515), the old entry stays as a dead one
+  for _ in range(40):
+    assert lib.swb_dist_next_merge(t.trainer, ctypes.byref(a), ctypes.byref(b), ctypes.byref(nid))
+    pick = rng.choice(P, size=60, replace=False)
+    touch = np.ascontiguousarray(np.stack([first[pick], second[pick], np.zeros(60, np.int64), np.arange(60, dtype=np.int64)], axis=1))
+    lib.swb_dist_apply(t.trainer, _ptr(touch), 60)
+  # phase C: nothing is pushed any more; look-ahead vs the real pops
+  out = np.zeros(3 * 8, dtype=np.int64)
+  checked = 0
+  for _ in range(60):
+    if not lib.swb_dist_next_merge(t.trainer, ctypes.byref(a), ctypes.byref(b), ctypes.byref(nid)):
+      break
+    got = lib.swb_dist_peek_list(t.trainer, _ptr(out), 8)
+    lib.swb_dist_apply(t.trainer, _ptr(empty), 0)
+    # (fewer than 8 entries come back when an element at the tail of the array is as frequent as the entries at the top --
+    # then the pops would move an element of the top region itself to the root and no statement is made; common for span = 3)
+    for i in range(got):
+      assert lib.swb_dist_next_merge(t.trainer, ctypes.byref(a), ctypes.byref(b), ctypes.byref(nid))
+      assert (a.value, b.value) == (int(out[3 * i]), int(out[3 * i + 1])), f"entry {i} of the look-ahead is not the pair the heap popped"
+      lib.swb_dist_apply(t.trainer, _ptr(empty), 0)
+      checked += 1
+  assert checked >= (400 if span >= 40 else 100), checked
