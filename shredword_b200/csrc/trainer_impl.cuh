@@ -713,8 +713,15 @@ class TrainerImpl {
   void wait_seq(unsigned long long seq) { wait_seq_at(seq, hdr_.host(), recs_.host(), recs_.size()); }
   void wait_seq_at(unsigned long long seq, volatile unsigned long long *h, const Rec *recs, size_t recs_cap) {
     uint64_t spin = 0;
+    double t_wait0 = 0;
     auto check_stream = [&]() {
       if ((++spin & 0x3FFF) != 0) return;
+      // A result normally arrives within tens of microseconds: the driver is only asked once the wait is unusually long
+      // (every driver call can block behind whatever else holds the driver's locks -- other ranks' NVML clock samplers,
+      // for one -- and a blocked host thread stalls the whole merge loop).
+      const double t = now_ms();
+      if (t_wait0 == 0) { t_wait0 = t; return; }
+      if (t - t_wait0 < 5.0) return;
       cudaError_t e = cudaStreamQuery(stream_);
       if (e == cudaSuccess) {
         if (++idle_polls_ > 64) {
