@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 from shredword_b200 import synth  # noqa: E402
 
 TRAIN_KW = dict(target_vocab_size=8192, unk_id=0, character_coverage=0.995, min_pair_freq=2000)
-CPU_SAMPLE_BYTES = 32 * 1000 * 1000
+CPU_SAMPLE_BYTES = int(os.environ.get("SWB_BENCH_CPU_SAMPLE_BYTES", 32 * 1000 * 1000))  # (the tests shrink the CPU sample)
 SHARDED_MERGE = bool(int(os.environ.get("SWB_BENCH_SHARDED_MERGE", "0")))  # N > 1: shard the merge loop too (slower: one collective per merge)
 
 
