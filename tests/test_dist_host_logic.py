@@ -206,3 +206,42 @@ def test_look_ahead_equals_pop_order_on_random_heaps(seed, span, product):
       lib.swb_dist_apply(t.trainer, _ptr(empty), 0)
       checked += 1
   assert checked >= (400 if span >= 40 else 100), checked
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_random_small_corpora_replica_matches_oracle(block, product, oracle_mod):
+  """Differential fuzzing of the host replica (pair table, exact heap, delta-map order, clamping, look-ahead) against the
+  oracle on tiny tie-heavy corpora: small alphabets, low min_pair_freq, unk ids inside and outside 0..255, emulated ranks."""
+  import ctypes
+  from shredword_b200.cbase import lib
+  from shredword_b200.trainer import _ptr
+  a, b, nid = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+  out = np.zeros(3 * 3, dtype=np.int64)
+  for seed in range(block * 8, block * 8 + 8):
+    rng = np.random.default_rng(1000 + seed)
+    alphabet = np.frombuffer(b"abcdefgh"[: int(rng.integers(2, 9))], dtype=np.uint8)
+    n_words = int(rng.integers(50, 1500))
+    words = [bytes(rng.choice(alphabet, size=int(rng.integers(1, 8)))) for _ in range(n_words)]
+    seps = [b" ", b"\n", b"\t", b"  ", b"\r\n"]
+    data = b"".join(w + seps[int(rng.integers(0, len(seps)))] for w in words)
+    kw = dict(target_vocab_size=int(rng.integers(257, 420)), min_pair_freq=int(rng.integers(1, 5)),
+              unk_id=int(rng.choice([0, 0, 97, 98, -1, -7, 300])), character_coverage=float(rng.choice([0.995, 0.9, 0.6])))
+    full = oracle_mod.Oracle(kw["target_vocab_size"], kw["unk_id"], kw["character_coverage"], kw["min_pair_freq"])
+    full.load_buffer(data); n_full = full.train()
+    sh = oracle_mod.Oracle(kw["target_vocab_size"], kw["unk_id"], kw["character_coverage"], kw["min_pair_freq"])
+    sh.load_buffer(data)
+    t = product.BPETrainer(**kw)
+    R = int(rng.integers(1, 4))
+    recs = np.ascontiguousarray(np.concatenate([sh.shard_count(r, R) for r in range(R)]))
+    n = lib.swb_dist_reduce_records(_ptr(recs), recs.shape[0]) if recs.shape[0] else 0
+    lib.swb_dist_seed(t.trainer, _ptr(recs), n)
+    done = 0
+    while done < kw["target_vocab_size"] - 256 and lib.swb_dist_next_merge(t.trainer, ctypes.byref(a), ctypes.byref(b), ctypes.byref(nid)):
+      lib.swb_dist_peek_list(t.trainer, _ptr(out), 3)  # (must not disturb anything)
+      parts = [sh.shard_merge(r, R, a.value, b.value, nid.value) for r in range(R)]
+      recs = np.ascontiguousarray(np.concatenate(parts)) if sum(len(p) for p in parts) else np.zeros((0, 4), np.int64)
+      n = lib.swb_dist_reduce_records(_ptr(recs), recs.shape[0]) if recs.shape[0] else 0
+      lib.swb_dist_apply(t.trainer, _ptr(recs) if n else _ptr(np.zeros((1, 4), np.int64)), n)
+      done += 1
+    assert done == n_full, (seed, kw, done, n_full)
+    assert np.array_equal(full.merges, t.merges_array()), (seed, kw)
