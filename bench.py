@@ -1,26 +1,36 @@
 #!/usr/bin/env python
 """bench.py -- BPE trainer + encoder hot path on B200, one JSON line (contract: see DESIGN.md, "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2_1GB]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config3_10GB]
 
 A "step" is one full pass of the training hot path over the workload corpus: load (tokenise, unique
 word table, row packing) + initial pair count + every merge. Metric: train corpus-GB/s (corpus bytes
 per step second); merges/s and the encoder's MB/s ride along in `extra`.
 
-  value : corpus already resident in HBM when the step starts (swb_load_corpus_device + bpe_train)
-  e2e   : the same through the host-buffer C-ABI call (swb_load_corpus_buffer from PINNED host memory,
-          H2D inside the timed region, merge list read back on the host)
-  roofline     : the dominant kernel (merge_rows), algorithmic bytes 4*S_live + 8*W per launch
-                  over its CUDA-event time, against MEASURED_PEAKS.json's HBM figure
+  workload : config3_10GB by default (BASELINE.json configs[2]: vocab 32k on 10 GB, the configuration the 1/2/4/8-GPU
+             metric is quoted on; it fits one GPU). --workload config2_1GB / config1_10MB run the smaller ones.
+  N > 1    : STRONG scaling on that one fixed corpus: rank r holds bytes [r/N, (r+1)/N) of it (cut on a line end).
+             The load (tokenise + dedupe) is range-split and the word tables are exchanged over NCCL; the merge
+             loop is one latency chain and runs on rank 0 (merge list broadcast afterwards).
+  value    : corpus already resident in HBM when the step starts
+  e2e      : the same through the host-buffer C-ABI calls from PINNED host memory, H2D inside the timed region, merge
+             list read back on the host
+  parity   : before the line is printed, the merge list of EVERY step (at every N) is compared with the committed
+             golden digest of the workload (tests/golden/digests.json: the unmodified reference's .model for
+             configs 1-2, the pinned oracle's for config 3) -- a mismatch fails the run
+  roofline : the dominant kernel (merge_cluster, resident), algorithmic bytes 4*S_live + 8*W per merge
+              over its own per-merge device time, against MEASURED_PEAKS.json's HBM figure; the
+             bytes the index-driven kernel actually moves (ncu, profiles/) are reported next to it
   cpu_baseline : the UNMODIFIED reference (oracle/_ref, zero-filling malloc), one host core, on a bounded
-                 prefix of the same corpus; falls back to the oracle port where oracle/_ref is not built
+             prefix of the same corpus, next to OUR arm on that same prefix (like for like) and the committed
+             full-size reference timing of config 2
 
 --impl reference times that same CPU reference on the bounded sample as the step.
-Under torchrun (N > 1) the unique words are sharded over the ranks (shredword_b200.distributed).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -28,6 +38,7 @@ import sys
 import tempfile
 import threading
 import time
+import traceback
 
 import numpy as np
 
@@ -36,13 +47,26 @@ sys.path.insert(0, ROOT)
 
 from shredword_b200 import synth  # noqa: E402
 
-TRAIN_KW = dict(target_vocab_size=8192, unk_id=0, character_coverage=0.995, min_pair_freq=2000)
+TRAIN_KWS = {
+  "config1_10MB": dict(target_vocab_size=500, unk_id=0, character_coverage=0.995, min_pair_freq=1000),
+  "config2_1GB": dict(target_vocab_size=8192, unk_id=0, character_coverage=0.995, min_pair_freq=2000),
+  "config3_10GB": dict(target_vocab_size=32768, unk_id=0, character_coverage=0.995, min_pair_freq=2000),
+  "config5_50GB": dict(target_vocab_size=100000, unk_id=0, character_coverage=0.995, min_pair_freq=2000),
+}
 CPU_SAMPLE_BYTES = int(os.environ.get("SWB_BENCH_CPU_SAMPLE_BYTES", 32 * 1000 * 1000))  # (the tests shrink the CPU sample)
-SHARDED_MERGE = bool(int(os.environ.get("SWB_BENCH_SHARDED_MERGE", "0")))  # N > 1: shard the merge loop too (slower: one collective per merge)
+MERGE_LOOP = os.environ.get("SWB_BENCH_MERGE_LOOP", "rank0")  # N > 1: rank0 | replicated | sharded
+STATE = {"rank": 0, "phase": "start", "step": -1}
 
 
 def log(*a):
   print(*a, file=sys.stderr, flush=True)
+
+
+def golden_digest(workload: str):
+  try:
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "digests.json"))).get(workload)
+  except Exception:
+    return None
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -107,47 +131,64 @@ def cpu_sample_path(corpus: np.ndarray, workdir: str) -> tuple[str, int]:
   return p, end
 
 
-def run_cpu_once(sample_path: str, nbytes: int, workdir: str) -> dict:
+def run_cpu_once(sample_path: str, nbytes: int, kw: dict) -> dict:
   """One full train of the CPU implementation on the sample: the unmodified reference if oracle/_ref is
   built, else the oracle port. Returns value in corpus-GB/s and details."""
   sys.path.insert(0, os.path.join(ROOT, "oracle"))
   import oracle as O
   t0 = time.perf_counter()
   if O.ref_available():
-    tm = O.run_reference(sample_path, TRAIN_KW["target_vocab_size"], TRAIN_KW["min_pair_freq"], "-", "-",
-                         unk_id=TRAIN_KW["unk_id"], coverage=TRAIN_KW["character_coverage"])
+    tm = O.run_reference(sample_path, kw["target_vocab_size"], kw["min_pair_freq"], "-", "-",
+                         unk_id=kw["unk_id"], coverage=kw["character_coverage"])
     secs = tm["load_s"] + tm["init_s"] + tm["merge_s"]
     kind, merges = "reference", tm["merges"]
     detail = {k: tm[k] for k in ("load_s", "merge_s")}
   else:
     O.build(ref=False)
-    o = O.Oracle(**TRAIN_KW)
+    o = O.Oracle(**kw)
     o.load_corpus(sample_path)
     merges = o.train()
     secs = time.perf_counter() - t0
     kind, detail = "port", {}
   return {"value": nbytes / 1e9 / secs, "unit": "GB/s", "cores": 1, "kind": kind, "seconds": secs, "merges": merges,
           "merges_per_s": merges / secs if secs > 0 else None,
-          "sample": f"first {nbytes} bytes of the workload corpus, full train (load+count+all merges), {TRAIN_KW}", **detail}
+          "sample": f"first {nbytes} bytes of the workload corpus, full train (load+count+all merges), {kw}", **detail}
+
+
+def full_config_reference() -> dict | None:
+  """The one full-size run of the unmodified reference that is feasible (config 2, 1 GB: tens of minutes), measured once
+  in the build container and committed with its outputs' digests (profiles/r2_reference_config2_full.json)."""
+  try:
+    return json.load(open(os.path.join(ROOT, "profiles", "r2_reference_config2_full.json")))
+  except Exception:
+    return None
 
 
 # ----------------------------------------------------------------------------- workload
-def make_corpus(spec: synth.CorpusSpec, pinned: bool, first_chunk: int = 0):
-  """The workload corpus as a uint8 numpy array (backed by pinned host memory when possible)."""
+def make_piece(spec: synth.CorpusSpec, rank: int, world: int, gather_sizes):
+  """This rank's byte range of the workload corpus in PINNED host memory: (torch tensor, numpy view, global offset).
+  The corpus is one fixed byte string whatever `world` is (synth.generate_chunks / cut_piece)."""
   import torch
   t0 = time.perf_counter()
-  if pinned and torch.cuda.is_available():
-    host = torch.empty(spec.nbytes, dtype=torch.uint8, pin_memory=True)
-  else:
-    host = torch.empty(spec.nbytes, dtype=torch.uint8)
-  arr = host.numpy()
+  c0, c1 = synth.piece_chunk_range(spec, rank, world)
+  chunks = list(synth.generate_chunks(spec, c0, c1))
+  uncut = int(sum(c.size for c in chunks))
+  sizes = gather_sizes(uncut)
+  off, n = synth.cut_piece(spec, sizes, rank)
+  host = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+  arr = host.numpy()[:n]
   pos = 0
-  for chunk in synth.generate(spec, first_chunk=first_chunk):
-    arr[pos: pos + chunk.size] = chunk
-    pos += chunk.size
-  assert pos == spec.nbytes
-  log(f"[bench] corpus {spec.name}: {spec.nbytes} bytes generated in {time.perf_counter() - t0:.1f}s")
-  return host, arr
+  for c in chunks:
+    take = min(c.size, n - pos)
+    if take <= 0:
+      break
+    arr[pos: pos + take] = c[:take]
+    pos += take
+  assert pos == n
+  if n and off + n == spec.nbytes:
+    arr[-1] = ord("\n")
+  log(f"[bench] rank {rank}: bytes [{off}, {off + n}) of {spec.name} ({n / 1e9:.3f} GB) generated in {time.perf_counter() - t0:.1f}s")
+  return host, arr, off
 
 
 def main():
@@ -164,7 +205,7 @@ def main():
   ap.add_argument("--steps", type=int, default=3)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  ap.add_argument("--workload", default="config2_1GB", choices=list(synth.CONFIGS))
+  ap.add_argument("--workload", default=os.environ.get("SWB_BENCH_WORKLOAD", "config3_10GB"), choices=list(TRAIN_KWS))
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-encode", action="store_true")
   args = ap.parse_args()
@@ -172,17 +213,21 @@ def main():
   rank = int(os.environ.get("RANK", "0"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
+  STATE["rank"] = rank
   spec = synth.CONFIGS[args.workload]
-  config = {"workload": f"{args.workload}: train vocab {TRAIN_KW['target_vocab_size']} on a {spec.nbytes / 1e9:g} GB synthetic Zipfian "
+  KW = TRAIN_KWS[args.workload]
+  loop_desc = {"rank0": "the merge loop (one latency chain: every merge waits for the heap decision after the one before) runs on rank 0, "
+                        "the merge list is broadcast",
+               "replicated": "every rank runs the latency-bound merge loop on all unique words (no per-merge collective)",
+               "sharded": "unique words sharded over the ranks, per-merge NCCL all-gather of delta records, replicated frequency table + heap"}[MERGE_LOOP]
+  config = {"workload": f"{args.workload}: train vocab {KW['target_vocab_size']} on a {spec.nbytes / 1e9:g} GB synthetic Zipfian "
                         f"{spec.alphabet} corpus ({spec.n_types} word types, s={spec.zipf_s}, seed {spec.seed}), "
-                        f"min_pair_freq {TRAIN_KW['min_pair_freq']}, unk_id 0, coverage 0.995",
-            "corpus_bytes": spec.nbytes, "l2": "input (1 GB) and the first-pass word table are larger than L2; no flush between steps",
+                        f"min_pair_freq {KW['min_pair_freq']}, unk_id 0, coverage 0.995",
+            "corpus_bytes": spec.nbytes,
+            "l2": f"input ({spec.nbytes / 1e9:g} GB) and the word hash table are far larger than the 126 MB L2; no flush between steps",
             "parallelism": "1 GPU" if world == 1 else
-                           f"weak scaling: {world} GPUs x one {spec.nbytes / 1e9:g} GB piece each (same word types, disjoint sampling streams) = one "
-                           f"{world * spec.nbytes / 1e9:g} GB corpus; range-split tokenising + NCCL word-table exchange (the part that scales with "
-                           f"the corpus), then " + ("unique words sharded over the ranks, per-merge NCCL all-gather of delta records, replicated "
-                           "frequency table + heap" if SHARDED_MERGE else "every rank runs the latency-bound merge loop on all unique words "
-                           "(replicated, no per-merge collective)")}
+                           f"strong scaling: the same {spec.nbytes / 1e9:g} GB corpus split into {world} byte ranges, one per GPU; range-split "
+                           f"tokenising + NCCL word-table exchange, then {loop_desc}"}
 
   # ------------------------------------------------------------------ reference arm
   if args.impl == "reference":
@@ -193,19 +238,25 @@ def main():
     sample, nbytes = cpu_sample_path(corpus, workdir)
     runs = []
     for i in range(args.warmup + args.steps):
-      r = run_cpu_once(sample, nbytes, workdir)
+      r = run_cpu_once(sample, nbytes, KW)
       log(f"[bench] reference step {i}: {r['seconds']:.2f}s {r['value']:.5f} GB/s")
       if i >= args.warmup:
         runs.append(r)
     secs = float(np.mean([r["seconds"] for r in runs]))
     value = nbytes / 1e9 / secs
     cb = dict(runs[-1]); cb["value"] = value
+    full = full_config_reference()
+    if full:
+      cb["full_config2"] = full
     emit(({
       "impl": "reference", "metric": "train_corpus_GB_per_s", "value": value, "unit": "GB/s", "n_gpus": args.gpus,
-      "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak",
+      "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
+      "scaling": "strong" if args.gpus > 1 else "weak",
       "vs_baseline": None, "dtype": "int32 symbols, uint64 counts", "data": "synthetic", "config": config,
       "cpu_baseline": cb, "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-      "extra": {"merges_per_s": runs[-1]["merges_per_s"], "note": "reference is single-threaded; each step = full train on the bounded sample"},
+      "extra": {"merges_per_s": runs[-1]["merges_per_s"],
+                "note": "reference is single-threaded; each step = full train on the bounded sample (a prefix of the workload corpus): its GB/s falls "
+                        "with corpus size (4096-bucket hash maps, full-scan merges), so the sample flatters it"},
     }))
     return
 
@@ -225,18 +276,27 @@ def main():
   if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=dev)
-    from shredword_b200.distributed import DistributedBPETrainer
+    from shredword_b200.distributed import DistributedBPETrainer, gather_token_offsets
 
-  # N > 1: rank r holds piece r of an N x 1 GB corpus (bytes [r, r+1) GB of the whole)
-  host, arr = make_corpus(spec, pinned=True, first_chunk=rank * synth.PIECE_STRIDE)
-  d_corpus = host.to(dev, non_blocking=False)
-  nbytes = spec.nbytes
-  total_bytes = nbytes * world
+  def gather_sizes(mine: int) -> list[int]:
+    if world == 1:
+      return [mine]
+    t = torch.tensor([mine], dtype=torch.int64, device=dev)
+    out = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [int(x.item()) for x in out]
+
+  STATE["phase"] = "corpus"
+  host, arr, goff = make_piece(spec, rank, world, gather_sizes)
+  nbytes = arr.size
+  d_corpus = host[:max(nbytes, 1)].to(dev, non_blocking=False)
+  total_bytes = spec.nbytes
+  golden = golden_digest(args.workload)
 
   def new_trainer():
     if world > 1:
-      return DistributedBPETrainer(**TRAIN_KW, device=dev, sharded_merge=SHARDED_MERGE)
-    return BPETrainer(**TRAIN_KW)
+      return DistributedBPETrainer(**KW, device=dev, merge_loop=MERGE_LOOP)
+    return BPETrainer(**KW)
 
   def barrier():
     if world > 1:
@@ -244,8 +304,10 @@ def main():
     torch.cuda.synchronize()
 
   last = {}
+  digests = set()
 
   def step(resident: bool, timing: bool):
+    STATE["step"] += 1
     w0 = time.perf_counter()
     old = last.pop("trainer", None)
     if old is not None:
@@ -254,7 +316,7 @@ def main():
     t = new_trainer()
     t.set_kernel_timing(timing)
     if world > 1:
-      t.load_shard(d_corpus if resident else arr, rank * nbytes)
+      t.load_shard(d_corpus[:nbytes] if resident else arr, goff)
     elif resident:
       t.load_device(d_corpus.data_ptr(), nbytes)
     else:
@@ -267,6 +329,7 @@ def main():
     st["merges"] = merges; st["merge_bytes"] = m.nbytes
     st["wall_ms"] = {"destroy_prev": (w1 - w0) * 1e3, "create+load": (w2 - w1) * 1e3, "train": (w3 - w2) * 1e3,
                      "read": (time.perf_counter() - w3) * 1e3}
+    digests.add((merges, hashlib.md5(np.ascontiguousarray(m, dtype="<i4").tobytes()).hexdigest()))
     last["trainer"] = t
     return st
 
@@ -291,17 +354,39 @@ def main():
   # driver for tens of ms, which must not land inside the timed region; it keeps sampling through it
   sampler = ClockSampler(local_rank)
   sampler.start()
+  STATE["phase"] = "warmup"
   for i in range(args.warmup):
     s = step(True, False)
-    log(f"[bench] warmup {i}: merges={s['merges']} load={s['load_ms']:.1f}ms count={s['count_ms']:.1f}ms merge={s['merge_ms']:.1f}ms")
+    log(f"[bench] rank {rank} warmup {i}: merges={s['merges']} load={s['load_ms']:.1f}ms count={s['count_ms']:.1f}ms merge={s['merge_ms']:.1f}ms")
   step(False, False)  # e2e warm-up (pinned registration, first H2D)
 
+  STATE["phase"] = "timed resident"
   ms_res, wall_res, st_res = timed(True, args.steps, timing=False)
+  STATE["phase"] = "timed e2e"
   ms_e2e, wall_e2e, st_e2e = timed(False, args.steps, timing=False)
   clocks = sampler.stop()
-  # roofline pass: same steps with the dominant kernel bracketed by CUDA events (kept out of `value`,
-  # the two event records per launch add latency to a launch-latency-bound loop)
-  ms_tim, _, st_tim = timed(True, args.steps, timing=True)
+  # parity gate: every step of this run (warm-up included, every rank) produced the golden merge list
+  STATE["phase"] = "parity check"
+  if len(digests) != 1:
+    raise RuntimeError(f"steps of one run disagree on the merge list: {sorted(digests)}")
+  n_merges_seen, md5_seen = next(iter(digests))
+  parity = {"merges": n_merges_seen, "model_md5": md5_seen, "golden": None, "equal": None}
+  if golden:
+    parity["golden"] = {k: golden[k] for k in ("merges", "model_md5", "source")}
+    parity["equal"] = (golden["merges"] == n_merges_seen and golden["model_md5"] == md5_seen)
+    if not parity["equal"]:
+      raise RuntimeError(f"merge list differs from the golden digest of {args.workload}: got {n_merges_seen} merges md5 {md5_seen}, "
+                         f"golden {golden['merges']} merges md5 {golden['model_md5']} ({golden['source']})")
+  if world > 1:  # every rank holds the same list
+    box = [None] * world
+    dist.all_gather_object(box, md5_seen)
+    if len(set(box)) != 1:
+      raise RuntimeError(f"ranks disagree on the merge list: {box}")
+
+  # per-launch check: a few of the same steps with one merge_rows launch per merge, each bracketed by CUDA events (kept
+  # out of `value`: the event records add latency to a latency-bound loop)
+  STATE["phase"] = "per-launch pass"
+  ms_tim, _, st_tim = timed(True, min(args.steps, 2), timing=True)
 
   merges = st_res[-1]["merges"]
   value = total_bytes / 1e9 / (ms_res / 1e3)
@@ -320,26 +405,29 @@ def main():
   # kernel) is the "launch duration" of the roofline. The CUDA-event pass over the per-launch kernel (merge_rows) rides along.
   def kernel_numbers(stats):
     alg = sum(s["merge_alg_bytes"] for s in stats); kms = sum(s["merge_kernel_ms"] for s in stats)
-    n = sum(s["merges"] for s in stats)
+    n = sum(s["merges"] for s in stats if s["merge_kernel_ms"] > 0)
     return alg, kms, n
   alg, kms, nl = kernel_numbers(st_res)
   resident = sum(s.get("resident_local_merges", 0) + s.get("resident_grid_merges", 0) for s in st_res) > 0
-  if not resident:  # (multi-GPU and fallback paths launch merge_rows per merge: use the CUDA-event pass)
+  if not resident:  # (the sharded multi-GPU loop launches merge_rows per merge: use the CUDA-event pass)
     alg, kms, nl = kernel_numbers(st_tim)
   alg_t, kms_t, nl_t = kernel_numbers(st_tim)
-  scan = sum(s["merge_scan_bytes"] for s in st_res)
   achieved = alg / 1e9 / (kms / 1e3) if kms > 0 else None
-  traffic = None
-  try:  # dram bytes per launch of the merge kernel from the committed ncu capture of this round
-    traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_merge_kernel_traffic.json")))["dram_bytes_per_launch"]
+  traffic = actual = None
+  try:  # dram bytes per merge of merge_cluster from this round's ncu capture of a scripted (host-free) launch of it
+    tj = json.load(open(os.path.join(ROOT, "profiles", "r2_merge_cluster_traffic.json")))
+    traffic = tj.get("dram_bytes_per_merge"); actual = tj
   except Exception:
     pass
   roofline = {"bound": "hbm", "kernel": "merge_cluster (resident, per merge)" if resident else "merge_rows (per launch)",
               "achieved": achieved, "peak": peak, "unit": "GB/s",
               "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-              "alg_bytes_per_launch": alg / nl if nl else None, "launched_over_bytes_per_launch": scan / nl if nl else None,
+              "alg_bytes_per_launch": alg / nl if nl else None,
               "avg_launch_us": kms * 1e3 / nl if nl else None, "launches": nl,
-              "kernel_share_of_step": (kms / args.steps) / ms_res if (ms_res and resident) else ((kms / args.steps) / ms_tim if ms_tim else None),
+              "kernel_share_of_step": (kms / args.steps) / ms_res if (ms_res and resident) else None,
+              "actual_dram": ({"bytes_per_merge": traffic, "GB_per_s": traffic / (kms * 1e3 / nl) / 1e3 if (traffic and nl and kms) else None,
+                               "frac_of_peak": (traffic / (kms * 1e3 / nl) / 1e3 / peak) if (traffic and nl and kms) else None,
+                               "source": actual.get("source") if actual else None}),
               "resident_split": {"local_merges": sum(s.get("resident_local_merges", 0) for s in st_res),
                                  "grid_merges": sum(s.get("resident_grid_merges", 0) for s in st_res),
                                  "local_us_per_merge": (sum(s.get("resident_local_ms", 0) for s in st_res) * 1e3 /
@@ -349,73 +437,135 @@ def main():
               "per_launch_check": {"kernel": "merge_rows (one launch per merge, CUDA events)",
                                    "achieved": alg_t / 1e9 / (kms_t / 1e3) if kms_t > 0 else None,
                                    "avg_launch_us": kms_t * 1e3 / nl_t if nl_t else None, "launches": nl_t},
-              "note": "algorithmic bytes = 4*S_live + 8*W per merge (SURVEY.md 8(d), full-scan form); the birth-log index makes a merge touch "
-                      "far fewer bytes than that, and the row stream is L2-resident, so achieved may exceed the HBM copy peak; `traffic` = "
-                      "dram bytes per launch of the per-launch kernel from the ncu capture in profiles/"}
+              "note": "NOMINAL figure: algorithmic bytes = the reference's full scan, 4*S_live + 8*W per merge (SURVEY.md 8(d)), over the kernel's own "
+                      "per-merge device time. The kernel is index-driven and latency-bound: it moves only `traffic` bytes per merge (actual_dram), "
+                      "so frac says how far a merge is from one full scan at copy speed, not how busy the DRAM is."}
+  tok_ms = [s["tokenize_ms"] for s in st_res if s.get("tokenize_ms")]
+  tok = None
+  if tok_ms:
+    tms = float(np.mean(tok_ms))
+    tok = {"kernel": "wt_tokenize", "ms": tms, "bytes": int(st_res[-1]["tokenize_bytes"]), "GB_per_s": st_res[-1]["tokenize_bytes"] / 1e9 / (tms / 1e3),
+           "hbm_frac": st_res[-1]["tokenize_bytes"] / 1e9 / (tms / 1e3) / peak, "alg_bytes": "1 B read per corpus byte"}
 
+  def phase(stats, key):
+    return float(np.mean([s[key] for s in stats]))
   out = {
     "metric": "train_corpus_GB_per_s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-    "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
     "dtype": "int32 symbols, uint64 counts", "data": "synthetic", "config": config, "clocks": clocks,
     "e2e": {"value": e2e_value, "unit": "GB/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(total_bytes),
             "d2h_bytes_per_step": int(st_e2e[-1]["merge_bytes"])},
-    "gpu_launches": launches, "roofline": roofline,
-    "extra": {"merges": merges, "merges_per_s": merges / (st_res[-1]["merge_ms"] / 1e3) if st_res[-1]["merge_ms"] else None,
-              "us_per_merge": st_res[-1]["merge_ms"] * 1e3 / max(merges, 1),
-              "phase_ms": {k: st_res[-1][k] for k in ("load_ms", "count_ms", "merge_ms")},
-              "e2e_phase_ms": {k: st_e2e[-1][k] for k in ("load_ms", "count_ms", "merge_ms")},
-              "wall_ms": [s_["wall_ms"] for s_ in st_res], "e2e_wall_ms": [s_["wall_ms"] for s_ in st_e2e],
+    "gpu_launches": launches, "roofline": roofline, "parity": parity,
+    "extra": {"merges": merges, "merges_per_s": merges / (phase(st_res, "merge_ms") / 1e3) if (rank == 0 and phase(st_res, "merge_ms")) else None,
+              "us_per_merge": phase(st_res, "merge_ms") * 1e3 / max(merges, 1),
+              "phase_ms": {k: phase(st_res, k) for k in ("load_ms", "count_ms", "merge_ms")},
+              "e2e_phase_ms": {k: phase(st_e2e, k) for k in ("load_ms", "count_ms", "merge_ms")},
+              "tokenize": tok,
+              "wall_ms": [s_["wall_ms"] for s_ in st_res[-3:]], "e2e_wall_ms": [s_["wall_ms"] for s_ in st_e2e[-3:]],
               "unique_words": st_res[-1]["words"], "rows": st_res[-1]["rows"],
               "look_ahead": {k: st_res[-1].get(k) for k in ("hints_sent", "hints_taken", "hints_rejected", "host_peek_ms")},
               "host_split_ms": {k: st_res[-1].get(k) for k in ("host_pop_ms", "host_wait_ms", "host_apply_ms")},
+              "merge_loop": MERGE_LOOP if world > 1 else "single GPU",
               "collectives_per_step": st_res[-1].get("collectives"), "exchange_bytes_per_step": st_res[-1].get("exchange_bytes"), "wall_ms_per_step": wall_res,
               "ms_per_step_with_kernel_timing": ms_tim},
   }
 
-  # ------------------------------------------------------------------ encoder (rides along)
-  if not args.no_encode and world == 1:
+  # ------------------------------------------------------------------ encoder (config 4: document-parallel, every N)
+  if not args.no_encode:
+    STATE["phase"] = "encode"
     enc = last["trainer"].encoder()
-    d_out = torch.empty(nbytes, dtype=torch.int32, device=dev)
+    d_out = torch.empty(max(nbytes, 1), dtype=torch.int32, device=dev)
     h_out = torch.empty(nbytes // 2 + 16, dtype=torch.int32, pin_memory=True)
+    ksteps = max(2, min(args.steps, 5))
     for _ in range(2):
       ntok = enc.encode_device(d_corpus.data_ptr(), nbytes, d_out.data_ptr(), d_out.numel())
-    torch.cuda.synchronize()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = enc.kernel_launches
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(ksteps):
       ntok = enc.encode_device(d_corpus.data_ptr(), nbytes, d_out.data_ptr(), d_out.numel())
-    e1.record(); torch.cuda.synchronize()
-    enc_ms = e0.elapsed_time(e1) / args.steps
-    enc.encode_into(arr[: 64 << 20], h_out.numpy())
+      if world > 1:
+        tok_off, tok_total, _ = gather_token_offsets(ntok, None, dev)  # the path's one collective: where this rank's ids sit
+    e1.record(); barrier()
+    enc_ms = e0.elapsed_time(e1) / ksteps
+    enc.encode_into(arr[: min(nbytes, 64 << 20)], h_out.numpy())
+    barrier()
     e0.record()
-    t0 = time.perf_counter()
-    ntok2 = enc.encode_into(arr, h_out.numpy())
-    e1.record(); torch.cuda.synchronize()
-    enc_e2e_ms = e0.elapsed_time(e1)
+    for _ in range(ksteps):
+      ntok2 = enc.encode_into(arr, h_out.numpy())
+      if world > 1:
+        gather_token_offsets(ntok2, None, dev)
+    e1.record(); barrier()
+    enc_e2e_ms = e0.elapsed_time(e1) / ksteps
+    tot_tok = ntok
+    if world > 1:
+      tt = torch.tensor([enc_ms, enc_e2e_ms], device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+      enc_ms, enc_e2e_ms = float(tt[0].item()), float(tt[1].item())
+      tn = torch.tensor([ntok], dtype=torch.int64, device=dev); dist.all_reduce(tn)
+      tot_tok = int(tn.item())
+    # parity of the encoding, size-independent: histogram(encode(training corpus)) == the trainer's own token histogram
+    hist = torch.bincount(d_out[:ntok].to(torch.int64), minlength=256 + merges)
+    if world > 1:
+      dist.all_reduce(hist)
+    tf = torch.from_numpy(last["trainer"].token_freq().astype(np.int64)).to(dev)
+    hist_equal = bool(torch.equal(hist[: tf.numel()], tf)) and int(hist[tf.numel():].sum().item()) == 0
+    if not hist_equal:
+      raise RuntimeError("histogram of encode(training corpus) differs from the trainer's token histogram (.vocab frequency column)")
     out["gpu_launches"] += int(enc.kernel_launches - l0)
-    out["extra"]["encode"] = {"MB_per_s": nbytes / 1e6 / (enc_ms / 1e3), "e2e_MB_per_s": nbytes / 1e6 / (enc_e2e_ms / 1e3),
-                              "tokens": int(ntok), "bytes_per_token": nbytes / max(ntok, 1),
-                              "alg_bytes_per_input_byte": 1 + 4 * ntok / nbytes,
-                              "hbm_frac": (nbytes + 4 * ntok) / 1e9 / (enc_ms / 1e3) / peak,
-                              "e2e_h2d_bytes": int(nbytes), "e2e_d2h_bytes": int(4 * ntok2)}
+    out["extra"]["encode"] = {"MB_per_s": total_bytes / 1e6 / (enc_ms / 1e3), "e2e_MB_per_s": total_bytes / 1e6 / (enc_e2e_ms / 1e3),
+                              "tokens": int(tot_tok), "bytes_per_token": total_bytes / max(tot_tok, 1),
+                              "alg_bytes_per_input_byte": 1 + 4 * tot_tok / total_bytes,
+                              "hbm_frac": (total_bytes / world + 4 * tot_tok / world) / 1e9 / (enc_ms / 1e3) / peak,
+                              "e2e_h2d_bytes": int(total_bytes), "e2e_d2h_bytes": int(4 * tot_tok),
+                              "document_parallel": f"{world} ranks, byte ranges cut on line ends, token counts all-gathered" if world > 1 else "1 GPU",
+                              "histogram_equals_vocab_column": hist_equal}
     del d_out
 
   # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
   if world == 1 and rank == 0 and not args.no_cpu_baseline:
+    STATE["phase"] = "cpu baseline"
     workdir = tempfile.mkdtemp(prefix="swb_bench_")
     sample, sb = cpu_sample_path(arr, workdir)
-    cb = run_cpu_once(sample, sb, workdir)
+    cb = run_cpu_once(sample, sb, KW)
     log(f"[bench] cpu baseline ({cb['kind']}): {cb['seconds']:.1f}s on {sb} bytes -> {cb['value']:.5f} GB/s")
+    # like for like: our arm on exactly that sample, end to end from host memory
+    t = BPETrainer(**KW)
+    for _ in range(3):
+      t.destroy(); t = BPETrainer(**KW)
+      torch.cuda.synchronize(); t0 = time.perf_counter()
+      t.load_buffer(arr[:sb]); got = t.train_quiet(); t.merges_array()
+      same_s = time.perf_counter() - t0
+    t.destroy()
+    cb["ours_on_same_sample"] = {"seconds": same_s, "GB_per_s": sb / 1e9 / same_s, "merges": got, "speedup": cb["seconds"] / same_s,
+                                 "merges_equal_count": got == cb["merges"]}
+    full = full_config_reference()
+    if full:
+      cb["full_config2"] = full
     out["cpu_baseline"] = cb
 
   if rank == 0:
     emit(out)
+  STATE["phase"] = "shutdown"
+  last.pop("trainer").destroy()
   if world > 1:
-    last.pop("trainer").destroy()
     lib.swb_dist_shutdown()
     dist.destroy_process_group()
 
 
 if __name__ == "__main__":
-  main()
+  try:
+    main()
+  except SystemExit:
+    raise
+  except BaseException as e:  # the LAST stderr line names the rank, the phase and the library's own message
+    traceback.print_exc()
+    err = ""
+    try:
+      from shredword_b200.cbase import last_error
+      err = last_error()
+    except Exception:
+      pass
+    print(f"[bench] FAILED rank {STATE['rank']} phase '{STATE['phase']}' step {STATE['step']}: {type(e).__name__}: {e} | swb_last_error: {err!r}",
+          file=sys.stderr, flush=True)
+    os._exit(1)

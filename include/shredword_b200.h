@@ -143,7 +143,7 @@ typedef struct SwbStats {
   double host_pop_ms, host_launch_ms, host_wait_ms, host_apply_ms; /* merge loop split on the host */
   uint64_t records, heap_pushes, heap_pops, heap_peak;             /* host replica counters */
   uint64_t collectives, exchange_bytes;                            /* multi-GPU: NCCL all-gathers and their bytes */
-  uint64_t loop_runs, loop_stop_tie, loop_stop_big, loop_stop_rebuild, loop_stop_other; /* device-resident loop */
+  uint64_t reserved_[5];
   /* resident cluster kernel: merges done by the leader cluster alone / by the whole grid, and the device time
    * they took (command seen -> result published, %globaltimer; also added to merge_kernel_ms) */
   uint64_t resident_local_merges, resident_grid_merges;
@@ -152,10 +152,21 @@ typedef struct SwbStats {
    * from one without waiting for the command, hints it turned down; host time spent looking ahead */
   uint64_t hints_sent, hints_taken, hints_rejected;
   double host_peek_ms;
+  /* device time of the tokenise + dedupe kernel(s) of the last load (CUDA events on the launch stream; for a host
+   * buffer this spans the pipelined host-to-device copy as well) and the corpus bytes they covered */
+  double tokenize_ms;
+  uint64_t tokenize_bytes;
 } SwbStats;
 void swb_get_stats(const Trainer *trainer, SwbStats *out);
 /* 1: bracket every merge-scan launch with CUDA events (adds a little latency); 0: off (default). */
 void swb_set_kernel_timing(Trainer *trainer, int enabled);
+/* Profiling aid. After bpe_init on a freshly loaded corpus (one GPU, no long words): runs the first n merges of
+ * `merge_triples` -- a merge list this same corpus produced before -- inside ONE launch of the resident merge kernel
+ * (merge_cluster) whose commands come from a script in device memory instead of the host mailbox. The launch never
+ * waits for the host, so a profiler's kernel replay can capture it and its duration is the device-side floor of the
+ * merge loop. The handle is consumed: only swb_get_stats / bpe_trainer_destroy are meaningful afterwards.
+ * *kernel_ms receives the launch duration (CUDA events). 0 on success, -1 on error. */
+int swb_profile_scripted_merges(Trainer *trainer, const int32_t *merge_triples, size_t n, double *kernel_ms);
 
 /* ---- encoder (no reference entry point exists; semantics: reference base.py:10-36 applied
  * lowest merge rank first, per whitespace-delimited word; delimiters \t \r \n space) ---- */

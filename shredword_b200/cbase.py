@@ -43,11 +43,11 @@ class SwbStats(Structure):
               ("host_pop_ms", c_double), ("host_launch_ms", c_double), ("host_wait_ms", c_double), ("host_apply_ms", c_double),
               ("records", c_uint64), ("heap_pushes", c_uint64), ("heap_pops", c_uint64), ("heap_peak", c_uint64),
               ("collectives", c_uint64), ("exchange_bytes", c_uint64),
-              ("loop_runs", c_uint64), ("loop_stop_tie", c_uint64), ("loop_stop_big", c_uint64), ("loop_stop_rebuild", c_uint64),
-              ("loop_stop_other", c_uint64),
+              ("reserved_", c_uint64 * 5),
               ("resident_local_merges", c_uint64), ("resident_grid_merges", c_uint64),
               ("resident_local_ms", c_double), ("resident_grid_ms", c_double),
-              ("hints_sent", c_uint64), ("hints_taken", c_uint64), ("hints_rejected", c_uint64), ("host_peek_ms", c_double)]
+              ("hints_sent", c_uint64), ("hints_taken", c_uint64), ("hints_rejected", c_uint64), ("host_peek_ms", c_double),
+              ("tokenize_ms", c_double), ("tokenize_bytes", c_uint64)]
 
 # ---- the reference's eight entry points (reference cbase.py:44-59)
 lib.create_trainer.argtypes = [POINTER(BPEConfig)]
@@ -88,6 +88,7 @@ _sigs = {
   "swb_get_words": ([T, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
   "swb_get_stats": ([T, POINTER(SwbStats)], None),
   "swb_set_kernel_timing": ([T, c_int], None),
+  "swb_profile_scripted_merges": ([T, c_void_p, c_size_t, POINTER(c_double)], c_int),
   "swb_encoder_create": ([c_void_p, c_size_t, c_void_p], c_void_p),
   "swb_encoder_from_trainer": ([T], c_void_p),
   "swb_encoder_destroy": ([c_void_p], None),

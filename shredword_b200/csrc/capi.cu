@@ -265,6 +265,15 @@ void swb_set_kernel_timing(Trainer *trainer, int enabled) {
   if (trainer) impl_of(trainer)->timing = enabled != 0;
 }
 
+int swb_profile_scripted_merges(Trainer *trainer, const int32_t *merge_triples, size_t n, double *kernel_ms) {
+  if (!trainer || (!merge_triples && n)) { set_err("swb_profile_scripted_merges: NULL argument"); return -1; }
+  SWB_TRY
+  const double ms = impl_of(trainer)->profile_scripted(merge_triples, n);
+  if (kernel_ms) *kernel_ms = ms;
+  return 0;
+  SWB_CATCH(-1)
+}
+
 // ---- encoder
 struct SwbEncoder { EncoderImpl *impl; };
 

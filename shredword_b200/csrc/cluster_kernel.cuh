@@ -35,17 +35,32 @@ constexpr int CL_REC_STAGE = 512;          // records staged per CTA and merge
 constexpr unsigned int CL_LOCAL_MAX = CL_SIZE * CL_THREADS * 64;  // longest birth log the leader cluster takes alone (entries)
 constexpr int CL_CAND_CAP = 1024;          // candidate words listed per CTA and merge (more: rewritten where they are found)
 constexpr int CL_MAX_PROBES = 256;
+// Effective limits of one launch. The defaults are the compile-time capacities above; the parity tests shrink them
+// (SWB_TEST_* environment variables, see TrainerImpl::cluster_tune) so that the overflow paths -- candidate lists past
+// the shared-memory list, inbox and table spills into the global pair table, records and log entries past their stages,
+// GRID merges from long logs -- run on corpora small enough for the CPU oracle.
+struct ClusterTune { unsigned int local_max, cand_cap, inbox_cap, rec_stage, birth_stage, max_probes; };
+__host__ __device__ __forceinline__ ClusterTune cluster_tune_default() {
+  return ClusterTune{CL_LOCAL_MAX, (unsigned int)CL_CAND_CAP, (unsigned int)CL_INBOX, (unsigned int)CL_REC_STAGE, (unsigned int)CL_BIRTH_STAGE, (unsigned int)CL_MAX_PROBES};
+}
 constexpr unsigned int CL_IP_LOCAL_MAX = 8192;  // longest occurrence list of a pair of two initial symbols the leader cluster takes alone (every entry is a candidate word: two per thread)
 
 // host -> device command: ONE 16-byte word in mapped host memory, written with a single 16-byte store and read with a
 // single 16-byte load (one PCIe read per poll, no second trip for a payload):
-//   x, y = the pair (second, first);  z = new_id | op << 28 (op 0 = merge, 1 = stop);  w = seq (24 bits) << 8 | check (8 bits)
+//   x, y = the pair (second, first);  z = new_id | op << 28 (op 0 = merge, 1 = stop);  w = 32-bit check over (seq, x, y, z)
+// The sequence number is not carried in the clear: the device knows which one it waits for, and a word that was written
+// for any other sequence number (a stale command, an old hint) fails the check. The check is never 0, so a zeroed mailbox
+// word matches nothing. Atomicity assumption: a 16-byte aligned store of the host reaches memory as one unit (true for SSE
+// stores on every x86-64 with AVX, and for the two-register store pair used elsewhere, see host_store16 in trainer_impl.cuh);
+// a torn word would still have to pass the 32-bit check to be taken.
 struct __align__(16) HostCmd2 { unsigned int x, y, z, w; };
 __host__ __device__ __forceinline__ unsigned int cmd3_word(unsigned long long seq, unsigned int x, unsigned int y, unsigned int z) {
-  const unsigned int s24 = (unsigned int)seq & 0xFFFFFFu;
-  unsigned int f = x ^ (y * 0x9E3779B1u) ^ (z * 0x85EBCA6Bu) ^ (s24 * 0xC2B2AE35u);
-  f ^= f >> 16; f ^= f >> 8;
-  return (s24 << 8) | (f & 0xFFu);
+  unsigned long long f = (seq + 0x9E3779B97F4A7C15ull) * 0xD6E8FEB86659FD93ull;
+  f ^= (unsigned long long)x * 0x9E3779B1ull; f = (f << 23 | f >> 41) * 0xA24BAED4963EE407ull;
+  f ^= (unsigned long long)y * 0x85EBCA6Bull; f = (f << 29 | f >> 35) * 0x9FB21C651E98DF25ull;
+  f ^= (unsigned long long)z * 0xC2B2AE35ull; f ^= f >> 32; f *= 0xD6E8FEB86659FD93ull; f ^= f >> 29;
+  const unsigned int w = (unsigned int)f ^ (unsigned int)(f >> 32);
+  return w ? w : 0x5BD1E995u;
 }
 // leader -> other clusters (device memory)
 struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, t_cmd /* %globaltimer when the command arrived */, spec /* started from a hint */; };
@@ -130,11 +145,11 @@ __device__ __forceinline__ ClusterSmem cluster_smem(unsigned char *base) {
 // (key, delta, first-touch key) -> a table in THIS CTA's shared memory. false: no room within the probe limit.
 __device__ __forceinline__ bool smem_table_add(unsigned long long *keys, unsigned long long *val, unsigned long long *mk,
                                                unsigned long long k, long long delta, unsigned long long key,
-                                               unsigned short *occ, unsigned int *n_occ,
+                                               unsigned short *occ, unsigned int *n_occ, int max_probes,
                                                const PairTableDev::GSlotRef pf = PairTableDev::GSlotRef{nullptr, 0}) {
   uint32_t sl = (uint32_t)(dmix64(k) >> 3) & (CL_HT_SLOTS - 1);
 #pragma unroll 1
-  for (int probe = 0; probe < CL_MAX_PROBES; probe++) {
+  for (int probe = 0; probe < max_probes; probe++) {
     const unsigned long long cur = atomicCAS(&keys[sl], PT_EMPTY, k);
     if (cur == PT_EMPTY) occ[atomicAdd(n_occ, 1u)] = (unsigned short)sl;  // the list of occupied slots, for whoever empties the table
     if (cur == PT_EMPTY && pf.slots)  // first touch: pull the pair's frequency-table slot into L2 for the emit phase
@@ -168,13 +183,14 @@ struct ClusterSink {
   const ClusterSmem &m;
   const PairTableDev &t;      // spill target + canonicalisation of a negative unk_id
   const BirthLogDev &lg;
+  const ClusterTune &tune;
   __device__ __forceinline__ void add_batch(int n, const int32_t *x, const int32_t *y, const long long *delta, const uint64_t *key) {
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
       int32_t xx = x[i];
       if (t.canon_on && y[i] == UNK_CODE) xx = t.canon_first;
       const unsigned long long k = ((unsigned long long)(uint32_t)xx << 32) | (uint32_t)y[i];
-      if (!smem_table_add(m.k1, m.v1, m.m1, k, delta[i], (unsigned long long)key[i], m.occ1, &m.ctl->n_occ1, t.gpf)) {
+      if (!smem_table_add(m.k1, m.v1, m.m1, k, delta[i], (unsigned long long)key[i], m.occ1, &m.ctl->n_occ1, (int)tune.max_probes, t.gpf)) {
         // T1 is (nearly) full: this delta goes to the global table, and so will everything else of this merge
         atomicOr(&cluster.map_shared_rank(m.ctl, 0)->spill, 1u);
         pt_add(t, xx, y[i], delta[i], key[i]);
@@ -184,7 +200,7 @@ struct ClusterSink {
   __device__ __forceinline__ void birth(uint32_t other, bool right_side, uint32_t wi, uint64_t hloc) {
     const uint4 e = log_entry(other, right_side, wi, hloc);
     const unsigned int i = atomicAdd(&m.ctl->n_births, 1u);
-    if (i < CL_BIRTH_STAGE) m.births[i] = e;
+    if (i < tune.birth_stage) m.births[i] = e;
     else {  // past the stage: straight to its final place
       ClusterCtl *c0 = cluster.map_shared_rank(m.ctl, 0);
       const unsigned int idx = c0->log_cursor + atomicAdd(&c0->births_total, 1u);
@@ -205,7 +221,7 @@ __device__ __forceinline__ void cluster_clear_tables(const ClusterSmem &m) {
 // LOCAL merge, exchange: every partial sum of T1 goes to the CTA that owns its pair -- straight into T2 when that is
 // this CTA, otherwise as one message into the owner's inbox (one remote 32-bit atomic for the place, two remote
 // 16-byte stores). Remote 64-bit min/xor atomics are avoided altogether (wrong results on this toolchain).
-__device__ __forceinline__ void cluster_exchange(const ClusterSmem &m, const PairTableDev &t, cg::cluster_group &cluster, unsigned int crank) {
+__device__ __forceinline__ void cluster_exchange(const ClusterSmem &m, const PairTableDev &t, cg::cluster_group &cluster, unsigned int crank, const ClusterTune &tune) {
   const unsigned int n1 = m.ctl->n_occ1;  // (listed while the deltas were added; the caller has synchronised the block)
 #pragma unroll 1
   for (unsigned int i = threadIdx.x; i < n1; i += CL_THREADS) {
@@ -214,11 +230,11 @@ __device__ __forceinline__ void cluster_exchange(const ClusterSmem &m, const Pai
     m.k1[sl] = PT_EMPTY; m.v1[sl] = 0; m.m1[sl] = ~0ull;
     const unsigned int owner = (unsigned int)dmix64(k) & (CL_SIZE - 1);
     bool ok;
-    if (owner == crank) ok = smem_table_add(m.keys, m.val, m.mk, k, (long long)d, mk, m.occ, &m.ctl->n_occ);
+    if (owner == crank) ok = smem_table_add(m.keys, m.val, m.mk, k, (long long)d, mk, m.occ, &m.ctl->n_occ, (int)tune.max_probes);
     else {
       ClusterCtl *oc = cluster.map_shared_rank(m.ctl, owner);
       const unsigned int j = atomicAdd(&oc->inbox_n, 1u);
-      ok = j < CL_INBOX;
+      ok = j < tune.inbox_cap;
       if (ok) {
         uint4 *ob = cluster.map_shared_rank(m.inbox, owner);
         ob[2 * j] = make_uint4((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)d, (uint32_t)(d >> 32));
@@ -232,14 +248,14 @@ __device__ __forceinline__ void cluster_exchange(const ClusterSmem &m, const Pai
   }
 }
 // ... and after the cluster barrier the owner folds its inbox into T2
-__device__ __forceinline__ void cluster_fold_inbox(const ClusterSmem &m, const PairTableDev &t, cg::cluster_group &cluster) {
-  const unsigned int nin = min(m.ctl->inbox_n, (unsigned int)CL_INBOX);
+__device__ __forceinline__ void cluster_fold_inbox(const ClusterSmem &m, const PairTableDev &t, cg::cluster_group &cluster, const ClusterTune &tune) {
+  const unsigned int nin = min(m.ctl->inbox_n, tune.inbox_cap);
 #pragma unroll 1
   for (unsigned int i = threadIdx.x; i < nin; i += CL_THREADS) {
     const uint4 q0 = m.inbox[2 * i], q1 = m.inbox[2 * i + 1];
     const unsigned long long k = ((unsigned long long)q0.y << 32) | q0.x, d = ((unsigned long long)q0.w << 32) | q0.z,
                              mk = ((unsigned long long)q1.y << 32) | q1.x;
-    if (!smem_table_add(m.keys, m.val, m.mk, k, (long long)d, mk, m.occ, &m.ctl->n_occ)) {
+    if (!smem_table_add(m.keys, m.val, m.mk, k, (long long)d, mk, m.occ, &m.ctl->n_occ, CL_MAX_PROBES * 8)) {
       atomicOr(t.flags, 1u);  // cannot happen (T2 is at most 2/3 full with a whole inbox): reported as an internal sizing error
     }
   }
@@ -249,7 +265,7 @@ __device__ __forceinline__ void cluster_fold_inbox(const ClusterSmem &m, const P
 // LOCAL merge, phase 2 of one CTA: apply this CTA's pairs to the device frequency table and stage the records
 __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const EmitMode &em, const PairTableDev &t, bool spill,
                                                   unsigned long long &cx, unsigned long long &cs, unsigned int &inserted,
-                                                  unsigned long long &maxpush, Rec *__restrict__ out, size_t out_cap, cg::cluster_group &cluster, int32_t new_id) {
+                                                  unsigned long long &maxpush, Rec *__restrict__ out, size_t out_cap, cg::cluster_group &cluster, int32_t new_id, const ClusterTune &tune) {
   const unsigned int n_occ = m.ctl->n_occ;  // (listed while T2 was filled; the caller has synchronised the block)
   ClusterCtl *c0 = cluster.map_shared_rank(m.ctl, 0);
 #pragma unroll 1
@@ -286,7 +302,7 @@ __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const Em
     if (old >= em.min_freq || nw >= em.min_freq) {
       if (nw >= em.min_freq && nw > maxpush) maxpush = nw;  // the host pushes this pair (reference bpe.cpp:512-515)
       const unsigned int j = atomicAdd(&m.ctl->n_recs, 1u);
-      if (j < CL_REC_STAGE) rec_out(m.recs, CL_REC_STAGE, j, k, (long long)nw, mk, cx, cs);
+      if (j < tune.rec_stage) rec_out(m.recs, CL_REC_STAGE, j, k, (long long)nw, mk, cx, cs);
       else rec_out(out, out_cap, atomicAdd(&c0->n_recs_total, 1u), k, (long long)nw, mk, cx, cs);  // past the stage: straight to its final place
     }
   }
@@ -297,7 +313,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
               unsigned long long *__restrict__ out_hdr0, unsigned long long *__restrict__ out_hdr1, unsigned long long seq_base, unsigned long long op_base,
               volatile HostCmd2 *hcmd /* [3] in mapped host memory: the command, the hints for even / odd sequence numbers */, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace,
               uint4 *ovf /* [CL_LOCAL_MAX]: candidate words that did not fit a CTA's shared-memory list */,
-              unsigned long long *acct /* [8]: LOCAL merges, their device ns, GRID merges, their device ns, hints accepted, hints rejected, hints accepted without a PCIe trip, LOCAL merges that spilled to the global table */) {
+              const HostCmd2 *__restrict__ script /* nullptr, or [script_n] commands in DEVICE memory that replace the mailbox: the kernel then runs without the host (profiling under ncu's kernel replay, see TrainerImpl::profile_scripted) */, unsigned long long script_n, ClusterTune tune,
+              unsigned long long *acct /* [16]: LOCAL merges, their device ns, GRID merges, their device ns, hints accepted, hints rejected, hints accepted without a PCIe trip, LOCAL merges that spilled to the global table, [8] sequence number the watchdog gave up on, [9] after how many ns */) {
   extern __shared__ __align__(16) unsigned char cl_dyn_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const ClusterSmem m = cluster_smem(cl_dyn_smem);
@@ -334,7 +351,10 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           uint4 v = make_uint4(0u, 0u, 0u, 0u), hv = make_uint4(0u, 0u, 0u, 0u);  // one 16-byte load from mapped host memory = one PCIe read (the two are in flight together)
           bool have_v = true;
           if (spin == 0 && hint_ok && pre_hv.z != 0u && pre_hv.w == cmd3_word(want, pre_hv.x, pre_hv.y, pre_hv.z)) { hv = pre_hv; have_v = false; }  // already here: no trip at all
-          else {
+          else if (script) {
+            if (k >= script_n) { nio = 1ull << 32; break; }  // end of the script: stop
+            v = __ldcg(reinterpret_cast<const uint4 *>(script + k));
+          } else {
             asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(hcmd) : "memory");
             if (hint_ok) asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hv.x), "=r"(hv.y), "=r"(hv.z), "=r"(hv.w) : "l"(hcmd + 1 + (want & 1ull)) : "memory");
           }
@@ -361,7 +381,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
             acct[5] += 1;
             hint_ok = false;
           }
-          if ((spin & 63) == 63 && gtime_ns() - t0 > timeout_ns) break;  // abort: the host went away
+          if ((spin & 63) == 63 && gtime_ns() - t0 > timeout_ns) { acct[8] = want; acct[9] = gtime_ns() - t0; break; }  // abort: the host went away (the host reads why)
         }
         hint_ok = false;
         if (!(nio >> 32)) {  // the birth log of the newer token of the pair (device-side bookkeeping: cheaper than a second PCIe trip)
@@ -380,7 +400,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         }
         const unsigned long long t_cmd = gtime_ns();
         const unsigned int stop = (unsigned int)(nio >> 32);
-        const unsigned int mode = (lr == ~0ull || (unsigned int)(lr & 0xFFFFFFFFu) > CL_LOCAL_MAX) ? 1u : 0u;
+        const unsigned int mode = (lr == ~0ull || (unsigned int)(lr & 0xFFFFFFFFu) > tune.local_max) ? 1u : 0u;
         for (unsigned int r = 0; r < CL_SIZE; r++) {
           ClusterCtl *c = cluster.map_shared_rank(m.ctl, r);
           c->pair = pair; c->new_id_op = nio; c->log_range = lr; c->k = k; c->mode = mode; c->stop = stop; c->t_cmd = t_cmd; c->spec = spec;
@@ -447,7 +467,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       if (is_last) {
         __threadfence();
         TailSmem ts{m.tail_stage, m.csum, m.tail_count};
-        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag, nullptr, nullptr);
+        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag);
         if (threadIdx.x == 0) {  // (one publisher at a time)
           const unsigned long long dt = gtime_ns() - m.ctl->t_cmd;
           acct[2] += 1; acct[3] += dt;
@@ -473,7 +493,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       bool have_log = log_lookup(em.log, a, b, merge, other, side);  // (true: the command came with a log range)
       const uint4 *__restrict__ ent = em.log.ent;
       if (!have_log && ip_lookup(em.log, a, b)) { have_log = true; other = (uint32_t)a; side = 0u; ent = em.log.ip_ent; }  // the occurrence index has the same format
-      ClusterSink sink{cluster, m, t, em.log};
+      ClusterSink sink{cluster, m, t, em.log, tune};
       uint32_t removed = 0;
       // Eight log entries per thread are requested together (one round trip); the matching ones are listed in
       // shared memory and then dealt out evenly, so that no thread rewrites more words than its neighbours.
@@ -495,7 +515,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
               asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const int32_t *>(s.rows) + hl));
               asm volatile("prefetch.global.L2 [%0];" ::"l"(s.cnt + (e.y & 0x7FFFFFFFu)));
             }
-            if (ci < CL_CAND_CAP) m.cand[ci] = make_uint4(e.y & 0x7FFFFFFFu, e.z, e.w, 0u);
+            if (ci < tune.cand_cap) m.cand[ci] = make_uint4(e.y & 0x7FFFFFFFu, e.z, e.w, 0u);
             else ovf[(size_t)crank * (CL_LOCAL_MAX / CL_SIZE) + atomicAdd(&m.ctl->n_ovf, 1u)] = make_uint4(e.y & 0x7FFFFFFFu, e.z, e.w, 0u);  // rare: listed in global memory
           }
         }
@@ -505,7 +525,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       {
         // candidate i goes to warp i % 16, lane i / 16: the work is spread over all warps (and schedulers) of the CTA;
         // candidates past the shared-memory list (rare) follow from this CTA's part of the global overflow list
-        const unsigned int nc = min(m.ctl->n_cand, (unsigned int)CL_CAND_CAP), nall = nc + m.ctl->n_ovf;
+        const unsigned int nc = min(m.ctl->n_cand, tune.cand_cap), nall = nc + m.ctl->n_ovf;
         const uint4 *ovf_mine = ovf + (size_t)crank * (CL_LOCAL_MAX / CL_SIZE);
 #pragma unroll 1
         for (unsigned int i = (threadIdx.x >> 5) + (unsigned int)CL_WARPS * (threadIdx.x & 31); i < nall; i += CL_THREADS) {
@@ -521,7 +541,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
     }
     __syncthreads();
     if (trace && crank == 0 && threadIdx.x == 0) trace[7] += (unsigned long long)(clock64() - c1);
-    cluster_exchange(m, t, cluster, crank);
+    cluster_exchange(m, t, cluster, crank, tune);
     cluster_barrier(cluster);  // every partial sum of this merge has reached the CTA that owns its pair
     const long long c2 = clock64();
     {
@@ -540,15 +560,15 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;
         if (ins) atomicAdd(em.g.n_used, ins);
       }
-      cluster_fold_inbox(m, t, cluster);
+      cluster_fold_inbox(m, t, cluster, tune);
       unsigned long long cx = 0, cs = 0;
       unsigned int inserted = 0;
       if (threadIdx.x == 64) {  // this CTA's range in the birth log: requested now, needed after the records are staged
-        const unsigned int nb = min(m.ctl->n_births, (unsigned int)CL_BIRTH_STAGE);
+        const unsigned int nb = min(m.ctl->n_births, tune.birth_stage);
         m.ctl->birth_base = c0->log_cursor + (nb ? atomicAdd(&c0->births_total, nb) : 0u);
       }
       unsigned long long maxpush = 0;
-      cluster_emit_part(m, em, t, spill, cx, cs, inserted, maxpush, out, out_cap, cluster, new_id);
+      cluster_emit_part(m, em, t, spill, cx, cs, inserted, maxpush, out, out_cap, cluster, new_id, tune);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) {
         inserted += __shfl_down_sync(0xffffffffu, inserted, d);
@@ -559,18 +579,18 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       if (lane == 0 && maxpush) atomicMax(&m.ctl->maxpush, maxpush);
       __syncthreads();
       if (threadIdx.x == 0) {  // this CTA's ranges in the record buffer and in the birth log
-        const unsigned int nr = min(m.ctl->n_recs, (unsigned int)CL_REC_STAGE);
+        const unsigned int nr = min(m.ctl->n_recs, tune.rec_stage);
         m.ctl->rec_base = nr ? atomicAdd(&c0->n_recs_total, nr) : 0u;
       }
       __syncthreads();
       {
-        const unsigned int nr = min(m.ctl->n_recs, (unsigned int)CL_REC_STAGE), base = m.ctl->rec_base;
+        const unsigned int nr = min(m.ctl->n_recs, tune.rec_stage), base = m.ctl->rec_base;
         const uint4 *src = reinterpret_cast<const uint4 *>(m.recs);
         for (unsigned int i = threadIdx.x; i < 2u * nr; i += CL_THREADS) {
           const size_t r = (size_t)base + (i >> 1);
           if (r < out_cap) reinterpret_cast<uint4 *>(out)[2 * r + (i & 1)] = src[i];
         }
-        const unsigned int nb = min(m.ctl->n_births, (unsigned int)CL_BIRTH_STAGE), bbase = m.ctl->birth_base;
+        const unsigned int nb = min(m.ctl->n_births, tune.birth_stage), bbase = m.ctl->birth_base;
         for (unsigned int i = threadIdx.x; i < nb; i += CL_THREADS) {
           if (bbase + i < em.log.cap) em.log.ent[bbase + i] = m.births[i];
           else atomicOr(em.log.flags, 1u);
@@ -595,7 +615,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         __threadfence();
         __syncthreads();
         TailSmem ts{m.tail_stage, m.csum, m.tail_count};
-        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag, nullptr, nullptr);
+        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag);
         __syncthreads();
         cluster_clear_tables(m);
         if (threadIdx.x == 0) { acct[0] += 1; acct[1] += gtime_ns() - c->t_cmd; acct[7] += 1; }
@@ -615,7 +635,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
 #pragma unroll
         for (int r = 0; r < CL_SIZE; r++) { x ^= c->part_cx[r]; sm += c->part_cs[r]; mxp = c->part_max[r] > mxp ? c->part_max[r] : mxp; }
         // the next merge may start from a hint: this one was LOCAL, complete and raised no flag
-        hint_ok = pre_flags == 0u && n <= out_cap;
+        hint_ok = pre_flags == 0u && n <= out_cap && script == nullptr;
         prev_maxpush = mxp; prev_new_id = (unsigned int)new_id;
         {  // the 64-byte header as four 16-byte stores (fewer PCIe writes than eight 8-byte ones; it validates itself)
           const unsigned long long rem = c->removed, chk = hdr_check(seq, n, flags, rem, x, sm);

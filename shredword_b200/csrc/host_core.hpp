@@ -512,6 +512,14 @@ class HostCore {
   const std::vector<PairKey> &merges() const { return merges_; }
   PairTable &pairs() { return pairs_; }
   bool pending() const { return pending_; }
+  // The merge announced by next_merge() could not be carried out (device error): take it off the merge list again, so
+  // that merge_ops[0 .. num_merges) stays exactly the merges that were applied.
+  void abort_pending() {
+    if (!pending_) return;
+    merges_.pop_back();
+    tr_->merge_ops = merges_.data();
+    pending_ = false;
+  }
 
  private:
   Trainer *tr_;

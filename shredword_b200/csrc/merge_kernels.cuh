@@ -120,34 +120,7 @@ __global__ void gt_dump(GlobalTableDev g, unsigned long long *__restrict__ out, 
   }
 }
 
-// ---- device-resident merge loop (single GPU, device-table mode)
-// The next pair to merge is the valid heap entry with the highest frequency; when that maximum is
-// UNIQUE it is the same pair whatever the heap's internal order, so the device can pick it itself and
-// the next merge kernel (already queued) can start without a host round trip. The device keeps every
-// pair with frequency >= theta in a candidate list (theta and the list are (re)built by the host from
-// its exact table); after the deltas of a merge are applied, the last block takes the arg-max over the
-// list. A tie at the maximum, an exhausted list, an overflow or a too-long record list hands control
-// back to the host, whose exact heap replica arbitrates. The host replays every merge from the record
-// ring in any case and checks that its own pop equals the device's choice.
 constexpr int HDR_WORDS = 32;
-enum : uint32_t { LOOP_RUN = 0, LOOP_TIE = 1, LOOP_BIG_EMIT = 2, LOOP_REBUILD = 3, LOOP_STOP = 4 };
-struct LoopState {
-  int32_t a, b, new_id;
-  uint32_t status;
-  unsigned long long done;    // merges performed by the device since the host last set the state
-  unsigned long long theta;   // every pair with frequency >= theta is in the candidate list
-  uint32_t n_cand, pad;
-};
-struct __align__(16) CandEntry { unsigned long long key; uint32_t slot, pad; };
-struct LoopDev {
-  LoopState *st;              // nullptr: classic mode (the host passes the pair with every launch)
-  CandEntry *cand;
-  uint32_t cand_cap;
-  Rec *ring;                  // mapped host memory: ring_slots x slot_recs records
-  unsigned long long *ring_hdr;  // mapped host memory: ring_slots x HDR_WORDS
-  uint32_t ring_slots, slot_recs;
-  unsigned long long seq_base, op_base;
-};
 
 // ---- birth log: pair -> words that can contain it
 // An adjacent pair (x, y) with max(x, y) >= 256 comes into existence only while the NEWER of its two
@@ -224,11 +197,6 @@ struct EmitMode {
   unsigned long long stamp_base;  // operation index << 10
   int32_t neg_unk_bucket;         // >= 0: a pair whose second is UNK_CODE lives in this delta-map bucket (negative unk_id)
   GlobalTableDev g;
-  // candidate list of the device-resident loop (nullptr: not in use): pairs crossing theta upwards are appended
-  LoopState *lst;
-  CandEntry *cand;
-  uint32_t cand_cap;
-  unsigned long long theta;
   unsigned int fused_max;  // touched pairs the single-block tail takes; more -> flag 8, the host runs the full-grid pt_emit
   BirthLogDev log;         // ent == nullptr: no birth log
 };
@@ -353,10 +321,6 @@ __device__ __forceinline__ void pt_emit_range(const PairTableDev &t, const EmitM
     if (d < 0) { const unsigned long long ad = (unsigned long long)(-d); nw = old >= ad ? old - ad : 0ull; }
     else nw = old + (unsigned long long)d;
     em.g.slots[g].freq = nw;
-    if (em.cand && nw >= em.theta && old < em.theta) {
-      const unsigned int ci = atomicAdd(&em.lst->n_cand, 1u);
-      if (ci < em.cand_cap) em.cand[ci] = CandEntry{k, g, 0u};
-    }
     if (old >= em.min_freq || nw >= em.min_freq)
       rec_out(out, out_cap, atomicAdd(out_count, 1u), k, (long long)nw, mk, cx, cs, direct, stage_cap);
   }
@@ -442,51 +406,9 @@ constexpr unsigned int STAGE_RECS = 384;        // records staged in shared memo
 // host memory becomes a PCIe write, and scattered per-thread writes cost ~16x more transactions than full
 // lines), applies them to the device frequency table when em.mode != 0, and publishes the header.
 struct TailSmem { Rec *stage; unsigned long long *csum; unsigned int *count; };
-// arg-max over the candidate list (all 256 threads of the block); returns the status for the next merge
-// and, for LOOP_RUN, its pair. Each thread owns up to CAND_PER_THREAD entries; their list entries and then
-// their frequencies are fetched as two batches of independent loads (two L2 round trips in total, not two
-// per entry), and the tie test at the maximum reuses the registers.
-constexpr int CAND_PER_THREAD = 16;  // x 256 threads = the largest candidate list (4096)
-__device__ __forceinline__ uint32_t loop_pick_next(const LoopDev &lp, const GlobalTableDev &g, unsigned long long *scratch /* >= 4 u64, shared */,
-                                                   unsigned long long &next_key) {
-  const uint32_t n_raw = __ldcg(&lp.st->n_cand);
-  const uint32_t n = min(n_raw, lp.cand_cap);
-  const unsigned long long theta = __ldcg(&lp.st->theta);
-  if (threadIdx.x == 0) { scratch[0] = 0; scratch[1] = ~0ull; scratch[2] = 0; }
-  __syncthreads();
-  unsigned long long key[CAND_PER_THREAD], freq[CAND_PER_THREAD];
-  uint32_t slot[CAND_PER_THREAD];
-#pragma unroll
-  for (int j = 0; j < CAND_PER_THREAD; j++) {
-    const uint32_t i = threadIdx.x + j * 256;
-    if (i < n) { const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(lp.cand) + i); key[j] = ((unsigned long long)e.y << 32) | e.x; slot[j] = e.z; }
-    else { key[j] = 0; slot[j] = 0xFFFFFFFFu; }
-  }
-  unsigned long long best = 0;
-#pragma unroll
-  for (int j = 0; j < CAND_PER_THREAD; j++) {
-    freq[j] = slot[j] != 0xFFFFFFFFu ? __ldcg(&g.slots[slot[j]].freq) : 0ull;
-    best = max(best, freq[j]);
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) best = max(best, __shfl_down_sync(0xffffffffu, best, d));
-  if ((threadIdx.x & 31) == 0 && best) atomicMax(&scratch[0], best);
-  __syncthreads();
-  const unsigned long long fmax = scratch[0];
-#pragma unroll
-  for (int j = 0; j < CAND_PER_THREAD; j++)
-    if (fmax && freq[j] == fmax) { atomicMin(&scratch[1], key[j]); atomicMax(&scratch[2], key[j]); }
-  __syncthreads();
-  next_key = scratch[1];
-  if (n_raw > lp.cand_cap || fmax < theta || fmax == 0) return LOOP_REBUILD;
-  if (scratch[1] != scratch[2]) return LOOP_TIE;
-  return LOOP_RUN;
-}
-
 __device__ __forceinline__ void fused_tail(const PairTableDev &t, const EmitMode &em, const TailSmem &ts, Rec *__restrict__ out,
                                            size_t out_cap, unsigned long long *__restrict__ out_hdr, unsigned long long *removed,
-                                           unsigned long long seq, unsigned int extra_flags, const LoopDev *lp = nullptr,
-                                           unsigned long long *trace = nullptr) {
+                                           unsigned long long seq, unsigned int extra_flags, unsigned long long *trace = nullptr) {
   const long long tc0 = clock64();
   const unsigned int n = __ldcg(t.n_touched);
   const bool small = n <= em.fused_max;
@@ -516,27 +438,8 @@ __device__ __forceinline__ void fused_tail(const PairTableDev &t, const EmitMode
     gt_account(em.g, ins);
   }
   const long long tc5 = clock64();
-  uint32_t next_status = LOOP_STOP;
-  unsigned long long next_key = 0;
-  if (lp) {  // device-resident loop: choose the next pair (block-wide arg-max over the candidate list)
-    __threadfence();
-    __syncthreads();  // the zeroed frequency of the merged pair and all updates of this block are visible
-    if (small) next_status = loop_pick_next(*lp, em.g, ts.csum, next_key);
-    else next_status = LOOP_BIG_EMIT;
-  }
   if (threadIdx.x == 0) {
     const unsigned int gflag = (em.mode != 0 && __ldcg(em.g.flags)) ? 16u : 0u;  // frequency table past 50 % load
-    if (lp) {
-      LoopState *st = lp->st;
-      if (gflag && next_status == LOOP_RUN) next_status = LOOP_STOP;  // the host must grow the table first
-      out_hdr[16] = em.merged_key;
-      out_hdr[17] = (unsigned long long)(uint32_t)st->new_id | ((unsigned long long)next_status << 32);
-      out_hdr[18] = st->n_cand;
-      out_hdr[19] = out_hdr[16] ^ (out_hdr[17] * HDR_MAGIC) ^ seq;  // check word of the loop fields (see hdr_check)
-      if (next_status == LOOP_RUN) { st->a = (int32_t)(next_key >> 32); st->b = (int32_t)(next_key & 0xFFFFFFFFu); st->new_id = st->new_id + 1; }
-      st->status = next_status;
-      st->done = st->done + 1;
-    }
 #ifdef SWB_KERNEL_TRACE
     unsigned long long tr_emit_done; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_emit_done));
     out_hdr[9] = tr_emit_done; out_hdr[10] = n;
@@ -994,20 +897,7 @@ __device__ __forceinline__ uint32_t scan_merge(const StreamDev &s, const PairTab
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, unsigned long long *removed_total,
            int fused, EmitMode em, Rec *__restrict__ out, size_t out_cap, unsigned long long *__restrict__ out_hdr,
-           unsigned long long seq, LoopDev lp) {
-  if (lp.st) {  // device-resident loop: the pair, the record slot and the sequence number come from the device state
-    if (__ldcg(&lp.st->status) != LOOP_RUN) return;  // control is with the host: this queued launch is a no-op
-    a = __ldcg(&lp.st->a); b = __ldcg(&lp.st->b); new_id = __ldcg(&lp.st->new_id);
-    const unsigned long long done = __ldcg(&lp.st->done);
-    const uint32_t slot = (uint32_t)((lp.seq_base + done) % lp.ring_slots);
-    out = lp.ring + (size_t)slot * lp.slot_recs;
-    out_cap = lp.slot_recs;
-    out_hdr = lp.ring_hdr + (size_t)slot * HDR_WORDS;
-    seq = lp.seq_base + done + 1;
-    em.merged_key = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
-    em.stamp_base = (lp.op_base + done) << 10;
-    em.log.m_cur += (uint32_t)done;
-  }
+           unsigned long long seq) {
   __shared__ __align__(16) int sm[MERGE_WARPS][ROW];
   __shared__ Match ml[MERGE_WARPS][MATCH_CAP];
   __shared__ unsigned int n_match[MERGE_WARPS];
@@ -1045,117 +935,10 @@ merge_rows(StreamDev s, PairTableDev t, int32_t a, int32_t b, int32_t new_id, un
 #ifdef SWB_KERNEL_TRACE
   out_hdr[8] = tr_scan_done;
 #endif
-  fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u, lp.st ? &lp : nullptr);
+  fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, 0u);
 }
 
-// ---------------------------------------------------------------- persistent merge kernel
-// One cooperative launch serves a whole batch of merges: the grid stays resident, the host sends the
-// next pair through a mapped-memory mailbox and gets the records back the same way, so a merge costs one
-// PCIe round trip (~5 us on this box) instead of a kernel launch + completion (~9 us). Per merge: all
-// blocks scan; the last block to finish runs the tail (emit + publish), then polls the mailbox for the
-// next command and releases the other blocks through a device-memory epoch. Every spin has a time-out:
-// if the host goes away the kernel exits instead of hanging the GPU.
-struct HostCmd { unsigned long long seq, pair, new_id_op, check; };      // mapped host memory; op (bit 32 of new_id_op): 1 = stop
-struct DevCmd { unsigned long long epoch, pair, new_id_op, pad; };       // device memory
-__host__ __device__ __forceinline__ unsigned long long cmd_check(unsigned long long seq, unsigned long long pair,
-                                                                 unsigned long long nio) {
-  return (seq * HDR_MAGIC) ^ pair ^ (nio << 7 | nio >> 57);
-}
 __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-
-__global__ void __launch_bounds__(MERGE_THREADS)
-merge_persistent(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *removed_total, Rec *__restrict__ out, size_t out_cap,
-                 unsigned long long *__restrict__ out_hdr, unsigned long long seq_base, unsigned long long op_base,
-                 volatile HostCmd *hcmd, DevCmd *dcmd, int32_t a, int32_t b, int32_t new_id, unsigned long long timeout_ns,
-                 unsigned long long *trace /* nullptr or [16] accumulators (development aid) */) {
-  __shared__ __align__(16) int sm[MERGE_WARPS][ROW];
-  __shared__ Match ml[MERGE_WARPS][MATCH_CAP];
-  __shared__ unsigned int n_match[MERGE_WARPS];
-  __shared__ unsigned long long csum_sh[64];
-  __shared__ __align__(16) Rec stage[STAGE_RECS];
-  __shared__ unsigned int tail_count;
-  __shared__ bool is_last;
-  __shared__ unsigned long long s_pair, s_nio;
-  const int lane = threadIdx.x & 31;
-  const uint32_t log_m_base = em.log.m_cur;
-  unsigned long long tr_released = gtime_ns();  // (thread 0 only) when this block learnt about the current merge
-  long long tr_c0 = clock64();
-  for (unsigned long long k = 0;; k++) {
-    em.log.m_cur = log_m_base + (uint32_t)k;
-    uint32_t removed = scan_merge(s, t, em.log, a, b, new_id, sm, ml, n_match);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) removed += __shfl_down_sync(0xffffffffu, removed, d);
-    if (lane == 0 && removed) atomicAdd(removed_total, (unsigned long long)removed);
-    const long long tr_c1 = clock64();
-    __syncthreads();
-    if (threadIdx.x == 0) {  // (a release by one thread after the barrier covers the whole block's writes)
-      __threadfence();
-      is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (is_last) {
-      __threadfence();
-      const long long tr_c2 = clock64();
-      em.merged_key = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
-      em.stamp_base = (op_base + k) << 10;
-      TailSmem ts{stage, csum_sh, &tail_count};
-      fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq_base + k + 1, 0u, nullptr, trace);
-      if (threadIdx.x == 0) {  // next command from the host
-        const long long tr_c3 = clock64();
-        const unsigned long long want = seq_base + k + 2;
-        const unsigned long long t0 = gtime_ns();
-        unsigned long long pair = 0, nio = 1ull << 32;
-        for (unsigned long long spin = 0;; spin++) {
-          if (hcmd->seq == want) {
-            pair = hcmd->pair; nio = hcmd->new_id_op;
-            if (hcmd->check == cmd_check(want, pair, nio)) break;
-          }
-          if ((spin & 255) == 255 && gtime_ns() - t0 > timeout_ns) { pair = 0; nio = 3ull << 32; break; }  // abort
-        }
-        const unsigned long long t1 = gtime_ns();
-        if (trace) {
-          // [0] merges, [1] cycles scan (this block), [2] cycles sync+fence+count, [3] cycles tail, [4] ns host turnaround
-          // as seen here (publish -> next command), [5] ns from this block's release to its tail's end
-          trace[0] += 1; trace[1] += (unsigned long long)(tr_c1 - tr_c0); trace[2] += (unsigned long long)(tr_c2 - tr_c1);
-          trace[3] += (unsigned long long)(tr_c3 - tr_c2); trace[4] += t1 - t0; trace[5] += t0 - tr_released;
-        }
-        dcmd->pair = pair; dcmd->new_id_op = nio;
-        __threadfence();
-        *(volatile unsigned long long *)&dcmd->epoch = seq_base + k + 2;
-      }
-    }
-    if (threadIdx.x == 0) {  // every block: wait for the release of merge k+1
-      const unsigned long long want = seq_base + k + 2;
-      const unsigned long long t0 = gtime_ns();
-      unsigned long long nio = 0, pair = 0;
-      for (unsigned long long spin = 0;; spin++) {
-        if (*(volatile unsigned long long *)&dcmd->epoch >= want) {
-          __threadfence();
-          pair = *(volatile unsigned long long *)&dcmd->pair; nio = *(volatile unsigned long long *)&dcmd->new_id_op;
-          break;
-        }
-        if ((spin & 255) == 255 && gtime_ns() - t0 > 2 * timeout_ns) { nio = 3ull << 32; break; }
-      }
-      s_pair = pair; s_nio = nio;
-      tr_released = gtime_ns();
-    }
-    __syncthreads();
-    tr_c0 = clock64();
-    if (s_nio >> 32) return;  // stop (1) or abort (3)
-    a = (int32_t)(s_pair >> 32); b = (int32_t)(s_pair & 0xFFFFFFFFu); new_id = (int32_t)(s_nio & 0xFFFFFFFFu);
-    __syncthreads();
-  }
-}
-
-// candidate keys -> frequency-table slots (after the host rebuilt the list)
-__global__ void cand_resolve(GlobalTableDev g, CandEntry *cand, uint32_t n) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned long long k = cand[i].key;
-    uint32_t h = gt_home(g, k);
-    while (g.slots[h].key != k && g.slots[h].key != PT_EMPTY) h = (h + 1) & g.mask;
-    cand[i].slot = h;  // the key exists: the host only lists pairs it received from this table
-  }
-}
 
 // long words: lanes stride over the word to detect; the rare word with a match is rewritten by lane 0
 __global__ void __launch_bounds__(128)

@@ -107,7 +107,7 @@ class TrainerImpl {
   // ---------------------------------------------------------------- device bring-up
   // Per-process, per-device facts (cudaGetDeviceProperties, occupancy and attribute calls take the driver's
   // global lock and cost from 1 to 100+ ms each while other work is in flight): queried once, not per handle.
-  struct DeviceFacts { int sms = 0, coop_blocks_per_sm = 0; bool coop_ok = false; };
+  struct DeviceFacts { int sms = 0; bool coop_ok = false; };
   static const DeviceFacts &device_facts(int device) {
     static std::mutex mu;
     static std::map<int, DeviceFacts> facts;
@@ -119,9 +119,7 @@ class TrainerImpl {
     SWB_CUDA(cudaFuncSetAttribute(wt_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
     int coop = 0;
     SWB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-    SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f.coop_blocks_per_sm, merge_persistent, MERGE_THREADS, 0));
-    f.coop_ok = coop != 0 && f.coop_blocks_per_sm >= 1;
-    f.coop_blocks_per_sm = std::min(f.coop_blocks_per_sm, 4);
+    f.coop_ok = coop != 0;
     return facts.emplace(device, f).first->second;
   }
   void ensure_device() {
@@ -134,7 +132,7 @@ class TrainerImpl {
                   " (this library has no CPU fallback)");
     SWB_CUDA(cudaGetDevice(&device_));
     const DeviceFacts &f = device_facts(device_);
-    sms_ = f.sms; coop_ok_ = f.coop_ok; coop_blocks_per_sm_ = f.coop_blocks_per_sm;
+    sms_ = f.sms; coop_ok_ = f.coop_ok;
     SWB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     SWB_CUDA(cudaEventCreate(&ev0_));
     SWB_CUDA(cudaEventCreate(&ev1_));
@@ -250,6 +248,7 @@ class TrainerImpl {
       wt_fill<<<sms_ * 8, 256, 0, stream_>>>(keys.get(), counts.get(), cap); launched();
       SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
       WordTableDev tbl{keys.get(), counts.get(), cap - 1, d_nuniq, d_flags, (uint64_t)(cap * 0.6)};
+      SWB_CUDA(cudaEventRecord(ev0_, stream_));
       if (n && host_src) {
         const uint64_t PIECE = load_piece_bytes();  // (a multiple of 16: see wt_tokenize)
         if (!copy_stream_) SWB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
@@ -282,8 +281,14 @@ class TrainerImpl {
         host_src = nullptr;  // (a rerun with a larger table finds the corpus on the device)
       } else if (n) { wt_tokenize<<<sms_ * 4, WT_THREADS, WT_SMEM_BYTES, stream_>>>(corpus.get(), n, tbl, 0, n); launched(); }
       SWB_CUDA(cudaGetLastError());
+      SWB_CUDA(cudaEventRecord(ev1_, stream_));
       SWB_CUDA(cudaMemcpyAsync(h_scal, scalars_.get(), sizeof h_scal, cudaMemcpyDeviceToHost, stream_));
       sync();
+      {
+        float tms = 0;
+        SWB_CUDA(cudaEventElapsedTime(&tms, ev0_, ev1_));
+        stats.tokenize_ms = tms; stats.tokenize_bytes = n;
+      }
       if (h_scal[1] & 2u) throw Error("NUL byte in corpus: outside the parity domain (the reference drops a libc-buffer-dependent span)");
       if (!(h_scal[1] & 1u)) break;
       cap *= 8;  // more unique words than expected: bigger table, run again
@@ -616,9 +621,20 @@ class TrainerImpl {
     static const bool forced_host = getenv("SWB_HOST_TABLE") && atoi(getenv("SWB_HOST_TABLE")) > 0;
     return (mnranks() == 1 || mcomm() != nullptr) && !forced_host;
   }
+  // SWB_TEST_SMALL_GT=1 (tests): the frequency table starts just large enough for the counted pairs, so that it passes
+  // 50 % load, stops the resident kernel, grows and is rehashed several times during a small training run.
+  static bool gt_small_for_tests() {
+    static const bool on = getenv("SWB_TEST_SMALL_GT") && atoi(getenv("SWB_TEST_SMALL_GT")) > 0;
+    return on;
+  }
+  uint64_t gt_presize(uint64_t n_pairs) const {
+    if (gt_small_for_tests()) return 2 * n_pairs + 16ull * 260;
+    // sized up front so that growing (alloc + rehash, ~10 ms each) is rare: pairs ever touched ~ O(words)
+    return std::max<uint64_t>(4ull * n_pairs + 16 * (258 + tr_->config.target_vocab_size), 4 * W);
+  }
   void ensure_global_table(uint64_t min_cap) {
     ensure_device();
-    const uint64_t cap = std::max<uint64_t>(1ull << 20, pow2_ceil(min_cap));
+    const uint64_t cap = std::max<uint64_t>(gt_small_for_tests() ? 1ull << 10 : 1ull << 20, pow2_ceil(min_cap));
     if (gt_cap_ >= cap) return;
     if (cap > (1ull << 31)) throw Error("frequency table would exceed 2^31 slots");
     sync();
@@ -629,12 +645,10 @@ class TrainerImpl {
     if (gt_cap_) { gt_rehash<<<sms_ * 8, 256, 0, stream_>>>(gt_, ng); launched(); }
     sync();
     gt_slots_ = std::move(k); gt_scal_ = std::move(scal);
-    cand_valid_ = false;  // the candidate list holds slot indices of the old table
     gt_ = ng;
     gt_cap_ = cap;
   }
   void reset_global_table() {
-    cand_valid_ = false;
     if (!gt_cap_) return;
     gt_clear<<<sms_ * 8, 256, 0, stream_>>>(gt_); launched();
   }
@@ -655,7 +669,6 @@ class TrainerImpl {
     em.neg_unk_bucket = tr_->config.unk_id < 0 ? (int32_t)((uint32_t)tr_->config.unk_id & 1023u) : -1;
     em.g = gt_;
     em.fused_max = 384;  // measured: beyond this a 32-block pt_emit (one more launch) beats the single-block tail
-    if (device_tables_ && cand_valid_) { em.lst = loop_state_.get(); em.cand = cand_.get(); em.cand_cap = CAND_CAP; em.theta = theta_; }
     return em;
   }
   // caller id -> device code (negative ids: unk_id travels as UNK_CODE, the -1 of a sign-extended key as NEG1_CODE)
@@ -736,7 +749,15 @@ class TrainerImpl {
           snprintf(msg, sizeof msg, "merge kernels finished without publishing a valid result (want seq %llu; header seq %llu/%llu n %llu flags %llx removed %llu; "
                    "header check %s; records xor %llx vs %llx, sum %llx vs %llx)", seq, (unsigned long long)h[0], (unsigned long long)h[7], n, fl, rem,
                    h[6] == hdr_check(h[0], n, fl, rem, cx, cs) ? "ok" : "BAD", x, cx, sm, cs);
-          throw Error(msg);
+          std::string full(msg);
+          if (cl_acct_.size() >= 16) {  // did the resident kernel's watchdog give up on the host?
+            unsigned long long ac[16] = {0};
+            if (cudaMemcpy(ac, cl_acct_.get(), sizeof ac, cudaMemcpyDeviceToHost) == cudaSuccess && ac[8]) {
+              snprintf(msg, sizeof msg, "; the resident kernel's watchdog gave up waiting for command %llu after %.1f ms (SWB_HOST_TIMEOUT_MS)", ac[8], (double)ac[9] * 1e-6);
+              full += msg;
+            }
+          }
+          throw Error(full);
         }
       }
       else if (e != cudaErrorNotReady) SWB_CUDA(e);
@@ -894,7 +915,7 @@ class TrainerImpl {
           unsigned int n_pairs = 0;
           SWB_CUDA(cudaMemcpyAsync(&n_pairs, pt_.n_touched, 4, cudaMemcpyDeviceToHost, stream_));
           sync();
-          ensure_global_table(std::max<uint64_t>(4ull * n_pairs * nranks + 16 * (258 + tr_->config.target_vocab_size), 4 * W));
+          ensure_global_table(gt_presize((uint64_t)n_pairs * nranks));
         }
         EmitMode em = emit_mode(mode, 0, 0);
         n = exchange_and_reduce(em, &flags, nullptr);
@@ -920,8 +941,7 @@ class TrainerImpl {
           unsigned int n_pairs = 0;
           SWB_CUDA(cudaMemcpyAsync(&n_pairs, pt_.n_touched, 4, cudaMemcpyDeviceToHost, stream_));
           sync();
-          // sized up front so that growing (alloc + rehash, ~10 ms each) is rare: pairs ever touched ~ O(words)
-          ensure_global_table(std::max<uint64_t>(4ull * n_pairs + 16 * (258 + tr_->config.target_vocab_size), 4 * W));
+          ensure_global_table(gt_presize(n_pairs));
         }
         EmitMode em = emit_mode(mode, 0, 0);
         n = emit_and_wait(em, &flags, nullptr);
@@ -967,10 +987,8 @@ class TrainerImpl {
       const uint64_t warps_needed = (n_rows_ + 31) / 32;  // one warp tests 32 row signatures per iteration
       const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 4, (warps_needed + MERGE_WARPS - 1) / MERGE_WARPS);
       if (fused) seq = ++seq_;
-      LoopDev no_loop;
-      memset(&no_loop, 0, sizeof no_loop);
       merge_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, da, db, new_id, removed_.get(), fused ? 1 : 0, em, recs_.dev(),
-                                                      recs_.size(), hdr_.dev(), seq, no_loop);
+                                                      recs_.size(), hdr_.dev(), seq);
       launched();
       stats.merge_launches++;
     }
@@ -1036,6 +1054,7 @@ class TrainerImpl {
 
   // ---------------------------------------------------------------- single-process drivers
   void count_bigrams() {  // reference bpe_count_bigrams
+    check_not_failed();
     size_t n = 0;
     if (tables_fresh_ && want_device_tables() && loaded_) {
       // fresh pair table (right after a load or a reset): the device keeps the frequencies from here on
@@ -1067,265 +1086,13 @@ class TrainerImpl {
     reset_tables();
     count_bigrams();
   }
-  // ---------------------------------------------------------------- device-resident merge loop
-  static constexpr uint32_t CAND_CAP = 4096, RING_SLOTS = 32;
-  uint32_t max_ahead_ = getenv("SWB_MAX_AHEAD") ? (uint32_t)atoi(getenv("SWB_MAX_AHEAD")) : 4;
-  bool use_device_loop() const {
-    // Experimental, off by default (SWB_DEVICE_LOOP=1): correct (the host validates every choice) but on the
-    // bench corpus a quarter of the merges tie at the maximum and hand control back, and the arg-max tail
-    // lengthens every kernel, so it does not beat the synchronous loop yet.
-    static const bool on = getenv("SWB_DEVICE_LOOP") && atoi(getenv("SWB_DEVICE_LOOP")) > 0;
-    return on && device_tables_ && !mcomm() && !timing && loaded_ && n_rows_ > 0 && n_long_ == 0;
-  }
-  void ensure_loop_buffers() {
-    if (loop_state_.size()) return;
-    loop_state_.alloc(1); cand_.alloc(CAND_CAP);
-    ring_.alloc((size_t)RING_SLOTS * FUSED_EMIT_MAX);  // a slot takes every record a single-block tail can produce
-    ring_hdr_.alloc((size_t)RING_SLOTS * HDR_WORDS);
-    memset(ring_hdr_.host(), 0, (size_t)RING_SLOTS * HDR_WORDS * 8);
-  }
-  // Candidate list = every pair with frequency >= theta, taken from the host's exact table (which holds
-  // every pair >= min_pair_freq in device-table mode). theta is chosen so that about half the list is used.
-  void rebuild_candidates() {
-    std::vector<PairInfo> v;
-    core.pairs_at_or_above_min(v);
-    std::sort(v.begin(), v.end(), [](const PairInfo &x, const PairInfo &y) { return x.freq > y.freq; });
-    size_t k = std::min<size_t>(v.size(), CAND_CAP / 2);
-    theta_ = tr_->config.min_pair_freq;
-    if (k < v.size()) {  // cut where the frequency changes, so that every pair >= theta is inside
-      uint64_t f = v[k - 1].freq;
-      size_t hi = k;
-      while (hi < v.size() && v[hi].freq == f) hi++;
-      if (hi <= CAND_CAP - 512) { k = hi; theta_ = f; }
-      else { while (k > 0 && v[k - 1].freq == f) k--; theta_ = f + 1; }
-    }
-    std::vector<CandEntry> h(k);
-    for (size_t i = 0; i < k; i++) {
-      const int32_t a = to_dev(v[i].first), b = to_dev(v[i].second);
-      h[i] = CandEntry{((unsigned long long)(uint32_t)a << 32) | (uint32_t)b, 0u, 0u};
-    }
-    n_cand_host_ = (uint32_t)k;
-    if (k) {
-      SWB_CUDA(cudaMemcpyAsync(cand_.get(), h.data(), k * sizeof(CandEntry), cudaMemcpyHostToDevice, stream_));
-      cand_resolve<<<std::min<uint32_t>(sms_, (uint32_t)(k + 255) / 256), 256, 0, stream_>>>(gt_, cand_.get(), (uint32_t)k); launched();
-      sync();  // h goes out of scope
-    }
-    cand_valid_ = true;
-    stats.repacks++;  // (counter reused: candidate-list rebuilds)
-  }
-  // Runs merges on the device starting with (a, b) -- already popped from the host heap and pending in
-  // `core` -- for as long as the device can choose the next pair itself (at most max_merges).
-  // Every merge is replayed on the host from the record ring. Returns the number of merges performed.
-  int run_device_loop(int32_t a, int32_t b, int32_t new_id, int max_merges) {
-    ensure_loop_buffers();
-    stats.loop_runs++;
-    ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
-    maybe_grow_global_table(gt_flagged_);
-    gt_flagged_ = false;
-    if (!cand_valid_) rebuild_candidates();
-    const int32_t unk = tr_->config.unk_id;
-    LoopState st;
-    memset(&st, 0, sizeof st);
-    st.a = to_dev(a); st.b = to_dev(b); st.new_id = new_id; st.status = LOOP_RUN; st.done = 0; st.theta = theta_; st.n_cand = n_cand_host_;
-    SWB_CUDA(cudaMemcpyAsync(loop_state_.get(), &st, sizeof st, cudaMemcpyHostToDevice, stream_));
-    LoopDev lp;
-    lp.st = loop_state_.get(); lp.cand = cand_.get(); lp.cand_cap = CAND_CAP;
-    lp.ring = ring_.dev(); lp.ring_hdr = ring_hdr_.dev(); lp.ring_slots = RING_SLOTS; lp.slot_recs = FUSED_EMIT_MAX;
-    lp.seq_base = seq_; lp.op_base = op_index_ + 1;
-    EmitMode em = emit_mode(1, 0, 0);
-    em.log = birth_log(new_id, (uint32_t)max_merges + 1);
-    em.fused_max = FUSED_EMIT_MAX;  // here a stop costs a relaunch: let the tail take everything a ring slot holds
-    pt_.canon_on = unk < 0 ? 1 : 0;
-    pt_.canon_first = unk == -1 ? UNK_CODE : NEG1_CODE;
-    pt_.gpf.slots = (void *)gt_.slots; pt_.gpf.mask = gt_.mask;
-    StreamDev s = stream_dev();
-    const uint64_t warps_needed = (n_rows_ + 31) / 32;
-    const int grid = (int)std::min<uint64_t>((uint64_t)sms_ * 4, (warps_needed + MERGE_WARPS - 1) / MERGE_WARPS);
-    const unsigned long long seq_base = seq_;
-    int launched_n = 0, consumed = 0;
-    bool stopped = false;
-    while (!stopped) {
-      while (launched_n < max_merges && launched_n - consumed < (int)max_ahead_) {
-        merge_rows<<<grid, MERGE_THREADS, 0, stream_>>>(s, pt_, 0, 0, 0, removed_.get(), 1, em, nullptr, 0, nullptr, 0ull, lp);
-        launched(); stats.merge_launches++;
-        launched_n++;
-      }
-      if (consumed == launched_n) break;
-      const uint32_t slot = (uint32_t)((seq_base + consumed) % RING_SLOTS);
-      volatile unsigned long long *h = ring_hdr_.host() + (size_t)slot * HDR_WORDS;
-      Rec *recs = ring_.host() + (size_t)slot * FUSED_EMIT_MAX;
-      const double tw0 = now_ms();
-      wait_seq_at(seq_base + consumed + 1, h, recs, FUSED_EMIT_MAX);
-      stats.host_wait_ms += now_ms() - tw0;
-      for (uint64_t spin = 0; h[19] != (h[16] ^ (h[17] * HDR_MAGIC) ^ (seq_base + consumed + 1)); spin++)  // loop fields still in flight
-        if (spin > (1ull << 28)) throw Error("device-resident loop: header never became consistent");
-      const unsigned long long n = h[1], flags = h[2], removed = h[3], pair = h[16];
-      const uint32_t status_after = (uint32_t)(h[17] >> 32);
-      if (consumed > 0) {  // the device chose this pair itself: the exact heap must agree
-        int32_t ha, hb, hn;
-        const double tp0 = now_ms();
-        if (!core.next_merge(&ha, &hb, &hn)) throw Error("device-resident loop ran a merge the host heap does not have");
-        stats.host_pop_ms += now_ms() - tp0;
-        const unsigned long long hk = ((unsigned long long)(uint32_t)to_dev(ha) << 32) | (uint32_t)to_dev(hb);
-        if (hk != pair || (uint32_t)hn != (uint32_t)(h[17] & 0xFFFFFFFFu))
-          throw Error("device-resident loop and host heap disagree on the next pair (internal error)");
-      }
-      // (flag 4 together with 8 only says that the list did not fit the ring slot: handled below)
-      if ((flags & 1u) || ((flags & 4u) && !(flags & 8u))) throw Error("pair table overflow during a merge (internal sizing error)");
-      op_index_++;
-      seq_ = seq_base + consumed + 1;
-      stats.merge_scan_bytes += n_rows_ * ROW * 4;
-      stats.merge_alg_bytes += 4 * live_symbols_ + 8 * W;
-      const double ta0 = now_ms();
-      if (flags & 8u) {  // too many records for the ring slot: finish this merge with the full-grid emit
-        // (the launches still queued are no-ops -- the device set its status before publishing -- and the
-        //  stream orders them before everything issued from here on: no need to wait for them)
-        unsigned int fl2 = 0;
-        uint64_t rem2 = 0;
-        EmitMode em2 = emit_mode(1, (int32_t)(pair >> 32), (int32_t)(pair & 0xFFFFFFFFu));
-        em2.log = em.log; em2.log.m_cur = stream_merges_;
-        t_launch0_ = now_ms();
-        const size_t n2 = emit_and_wait(em2, &fl2, &rem2);
-        if (fl2 & 5u) throw Error("pair table overflow during a merge (internal sizing error)");
-        if (fl2 & 16u) gt_flagged_ = true;
-        live_symbols_ -= rem2;
-        translate_out(recs_.host(), n2);
-        core.apply_absolute(recs_.host(), n2);
-        stopped = true;
-        stats.loop_stop_big++;
-      } else {
-        live_symbols_ -= removed;
-        translate_out(recs, (size_t)n);
-        core.apply_absolute(recs, (size_t)n);
-        if (flags & 16u) gt_flagged_ = true;
-        if (status_after != LOOP_RUN) {
-          stopped = true;
-          if (status_after == LOOP_REBUILD) { cand_valid_ = false; stats.loop_stop_rebuild++; }
-          else if (status_after == LOOP_TIE) stats.loop_stop_tie++;
-          else stats.loop_stop_other++;
-        }
-      }
-      stats.host_apply_ms += now_ms() - ta0;
-      stats.live_symbols = live_symbols_;
-      if ((flags & 32u)) throw Error("birth log overflow (internal sizing error)");
-      merge_done_on_stream((flags & 8u) ? hdr_.host()[2] : flags);
-      consumed++;
-      if (consumed == max_merges) break;
-    }
-    // after a stop the device counts its candidates itself; keep the host's idea of the list length in step
-    if (consumed) {
-      LoopState back;
-      SWB_CUDA(cudaMemcpyAsync(&back, loop_state_.get(), sizeof back, cudaMemcpyDeviceToHost, stream_));
-      sync();
-      n_cand_host_ = std::min<uint32_t>(back.n_cand, CAND_CAP);
-      if (back.n_cand > CAND_CAP) cand_valid_ = false;
-    }
-    return consumed;
-  }
-
-  // ---------------------------------------------------------------- persistent merge kernel (default single-GPU path)
+  // ---------------------------------------------------------------- when the resident kernel can serve the merges
+  // (SWB_NO_PERSISTENT=1: one merge_rows launch per merge instead -- the path the sharded multi-GPU loop, long words
+  // and kernel timing use anyway; tests/test_gpu_variants.py runs the parity suite over it)
   bool use_persistent() const {
     static const bool off = getenv("SWB_NO_PERSISTENT") && atoi(getenv("SWB_NO_PERSISTENT")) > 0;
     return !off && device_tables_ && !mcomm() && !timing && loaded_ && n_rows_ > 0 && n_long_ == 0 && coop_ok_;
   }
-  struct HostCmdSender {  // makes sure the resident kernel is always told to stop, also when an exception unwinds
-    volatile HostCmd *c = nullptr;
-    unsigned long long next_seq = 0;
-    bool running = false;
-    void send(unsigned long long pair, unsigned long long nio) {
-      c->pair = pair; c->new_id_op = nio; c->check = cmd_check(next_seq, pair, nio);
-      __atomic_thread_fence(__ATOMIC_RELEASE);
-      c->seq = next_seq;
-      __atomic_thread_fence(__ATOMIC_SEQ_CST);
-    }
-    ~HostCmdSender() { if (running) send(0, 1ull << 32); }
-  };
-  // Runs up to max_merges merges starting with (a, b) (already popped, pending in `core`) inside ONE
-  // cooperative launch. Returns the number performed; stops early when the heap is exhausted or a table
-  // has to grow.
-  int run_persistent(int32_t a, int32_t b, int32_t new_id, int max_merges) {
-    ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
-    maybe_grow_global_table(gt_flagged_);
-    gt_flagged_ = false;
-    if (!hcmd_.size()) { hcmd_.alloc(1); dcmd_.alloc(1); }
-    memset((void *)hcmd_.host(), 0, sizeof(HostCmd));
-    SWB_CUDA(cudaMemsetAsync(dcmd_.get(), 0, sizeof(DevCmd), stream_));
-    const int32_t unk = tr_->config.unk_id;
-    EmitMode em = emit_mode(1, 0, 0);
-    em.log = birth_log(new_id, (uint32_t)max_merges + 1);
-    em.fused_max = 0xFFFFFFFFu;  // the resident kernel's tail takes every merge, whatever its size
-    pt_.canon_on = unk < 0 ? 1 : 0;
-    pt_.canon_first = unk == -1 ? UNK_CODE : NEG1_CODE;
-    pt_.gpf.slots = (void *)gt_.slots; pt_.gpf.mask = gt_.mask;
-    StreamDev s = stream_dev();
-    const uint64_t warps_needed = (n_rows_ + 31) / 32;
-    int grid = (int)std::min<uint64_t>((uint64_t)sms_ * coop_blocks_per_sm_, (warps_needed + MERGE_WARPS - 1) / MERGE_WARPS);
-    grid = std::max(grid, 1);
-    const unsigned long long seq_base = seq_, op_base = op_index_ + 1;
-    unsigned long long *removed_p = removed_.get();
-    Rec *out = recs_.dev();
-    size_t out_cap = recs_.size();
-    unsigned long long *out_hdr = hdr_.dev();
-    volatile HostCmd *hc = hcmd_.dev();
-    DevCmd *dc = dcmd_.get();
-    int32_t da = to_dev(a), db = to_dev(b);
-    unsigned long long timeout_ns = 2000000000ull;
-    unsigned long long *trace_p = nullptr;
-    if (trace_wait_) {
-      if (!ptrace_.size()) { ptrace_.alloc(32); SWB_CUDA(cudaMemsetAsync(ptrace_.get(), 0, ptrace_.bytes(), stream_)); }
-      trace_p = ptrace_.get();
-    }
-    void *args[] = {&s, &pt_, &em, &removed_p, &out, &out_cap, &out_hdr, (void *)&seq_base, (void *)&op_base, &hc, &dc, &da, &db, &new_id, &timeout_ns, &trace_p};
-    SWB_CUDA(cudaLaunchCooperativeKernel((const void *)merge_persistent, dim3(grid), dim3(MERGE_THREADS), args, 0, stream_));
-    launched(); stats.merge_launches++;
-    HostCmdSender sender;
-    sender.c = hcmd_.host(); sender.running = true;
-    sender.next_seq = seq_base + 2;  // the command that follows the first merge
-    int done = 0;
-    for (;;) {
-      const double tw0 = now_ms();
-      wait_seq_at(seq_base + done + 1, hdr_.host(), recs_.host(), recs_.size());
-      const double tw1 = now_ms();
-      stats.host_wait_ms += tw1 - tw0;
-      const size_t n = (size_t)hdr_.host()[1];
-      const unsigned int flags = (unsigned int)hdr_.host()[2];
-      const uint64_t removed = hdr_.host()[3];
-      if (flags & 5u) throw Error("pair table overflow during a merge (internal sizing error)");
-      if (flags & 32u) throw Error("birth log overflow (internal sizing error)");
-      if (flags & 16u) gt_flagged_ = true;
-      op_index_++;
-      merge_done_on_stream(hdr_.host()[2]);
-      seq_ = seq_base + done + 1;
-      stats.merge_scan_bytes += n_rows_ * ROW * 4;
-      stats.merge_alg_bytes += 4 * live_symbols_ + 8 * W;
-      live_symbols_ -= removed;
-      stats.live_symbols = live_symbols_;
-      translate_out(recs_.host(), n);
-      core.apply_absolute(recs_.host(), n);
-      const double ta1 = now_ms();
-      stats.host_apply_ms += ta1 - tw1;
-      done++;
-      bool go = done < max_merges && !gt_flagged_;
-      int32_t na = 0, nb = 0, nn = 0;
-      if (go) { go = core.next_merge(&na, &nb, &nn); stats.host_pop_ms += now_ms() - ta1; }
-      sender.next_seq = seq_base + done + 1;
-      if (!go) { sender.send(0, 1ull << 32); sender.running = false; break; }
-      sender.send(((unsigned long long)(uint32_t)to_dev(na) << 32) | (uint32_t)to_dev(nb), (unsigned long long)(uint32_t)nn);
-    }
-    sync();
-    if (trace_p) {
-      unsigned long long h[16];
-      SWB_CUDA(cudaMemcpy(h, trace_p, sizeof h, cudaMemcpyDeviceToHost));
-      const double n = (double)std::max<unsigned long long>(h[0], 1), ghz = 1.965;
-      fprintf(stderr, "[trace] resident kernel, per merge (%llu merges): scan %.2f us, sync+fence+count %.2f us, tail %.2f us | release->tail end %.2f us, "
-              "host turnaround seen by the GPU %.2f us\n", h[0], h[1] / n / ghz / 1e3, h[2] / n / ghz / 1e3, h[3] / n / ghz / 1e3,
-              h[5] / n / 1e3, h[4] / n / 1e3);
-      fprintf(stderr, "[trace]   tail split (us): read count %.2f, emit range %.2f, checksum+sync %.2f, copy to host %.2f, merged-pair upsert %.2f, publish %.2f; touched pairs %.1f\n",
-              h[9] / n / ghz / 1e3, h[10] / n / ghz / 1e3, h[11] / n / ghz / 1e3, h[12] / n / ghz / 1e3, h[13] / n / ghz / 1e3, h[14] / n / ghz / 1e3, h[15] / n);
-    }
-    return done;
-  }
-
   // ---------------------------------------------------------------- resident cluster kernel (default single-GPU path)
   struct ClusterFacts { int clusters = 0; bool ok = false, cooperative = false; };
   static const ClusterFacts &cluster_facts(int device) {
@@ -1352,9 +1119,20 @@ class TrainerImpl {
     if (getenv("SWB_TRACE_INIT")) fprintf(stderr, "[trace] cluster kernel: %d resident clusters of %d CTAs, %zu bytes of shared memory each\n", f.clusters, CL_SIZE, CL_SMEM_BYTES);
     return facts.emplace(device, f).first->second;
   }
+  // Device-side watchdog of the resident kernel: how long its leader waits for the next command before it gives up
+  // (a host thread that died without telling it to stop). It is NOT a latency bound: a host thread that is descheduled
+  // for seconds (eight busy ranks on one box, a debugger, paging) must not lose the kernel, so the default is generous;
+  // an exception on the host side stops the kernel explicitly (HostCmd2Sender's destructor).
+  static unsigned long long host_timeout_ns() {
+    static const unsigned long long v = [] {
+      const char *e = getenv("SWB_HOST_TIMEOUT_MS");
+      const unsigned long long ms = e ? strtoull(e, nullptr, 10) : 0;
+      return (ms ? ms : 60000ull) * 1000000ull;
+    }();
+    return v;
+  }
   bool use_resident() const {
-    static const bool off = getenv("SWB_NO_CLUSTER") && atoi(getenv("SWB_NO_CLUSTER")) > 0;
-    return !off && use_persistent() && cluster_facts(device_).ok;
+    return use_persistent() && cluster_facts(device_).ok;
   }
   struct HostCmd2Sender {  // makes sure the resident kernel is always told to stop, also when an exception unwinds
     volatile HostCmd2 *c = nullptr;
@@ -1376,13 +1154,120 @@ class TrainerImpl {
     }
     ~HostCmd2Sender() { if (running) send(0, 0, 1); }
   };
+  // Limits of the resident kernel's fast paths; the SWB_TEST_* variables only ever SHRINK them (tests/test_gpu_variants.py
+  // drives the overflow paths on small corpora with them).
+  static ClusterTune cluster_tune() {
+    static const ClusterTune t = [] {
+      ClusterTune c = cluster_tune_default();
+      auto shrink = [](const char *name, unsigned int &v) {
+        const char *e = getenv(name);
+        if (e && *e) { const unsigned long x = strtoul(e, nullptr, 10); if (x < v) v = (unsigned int)x; }
+      };
+      shrink("SWB_TEST_LOCAL_MAX", c.local_max); shrink("SWB_TEST_CAND_CAP", c.cand_cap); shrink("SWB_TEST_INBOX", c.inbox_cap);
+      shrink("SWB_TEST_REC_STAGE", c.rec_stage); shrink("SWB_TEST_BIRTH_STAGE", c.birth_stage); shrink("SWB_TEST_MAX_PROBES", c.max_probes);
+      if (c.max_probes < 1) c.max_probes = 1;
+      return c;
+    }();
+    return t;
+  }
+  // One launch of the resident kernel: clusters of CL_SIZE CTAs, co-resident (cooperative attribute where available: GRID
+  // merges spin on a grid-wide counter), the symbol rows pinned in L2 for the duration of the launch.
+  void launch_merge_cluster(const StreamDev &s, const EmitMode &em, unsigned long long *removed_p, Rec *out0, Rec *out1, size_t out_cap,
+                            unsigned long long *out_hdr0, unsigned long long *out_hdr1, unsigned long long seq_base, unsigned long long op_base,
+                            volatile HostCmd2 *hc, DevCmd2 *dc, unsigned long long timeout_ns, unsigned long long *trace_p,
+                            const HostCmd2 *script, unsigned long long script_n) {
+    const ClusterFacts &cf = cluster_facts(device_);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(cf.clusters * CL_SIZE)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES; cfg.stream = stream_;
+    cudaLaunchAttribute at[3];
+    int n_at = 0;
+    at[n_at].id = cudaLaunchAttributeClusterDimension;
+    at[n_at].val.clusterDim.x = CL_SIZE; at[n_at].val.clusterDim.y = 1; at[n_at].val.clusterDim.z = 1;
+    n_at++;
+    if (cf.cooperative) { at[n_at].id = cudaLaunchAttributeCooperative; at[n_at].val.cooperative = 1; n_at++; }
+    {  // keep the symbol rows resident in L2 across the merges of this launch (the birth log streams through it)
+      static const bool no_persist = getenv("SWB_NO_L2_PERSIST") && atoi(getenv("SWB_NO_L2_PERSIST")) > 0;
+      int max_persist = 0, max_window = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device_);
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device_);
+      const size_t want = n_rows_ * (size_t)ROW * 4;
+      if (!no_persist && max_persist > 0 && max_window > 0 && want > 0) {
+        const size_t persist = std::min<size_t>((size_t)max_persist, want);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+          const size_t win = std::min<size_t>(want, (size_t)max_window);
+          at[n_at].id = cudaLaunchAttributeAccessPolicyWindow;
+          at[n_at].val.accessPolicyWindow.base_ptr = (void *)rows_.get();
+          at[n_at].val.accessPolicyWindow.num_bytes = win;
+          at[n_at].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)win);
+          at[n_at].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+          at[n_at].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+          n_at++;
+        }
+        cudaGetLastError();
+      }
+    }
+    cfg.attrs = at; cfg.numAttrs = n_at;
+    SWB_CUDA(cudaLaunchKernelEx(&cfg, merge_cluster, s, pt_, em, removed_p, out0, out1, out_cap, out_hdr0, out_hdr1, seq_base, op_base, hc, dc, timeout_ns, trace_p, cl_ovf_.get(), script, script_n, cluster_tune(), cl_acct_.get()));
+    SWB_CUDA(cudaGetLastError());
+  }
+  // Profiling aid (swb_profile_scripted_merges): runs the first n merges of `triples` -- a merge list this same corpus
+  // produced before -- inside ONE launch of merge_cluster whose commands come from a script in device memory instead of the
+  // mailbox. The kernel then never waits for the host, so (a) ncu's kernel replay can capture it (the product launch cannot be
+  // replayed: its commands depend on a host that has moved on) and (b) its duration is the device-side floor of the merge loop.
+  // Must follow init()/count_bigrams() on a freshly loaded corpus. The host's heap replica does not follow: the handle is
+  // consumed (marked failed) afterwards. Returns the kernel's duration in ms (CUDA events on the launch stream).
+  double profile_scripted(const int32_t *triples, size_t n) {
+    check_not_failed();
+    if (!use_resident() || tr_->num_merges != 0) throw Error("profile_scripted needs a freshly counted single-GPU corpus without long words");
+    if (tr_->config.unk_id < 0) throw Error("profile_scripted: negative unk_id is not supported");
+    ensure_pair_table(8ull * (258ull + n + 2));
+    ensure_global_table(std::max<uint64_t>(gt_cap_ * 4, 16ull * (258ull + n + 2)));  // (the script cannot stop to let the table grow)
+    if (!hcmd2_.size()) { hcmd2_.alloc(4); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(16); }
+    if (recs_b_.size() != recs_.size()) recs_b_.alloc(recs_.size());
+    if (!hdr_b_.size()) hdr_b_.alloc(HDR_WORDS);
+    SWB_CUDA(cudaMemsetAsync(cl_acct_.get(), 0, cl_acct_.bytes(), stream_));
+    memset((void *)hcmd2_.host(), 0, 4 * sizeof(HostCmd2));
+    SWB_CUDA(cudaMemsetAsync(dcmd2_.get(), 0, sizeof(DevCmd2), stream_));
+    EmitMode em = emit_mode(1, 0, 0);
+    em.log = birth_log(256, (uint32_t)n + 1);
+    em.fused_max = 0xFFFFFFFFu;
+    pt_.canon_on = 0; pt_.canon_first = NEG1_CODE;
+    pt_.gpf.slots = (void *)gt_.slots; pt_.gpf.mask = gt_.mask;
+    const unsigned long long seq_base = seq_, op_base = op_index_ + 1;
+    std::vector<HostCmd2> h(n);
+    for (size_t m = 0; m < n; m++) {
+      HostCmd2 c;
+      c.x = (unsigned int)triples[3 * m + 1]; c.y = (unsigned int)triples[3 * m]; c.z = (unsigned int)triples[3 * m + 2] & 0x0FFFFFFFu;
+      c.w = cmd3_word(seq_base + m + 1, c.x, c.y, c.z);
+      h[m] = c;
+    }
+    DevBuf<HostCmd2> script(n ? n : 1);
+    if (n) SWB_CUDA(cudaMemcpyAsync(script.get(), h.data(), n * sizeof(HostCmd2), cudaMemcpyHostToDevice, stream_));
+    failed_ = "consumed by swb_profile_scripted_merges (the heap replica did not follow the device)";
+    SWB_CUDA(cudaEventRecord(ev0_, stream_));
+    launch_merge_cluster(stream_dev(), em, removed_.get(), recs_.dev(), recs_b_.dev(), recs_.size(), hdr_.dev(), hdr_b_.dev(), seq_base, op_base,
+                         hcmd2_.dev(), dcmd2_.get(), host_timeout_ns(), nullptr, script.get(), n);
+    launched(); stats.merge_launches++;
+    SWB_CUDA(cudaEventRecord(ev1_, stream_));
+    sync();
+    float ms = 0;
+    SWB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    unsigned long long ac[16];
+    SWB_CUDA(cudaMemcpy(ac, cl_acct_.get(), sizeof ac, cudaMemcpyDeviceToHost));
+    stats.resident_local_merges += ac[0]; stats.resident_local_ms += (double)ac[1] * 1e-6;
+    stats.resident_grid_merges += ac[2]; stats.resident_grid_ms += (double)ac[3] * 1e-6;
+    stats.merge_kernel_ms += (double)(ac[1] + ac[3]) * 1e-6;
+    if (ac[0] + ac[2] != n) throw Error("profile_scripted: the kernel performed " + std::to_string(ac[0] + ac[2]) + " of " + std::to_string(n) + " merges");
+    return (double)ms;
+  }
   // Runs up to max_merges merges starting with (a, b) (already popped, pending in `core`) inside ONE launch of
   // merge_cluster. Returns the number performed; stops early when the heap is exhausted or a table has to grow.
   int run_resident(int32_t a, int32_t b, int32_t new_id, int max_merges) {
     ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
     maybe_grow_global_table(gt_flagged_);
     gt_flagged_ = false;
-    if (!hcmd2_.size()) { hcmd2_.alloc(4); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(8); }
+    if (!hcmd2_.size()) { hcmd2_.alloc(4); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(16); }
     if (recs_b_.size() != recs_.size()) recs_b_.alloc(recs_.size());  // second record buffer + header: merges started from a hint
     if (!hdr_b_.size()) hdr_b_.alloc(HDR_WORDS);
     memset(hdr_b_.host(), 0, HDR_WORDS * sizeof(unsigned long long));
@@ -1397,7 +1282,6 @@ class TrainerImpl {
     pt_.canon_first = unk == -1 ? UNK_CODE : NEG1_CODE;
     pt_.gpf.slots = (void *)gt_.slots; pt_.gpf.mask = gt_.mask;
     StreamDev s = stream_dev();
-    const ClusterFacts &cf = cluster_facts(device_);
     const unsigned long long seq_base = seq_, op_base = op_index_ + 1;
     unsigned long long *removed_p = removed_.get();
     // results of the merge with sequence number q travel through buffer q & 1
@@ -1406,7 +1290,7 @@ class TrainerImpl {
     unsigned long long *out_hdr0 = hdr_.dev(), *out_hdr1 = hdr_b_.dev();
     volatile HostCmd2 *hc = hcmd2_.dev();
     DevCmd2 *dc = dcmd2_.get();
-    unsigned long long timeout_ns = 2000000000ull;
+    const unsigned long long timeout_ns = host_timeout_ns();
     static const bool no_hints = getenv("SWB_NO_HINTS") && atoi(getenv("SWB_NO_HINTS")) > 0;
     const bool hints = !no_hints && unk >= 0;  // (a negative unk_id canonicalises pairs on the device: no look-ahead there)
     constexpr unsigned long long NO_HINT = ~0ull;
@@ -1448,39 +1332,7 @@ class TrainerImpl {
     sender.next_seq = seq_base + 1;  // the first merge travels through the mailbox like all the others
     int32_t da = to_dev(a), db = to_dev(b);
     sender.send(((unsigned long long)(uint32_t)da << 32) | (uint32_t)db, (unsigned int)new_id, 0);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)(cf.clusters * CL_SIZE)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES; cfg.stream = stream_;
-    cudaLaunchAttribute at[3];
-    int n_at = 0;
-    at[n_at].id = cudaLaunchAttributeClusterDimension;
-    at[n_at].val.clusterDim.x = CL_SIZE; at[n_at].val.clusterDim.y = 1; at[n_at].val.clusterDim.z = 1;
-    n_at++;
-    if (cf.cooperative) { at[n_at].id = cudaLaunchAttributeCooperative; at[n_at].val.cooperative = 1; n_at++; }
-    {  // keep the symbol rows resident in L2 across the merges of this launch (the birth log streams through it)
-      static const bool no_persist = getenv("SWB_NO_L2_PERSIST") && atoi(getenv("SWB_NO_L2_PERSIST")) > 0;
-      int max_persist = 0, max_window = 0;
-      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device_);
-      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device_);
-      const size_t want = n_rows_ * (size_t)ROW * 4;
-      if (!no_persist && max_persist > 0 && max_window > 0 && want > 0) {
-        const size_t persist = std::min<size_t>((size_t)max_persist, want);
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
-          const size_t win = std::min<size_t>(want, (size_t)max_window);
-          at[n_at].id = cudaLaunchAttributeAccessPolicyWindow;
-          at[n_at].val.accessPolicyWindow.base_ptr = (void *)rows_.get();
-          at[n_at].val.accessPolicyWindow.num_bytes = win;
-          at[n_at].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)win);
-          at[n_at].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-          at[n_at].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-          n_at++;
-        }
-        cudaGetLastError();
-      }
-    }
-    cfg.attrs = at; cfg.numAttrs = n_at;
-    SWB_CUDA(cudaLaunchKernelEx(&cfg, merge_cluster, s, pt_, em, removed_p, out0, out1, out_cap, out_hdr0, out_hdr1, seq_base, op_base, hc, dc, timeout_ns, trace_p, cl_ovf_.get(), cl_acct_.get()));
-    SWB_CUDA(cudaGetLastError());
+    launch_merge_cluster(s, em, removed_p, out0, out1, out_cap, out_hdr0, out_hdr1, seq_base, op_base, hc, dc, timeout_ns, trace_p, nullptr, 0);
     launched(); stats.merge_launches++;
     sender.running = true;
     int done = 0;
@@ -1581,7 +1433,24 @@ class TrainerImpl {
     return done;
   }
 
+  // A device-side failure in the middle of a merge leaves the symbol stream, the frequency table and the heap replica
+  // out of step: the handle is marked failed (every later compute call reports the first error again), and the merge
+  // that was announced but not applied is taken off the merge list, so num_merges / merge_ops / bpe_save stay consistent.
+  std::string failed_;
+  void check_not_failed() const {
+    if (!failed_.empty()) throw Error("this trainer failed earlier and cannot continue (destroy it): " + failed_);
+  }
   int merge_batch(int batch) {  // reference bpe_merge_batch
+    check_not_failed();
+    try {
+      return merge_batch_unguarded(batch);
+    } catch (const std::exception &e) {
+      core.abort_pending();
+      failed_ = e.what();
+      throw;
+    }
+  }
+  int merge_batch_unguarded(int batch) {
     const double t0 = now_ms();
     int done = 0;
     if (use_resident()) {
@@ -1592,30 +1461,6 @@ class TrainerImpl {
         stats.host_pop_ms += now_ms() - tp0;
         tables_fresh_ = false;
         done += run_resident(a, b, nid, batch - done);
-      }
-      stats.merge_ms += now_ms() - t0;
-      return done;
-    }
-    if (use_persistent()) {
-      while (done < batch && !core.heap_empty()) {
-        int32_t a, b, nid;
-        const double tp0 = now_ms();
-        if (!core.next_merge(&a, &b, &nid)) break;
-        stats.host_pop_ms += now_ms() - tp0;
-        tables_fresh_ = false;
-        done += run_persistent(a, b, nid, batch - done);
-      }
-      stats.merge_ms += now_ms() - t0;
-      return done;
-    }
-    if (use_device_loop()) {
-      while (done < batch && !core.heap_empty()) {
-        int32_t a, b, nid;
-        const double tp0 = now_ms();
-        if (!core.next_merge(&a, &b, &nid)) break;
-        stats.host_pop_ms += now_ms() - tp0;
-        tables_fresh_ = false;
-        done += run_device_loop(a, b, nid, batch - done);
       }
       stats.merge_ms += now_ms() - t0;
       return done;
@@ -1741,22 +1586,12 @@ class TrainerImpl {
   bool gt_flagged_ = false;
   // persistent merge kernel
   bool coop_ok_ = false;
-  int coop_blocks_per_sm_ = 0;
-  PinnedBuf<HostCmd> hcmd_;
-  DevBuf<DevCmd> dcmd_;
   PinnedBuf<HostCmd2> hcmd2_;
   DevBuf<DevCmd2> dcmd2_;
   DevBuf<uint4> cl_ovf_;
   DevBuf<unsigned long long> cl_acct_;
   DevBuf<unsigned long long> ptrace_;
   // device-resident loop
-  DevBuf<LoopState> loop_state_;
-  DevBuf<CandEntry> cand_;
-  PinnedBuf<Rec> ring_;
-  PinnedBuf<unsigned long long> ring_hdr_;
-  bool cand_valid_ = false;
-  unsigned long long theta_ = 0;
-  uint32_t n_cand_host_ = 0;
   bool trace_wait_ = getenv("SWB_TRACE_WAIT") != nullptr;
   std::vector<float> wait_trace_;
   std::vector<uint32_t> trace_removed_, trace_nrec_, trace_cand_, trace_mrows_;

@@ -158,6 +158,53 @@ def generate(spec: CorpusSpec, chunk_words: int = 1_200_000, threads: int | None
 PIECE_STRIDE = 100_000  # chunk-number distance between the pieces of a multi-rank corpus
 
 
+# ---- strong scaling: rank r of N holds a contiguous byte range of THE SAME corpus -------------------------------------
+# The corpus is the concatenation of the chunks 0, 1, 2, ... cut at spec.nbytes. A chunk's content depends only on its
+# number, so rank r can produce chunks [c_r, c_{r+1}) on its own; only the chunk SIZES of the ranks before it are needed to
+# know where its range starts, and those are exchanged by the caller (one all-gather of N integers).
+def mean_chunk_bytes(spec: CorpusSpec, chunk_words: int = 1_200_000) -> float:
+  rng = np.random.default_rng(spec.seed)
+  _, lens = make_types(spec, rng)
+  ranks = np.arange(1, spec.n_types + 1, dtype=np.float64)
+  w = ranks ** (-spec.zipf_s)
+  w /= w.sum()
+  return float(chunk_words * (np.dot(w, lens) + 1.0))
+
+
+def piece_chunk_range(spec: CorpusSpec, rank: int, world: int, chunk_words: int = 1_200_000) -> tuple[int, int]:
+  """Chunks [c0, c1) of piece `rank`. The total is a slight over-estimate of what spec.nbytes needs (the last piece is
+  cut by `cut_piece`), so that the pieces of all ranks together always cover the corpus."""
+  total = int(np.ceil(spec.nbytes / mean_chunk_bytes(spec, chunk_words) * 1.003)) + 1
+  total = max(total, world)
+  return rank * total // world, (rank + 1) * total // world
+
+
+def generate_chunks(spec: CorpusSpec, c0: int, c1: int, chunk_words: int = 1_200_000, threads: int | None = None):
+  """Yields chunks c0 .. c1-1 of the corpus stream, uncut."""
+  from concurrent.futures import ThreadPoolExecutor
+  rng = np.random.default_rng(spec.seed)
+  mat, lens = make_types(spec, rng)
+  ranks = np.arange(1, spec.n_types + 1, dtype=np.float64)
+  cdf = np.cumsum(ranks ** (-spec.zipf_s))
+  cdf /= cdf[-1]
+  threads = threads or min(8, os.cpu_count() or 1)
+  with ThreadPoolExecutor(threads) as pool:
+    for b in range(c0, c1, threads):
+      futs = [pool.submit(_chunk, spec, mat, lens, cdf, k, chunk_words) for k in range(b, min(c1, b + threads))]
+      for f in futs:
+        yield f.result()
+
+
+def cut_piece(spec: CorpusSpec, piece_sizes: list[int], rank: int) -> tuple[int, int]:
+  """(global byte offset, byte count) of piece `rank`, given the UNCUT sizes of all pieces: the corpus ends at
+  spec.nbytes, so the piece that crosses that mark is cut there (its last byte becomes a newline, exactly as
+  generate() cuts the single-rank corpus) and later pieces are empty."""
+  start = int(sum(piece_sizes[:rank]))
+  end = min(start + int(piece_sizes[rank]), spec.nbytes)
+  assert sum(piece_sizes) >= spec.nbytes, "pieces do not cover the corpus (chunk estimate too low)"
+  return min(start, spec.nbytes), max(0, end - start)
+
+
 def corpus_bytes(spec: CorpusSpec, first_chunk: int = 0) -> np.ndarray:
   """Whole corpus as one uint8 array (use only for sizes that fit in host memory)."""
   out = np.empty(spec.nbytes, dtype=np.uint8)

@@ -171,7 +171,16 @@ class BPETrainer:
   def stats(self) -> dict:
     s = SwbStats()
     lib.swb_get_stats(self.trainer, ctypes.byref(s))
-    return {k: getattr(s, k) for k, _ in SwbStats._fields_}
+    return {k: getattr(s, k) for k, _ in SwbStats._fields_ if not k.endswith("_")}
+
+  def profile_scripted_merges(self, merge_triples: np.ndarray) -> float:
+    """Profiling aid (swb_profile_scripted_merges): after init() on a fresh load, runs the given merges inside one
+    launch of the resident kernel with no host in the loop; returns the launch duration in ms. Consumes the handle."""
+    m = np.ascontiguousarray(merge_triples, dtype=np.int32).reshape(-1, 3)
+    ms = ctypes.c_double(0.0)
+    if lib.swb_profile_scripted_merges(self.trainer, _ptr(m), m.shape[0], ctypes.byref(ms)) != 0:
+      raise RuntimeError(f"profile_scripted_merges failed: {last_error()}")
+    return float(ms.value)
 
   def set_kernel_timing(self, on: bool):
     lib.swb_set_kernel_timing(self.trainer, 1 if on else 0)

@@ -1,4 +1,4 @@
-"""GPU, 2+ devices: the multi-GPU trainer -- replicated merge loop (default), the sharded merge loop with the NCCL
+"""GPU, 2+ devices: the multi-GPU trainer -- merge loop on rank 0 + broadcast (default), replicated, the sharded merge loop with the NCCL
 exchange issued from inside the library, and the Python-driven torch.distributed exchange -- must reproduce the
 single-GPU / oracle merge list bit for bit.
 Skipped on a single-GPU box (the round-end -m gpu run); exercised with `gpurun --gpus 2`."""
@@ -26,8 +26,8 @@ def _worker(rank, world, port, name, mode, out_dir):
   dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
   from shredword_b200.distributed import DistributedBPETrainer
   kw = cases.kwargs(name)
-  t = DistributedBPETrainer(**kw, device=torch.device("cuda", rank), native=native, sharded_merge=(mode == "sharded"))
-  assert t.sharded == (mode != "replicated")
+  t = DistributedBPETrainer(**kw, device=torch.device("cuda", rank), native=native, merge_loop=("sharded" if mode == "python" else mode))
+  assert t.sharded == (mode in ("sharded", "python"))
   t.load_buffer(cases.corpus(name))
   n = t.train_quiet()
   np.save(os.path.join(out_dir, f"merges_{mode}_{rank}.npy"), t.merges_array())
@@ -37,15 +37,20 @@ def _worker(rank, world, port, name, mode, out_dir):
   assert n == len(t.merges_array())
   if mode == "sharded":
     assert st["collectives"] >= n
-  if mode == "replicated":
+  if mode == "replicated" or (mode == "rank0" and rank == 0):
     assert st["collectives"] == 0 and (n == 0 or st["resident_local_merges"] + st["resident_grid_merges"] > 0 or st["long_words"] > 0)
+  if mode == "rank0" and rank != 0:
+    assert st["merge_launches"] == 0 and st["resident_local_merges"] + st["resident_grid_merges"] == 0  # this rank ran no merge
+    ids = t.encoder().encode(cases.corpus(name))  # ... and still has the result: an encoder from the broadcast merges
+    np.save(os.path.join(out_dir, f"ids_{mode}_{rank}.npy"), ids)
   dist.barrier()
   t.destroy()
   lib.swb_dist_shutdown()
   dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,mode", [("ascii_ties", "replicated"), ("long_words", "replicated"),
+@pytest.mark.parametrize("name,mode", [("ascii_ties", "rank0"), ("multi_unk97", "rank0"), ("long_words", "rank0"),
+                                       ("ascii_ties", "replicated"), ("long_words", "replicated"),
                                        ("ascii_ties", "sharded"), ("multi_unk97", "sharded"), ("long_words", "sharded"), ("negative_unk", "sharded"),
                                        ("ascii_ties", "python"), ("multi_unk97", "python")])
 def test_two_gpus_match_oracle(name, mode, product, oracle_mod, tmp_path):
@@ -62,6 +67,9 @@ def test_two_gpus_match_oracle(name, mode, product, oracle_mod, tmp_path):
   for r in range(2):
     assert np.array_equal(np.load(tmp_path / f"merges_{mode}_{r}.npy"), o.merges), f"rank {r}"
     assert np.array_equal(np.load(tmp_path / f"freq_{mode}_{r}.npy"), o.token_freq()), f"rank {r}"
+  if mode == "rank0":
+    ids = np.load(tmp_path / f"ids_{mode}_1.npy")
+    assert np.array_equal(ids, oracle_mod.encode(o.merges, o.byte_map(kw.get("unk_id", 0)), cases.corpus(name)))
   assert (tmp_path / f"m_{mode}.model").read_bytes() == (tmp_path / "o.model").read_bytes()
   assert (tmp_path / f"m_{mode}.vocab").read_bytes() == (tmp_path / "o.vocab").read_bytes()
 
@@ -79,7 +87,7 @@ def _shard_worker(rank, world, port, sharded, out_dir):
   cuts = np.load(os.path.join(out_dir, "cuts.npy"))
   if not sharded:
     os.environ["SWB_LOAD_PIECE"] = "65536"  # rank 0's host buffer goes through the pipelined copy + tokenise path
-  t = DistributedBPETrainer(1500, min_pair_freq=5, device=torch.device("cuda", rank), sharded_merge=sharded)
+  t = DistributedBPETrainer(1500, min_pair_freq=5, device=torch.device("cuda", rank), merge_loop=("sharded" if sharded else "rank0"))
   piece = data[cuts[rank]:cuts[rank + 1]]
   if rank == 0:
     t.load_shard(piece, int(cuts[rank]))                                   # host buffer
