@@ -143,7 +143,8 @@ typedef struct SwbStats {
   double host_pop_ms, host_launch_ms, host_wait_ms, host_apply_ms; /* merge loop split on the host */
   uint64_t records, heap_pushes, heap_pops, heap_peak;             /* host replica counters */
   uint64_t collectives, exchange_bytes;                            /* multi-GPU: NCCL all-gathers and their bytes */
-  uint64_t reserved_[5];
+  uint64_t resident_spill_merges; /* LOCAL merges of the resident kernel whose deltas overflowed shared memory into the global pair table */
+  uint64_t reserved_[4];
   /* resident cluster kernel: merges done by the leader cluster alone / by the whole grid, and the device time
    * they took (command seen -> result published, %globaltimer; also added to merge_kernel_ms) */
   uint64_t resident_local_merges, resident_grid_merges;

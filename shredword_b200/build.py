@@ -45,6 +45,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
   ]
   if os.environ.get("SWB_KERNEL_TRACE"):
     cmd.insert(1, "-DSWB_KERNEL_TRACE")
+  if os.environ.get("SWB_DEBUG_BOUNDS"):  # index checks inside the merge kernels (device_util.cuh), reported by the host after a failure
+    cmd.insert(1, "-DSWB_DEBUG_BOUNDS")
   if verbose:
     cmd.insert(1, "-Xptxas=-v")
     print(" ".join(cmd), file=sys.stderr)

@@ -63,7 +63,7 @@ __host__ __device__ __forceinline__ unsigned int cmd3_word(unsigned long long se
   return w ? w : 0x5BD1E995u;
 }
 // leader -> other clusters (device memory)
-struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, t_cmd /* %globaltimer when the command arrived */, spec /* started from a hint */; };
+struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, t_cmd /* %globaltimer when the command arrived */, spec /* started from a hint */, tail_done /* GRID merges whose tail (emit + publish, run by whichever block finished last) is complete */; };
 __host__ __device__ __forceinline__ unsigned long long cmd2_check(unsigned long long seq, unsigned long long pair,
                                                                   unsigned long long nio, unsigned long long lr) {
   return (seq * HDR_MAGIC) ^ pair ^ (nio << 7 | nio >> 57) ^ (lr * 0xD6E8FEB86659FD93ull);
@@ -352,6 +352,10 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           bool have_v = true;
           if (spin == 0 && hint_ok && pre_hv.z != 0u && pre_hv.w == cmd3_word(want, pre_hv.x, pre_hv.y, pre_hv.z)) { hv = pre_hv; have_v = false; }  // already here: no trip at all
           else if (script) {
+            // (a host only sends the next command once it has seen the result; a script has to wait itself until the tail of
+            //  the GRID merge before -- run by whichever block finished last, possibly in another cluster -- is through)
+            while (*(volatile unsigned long long *)&dcmd->tail_done < grid_epoch) { if (gtime_ns() - t0 > timeout_ns) break; }
+            __threadfence();
             if (k >= script_n) { nio = 1ull << 32; break; }  // end of the script: stop
             v = __ldcg(reinterpret_cast<const uint4 *>(script + k));
           } else {
@@ -389,7 +393,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           const uint32_t mcur = (uint32_t)((uint32_t)(nio & 0xFFFFFFFFu) - 256u);
           if (em.log.ent != nullptr && newer >= 256 && (uint32_t)(newer - 256) < mcur) {
             const unsigned int lo = __ldcg(&em.log.start[newer - 256]), hi = __ldcg(&em.log.start[newer - 256 + 1]);
-            lr = ((unsigned long long)lo << 32) | (unsigned long long)(hi - lo);
+            if (hi >= lo && hi <= em.log.cap) lr = ((unsigned long long)lo << 32) | (unsigned long long)(hi - lo);
+            else atomicOr(em.log.flags, 2u);  // a log range that cannot be: reported to the host (header flag 32) instead of followed; this merge scans the rows
           } else if (em.log.ent != nullptr && ip_lookup(em.log, pa, pb)) {  // two initial symbols: their occurrence index, unless the list is long (then the whole grid scans)
             const unsigned int pk = (unsigned int)pa * 256u + (unsigned int)pb;
             const unsigned int lo = __ldcg(&em.log.ip_start[pk]), hi = __ldcg(&em.log.ip_start[pk + 1]);
@@ -469,6 +474,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         TailSmem ts{m.tail_stage, m.csum, m.tail_count};
         fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag);
         if (threadIdx.x == 0) {  // (one publisher at a time)
+          __threadfence();
+          *(volatile unsigned long long *)&dcmd->tail_done = grid_epoch;
           const unsigned long long dt = gtime_ns() - m.ctl->t_cmd;
           acct[2] += 1; acct[3] += dt;
           if (trace) {  // development aid: how long do GRID merges take? [16..23] = counts, [24..31] = ns, by duration class
@@ -503,7 +510,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
 #pragma unroll
         for (int u = 0; u < 8; u++) {
           const uint64_t i = base + (uint64_t)u * (CL_SIZE * CL_THREADS) + crank * CL_THREADS + threadIdx.x;
-          ev[u] = i < n ? __ldcg(&ent[lo + i]) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+          ev[u] = (i < n && SWB_DBG_OK(ent == em.log.ip_ent || lo + i < em.log.cap, 1, lo, i, n)) ? __ldcg(&ent[lo + i]) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -516,7 +523,10 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
               asm volatile("prefetch.global.L2 [%0];" ::"l"(s.cnt + (e.y & 0x7FFFFFFFu)));
             }
             if (ci < tune.cand_cap) m.cand[ci] = make_uint4(e.y & 0x7FFFFFFFu, e.z, e.w, 0u);
-            else ovf[(size_t)crank * (CL_LOCAL_MAX / CL_SIZE) + atomicAdd(&m.ctl->n_ovf, 1u)] = make_uint4(e.y & 0x7FFFFFFFu, e.z, e.w, 0u);  // rare: listed in global memory
+            else {  // rare: listed in global memory
+              const unsigned int oi = atomicAdd(&m.ctl->n_ovf, 1u);
+              if (SWB_DBG_OK(oi < CL_LOCAL_MAX / CL_SIZE, 2, oi, ci, n)) ovf[(size_t)crank * (CL_LOCAL_MAX / CL_SIZE) + oi] = make_uint4(e.y & 0x7FFFFFFFu, e.z, e.w, 0u);
+            }
           }
         }
       }
@@ -530,7 +540,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
 #pragma unroll 1
         for (unsigned int i = (threadIdx.x >> 5) + (unsigned int)CL_WARPS * (threadIdx.x & 31); i < nall; i += CL_THREADS) {
           const uint4 cnd = i < nc ? m.cand[i] : __ldcg(&ovf_mine[i - nc]);
-          removed += merge_one_word(s, ((uint64_t)cnd.z << 32) | cnd.y, cnd.x, a, b, new_id, sink);
+          if (SWB_DBG_OK((((uint64_t)cnd.z << 32) | cnd.y) < s.n_rows * ROW, 3, ((uint64_t)cnd.z << 32) | cnd.y, cnd.x, i))
+            removed += merge_one_word(s, ((uint64_t)cnd.z << 32) | cnd.y, cnd.x, a, b, new_id, sink);
         }
       }
       if (trace && crank == 0 && threadIdx.x == 0) trace[9] += (unsigned long long)(clock64() - cA);
@@ -619,7 +630,10 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         __syncthreads();
         cluster_clear_tables(m);
         if (threadIdx.x == 0) { acct[0] += 1; acct[1] += gtime_ns() - c->t_cmd; acct[7] += 1; }
-        if (threadIdx.x == 0) { c->spill = 0; c->n_recs_total = 0; c->removed = 0; }
+        if (threadIdx.x == 0) {
+          c->log_cursor += c->births_total;  // (the births of this merge are in the log: the next LOCAL merge appends after them)
+          c->spill = 0; c->n_recs_total = 0; c->removed = 0;
+        }
         __syncthreads();
       } else if (threadIdx.x == 0) {
         const unsigned int n = c->n_recs_total;

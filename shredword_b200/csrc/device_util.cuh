@@ -167,6 +167,23 @@ __host__ __device__ __forceinline__ bool is_delim(uint8_t c) {  // reference bpe
   return c == ' ' || c == '\n' || c == '\t' || c == '\r';
 }
 // first-touch key: word index major, then position, then slot (order of the 4 delta adds of a match)
+// Debug build (SWB_DEBUG_BOUNDS=1 python -m shredword_b200.build): every index the merge kernels derive from data they read
+// (log entries, header locations, candidate lists) is checked before use; the first violations are recorded here (code, three
+// values) and the access is skipped, so that a corrupted index shows up as a report instead of an illegal address. The pool
+// this was developed on does not allow compute-sanitizer.
+#ifdef SWB_DEBUG_BOUNDS
+__device__ unsigned long long g_dbg[1 + 4 * 16];  // [0] = number of violations, then 16 x {code, a, b, c}
+#define SWB_DBG_OK(cond, code, a, b, c) swb_dbg_ok((cond), (code), (unsigned long long)(a), (unsigned long long)(b), (unsigned long long)(c))
+__device__ __forceinline__ bool swb_dbg_ok(bool cond, unsigned long long code, unsigned long long a, unsigned long long b, unsigned long long c) {
+  if (cond) return true;
+  const unsigned long long i = atomicAdd(&g_dbg[0], 1ull);
+  if (i < 16) { g_dbg[1 + 4 * i] = code; g_dbg[2 + 4 * i] = a; g_dbg[3 + 4 * i] = b; g_dbg[4 + 4 * i] = c; }
+  return false;
+}
+#else
+#define SWB_DBG_OK(cond, code, a, b, c) (true)
+#endif
+
 __host__ __device__ __forceinline__ uint64_t touch_key(uint64_t wi, uint32_t pos, uint32_t slot) {
   return (wi << 30) | ((uint64_t)pos << 2) | slot;
 }

@@ -114,6 +114,203 @@ __device__ __forceinline__ uint32_t enc_word_len(const uint8_t *__restrict__ tex
   return (uint32_t)(i - off);
 }
 
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_tot /* [ENC_THREADS/32] shared */, uint32_t &total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < ENC_THREADS / 32; i++) { if (i < w) base += warp_tot[i]; tot += warp_tot[i]; }
+  __syncthreads();
+  total = tot;
+  return base + inc - v;
+}
+
+
+// Encodes one word of L <= ENC_SHORT bytes starting at text[off] into ids[0 .. nt) (shared memory, room for L ints);
+// wv = the word's first 16 bytes. Words of up to MEMO_MAX_LEN bytes go through the memo. Returns nt.
+__device__ __forceinline__ uint32_t enc_short_word(const uint8_t *__restrict__ text, uint64_t off, uint32_t L, uint4 wv, int *ids,
+                                                   const RankTableDev &tbl, const MemoDev &memo, const int32_t *bmap) {
+  if (L > MEMO_MAX_LEN) {
+    for (uint32_t k = 0; k < L; k++) ids[k] = bmap[text[off + k]];
+    return enc_word(ids, L, tbl);
+  }
+  uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};  // zero the bytes from L on
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int keep = (int)L - 4 * k;  // bytes of this word to keep
+    w4[k] = keep >= 4 ? w4[k] : (keep <= 0 ? 0u : (w4[k] & (0xFFFFFFFFu >> (8 * (4 - keep)))));
+  }
+  unsigned long long h = dmix64(((unsigned long long)w4[1] << 32 | w4[0]) ^ 0x9E3779B97F4A7C15ull) ^
+                         dmix64(((unsigned long long)w4[3] << 32 | w4[2]) + ((unsigned long long)L << 56) + 0x632BE59BD9B4E019ull);
+  h = dmix64(h) | 1ull;
+  MemoSlot *slot = memo.slots + ((uint32_t)(h >> 20) & memo.mask);
+  const uint4 q0 = __ldcg(reinterpret_cast<const uint4 *>(slot));       // tag, len, ntok, bytes[0..5]
+  const uint4 q1 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 1);   // bytes[6..13], tok[0..1]
+  const uint4 q2 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 2);   // tok[2..5]
+  const uint4 q3 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 3);   // tok[6..8], check
+  const unsigned long long tag = ((unsigned long long)q0.y << 32) | q0.x;
+  // expected image of {len, ntok, bytes}: len | ntok << 8 | bytes << 16 over q0.z, q0.w, q1.x, q1.y
+  const uint32_t e0 = L | (w4[0] << 16), m0 = 0xFFFF00FFu;          // ntok byte masked out
+  const uint32_t e1 = (w4[0] >> 16) | (w4[1] << 16);
+  const uint32_t e2 = (w4[1] >> 16) | (w4[2] << 16);
+  const uint32_t e3 = (w4[2] >> 16) | (w4[3] << 16);
+  if (tag == h && (q0.z & m0) == e0 && q0.w == e1 && q1.x == e2 && q1.y == e3) {
+    const uint32_t mt = (q0.z >> 8) & 0xFFu;
+    const int tk[MEMO_MAX_TOK] = {(int)q1.z, (int)q1.w, (int)q2.x, (int)q2.y, (int)q2.z, (int)q2.w, (int)q3.x, (int)q3.y, (int)q3.z};
+    uint32_t ck = (uint32_t)h ^ (uint32_t)(h >> 32) ^ mt;
+#pragma unroll
+    for (int k = 0; k < MEMO_MAX_TOK; k++) ck ^= (uint32_t)tk[k] * (2u * k + 3u);
+    if (ck == q3.w && mt >= 1 && mt <= MEMO_MAX_TOK && mt <= L) {
+#pragma unroll
+      for (int k = 0; k < MEMO_MAX_TOK; k++) if (k < (int)mt) ids[k] = tk[k];
+      return mt;
+    }
+  }
+  for (uint32_t k = 0; k < L; k++) ids[k] = bmap[(w4[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+  const uint32_t nt = enc_word(ids, L, tbl);
+  if (tag == 0ull && nt <= MEMO_MAX_TOK && atomicCAS(&slot->tag, 0ull, h) == 0ull) {  // first encoder fills the slot
+    int tk[MEMO_MAX_TOK];
+    uint32_t ck = (uint32_t)h ^ (uint32_t)(h >> 32) ^ nt;
+#pragma unroll
+    for (int k = 0; k < MEMO_MAX_TOK; k++) { tk[k] = k < (int)nt ? ids[k] : 0; ck ^= (uint32_t)tk[k] * (2u * k + 3u); }
+    uint4 *dst = reinterpret_cast<uint4 *>(slot);
+    // (the tag, in q0.x/q0.y, is already there: written by the CAS)
+    reinterpret_cast<uint32_t *>(slot)[2] = e0 | (nt << 8);
+    reinterpret_cast<uint32_t *>(slot)[3] = e1;
+    dst[1] = make_uint4(e2, e3, (uint32_t)tk[0], (uint32_t)tk[1]);
+    dst[2] = make_uint4((uint32_t)tk[2], (uint32_t)tk[3], (uint32_t)tk[4], (uint32_t)tk[5]);
+    dst[3] = make_uint4((uint32_t)tk[6], (uint32_t)tk[7], (uint32_t)tk[8], ck);
+  }
+  return nt;
+}
+
+// ---------------------------------------------------------------- single-pass encoder
+// One kernel, one pass over the text, no per-byte scratch: tiles are handed out in text order; a block finds the word
+// starts of its tile, encodes the words in shared memory (words dealt out evenly over the threads), scans the token counts,
+// learns where its tokens go from the tiles before it (decoupled look-back over one 64-bit descriptor per tile) and writes
+// them, compacted, with coalesced stores. Traffic = the text once + the ids once.
+//   descriptor = status << 62 | tokens << 31 | words   (status 1 = this tile's own totals, 2 = totals of all tiles up to it)
+// A word longer than ENC_SHORT bytes does not fit the tile's shared memory: it raises `fallback` and the host encodes the
+// whole piece with the three-kernel path above (enc_words / scan / enc_gather) instead.
+constexpr int ENCF_MAX_WORDS = ENC_TILE / 2;
+__global__ void __launch_bounds__(ENC_THREADS)
+enc_fused(const uint8_t *__restrict__ text, uint64_t n, uint64_t lo_b, uint64_t hi_b, RankTableDev tbl, MemoDev memo,
+          const int32_t *__restrict__ byte_map, unsigned long long *__restrict__ desc, unsigned int *__restrict__ tile_counter,
+          unsigned int *__restrict__ fallback, unsigned long long tok_base, unsigned long long word_base, int32_t *__restrict__ out,
+          uint64_t cap_ids, uint32_t *__restrict__ word_ntok, uint64_t cap_words, int32_t neg_id) {
+  __shared__ int stok[ENC_TILE + ENC_SHORT];       // tokens of the word that starts at byte r of the tile: stok[r ...]
+  __shared__ int ctok[ENC_TILE];                   // the tile's tokens, compacted in text order
+  __shared__ uint16_t wstart[ENCF_MAX_WORDS];      // ordered word starts (byte position in the tile)
+  __shared__ uint16_t wnt[ENCF_MAX_WORDS];         // tokens per word
+  __shared__ uint16_t woff[ENCF_MAX_WORDS];        // exclusive token offset of each word inside the tile
+  __shared__ int32_t bmap[256];
+  __shared__ uint32_t wt[ENC_THREADS / 32];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_excl;
+  for (int i = threadIdx.x; i < 256; i += ENC_THREADS) bmap[i] = byte_map[i];
+  const uint64_t seg_lo = lo_b / 16, seg_hi = (hi_b + 15) / 16;
+  const uint64_t n_tiles = (seg_hi - seg_lo + ENC_THREADS - 1) / ENC_THREADS;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const uint64_t tile = s_tile;
+    if (tile >= n_tiles) return;
+    const uint64_t seg = seg_lo + tile * ENC_THREADS + threadIdx.x;
+    const uint64_t tile_byte0 = (seg_lo + tile * ENC_THREADS) * 16;
+    // ---- word starts of this thread's 16 bytes, in text order
+    uint32_t starts = 0;
+    if (seg < seg_hi) {
+      starts = enc_starts(text, seg);
+      uint32_t st = starts;
+      while (st) {  // only the words that start inside [lo_b, hi_b) and before the end of the text
+        const int sb = __ffs(st) - 1;
+        st &= st - 1;
+        const uint64_t off = seg * 16 + sb;
+        if (off < lo_b || off >= hi_b || off >= n) starts &= ~(1u << sb);
+      }
+    }
+    uint32_t nw;
+    uint32_t wbase = block_excl_scan(__popc(starts), wt, nw);
+    {
+      uint32_t st = starts;
+      while (st) { const int sb = __ffs(st) - 1; st &= st - 1; wstart[wbase++] = (uint16_t)(threadIdx.x * 16 + sb); }
+    }
+    __syncthreads();
+    // ---- encode: word j -> thread j % ENC_THREADS
+    for (uint32_t j = threadIdx.x; j < nw; j += ENC_THREADS) {
+      const uint32_t rel = wstart[j];
+      const uint64_t off = tile_byte0 + rel;
+      const uint4 wv = enc_load16(text, off);
+      const uint32_t dmask = enc_delim_bits(wv.x) | (enc_delim_bits(wv.y) << 4) | (enc_delim_bits(wv.z) << 8) | (enc_delim_bits(wv.w) << 12);
+      uint32_t L = dmask ? (uint32_t)(__ffs(dmask) - 1) : 16u;
+      if (off + L > n) L = (uint32_t)(n - off);
+      if (L >= 15) L = enc_word_len(text, off, n);
+      uint32_t nt = 0;
+      if (L <= ENC_SHORT) nt = enc_short_word(text, off, L, wv, stok + rel, tbl, memo, bmap);
+      else atomicOr(fallback, 1u);
+      wnt[j] = (uint16_t)nt;
+    }
+    __syncthreads();
+    // ---- token offsets of the words (thread t scans words 8t .. 8t+7)
+    uint32_t mine[8], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { const uint32_t j = threadIdx.x * 8 + q; mine[q] = j < nw ? wnt[j] : 0u; sum += mine[q]; }
+    uint32_t ntok;
+    uint32_t tb = block_excl_scan(sum, wt, ntok);
+#pragma unroll
+    for (int q = 0; q < 8; q++) { const uint32_t j = threadIdx.x * 8 + q; if (j < nw) woff[j] = (uint16_t)tb; tb += mine[q]; }
+    // ---- where the tile's tokens and words go: look back over the tiles before this one (warp 0)
+    if (threadIdx.x < 32) {
+      const unsigned long long agg = ((unsigned long long)ntok << 31) | nw;
+      unsigned long long excl = 0;
+      if (tile == 0) {
+        if (threadIdx.x == 0) *(volatile unsigned long long *)&desc[0] = (2ull << 62) | agg;
+      } else {
+        if (threadIdx.x == 0) *(volatile unsigned long long *)&desc[tile] = (1ull << 62) | agg;
+        long long idx = (long long)tile - 1;
+        for (;;) {
+          const long long my = idx - (long long)threadIdx.x;
+          unsigned long long d = 2ull << 62;  // (before the first tile: an empty prefix)
+          if (my >= 0) { do { d = *(volatile unsigned long long *)&desc[my]; } while ((d >> 62) == 0ull); }
+          const unsigned int pm = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+          const int first = __ffs(pm) - 1;  // nearest tile (lowest lane) that already knows its inclusive prefix
+          unsigned long long v = ((int)threadIdx.x <= first || first < 0) ? (d & 0x3FFFFFFFFFFFFFFFull) : 0ull;
+#pragma unroll
+          for (int dd = 16; dd > 0; dd >>= 1) v += __shfl_down_sync(0xffffffffu, v, dd);
+          v = __shfl_sync(0xffffffffu, v, 0);
+          excl += v;
+          if (first >= 0) break;
+          idx -= 32;
+        }
+        if (threadIdx.x == 0) *(volatile unsigned long long *)&desc[tile] = (2ull << 62) | (excl + agg);
+      }
+      if (threadIdx.x == 0) s_excl = excl;
+    }
+    __syncthreads();
+    // ---- compact in shared memory, then coalesced stores
+    for (uint32_t j = threadIdx.x; j < nw; j += ENC_THREADS) {
+      const uint32_t rel = wstart[j], nt = wnt[j], o = woff[j];
+      for (uint32_t k = 0; k < nt; k++) ctok[o + k] = stok[rel + k];
+    }
+    __syncthreads();
+    const unsigned long long excl = s_excl;
+    const uint64_t to = tok_base + (excl >> 31), wo = word_base + (excl & 0x7FFFFFFFull);
+    for (uint32_t k = threadIdx.x; k < ntok; k += ENC_THREADS)
+      if (to + k < cap_ids) { const int v = ctok[k]; out[to + k] = (v == UNK_CODE) ? neg_id : v; }
+    if (word_ntok)
+      for (uint32_t j = threadIdx.x; j < nw; j += ENC_THREADS)
+        if (wo + j < cap_words) word_ntok[wo + j] = wnt[j];
+  }
+}
+
 // text: n bytes, 16-byte aligned, followed by >= 16 bytes of ' '. One tile per block iteration.
 __global__ void __launch_bounds__(ENC_THREADS)
 enc_words(const uint8_t *__restrict__ text, uint64_t n, RankTableDev tbl, MemoDev memo, const int32_t *__restrict__ byte_map,
@@ -154,64 +351,9 @@ enc_words(const uint8_t *__restrict__ text, uint64_t n, RankTableDev tbl, MemoDe
       if (off + L > n) L = (uint32_t)(n - off);
       if (L >= 15) L = enc_word_len(text, off, n);
       uint32_t nt;
-      if (L <= MEMO_MAX_LEN) {  // memoizable word
-        uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};  // zero the bytes from L on
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int keep = (int)L - 4 * k;  // bytes of this word to keep
-          w4[k] = keep >= 4 ? w4[k] : (keep <= 0 ? 0u : (w4[k] & (0xFFFFFFFFu >> (8 * (4 - keep)))));
-        }
-        unsigned long long h = dmix64(((unsigned long long)w4[1] << 32 | w4[0]) ^ 0x9E3779B97F4A7C15ull) ^
-                               dmix64(((unsigned long long)w4[3] << 32 | w4[2]) + ((unsigned long long)L << 56) + 0x632BE59BD9B4E019ull);
-        h = dmix64(h) | 1ull;
-        MemoSlot *slot = memo.slots + ((uint32_t)(h >> 20) & memo.mask);
-        const uint4 q0 = __ldcg(reinterpret_cast<const uint4 *>(slot));       // tag, len, ntok, bytes[0..5]
-        const uint4 q1 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 1);   // bytes[6..13], tok[0..1]
-        const uint4 q2 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 2);   // tok[2..5]
-        const uint4 q3 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 3);   // tok[6..8], check
-        const unsigned long long tag = ((unsigned long long)q0.y << 32) | q0.x;
-        // expected image of {len, ntok, bytes}: len | ntok << 8 | bytes << 16 over q0.z, q0.w, q1.x, q1.y
-        const uint32_t e0 = L | (w4[0] << 16), m0 = 0xFFFF00FFu;          // ntok byte masked out
-        const uint32_t e1 = (w4[0] >> 16) | (w4[1] << 16);
-        const uint32_t e2 = (w4[1] >> 16) | (w4[2] << 16);
-        const uint32_t e3 = (w4[2] >> 16) | (w4[3] << 16);
-        bool hit = false;
-        if (tag == h && (q0.z & m0) == e0 && q0.w == e1 && q1.x == e2 && q1.y == e3) {
-          const uint32_t mt = (q0.z >> 8) & 0xFFu;
-          const int tk[MEMO_MAX_TOK] = {(int)q1.z, (int)q1.w, (int)q2.x, (int)q2.y, (int)q2.z, (int)q2.w, (int)q3.x, (int)q3.y, (int)q3.z};
-          uint32_t ck = (uint32_t)h ^ (uint32_t)(h >> 32) ^ mt;
-#pragma unroll
-          for (int k = 0; k < MEMO_MAX_TOK; k++) ck ^= (uint32_t)tk[k] * (2u * k + 3u);
-          if (ck == q3.w && mt >= 1 && mt <= MEMO_MAX_TOK && mt <= L) {
-            hit = true;
-            nt = mt;
-#pragma unroll
-            for (int k = 0; k < MEMO_MAX_TOK; k++) if (k < (int)mt) tmp[off + k] = tk[k];
-          }
-        }
-        if (!hit) {
-          int *ids = stok + rel;
-          for (uint32_t k = 0; k < L; k++) ids[k] = bmap[(w4[k >> 2] >> (8 * (k & 3))) & 0xFFu];
-          nt = enc_word(ids, L, tbl);
-          for (uint32_t k = 0; k < nt; k++) tmp[off + k] = ids[k];
-          if (tag == 0ull && nt <= MEMO_MAX_TOK && atomicCAS(&slot->tag, 0ull, h) == 0ull) {  // first encoder fills the slot
-            int tk[MEMO_MAX_TOK];
-            uint32_t ck = (uint32_t)h ^ (uint32_t)(h >> 32) ^ nt;
-#pragma unroll
-            for (int k = 0; k < MEMO_MAX_TOK; k++) { tk[k] = k < (int)nt ? ids[k] : 0; ck ^= (uint32_t)tk[k] * (2u * k + 3u); }
-            uint4 *dst = reinterpret_cast<uint4 *>(slot);
-            // (the tag, in q0.x/q0.y, is already there: written by the CAS)
-            reinterpret_cast<uint32_t *>(slot)[2] = e0 | (nt << 8);
-            reinterpret_cast<uint32_t *>(slot)[3] = e1;
-            dst[1] = make_uint4(e2, e3, (uint32_t)tk[0], (uint32_t)tk[1]);
-            dst[2] = make_uint4((uint32_t)tk[2], (uint32_t)tk[3], (uint32_t)tk[4], (uint32_t)tk[5]);
-            dst[3] = make_uint4((uint32_t)tk[6], (uint32_t)tk[7], (uint32_t)tk[8], ck);
-          }
-        }
-      } else if (L <= ENC_SHORT) {
+      if (L <= ENC_SHORT) {
         int *ids = stok + rel;
-        for (uint32_t k = 0; k < L; k++) ids[k] = bmap[text[off + k]];
-        nt = enc_word(ids, L, tbl);
+        nt = enc_short_word(text, off, L, wv, ids, tbl, memo, bmap);
         for (uint32_t k = 0; k < nt; k++) tmp[off + k] = ids[k];
       } else {  // long word: encode in place in global memory
         int *ids = tmp + off;
@@ -226,24 +368,6 @@ enc_words(const uint8_t *__restrict__ text, uint64_t n, RankTableDev tbl, MemoDe
     if (threadIdx.x == 0) { tile_ntok[tile] = s_ntok; tile_nwords[tile] = nw; }
     __syncthreads();
   }
-}
-
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_tot /* [ENC_THREADS/32] shared */, uint32_t &total) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += t;
-  }
-  if (lane == 31) warp_tot[w] = inc;
-  __syncthreads();
-  uint32_t base = 0, tot = 0;
-#pragma unroll
-  for (int i = 0; i < ENC_THREADS / 32; i++) { if (i < w) base += warp_tot[i]; tot += warp_tot[i]; }
-  __syncthreads();
-  total = tot;
-  return base + inc - v;
 }
 
 __global__ void __launch_bounds__(ENC_THREADS)
@@ -364,12 +488,48 @@ class EncoderImpl {
     memo_ = MemoDev{memo_slots_.get(), (uint32_t)(memo_cap - 1)};
   }
 
+  // The single-pass kernel (enc_fused) over [0, n), in ranges of at most 1 GiB (31-bit token / word counts per range).
+  // false: the text holds a word longer than ENC_SHORT bytes -- the caller encodes the piece with the general path.
+  uint64_t general_pieces = 0;  // pieces that went through the general three-kernel path
+  static bool no_fused() {
+    static const bool off = getenv("SWB_NO_FUSED_ENCODE") && atoi(getenv("SWB_NO_FUSED_ENCODE")) > 0;  // (tests: force the general path)
+    return off;
+  }
+  bool encode_fused(const uint8_t *d_text, uint64_t n, int32_t *d_out, uint64_t cap_ids, uint64_t tok_base, uint32_t *d_word_ntok,
+                    uint64_t cap_words, uint64_t word_base, uint64_t *ntok, uint64_t *nwords) {
+    const uint64_t RANGE = 1ull << 30;
+    uint64_t tt = 0, tw = 0;
+    for (uint64_t lo = 0; lo < n; lo += RANGE) {
+      const uint64_t hi = std::min(n, lo + RANGE);
+      const uint64_t n_tiles = ((hi + 15) / 16 - lo / 16 + ENC_THREADS - 1) / ENC_THREADS;
+      if (desc_.size() < n_tiles + 1) desc_.alloc(n_tiles + 1);  // [n_tiles] = {tile counter, fallback flag}
+      SWB_CUDA(cudaMemsetAsync(desc_.get(), 0, (n_tiles + 1) * 8, stream_));
+      unsigned int *ctr = reinterpret_cast<unsigned int *>(desc_.get() + n_tiles);
+      const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)sms_ * 4);
+      enc_fused<<<grid, ENC_THREADS, 0, stream_>>>(d_text, n, lo, hi, tbl_, memo_, d_bmap_.get(), desc_.get(), ctr, ctr + 1, tok_base + tt,
+                                                   word_base + tw, d_out, cap_ids, d_word_ntok, cap_words, neg_id_);
+      launches++;
+      SWB_CUDA(cudaGetLastError());
+      unsigned long long h[2];
+      SWB_CUDA(cudaMemcpyAsync(&h[0], desc_.get() + n_tiles - 1, 8, cudaMemcpyDeviceToHost, stream_));
+      SWB_CUDA(cudaMemcpyAsync(&h[1], desc_.get() + n_tiles, 8, cudaMemcpyDeviceToHost, stream_));
+      SWB_CUDA(cudaStreamSynchronize(stream_));
+      if (h[1] >> 32) return false;  // a word longer than ENC_SHORT bytes
+      tt += (h[0] >> 31) & 0x7FFFFFFFull; tw += h[0] & 0x7FFFFFFFull;
+    }
+    if (tok_base + tt > cap_ids) throw Error("swb_encode: output capacity too small");
+    if (d_word_ntok && word_base + tw > cap_words) throw Error("swb_encode: word_ntok capacity too small");
+    *ntok = tt; *nwords = tw;
+    return true;
+  }
   // Encodes one device-resident piece [d_text, d_text+n) that is 16-byte aligned and padded with 16 ' '.
   // Appends to d_out at tok_base / d_word_ntok at word_base. Returns (tokens, words) of the piece.
   void encode_piece(const uint8_t *d_text, uint64_t n, int32_t *d_out, uint64_t cap_ids, uint64_t tok_base,
                     uint32_t *d_word_ntok, uint64_t cap_words, uint64_t word_base, uint64_t *ntok, uint64_t *nwords) {
     *ntok = 0; *nwords = 0;
     if (n == 0) return;
+    if (!no_fused() && encode_fused(d_text, n, d_out, cap_ids, tok_base, d_word_ntok, cap_words, word_base, ntok, nwords)) return;
+    general_pieces++;
     const uint64_t n_tiles = (n + ENC_TILE - 1) / ENC_TILE;
     if (tmp_.size() < n + 16) tmp_.alloc(n + 16);
     if (tile_tok_.size() < n_tiles + 1) {
@@ -528,6 +688,7 @@ class EncoderImpl {
   DevBuf<uint32_t> tile_tok_, tile_words_;
   DevBuf<unsigned long long> tile_tok_off_, tile_word_off_;
   DevBuf<uint8_t> scan_tmp_, dtext_;
+  DevBuf<unsigned long long> desc_;
 };
 
 }  // namespace swb

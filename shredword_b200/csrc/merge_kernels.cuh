@@ -877,8 +877,9 @@ __device__ __forceinline__ uint32_t scan_log_words(const StreamDev &s, const Pai
   uint32_t removed = 0;
 #pragma unroll 1
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (!SWB_DBG_OK(lo + i < lg.cap, 4, lo, i, n)) break;
     const uint4 e = __ldcg(&lg.ent[lo + i]);
-    if (e.x == want_other && (e.y & 0x80000000u) == want_side)
+    if (e.x == want_other && (e.y & 0x80000000u) == want_side && SWB_DBG_OK((((uint64_t)e.w << 32) | e.z) < s.n_rows * ROW, 5, ((uint64_t)e.w << 32) | e.z, e.y, i))
       removed += merge_one_word(s, ((uint64_t)e.w << 32) | e.z, e.y & 0x7FFFFFFFu, a, b, new_id, sink);
   }
   return removed;

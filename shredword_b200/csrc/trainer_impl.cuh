@@ -240,14 +240,18 @@ class TrainerImpl {
                  *d_nlong = scalars_.get() + 3;
     unsigned long long *d_u64 = reinterpret_cast<unsigned long long *>(scalars_.get() + 8);  // [0]=long syms [1]=bytes [2]=cursor
     // ---- 1. tokenise + dedupe
-    uint64_t cap = std::max<uint64_t>(1ull << 16, pow2_ceil(n / 64));
-    DevBuf<unsigned long long> keys, counts;
+    // Unique words grow far slower than the corpus (Heaps' law): the table starts at one 32-byte slot per 256 corpus bytes, at
+    // most 8 M slots (256 MB; what the tail of the distribution touches of it should stay in the 126 MB L2), and is rebuilt
+    // four times as large if the corpus turns out to hold more unique words than 60 % of that.
+    uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(1ull << 16, pow2_ceil(n / 256)), 1ull << 23);
+    DevBuf<WSlot> wslots;
     unsigned int h_scal[4];
+    const int tok_grid = (int)std::max<uint64_t>((uint64_t)sms_, (n >> 31) + 1);  // one block per SM; a block's span stays below 4 GB
     for (;;) {
-      keys.alloc(cap); counts.alloc(cap);
-      wt_fill<<<sms_ * 8, 256, 0, stream_>>>(keys.get(), counts.get(), cap); launched();
+      wslots.alloc(cap);
+      wt_fill<<<sms_ * 8, 256, 0, stream_>>>(wslots.get(), cap); launched();
       SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
-      WordTableDev tbl{keys.get(), counts.get(), cap - 1, d_nuniq, d_flags, (uint64_t)(cap * 0.6)};
+      WordTableDev tbl{wslots.get(), cap - 1, d_nuniq, d_flags, (uint64_t)(cap * 0.6)};
       SWB_CUDA(cudaEventRecord(ev0_, stream_));
       if (n && host_src) {
         const uint64_t PIECE = load_piece_bytes();  // (a multiple of 16: see wt_tokenize)
@@ -270,7 +274,7 @@ class TrainerImpl {
           if (c1 < n) while (tok_hi > tok_lo && !is_delim(host_src[tok_hi - 1])) tok_hi--;
           SWB_CUDA(cudaStreamWaitEvent(stream_, ev, 0));
           if (tok_hi > tok_lo) {
-            wt_tokenize<<<sms_ * 4, WT_THREADS, WT_SMEM_BYTES, stream_>>>(corpus.get(), n, tbl, tok_lo, tok_hi); launched();
+            wt_tokenize<<<tok_grid, WT_THREADS, WT_SMEM_BYTES, stream_>>>(corpus.get(), n, tbl, tok_lo, tok_hi); launched();
             tok_lo = tok_hi;
           }
         }
@@ -279,7 +283,7 @@ class TrainerImpl {
         for (cudaEvent_t ev : landed) cudaEventDestroy(ev);
         cudaEventDestroy(fill_done);
         host_src = nullptr;  // (a rerun with a larger table finds the corpus on the device)
-      } else if (n) { wt_tokenize<<<sms_ * 4, WT_THREADS, WT_SMEM_BYTES, stream_>>>(corpus.get(), n, tbl, 0, n); launched(); }
+      } else if (n) { wt_tokenize<<<tok_grid, WT_THREADS, WT_SMEM_BYTES, stream_>>>(corpus.get(), n, tbl, 0, n); launched(); }
       SWB_CUDA(cudaGetLastError());
       SWB_CUDA(cudaEventRecord(ev1_, stream_));
       SWB_CUDA(cudaMemcpyAsync(h_scal, scalars_.get(), sizeof h_scal, cudaMemcpyDeviceToHost, stream_));
@@ -291,7 +295,7 @@ class TrainerImpl {
       }
       if (h_scal[1] & 2u) throw Error("NUL byte in corpus: outside the parity domain (the reference drops a libc-buffer-dependent span)");
       if (!(h_scal[1] & 1u)) break;
-      cap *= 8;  // more unique words than expected: bigger table, run again
+      cap *= 4;  // more unique words than expected: bigger table, run again
     }
     W = h_scal[0];
     DevBuf<uint64_t> woff;
@@ -302,7 +306,7 @@ class TrainerImpl {
       cnt_.alloc(W);
       woff.alloc(W);
       if (W) {
-        wt_compact<<<sms_ * 8, 256, 0, stream_>>>(keys.get(), counts.get(), cap, skeys.get(), scnt.get(), d_cursor); launched();
+        wt_compact<<<sms_ * 8, 256, 0, stream_>>>(wslots.get(), cap, skeys.get(), scnt.get(), d_cursor); launched();
         size_t tmp_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, skeys.get(), skeys2.get(), scnt.get(), cnt_.get(), (int64_t)W, 0, 52, stream_);
         DevBuf<uint8_t> tmp(tmp_bytes);
@@ -311,7 +315,7 @@ class TrainerImpl {
         wt_unpack_sorted<<<sms_ * 4, 256, 0, stream_>>>(skeys2.get(), W, woff.get()); launched();
         sync();
       }
-      keys.release(); counts.release();
+      wslots.release();
     } else {
       // ---- 2'. export this rank's unique words, all-gather, merge into the global table
       NcclApi &api = NcclApi::get();
@@ -319,7 +323,7 @@ class TrainerImpl {
       DevBuf<unsigned long long> skeys(Wl), scnt(Wl), len1(Wl + 1), aoff(Wl + 1);
       unsigned long long arena_bytes = 0;
       if (Wl) {
-        wt_compact<<<sms_ * 8, 256, 0, stream_>>>(keys.get(), counts.get(), cap, skeys.get(), scnt.get(), d_cursor); launched();
+        wt_compact<<<sms_ * 8, 256, 0, stream_>>>(wslots.get(), cap, skeys.get(), scnt.get(), d_cursor); launched();
         wt_local_lens<<<sms_ * 8, 256, 0, stream_>>>(corpus.get(), n, skeys.get(), Wl, len1.get()); launched();
         SWB_CUDA(cudaMemsetAsync(len1.get() + Wl, 0, 8, stream_));
         size_t tb = 0;
@@ -330,7 +334,7 @@ class TrainerImpl {
         SWB_CUDA(cudaMemcpyAsync(&arena_bytes, aoff.get() + Wl, 8, cudaMemcpyDeviceToHost, stream_));
         sync();
       }
-      keys.release(); counts.release();
+      wslots.release();
       DevBuf<unsigned long long> d_sizes(2 * (size_t)nranks);
       const unsigned long long mine[2] = {Wl, arena_bytes};
       SWB_CUDA(cudaMemcpyAsync(d_sizes.get() + 2 * rank, mine, 16, cudaMemcpyHostToDevice, stream_));
@@ -361,7 +365,7 @@ class TrainerImpl {
       DevBuf<unsigned long long> gkeys(gcap), gcounts(gcap), gfirst(gcap);
       wt_fill3<<<sms_ * 8, 256, 0, stream_>>>(gkeys.get(), gcounts.get(), gfirst.get(), gcap); launched();
       SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
-      WordTableDev gtbl{gkeys.get(), gcounts.get(), gcap - 1, d_nuniq, d_flags, gcap};
+      WordTableSoA gtbl{gkeys.get(), gcounts.get(), gcap - 1, d_nuniq, d_flags, gcap};
       wt_insert_words<<<sms_ * 8, 256, 0, stream_>>>(arena_all.get(), base_n, meta_all.get(), d_sizes.get(), nranks, maxW, maxA, gtbl, gfirst.get());
       launched();
       SWB_CUDA(cudaMemcpyAsync(h_scal, scalars_.get(), sizeof h_scal, cudaMemcpyDeviceToHost, stream_));
@@ -1154,6 +1158,21 @@ class TrainerImpl {
     }
     ~HostCmd2Sender() { if (running) send(0, 0, 1); }
   };
+  // Debug builds (-DSWB_DEBUG_BOUNDS): index violations the kernels recorded instead of following them
+  void check_debug_bounds() {
+#ifdef SWB_DEBUG_BOUNDS
+    unsigned long long d[1 + 4 * 16];
+    SWB_CUDA(cudaMemcpyFromSymbol(d, g_dbg, sizeof d));
+    if (!d[0]) return;
+    std::string msg = "debug bounds: " + std::to_string(d[0]) + " violation(s):";
+    for (unsigned long long i = 0; i < d[0] && i < 16; i++) {
+      char b[160];
+      snprintf(b, sizeof b, " [code %llu: %llu %llu %llu]", d[1 + 4 * i], d[2 + 4 * i], d[3 + 4 * i], d[4 + 4 * i]);
+      msg += b;
+    }
+    throw Error(msg);
+#endif
+  }
   // Limits of the resident kernel's fast paths; the SWB_TEST_* variables only ever SHRINK them (tests/test_gpu_variants.py
   // drives the overflow paths on small corpora with them).
   static ClusterTune cluster_tune() {
@@ -1398,9 +1417,10 @@ class TrainerImpl {
     }
     sync();
     {  // device time of this launch's merges (command seen -> result published), per mode
+      check_debug_bounds();
       unsigned long long ac[8];
       SWB_CUDA(cudaMemcpy(ac, cl_acct_.get(), sizeof ac, cudaMemcpyDeviceToHost));
-      stats.hints_rejected += ac[5];
+      stats.hints_rejected += ac[5]; stats.resident_spill_merges += ac[7];
       stats.resident_local_merges += ac[0]; stats.resident_local_ms += (double)ac[1] * 1e-6;
       stats.resident_grid_merges += ac[2]; stats.resident_grid_ms += (double)ac[3] * 1e-6;
       stats.merge_kernel_ms += (double)(ac[1] + ac[3]) * 1e-6;

@@ -20,18 +20,34 @@ namespace swb {
 constexpr uint64_t WT_EMPTY = ~0ull;
 constexpr int WT_TAG_BITS = 24;
 constexpr uint64_t WT_TAG_MASK = (1ull << WT_TAG_BITS) - 1;
-constexpr int LT_SLOTS = 4096;   // block-private table (48 KB: 8 B key + 4 B count per slot)
-constexpr int LT_PROBES = 16;
-constexpr int WT_THREADS = 256;
-constexpr int WT_SMEM_BYTES = LT_SLOTS * 12 + 16;
+constexpr int LT_SLOTS = 4096;   // block-private table: tag 8 B + word bytes 16 B + count 4 B + first offset 4 B per slot = 128 KB
+constexpr int LT_PROBES = 4;
+constexpr int WT_THREADS = 1024; // one block per SM
+constexpr int WT_SMEM_BYTES = LT_SLOTS * 32 + 16;
+constexpr int WT_SHORT_MAX = 15; // words of up to 15 bytes are identified by their bytes (two 64-bit words, zero padded)
 
+// One slot of the global word table, one 32-byte sector:
+//   key   = (offset of the first occurrence seen << 24) | tag24 ; tag low 12 bits = djb2 & 4095 (the reference's StrMap bucket)
+//   count = occurrences
+//   lo,hi = the word's bytes, zero padded, for words of up to WT_SHORT_MAX bytes (a corpus holds no NUL byte, so the padded
+//           bytes identify the word); written once by whoever claims the slot, as ONE 16-byte store, read as one 16-byte
+//           load: (0, 0) = not there (yet) -- then, and for longer words, the bytes are compared through the offset in `key`.
+struct __align__(32) WSlot { unsigned long long key, count, lo, hi; };
 struct WordTableDev {
-  unsigned long long *keys;    // (first offset seen << 24) | tag24 ; tag low 12 bits = djb2 & 4095
-  unsigned long long *counts;
+  WSlot *slots;
   uint64_t mask;               // capacity - 1
   unsigned int *n_unique;
   unsigned int *flags;         // bit 0: table overflow, bit 1: NUL byte seen
   uint64_t limit;              // max unique words before overflow is declared
+};
+// the table the ranks' exported words are merged into (multi-GPU load): keys / counts / global first offsets side by side
+struct WordTableSoA {
+  unsigned long long *keys;
+  unsigned long long *counts;
+  uint64_t mask;
+  unsigned int *n_unique;
+  unsigned int *flags;
+  uint64_t limit;
 };
 
 // Scans the word starting at `off`: returns its length, fills both hashes.
@@ -62,27 +78,62 @@ __device__ __forceinline__ bool wt_same_word(const uint8_t *__restrict__ p, uint
   return offB + len == n || is_delim(p[offB + len]);
 }
 
+// one 16-byte access to shared memory (the word bytes of a block-private slot are written and read as a unit)
+__device__ __forceinline__ ulonglong2 wt_lds16(const ulonglong2 *p) {
+  ulonglong2 r;
+  asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "r"((unsigned int)__cvta_generic_to_shared(p)) : "memory");
+  return r;
+}
+__device__ __forceinline__ void wt_sts16(ulonglong2 *p, unsigned long long x, unsigned long long y) {
+  asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"((unsigned int)__cvta_generic_to_shared(p)), "l"(x), "l"(y) : "memory");
+}
+// hash of a short word's padded bytes (never 0: 0 marks a free slot of the block-private table)
+__device__ __forceinline__ uint64_t wt_short_hash(uint64_t lo, uint64_t hi) {
+  const uint64_t h = dmix64(lo ^ dmix64(hi + 0x632BE59BD9B4E019ull));
+  return h ? h : 0x9E3779B97F4A7C15ull;
+}
+// length and djb2 (reference hash.cpp:35-38) of a short word from its padded bytes
+__device__ __forceinline__ uint32_t wt_short_len_djb(uint64_t lo, uint64_t hi, uint32_t &djb) {
+  uint32_t d = 5381u, len = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const uint32_t c = (uint32_t)((k < 8 ? lo >> (8 * k) : hi >> (8 * (k - 8))) & 0xFFu);
+    if (c) { d = d * 33u + c; len = k + 1; }  // (bytes are contiguous from 0: a zero byte ends the word)
+  }
+  djb = d;
+  return len;
+}
+
+// Adds `cnt` occurrences of the word at `off` to the global table. short_word: (lo, hi) are its padded bytes.
 __device__ __forceinline__ void wt_global_insert(const WordTableDev &t, const uint8_t *__restrict__ p, uint64_t n,
                                                  uint64_t off, uint32_t len, uint64_t h64, uint64_t tag,
-                                                 unsigned long long cnt) {
+                                                 unsigned long long cnt, bool short_word, uint64_t lo, uint64_t hi) {
   const unsigned long long key = (off << WT_TAG_BITS) | tag;
   uint64_t slot = h64 & t.mask;
   for (uint64_t probe = 0; probe <= t.mask; probe++) {
-    unsigned long long cur = t.keys[slot];
+    WSlot *sl = t.slots + slot;
+    unsigned long long cur = __ldcg(&sl->key);
     if (cur == WT_EMPTY) {
-      const unsigned long long prev = atomicCAS(&t.keys[slot], WT_EMPTY, key);
+      const unsigned long long prev = atomicCAS(&sl->key, WT_EMPTY, key);
       if (prev == WT_EMPTY) {
-        atomicAdd(&t.counts[slot], cnt);
+        if (short_word) *reinterpret_cast<ulonglong2 *>(&sl->lo) = make_ulonglong2(lo, hi);  // one 16-byte store
+        atomicAdd(&sl->count, cnt);
         const unsigned int u = atomicAdd(t.n_unique, 1u);
         if (u >= t.limit) atomicOr(t.flags, 1u);
         return;
       }
       cur = prev;
     }
-    if ((cur & WT_TAG_MASK) == tag && wt_same_word(p, n, off, cur >> WT_TAG_BITS, len)) {
-      atomicAdd(&t.counts[slot], cnt);
-      if (key < cur) atomicMin(&t.keys[slot], key);  // same tag => orders by offset: keeps the first occurrence
-      return;
+    if ((cur & WT_TAG_MASK) == tag) {
+      bool same;
+      const ulonglong2 pay = short_word ? __ldcg(reinterpret_cast<const ulonglong2 *>(&sl->lo)) : make_ulonglong2(0ull, 0ull);
+      if (pay.x != 0ull) same = pay.x == lo && pay.y == hi;          // both short: the bytes themselves
+      else same = wt_same_word(p, n, off, cur >> WT_TAG_BITS, len);   // a long word, or bytes not published yet: through the corpus
+      if (same) {
+        atomicAdd(&sl->count, cnt);
+        if (key < cur) atomicMin(&sl->key, key);  // same tag => orders by offset: keeps the first occurrence
+        return;
+      }
     }
     slot = (slot + 1) & t.mask;
   }
@@ -96,105 +147,142 @@ __device__ __forceinline__ uint32_t wt_delim_bits(uint32_t w, uint32_t &nul) {
   return ((m & 0x01010101u) * 0x01020408u) >> 24;  // one bit per byte, byte 0 -> bit 0
 }
 
-// corpus must be 16-byte aligned and padded with >= 16 delimiter bytes after n.
+// corpus must be 16-byte aligned and padded with >= 48 delimiter bytes after n.
 // Counts the words that START in [lo, hi) (the whole corpus: lo = 0, hi = n). A range lets the host-buffer load
 // tokenise a piece of the corpus while the next piece is still crossing PCIe: `hi` is then cut right after a
 // delimiter, so every word that starts before it also ends before it, and the bytes of the 16-byte segments the
 // range touches have all arrived (the copy granularity is a multiple of 16).
-__global__ void __launch_bounds__(WT_THREADS)
-wt_tokenize(const uint8_t *__restrict__ corpus, uint64_t n, WordTableDev tbl, uint64_t lo, uint64_t hi) {
+//
+// One block per SM, each over one contiguous span of the range. A thread takes 16 bytes (one streaming load), gets the
+// next 16 from its neighbour lane, and handles the words that start in its segment entirely in registers: the 16 bytes
+// from the word start are cut out of that 32-byte window with funnel shifts, the delimiter mask gives the length, and a
+// word of up to 15 bytes IS its key (two zero-padded 64-bit words; no byte loop, no compare against an earlier occurrence).
+// Occurrences are summed in a block-private table in shared memory that keeps the first LT_SLOTS distinct words the
+// block meets -- in Zipfian text those contain the head of the distribution -- and is flushed once, at the end of the span;
+// words that find no place there, and words of 16+ bytes, go to the global table directly (one 32-byte sector per probe).
+__global__ void __launch_bounds__(WT_THREADS, 1)
+wt_tokenize(const uint8_t *__restrict__ corpus, uint64_t n, WordTableDev tbl, uint64_t lo_b, uint64_t hi_b) {
   extern __shared__ __align__(16) unsigned long long wt_dyn_smem[];  // WT_SMEM_BYTES, opt-in above 48 KB
-  unsigned long long *lkeys = wt_dyn_smem;
-  unsigned int *lcnt = reinterpret_cast<unsigned int *>(wt_dyn_smem + LT_SLOTS);
-  unsigned int &lused = lcnt[LT_SLOTS];
-  for (int i = threadIdx.x; i < LT_SLOTS; i += WT_THREADS) { lkeys[i] = WT_EMPTY; lcnt[i] = 0; }
-  if (threadIdx.x == 0) lused = 0;
+  ulonglong2 *lpay = reinterpret_cast<ulonglong2 *>(wt_dyn_smem);                 // [LT_SLOTS] word bytes
+  unsigned long long *ltag = wt_dyn_smem + 2 * LT_SLOTS;                          // [LT_SLOTS] hash, 0 = free
+  unsigned int *lcnt = reinterpret_cast<unsigned int *>(wt_dyn_smem + 3 * LT_SLOTS);  // [LT_SLOTS]
+  unsigned int *lmin = lcnt + LT_SLOTS;                                           // [LT_SLOTS] first offset, relative to the span
+  for (int i = threadIdx.x; i < LT_SLOTS; i += WT_THREADS) { lpay[i] = make_ulonglong2(0ull, 0ull); ltag[i] = 0ull; lcnt[i] = 0u; lmin[i] = 0xFFFFFFFFu; }
   __syncthreads();
 
-  const uint64_t seg_lo = lo / 16, seg_hi = (hi + 15) / 16, nseg = seg_hi - seg_lo;
-  // each block owns a contiguous span of segments so that its private table sees a long stretch of text
+  const uint64_t seg_lo = lo_b / 16, seg_hi = (hi_b + 15) / 16, nseg = seg_hi - seg_lo;
   const uint64_t per_block = ((nseg + gridDim.x - 1) / gridDim.x + WT_THREADS - 1) / WT_THREADS * WT_THREADS;
   const uint64_t seg_begin = seg_lo + (uint64_t)blockIdx.x * per_block;
   const uint64_t seg_end = min(seg_hi, seg_begin + per_block);
+  const uint64_t span0 = seg_begin * 16;  // (spans are < 4 GB: the host sizes the grid accordingly)
+  const int lane = threadIdx.x & 31;
   uint32_t nul = 0;
 
   for (uint64_t base = seg_begin; base < seg_end; base += WT_THREADS) {
     const uint64_t seg = base + threadIdx.x;
-    if (seg < seg_end) {
-      const uint4 v = *reinterpret_cast<const uint4 *>(corpus + seg * 16);
-      uint32_t dm = wt_delim_bits(v.x, nul) | (wt_delim_bits(v.y, nul) << 4) | (wt_delim_bits(v.z, nul) << 8) |
-                    (wt_delim_bits(v.w, nul) << 12);
-      const uint32_t prev_delim = (seg == 0) ? 1u : (is_delim(corpus[seg * 16 - 1]) ? 1u : 0u);
-      uint32_t starts = ~dm & ((dm << 1) | prev_delim) & 0xFFFFu;
-      while (starts) {
-        const int s = __ffs(starts) - 1;
-        starts &= starts - 1;
-        const uint64_t off = seg * 16 + s;
-        if (off >= hi) break;
-        if (off < lo) continue;
+    const bool live = seg < seg_end;
+    uint4 v = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
+    if (live) v = __ldcs(reinterpret_cast<const uint4 *>(corpus + seg * 16));
+    // the 16 bytes after this segment: the neighbour lane's, or (last lane of the warp) one more load
+    uint4 nx;
+    nx.x = __shfl_down_sync(0xffffffffu, v.x, 1); nx.y = __shfl_down_sync(0xffffffffu, v.y, 1);
+    nx.z = __shfl_down_sync(0xffffffffu, v.z, 1); nx.w = __shfl_down_sync(0xffffffffu, v.w, 1);
+    uint32_t prev_last = __shfl_up_sync(0xffffffffu, v.w, 1) >> 24;
+    if (!live) continue;  // (whole warps leave together except in the last tile, where the shuffles above have already happened)
+    if (lane == 31 || seg + 1 >= seg_end) nx = __ldg(reinterpret_cast<const uint4 *>(corpus + seg * 16 + 16));  // (padding makes this safe)
+    if (lane == 0) prev_last = seg == 0 ? 0x20u : (uint32_t)corpus[seg * 16 - 1];
+    const uint32_t dm = wt_delim_bits(v.x, nul) | (wt_delim_bits(v.y, nul) << 4) | (wt_delim_bits(v.z, nul) << 8) | (wt_delim_bits(v.w, nul) << 12);
+    const uint32_t prev_delim = is_delim((uint8_t)prev_last) ? 1u : 0u;
+    uint32_t starts = ~dm & ((dm << 1) | prev_delim) & 0xFFFFu;
+    while (starts) {
+      const int s = __ffs(starts) - 1;
+      starts &= starts - 1;
+      const uint64_t off = seg * 16 + s;
+      if (off >= hi_b) break;
+      if (off < lo_b) continue;
+      // the 16 bytes from the word start on
+      uint32_t w0, w1, w2, w3, w4;
+      switch (s >> 2) {
+        case 0: w0 = v.x; w1 = v.y; w2 = v.z; w3 = v.w; w4 = nx.x; break;
+        case 1: w0 = v.y; w1 = v.z; w2 = v.w; w3 = nx.x; w4 = nx.y; break;
+        case 2: w0 = v.z; w1 = v.w; w2 = nx.x; w3 = nx.y; w4 = nx.z; break;
+        default: w0 = v.w; w1 = nx.x; w2 = nx.y; w3 = nx.z; w4 = nx.w; break;
+      }
+      const uint32_t bs = (uint32_t)(s & 3) * 8u;
+      uint32_t b0 = __funnelshift_r(w0, w1, bs), b1 = __funnelshift_r(w1, w2, bs), b2 = __funnelshift_r(w2, w3, bs), b3 = __funnelshift_r(w3, w4, bs);
+      uint32_t dummy = 0;
+      const uint32_t wm = wt_delim_bits(b0, dummy) | (wt_delim_bits(b1, dummy) << 4) | (wt_delim_bits(b2, dummy) << 8) | (wt_delim_bits(b3, dummy) << 12);
+      const uint32_t L = wm ? (uint32_t)(__ffs(wm) - 1) : 16u;
+      if (L > WT_SHORT_MAX) {  // 16 bytes or more: byte loop + comparison through the corpus (rare)
         uint64_t h64; uint32_t djb;
         const uint32_t len = wt_scan_word(corpus, off, n, h64, djb);
         const uint64_t tag = (djb & 0xFFFu) | (((h64 >> 40) & 0xFFFu) << 12);
-        const unsigned long long key = (off << WT_TAG_BITS) | tag;
-        // block-private table first
-        uint32_t slot = (uint32_t)h64 & (LT_SLOTS - 1);
-        bool done = false;
-        for (int probe = 0; probe < LT_PROBES && !done; probe++) {
-          unsigned long long cur = lkeys[slot];
-          if (cur == WT_EMPTY) {
-            const unsigned long long prev = atomicCAS(&lkeys[slot], WT_EMPTY, key);
-            if (prev == WT_EMPTY) { atomicAdd(&lcnt[slot], 1u); atomicAdd(&lused, 1u); done = true; break; }
-            cur = prev;
-          }
-          if ((cur & WT_TAG_MASK) == tag && wt_same_word(corpus, n, off, cur >> WT_TAG_BITS, len)) {
-            atomicAdd(&lcnt[slot], 1u);
-            if (key < cur) atomicMin(&lkeys[slot], key);
-            done = true;
-            break;
-          }
-          slot = (slot + 1) & (LT_SLOTS - 1);
+        wt_global_insert(tbl, corpus, n, off, len, h64, tag, 1ull, false, 0ull, 0ull);
+        continue;
+      }
+      // zero the bytes from L on: (lo, hi) is the word
+      {
+        const uint32_t k0 = L >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - L))) & (L ? 0xFFFFFFFFu : 0u);
+        const uint32_t k1 = L >= 8 ? 0xFFFFFFFFu : (L <= 4 ? 0u : 0xFFFFFFFFu >> (8 * (8 - L)));
+        const uint32_t k2 = L >= 12 ? 0xFFFFFFFFu : (L <= 8 ? 0u : 0xFFFFFFFFu >> (8 * (12 - L)));
+        const uint32_t k3 = L <= 12 ? 0u : 0xFFFFFFFFu >> (8 * (16 - L));
+        b0 &= k0; b1 &= k1; b2 &= k2; b3 &= k3;
+      }
+      const uint64_t wlo = ((uint64_t)b1 << 32) | b0, whi = ((uint64_t)b3 << 32) | b2;
+      const uint64_t h = wt_short_hash(wlo, whi);
+      const uint32_t rel = (uint32_t)(off - span0);
+      uint32_t slot = (uint32_t)h & (LT_SLOTS - 1);
+      bool done = false;
+#pragma unroll 1
+      for (int probe = 0; probe < LT_PROBES; probe++) {
+        unsigned long long cur = *(volatile unsigned long long *)&ltag[slot];
+        if (cur == 0ull) {
+          cur = atomicCAS(&ltag[slot], 0ull, (unsigned long long)h);
+          if (cur == 0ull) { wt_sts16(&lpay[slot], wlo, whi); cur = h; atomicAdd(&lcnt[slot], 1u); atomicMin(&lmin[slot], rel); done = true; break; }
         }
-        if (!done) wt_global_insert(tbl, corpus, n, off, len, h64, tag, 1ull);
+        if (cur == h) {
+          const ulonglong2 pay = wt_lds16(&lpay[slot]);
+          if (pay.x == wlo && pay.y == whi) { atomicAdd(&lcnt[slot], 1u); atomicMin(&lmin[slot], rel); done = true; break; }
+          // (bytes not written yet, or another word with the same hash: try the next slot; a word may end up in two
+          //  slots or go to the global table directly -- the global table is the one that decides identity)
+        }
+        slot = (slot + 1) & (LT_SLOTS - 1);
+      }
+      if (!done) {
+        uint32_t djb;
+        wt_short_len_djb(wlo, whi, djb);
+        const uint64_t tag = (djb & 0xFFFu) | (((h >> 40) & 0xFFFu) << 12);
+        wt_global_insert(tbl, corpus, n, off, L, h, tag, 1ull, true, wlo, whi);
       }
     }
-    __syncthreads();
-    const bool last = base + WT_THREADS >= seg_end;
-    // block-uniform decision: everybody reads `lused` before anybody starts the next tile's inserts
-    if (__syncthreads_or(lused > LT_SLOTS / 2 || last)) {
-      for (int i = threadIdx.x; i < LT_SLOTS; i += WT_THREADS) {
-        const unsigned long long k = lkeys[i];
-        if (k != WT_EMPTY) {
-          const uint64_t off = k >> WT_TAG_BITS;
-          uint64_t h64; uint32_t djb;
-          const uint32_t len = wt_scan_word(corpus, off, n, h64, djb);
-          wt_global_insert(tbl, corpus, n, off, len, h64, k & WT_TAG_MASK, (unsigned long long)lcnt[i]);
-          lkeys[i] = WT_EMPTY; lcnt[i] = 0;
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) lused = 0;
-      __syncthreads();
-    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < LT_SLOTS; i += WT_THREADS) {
+    const unsigned long long h = ltag[i];
+    if (h == 0ull) continue;
+    const ulonglong2 pay = lpay[i];
+    uint32_t djb;
+    const uint32_t len = wt_short_len_djb(pay.x, pay.y, djb);
+    const uint64_t tag = (djb & 0xFFFu) | (((h >> 40) & 0xFFFu) << 12);
+    wt_global_insert(tbl, corpus, n, span0 + lmin[i], len, h, tag, (unsigned long long)lcnt[i], true, pay.x, pay.y);
   }
   if (nul) atomicOr(tbl.flags, 2u);
 }
 
-__global__ void wt_fill(unsigned long long *keys, unsigned long long *counts, uint64_t cap) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-    keys[i] = WT_EMPTY; counts[i] = 0;
-  }
+__global__ void wt_fill(WSlot *slots, uint64_t cap) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
+    slots[i] = WSlot{WT_EMPTY, 0ull, 0ull, 0ull};
 }
 
 // occupied slots -> (bucket << 40 | first offset, count); order is fixed by the sort that follows
-__global__ void wt_compact(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ counts,
-                           uint64_t cap, unsigned long long *__restrict__ sort_keys,
+__global__ void wt_compact(const WSlot *__restrict__ slots, uint64_t cap, unsigned long long *__restrict__ sort_keys,
                            unsigned long long *__restrict__ out_counts, unsigned int *cursor) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-    const unsigned long long k = keys[i];
+    const unsigned long long k = slots[i].key;
     if (k != WT_EMPTY) {
       const unsigned int j = atomicAdd(cursor, 1u);
       sort_keys[j] = ((k & 0xFFFull) << 40) | (k >> WT_TAG_BITS);
-      out_counts[j] = counts[i];
+      out_counts[j] = slots[i].count;
     }
   }
 }
@@ -278,7 +366,7 @@ __global__ void wt_export(const uint8_t *__restrict__ corpus, const unsigned lon
 __global__ void __launch_bounds__(256)
 wt_insert_words(const uint8_t *__restrict__ base, uint64_t base_n, const WordMeta *__restrict__ meta_all,
                 const unsigned long long *__restrict__ sizes /* [2*R]: Wl, arena bytes */, int R, uint64_t maxW, uint64_t maxA,
-                WordTableDev tbl, unsigned long long *__restrict__ gfirst) {
+                WordTableSoA tbl, unsigned long long *__restrict__ gfirst) {
   for (int r = 0; r < R; r++) {
     const uint64_t Wl = sizes[2 * r];
     for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < Wl; j += (uint64_t)gridDim.x * blockDim.x) {

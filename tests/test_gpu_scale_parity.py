@@ -45,7 +45,9 @@ def test_config2_full_size_equals_reference_files(product, tmp_path):
   freqs = [int(ln.rsplit(b" ", 1)[1]) for ln in (tmp_path / "v").read_bytes().split(b"\n") if b" " in ln and ln.rsplit(b" ", 1)[1].isdigit()]
   assert len(freqs) == T and np.array_equal(hist, np.array(freqs)), "histogram(encode(corpus)) != .vocab frequency column"
   cut = 2_000_000 + int(np.nonzero(data[2_000_000:2_001_000] == 10)[0][0]) + 1
-  assert enc.decode(enc.encode(data[:cut])) == bytes(data[:cut]).translate(None, b" \t\r\n")
+  bm = t.byte_map()  # bytes the coverage rule dropped come back as unk_id (0)
+  table = bytes(int(bm[b]) & 255 for b in range(256))
+  assert enc.decode(enc.encode(data[:cut])) == bytes(data[:cut]).translate(None, b" \t\r\n").translate(table)
   t.destroy()
 
 
