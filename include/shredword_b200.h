@@ -188,6 +188,13 @@ int64_t swb_encode_device(SwbEncoder *enc, const void *d_text, size_t nbytes, in
 size_t swb_decode(const SwbEncoder *enc, const int32_t *ids, size_t n, uint8_t *out, size_t cap);
 uint64_t swb_encoder_kernel_launches(const SwbEncoder *enc);
 
+/* ---- optional pre-pass: the reference's normalize_line (reference csrc/bpe/normalize.cpp:24-59; it has
+ * no caller there) applied to every line of `text`: ASCII lower-casing, whitespace runs inside a line -> U+2581, runs at
+ * the start / end of a line dropped, lines joined by their '\n' again. text / out are host pointers, or device pointers
+ * when on_device != 0. Returns the length of the full result (when it exceeds cap only the first cap bytes were
+ * written; 3 * nbytes always suffices), or -1 on error. */
+int64_t swb_normalize(const void *text, size_t nbytes, void *out, size_t cap, int on_device);
+
 /* ---- building blocks of the multi-GPU merge loop ----
  * Unique words are sharded over ranks (word wi belongs to rank wi % nranks); every rank keeps an
  * identical replica of the pair table + heap. A record is 4 x int64: first, second, delta, key

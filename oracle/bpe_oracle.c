@@ -641,3 +641,43 @@ size_t oracle_decode(const int32_t *merges, size_t M, const int32_t *ids, size_t
   free(stack);
   return pos;
 }
+
+/* ---------------------------------------------------------------- normalize (csrc/bpe/normalize.cpp:24-59) */
+static int orc_is_ws(uint8_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }  /* normalize.cpp:13-15 */
+
+size_t oracle_normalize_line(const uint8_t *line, size_t n, uint8_t *out, size_t cap) {
+  size_t o = 0;
+  int in_space = 1;  /* normalize.cpp:32: the start of the line counts as a space */
+  uint8_t t3[3] = {0, 0, 0};  /* the last three bytes written */
+#define ORC_PUT(b) do { if (o < cap) out[o] = (b); o++; t3[0] = t3[1]; t3[1] = t3[2]; t3[2] = (b); } while (0)
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t c = line[i];
+    if (orc_is_ws(c)) {
+      if (!in_space) {  /* normalize.cpp:36-45: one marker per run */
+        ORC_PUT(0xE2); ORC_PUT(0x96); ORC_PUT(0x81);
+        in_space = 1;
+      }
+    } else {
+      const uint8_t lc = (c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c;  /* normalize.cpp:47 tolower, C locale */
+      ORC_PUT(lc);
+      in_space = 0;
+    }
+  }
+#undef ORC_PUT
+  /* normalize.cpp:52-55: if the output ENDS WITH the three marker bytes they are removed, once -- whether they came from
+   * a trailing whitespace run or were already in the input */
+  if (o >= 3 && t3[0] == 0xE2 && t3[1] == 0x96 && t3[2] == 0x81) o -= 3;
+  return o;
+}
+
+size_t oracle_normalize_text(const uint8_t *text, size_t n, uint8_t *out, size_t cap) {
+  size_t o = 0, i = 0;
+  while (i < n) {
+    size_t e = i;
+    while (e < n && text[e] != '\n') e++;
+    o += oracle_normalize_line(text + i, e - i, o < cap ? out + o : out, o < cap ? cap - o : 0);
+    if (e < n) { if (o < cap) out[o] = '\n'; o++; }
+    i = e + 1;
+  }
+  return o;
+}

@@ -83,6 +83,16 @@ size_t oracle_encode(const int32_t *merges /* [3*M] */, size_t M, const int32_t 
 size_t oracle_decode(const int32_t *merges, size_t M, const int32_t *ids, size_t n, uint8_t *out,
                      size_t cap);
 
+/* ---- optional pre-pass: csrc/bpe/normalize.cpp:24-59, normalize_line restated ----
+ * One line (no NUL inside): ASCII upper case -> lower case (tolower in the C locale), every run of ' ' '\t' '\n' '\r'
+ * between two other bytes -> U+2581 (E2 96 81), runs at the start and at the end of the line dropped.
+ * Writes at most cap bytes (no terminator) and returns the length the full result has. PINNED: tests/golden/
+ * normalize_cases.json holds outputs of the reference's own normalize_line (oracle/_ref) for the same inputs. */
+size_t oracle_normalize_line(const uint8_t *line, size_t n, uint8_t *out, size_t cap);
+/* A whole text, line by line: the lines (split at '\n') are normalised one by one and joined by '\n' again (a final
+ * '\n' is kept). This is how the device pre-pass (swb_normalize) applies the reference function to a corpus. */
+size_t oracle_normalize_text(const uint8_t *text, size_t n, uint8_t *out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

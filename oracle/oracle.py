@@ -57,6 +57,8 @@ def lib():
     L.oracle_shard_merge.argtypes = [vp, C.c_int, C.c_int, i32, i32, i32, vp, sz]; L.oracle_shard_merge.restype = sz
     L.oracle_encode.argtypes = [vp, sz, vp, vp, sz, vp, sz, vp, sz, vp]; L.oracle_encode.restype = sz
     L.oracle_decode.argtypes = [vp, sz, vp, sz, vp, sz]; L.oracle_decode.restype = sz
+    L.oracle_normalize_line.argtypes = [vp, sz, vp, sz]; L.oracle_normalize_line.restype = sz
+    L.oracle_normalize_text.argtypes = [vp, sz, vp, sz]; L.oracle_normalize_text.restype = sz
     _lib = L
   return _lib
 
@@ -205,6 +207,32 @@ def decode(merges: np.ndarray, ids: np.ndarray) -> bytes:
 
 
 # ---------------------------------------------------------------- the unmodified reference
+def normalize_line(line: bytes) -> bytes:
+  """normalize_line of reference csrc/bpe/normalize.cpp:24-59, restated (one line, no NUL)."""
+  a = np.frombuffer(bytes(line), dtype=np.uint8)
+  out = np.zeros(3 * a.size + 8, dtype=np.uint8)
+  n = lib().oracle_normalize_line(_p(a) if a.size else None, a.size, _p(out), out.size)
+  return out[:n].tobytes()
+
+
+def normalize_text(text) -> bytes:
+  """The restated normalize_line applied to every line of a text (lines joined by the newline again)."""
+  a = np.ascontiguousarray(text if isinstance(text, np.ndarray) else np.frombuffer(bytes(text), dtype=np.uint8), dtype=np.uint8)
+  out = np.zeros(3 * a.size + 8, dtype=np.uint8)
+  n = lib().oracle_normalize_text(_p(a) if a.size else None, a.size, _p(out), out.size)
+  return out[:n].tobytes()
+
+
+def ref_normalize_line(line: bytes, cap: int = 1 << 20) -> bytes:
+  """The REFERENCE's own normalize_line (oracle/_ref/libtrainer_ref.so), for generating / checking golden vectors."""
+  L = C.CDLL(REF_LIB)
+  L.normalize_line.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]; L.normalize_line.restype = C.c_int
+  buf = C.create_string_buffer(cap)
+  n = L.normalize_line(bytes(line), buf, cap)
+  assert n >= 0
+  return buf.raw[:n]
+
+
 def ref_available() -> bool:
   return os.path.exists(REF_DRIVER) and os.path.exists(REF_LIB)
 

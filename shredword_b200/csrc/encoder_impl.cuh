@@ -133,6 +133,41 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_t
 }
 
 
+// Memo probe only: the tokens of a word of L <= MEMO_MAX_LEN bytes if the memo has them (returns nt >= 1 and fills
+// ids[0 .. nt)), 0 if not. Cheap and uniform -- the single-pass kernel runs it for every word first and hands the
+// misses, whose full encoding is long and data dependent, to a second phase where they are dealt out evenly.
+__device__ __forceinline__ uint32_t enc_memo_probe(uint32_t L, uint4 wv, int *ids, const MemoDev &memo) {
+  uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int keep = (int)L - 4 * k;
+    w4[k] = keep >= 4 ? w4[k] : (keep <= 0 ? 0u : (w4[k] & (0xFFFFFFFFu >> (8 * (4 - keep)))));
+  }
+  unsigned long long h = dmix64(((unsigned long long)w4[1] << 32 | w4[0]) ^ 0x9E3779B97F4A7C15ull) ^
+                         dmix64(((unsigned long long)w4[3] << 32 | w4[2]) + ((unsigned long long)L << 56) + 0x632BE59BD9B4E019ull);
+  h = dmix64(h) | 1ull;
+  const MemoSlot *slot = memo.slots + ((uint32_t)(h >> 20) & memo.mask);
+  const uint4 q0 = __ldcg(reinterpret_cast<const uint4 *>(slot));
+  const uint4 q1 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 1);
+  const uint4 q2 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 2);
+  const uint4 q3 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 3);
+  const unsigned long long tag = ((unsigned long long)q0.y << 32) | q0.x;
+  const uint32_t e0 = L | (w4[0] << 16), m0 = 0xFFFF00FFu;
+  const uint32_t e1 = (w4[0] >> 16) | (w4[1] << 16);
+  const uint32_t e2 = (w4[1] >> 16) | (w4[2] << 16);
+  const uint32_t e3 = (w4[2] >> 16) | (w4[3] << 16);
+  if (!(tag == h && (q0.z & m0) == e0 && q0.w == e1 && q1.x == e2 && q1.y == e3)) return 0;
+  const uint32_t mt = (q0.z >> 8) & 0xFFu;
+  const int tk[MEMO_MAX_TOK] = {(int)q1.z, (int)q1.w, (int)q2.x, (int)q2.y, (int)q2.z, (int)q2.w, (int)q3.x, (int)q3.y, (int)q3.z};
+  uint32_t ck = (uint32_t)h ^ (uint32_t)(h >> 32) ^ mt;
+#pragma unroll
+  for (int k = 0; k < MEMO_MAX_TOK; k++) ck ^= (uint32_t)tk[k] * (2u * k + 3u);
+  if (!(ck == q3.w && mt >= 1 && mt <= MEMO_MAX_TOK && mt <= L)) return 0;
+#pragma unroll
+  for (int k = 0; k < MEMO_MAX_TOK; k++) if (k < (int)mt) ids[k] = tk[k];
+  return mt;
+}
+
 // Encodes one word of L <= ENC_SHORT bytes starting at text[off] into ids[0 .. nt) (shared memory, room for L ints);
 // wv = the word's first 16 bytes. Words of up to MEMO_MAX_LEN bytes go through the memo. Returns nt.
 __device__ __forceinline__ uint32_t enc_short_word(const uint8_t *__restrict__ text, uint64_t off, uint32_t L, uint4 wv, int *ids,
@@ -212,7 +247,7 @@ enc_fused(const uint8_t *__restrict__ text, uint64_t n, uint64_t lo_b, uint64_t 
   __shared__ uint16_t woff[ENCF_MAX_WORDS];        // exclusive token offset of each word inside the tile
   __shared__ int32_t bmap[256];
   __shared__ uint32_t wt[ENC_THREADS / 32];
-  __shared__ unsigned int s_tile;
+  __shared__ unsigned int s_tile, s_nmiss;
   __shared__ unsigned long long s_excl;
   for (int i = threadIdx.x; i < 256; i += ENC_THREADS) bmap[i] = byte_map[i];
   const uint64_t seg_lo = lo_b / 16, seg_hi = (hi_b + 15) / 16;
@@ -244,7 +279,10 @@ enc_fused(const uint8_t *__restrict__ text, uint64_t n, uint64_t lo_b, uint64_t 
       while (st) { const int sb = __ffs(st) - 1; st &= st - 1; wstart[wbase++] = (uint16_t)(threadIdx.x * 16 + sb); }
     }
     __syncthreads();
-    // ---- encode: word j -> thread j % ENC_THREADS
+    // ---- encode, phase 1: word j -> thread j % ENC_THREADS looks it up in the memo (uniform work); what the memo does not
+    // have is listed (the ordered list of starts is no longer needed as a whole: woff doubles as the miss list until the scan)
+    if (threadIdx.x == 0) s_nmiss = 0;
+    __syncthreads();
     for (uint32_t j = threadIdx.x; j < nw; j += ENC_THREADS) {
       const uint32_t rel = wstart[j];
       const uint64_t off = tile_byte0 + rel;
@@ -252,11 +290,29 @@ enc_fused(const uint8_t *__restrict__ text, uint64_t n, uint64_t lo_b, uint64_t 
       const uint32_t dmask = enc_delim_bits(wv.x) | (enc_delim_bits(wv.y) << 4) | (enc_delim_bits(wv.z) << 8) | (enc_delim_bits(wv.w) << 12);
       uint32_t L = dmask ? (uint32_t)(__ffs(dmask) - 1) : 16u;
       if (off + L > n) L = (uint32_t)(n - off);
-      if (L >= 15) L = enc_word_len(text, off, n);
       uint32_t nt = 0;
-      if (L <= ENC_SHORT) nt = enc_short_word(text, off, L, wv, stok + rel, tbl, memo, bmap);
-      else atomicOr(fallback, 1u);
+      if (L <= MEMO_MAX_LEN) nt = enc_memo_probe(L, wv, stok + rel, memo);
+      if (!nt) woff[atomicAdd(&s_nmiss, 1u)] = (uint16_t)j;
       wnt[j] = (uint16_t)nt;
+    }
+    __syncthreads();
+    // ---- phase 2: the misses, dealt out evenly (the long, data-dependent path runs with as many lanes busy as there are misses)
+    {
+      const uint32_t nmiss = s_nmiss;
+      for (uint32_t q = threadIdx.x; q < nmiss; q += ENC_THREADS) {
+        const uint32_t j = woff[q];
+        const uint32_t rel = wstart[j];
+        const uint64_t off = tile_byte0 + rel;
+        const uint4 wv = enc_load16(text, off);
+        const uint32_t dmask = enc_delim_bits(wv.x) | (enc_delim_bits(wv.y) << 4) | (enc_delim_bits(wv.z) << 8) | (enc_delim_bits(wv.w) << 12);
+        uint32_t L = dmask ? (uint32_t)(__ffs(dmask) - 1) : 16u;
+        if (off + L > n) L = (uint32_t)(n - off);
+        if (L >= 15) L = enc_word_len(text, off, n);
+        uint32_t nt = 0;
+        if (L <= ENC_SHORT) nt = enc_short_word(text, off, L, wv, stok + rel, tbl, memo, bmap);
+        else atomicOr(fallback, 1u);
+        wnt[j] = (uint16_t)nt;
+      }
     }
     __syncthreads();
     // ---- token offsets of the words (thread t scans words 8t .. 8t+7)

@@ -40,6 +40,19 @@ def bind_host_thread_to_gpu(device_index: int) -> list[int] | None:
     return None
 
 
+def normalize(text) -> bytes:
+  """Optional pre-pass on the GPU: the reference's normalize_line (reference csrc/bpe/normalize.cpp:24-59) applied to every
+  line of `text` (bytes / uint8 array): lower-cases ASCII, turns whitespace runs inside a line into U+2581, drops them at
+  the ends of a line. Feed the result to load_buffer / encode for a SentencePiece-style pipeline."""
+  a = text if isinstance(text, np.ndarray) else np.frombuffer(bytes(text), dtype=np.uint8)
+  a = np.ascontiguousarray(a, dtype=np.uint8)
+  out = np.empty(3 * a.size + 16, dtype=np.uint8)
+  n = lib.swb_normalize(_ptr(a), a.size, _ptr(out), out.size, 0)
+  if n < 0:
+    raise RuntimeError(f"normalize failed: {last_error()}")
+  return out[:n].tobytes()
+
+
 class BPETrainer:
   def __init__(self, target_vocab_size=8192, unk_id=0, character_coverage=0.995, min_pair_freq=2000):
     self.config = BPEConfig(
