@@ -157,6 +157,11 @@ typedef struct SwbStats {
    * buffer this spans the pipelined host-to-device copy as well) and the corpus bytes they covered */
   double tokenize_ms;
   uint64_t tokenize_bytes;
+  /* LOCAL merges of the resident kernel by the length of the birth log they read (<= 512, <= 4096, <= 32768, more
+   * entries): how many, their device time, the records they sent to the host */
+  uint64_t local_by_log[4];
+  double local_by_log_ms[4];
+  uint64_t local_by_log_recs[4];
 } SwbStats;
 void swb_get_stats(const Trainer *trainer, SwbStats *out);
 /* 1: bracket every merge-scan launch with CUDA events (adds a little latency); 0: off (default). */

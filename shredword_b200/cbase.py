@@ -47,7 +47,8 @@ class SwbStats(Structure):
               ("resident_local_merges", c_uint64), ("resident_grid_merges", c_uint64),
               ("resident_local_ms", c_double), ("resident_grid_ms", c_double),
               ("hints_sent", c_uint64), ("hints_taken", c_uint64), ("hints_rejected", c_uint64), ("host_peek_ms", c_double),
-              ("tokenize_ms", c_double), ("tokenize_bytes", c_uint64)]
+              ("tokenize_ms", c_double), ("tokenize_bytes", c_uint64),
+              ("local_by_log", c_uint64 * 4), ("local_by_log_ms", c_double * 4), ("local_by_log_recs", c_uint64 * 4)]
 
 # ---- the reference's eight entry points (reference cbase.py:44-59)
 lib.create_trainer.argtypes = [POINTER(BPEConfig)]

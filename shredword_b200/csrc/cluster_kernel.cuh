@@ -314,7 +314,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
               volatile HostCmd2 *hcmd /* [3] in mapped host memory: the command, the hints for even / odd sequence numbers */, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace,
               uint4 *ovf /* [CL_LOCAL_MAX]: candidate words that did not fit a CTA's shared-memory list */,
               const HostCmd2 *__restrict__ script /* nullptr, or [script_n] commands in DEVICE memory that replace the mailbox: the kernel then runs without the host (profiling under ncu's kernel replay, see TrainerImpl::profile_scripted) */, unsigned long long script_n, ClusterTune tune,
-              unsigned long long *acct /* [16]: LOCAL merges, their device ns, GRID merges, their device ns, hints accepted, hints rejected, hints accepted without a PCIe trip, LOCAL merges that spilled to the global table, [8] sequence number the watchdog gave up on, [9] after how many ns */) {
+              unsigned long long *acct /* [32]: LOCAL merges, their device ns, GRID merges, their device ns, hints accepted, hints rejected, hints accepted without a PCIe trip, LOCAL merges that spilled to the global table, [8] sequence number the watchdog gave up on, [9] after how many ns */) {
   extern __shared__ __align__(16) unsigned char cl_dyn_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const ClusterSmem m = cluster_smem(cl_dyn_smem);
@@ -657,7 +657,14 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(out_hdr + 4), "l"(x), "l"(sm) : "memory");
           asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(out_hdr + 0), "l"(seq), "l"((unsigned long long)n) : "memory");
           asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(out_hdr + 6), "l"(chk), "l"(seq) : "memory");
-          acct[0] += 1; acct[1] += gtime_ns() - c->t_cmd;
+          const unsigned long long dt = gtime_ns() - c->t_cmd;
+          acct[0] += 1; acct[1] += dt;
+          {  // LOCAL merges by length of the log they read: [16 + cls] merges, [24 + cls] their ns (cls: <=512, <=4096, <=32768, more entries)
+            const unsigned int ln = (unsigned int)(c->log_range & 0xFFFFFFFFu);
+            const int cls = ln <= 512u ? 0 : ln <= 4096u ? 1 : ln <= 32768u ? 2 : 3;
+            acct[16 + cls] += 1; acct[24 + cls] += dt;
+            acct[20 + cls] += n;  // records sent to the host
+          }
         }
         c->n_recs_total = 0; c->removed = 0;
         if (trace) {

@@ -133,39 +133,57 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_t
 }
 
 
+// ---- memo helpers. A word of up to MEMO_MAX_LEN bytes has two candidate slots (two-way: a word whose first slot belongs to
+// another word still gets memoised); whoever encodes it first fills the first free one.
+struct MemoKey { unsigned long long h; uint32_t e0, e1, e2, e3; uint32_t w4[4]; };
+__device__ __forceinline__ MemoKey memo_key(uint32_t L, uint4 wv) {
+  MemoKey k;
+  k.w4[0] = wv.x; k.w4[1] = wv.y; k.w4[2] = wv.z; k.w4[3] = wv.w;  // zero the bytes from L on
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int keep = (int)L - 4 * q;
+    k.w4[q] = keep >= 4 ? k.w4[q] : (keep <= 0 ? 0u : (k.w4[q] & (0xFFFFFFFFu >> (8 * (4 - keep)))));
+  }
+  unsigned long long h = dmix64(((unsigned long long)k.w4[1] << 32 | k.w4[0]) ^ 0x9E3779B97F4A7C15ull) ^
+                         dmix64(((unsigned long long)k.w4[3] << 32 | k.w4[2]) + ((unsigned long long)L << 56) + 0x632BE59BD9B4E019ull);
+  k.h = dmix64(h) | 1ull;
+  // expected image of {len, ntok, bytes}: len | ntok << 8 | bytes << 16 over words 2..5 of the slot (ntok byte masked out)
+  k.e0 = L | (k.w4[0] << 16);
+  k.e1 = (k.w4[0] >> 16) | (k.w4[1] << 16);
+  k.e2 = (k.w4[1] >> 16) | (k.w4[2] << 16);
+  k.e3 = (k.w4[2] >> 16) | (k.w4[3] << 16);
+  return k;
+}
+__device__ __forceinline__ MemoSlot *memo_way(const MemoDev &memo, unsigned long long h, int way) {
+  return memo.slots + ((uint32_t)(way == 0 ? h >> 20 : h >> 42) & memo.mask);
+}
+// tokens of the word if `slot` holds them (nt >= 1, ids[0 .. nt) filled), else 0; *tag = the slot's tag (0 = free)
+__device__ __forceinline__ uint32_t memo_read(const MemoSlot *slot, const MemoKey &k, uint32_t L, int *ids, unsigned long long *tag) {
+  const uint4 q0 = __ldcg(reinterpret_cast<const uint4 *>(slot));       // tag, len, ntok, bytes[0..5]
+  const uint4 q1 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 1);   // bytes[6..13], tok[0..1]
+  const uint4 q2 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 2);   // tok[2..5]
+  const uint4 q3 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 3);   // tok[6..8], check
+  *tag = ((unsigned long long)q0.y << 32) | q0.x;
+  if (!(*tag == k.h && (q0.z & 0xFFFF00FFu) == k.e0 && q0.w == k.e1 && q1.x == k.e2 && q1.y == k.e3)) return 0;
+  const uint32_t mt = (q0.z >> 8) & 0xFFu;
+  const int tk[MEMO_MAX_TOK] = {(int)q1.z, (int)q1.w, (int)q2.x, (int)q2.y, (int)q2.z, (int)q2.w, (int)q3.x, (int)q3.y, (int)q3.z};
+  uint32_t ck = (uint32_t)k.h ^ (uint32_t)(k.h >> 32) ^ mt;
+#pragma unroll
+  for (int q = 0; q < MEMO_MAX_TOK; q++) ck ^= (uint32_t)tk[q] * (2u * q + 3u);
+  if (!(ck == q3.w && mt >= 1 && mt <= MEMO_MAX_TOK && mt <= L)) return 0;
+#pragma unroll
+  for (int q = 0; q < MEMO_MAX_TOK; q++) if (q < (int)mt) ids[q] = tk[q];
+  return mt;
+}
 // Memo probe only: the tokens of a word of L <= MEMO_MAX_LEN bytes if the memo has them (returns nt >= 1 and fills
 // ids[0 .. nt)), 0 if not. Cheap and uniform -- the single-pass kernel runs it for every word first and hands the
 // misses, whose full encoding is long and data dependent, to a second phase where they are dealt out evenly.
 __device__ __forceinline__ uint32_t enc_memo_probe(uint32_t L, uint4 wv, int *ids, const MemoDev &memo) {
-  uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int keep = (int)L - 4 * k;
-    w4[k] = keep >= 4 ? w4[k] : (keep <= 0 ? 0u : (w4[k] & (0xFFFFFFFFu >> (8 * (4 - keep)))));
-  }
-  unsigned long long h = dmix64(((unsigned long long)w4[1] << 32 | w4[0]) ^ 0x9E3779B97F4A7C15ull) ^
-                         dmix64(((unsigned long long)w4[3] << 32 | w4[2]) + ((unsigned long long)L << 56) + 0x632BE59BD9B4E019ull);
-  h = dmix64(h) | 1ull;
-  const MemoSlot *slot = memo.slots + ((uint32_t)(h >> 20) & memo.mask);
-  const uint4 q0 = __ldcg(reinterpret_cast<const uint4 *>(slot));
-  const uint4 q1 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 1);
-  const uint4 q2 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 2);
-  const uint4 q3 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 3);
-  const unsigned long long tag = ((unsigned long long)q0.y << 32) | q0.x;
-  const uint32_t e0 = L | (w4[0] << 16), m0 = 0xFFFF00FFu;
-  const uint32_t e1 = (w4[0] >> 16) | (w4[1] << 16);
-  const uint32_t e2 = (w4[1] >> 16) | (w4[2] << 16);
-  const uint32_t e3 = (w4[2] >> 16) | (w4[3] << 16);
-  if (!(tag == h && (q0.z & m0) == e0 && q0.w == e1 && q1.x == e2 && q1.y == e3)) return 0;
-  const uint32_t mt = (q0.z >> 8) & 0xFFu;
-  const int tk[MEMO_MAX_TOK] = {(int)q1.z, (int)q1.w, (int)q2.x, (int)q2.y, (int)q2.z, (int)q2.w, (int)q3.x, (int)q3.y, (int)q3.z};
-  uint32_t ck = (uint32_t)h ^ (uint32_t)(h >> 32) ^ mt;
-#pragma unroll
-  for (int k = 0; k < MEMO_MAX_TOK; k++) ck ^= (uint32_t)tk[k] * (2u * k + 3u);
-  if (!(ck == q3.w && mt >= 1 && mt <= MEMO_MAX_TOK && mt <= L)) return 0;
-#pragma unroll
-  for (int k = 0; k < MEMO_MAX_TOK; k++) if (k < (int)mt) ids[k] = tk[k];
-  return mt;
+  const MemoKey k = memo_key(L, wv);
+  unsigned long long tag;
+  uint32_t nt = memo_read(memo_way(memo, k.h, 0), k, L, ids, &tag);
+  if (!nt && tag != 0ull && tag != k.h) nt = memo_read(memo_way(memo, k.h, 1), k, L, ids, &tag);  // first slot is another word's
+  return nt;
 }
 
 // Encodes one word of L <= ENC_SHORT bytes starting at text[off] into ids[0 .. nt) (shared memory, room for L ints);
@@ -176,50 +194,28 @@ __device__ __forceinline__ uint32_t enc_short_word(const uint8_t *__restrict__ t
     for (uint32_t k = 0; k < L; k++) ids[k] = bmap[text[off + k]];
     return enc_word(ids, L, tbl);
   }
-  uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};  // zero the bytes from L on
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int keep = (int)L - 4 * k;  // bytes of this word to keep
-    w4[k] = keep >= 4 ? w4[k] : (keep <= 0 ? 0u : (w4[k] & (0xFFFFFFFFu >> (8 * (4 - keep)))));
+  const MemoKey k = memo_key(L, wv);
+  MemoSlot *slot = memo_way(memo, k.h, 0);
+  unsigned long long tag;
+  uint32_t nt = memo_read(slot, k, L, ids, &tag);
+  if (nt) return nt;
+  if (tag != 0ull && tag != k.h) {
+    slot = memo_way(memo, k.h, 1);
+    nt = memo_read(slot, k, L, ids, &tag);
+    if (nt) return nt;
   }
-  unsigned long long h = dmix64(((unsigned long long)w4[1] << 32 | w4[0]) ^ 0x9E3779B97F4A7C15ull) ^
-                         dmix64(((unsigned long long)w4[3] << 32 | w4[2]) + ((unsigned long long)L << 56) + 0x632BE59BD9B4E019ull);
-  h = dmix64(h) | 1ull;
-  MemoSlot *slot = memo.slots + ((uint32_t)(h >> 20) & memo.mask);
-  const uint4 q0 = __ldcg(reinterpret_cast<const uint4 *>(slot));       // tag, len, ntok, bytes[0..5]
-  const uint4 q1 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 1);   // bytes[6..13], tok[0..1]
-  const uint4 q2 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 2);   // tok[2..5]
-  const uint4 q3 = __ldcg(reinterpret_cast<const uint4 *>(slot) + 3);   // tok[6..8], check
-  const unsigned long long tag = ((unsigned long long)q0.y << 32) | q0.x;
-  // expected image of {len, ntok, bytes}: len | ntok << 8 | bytes << 16 over q0.z, q0.w, q1.x, q1.y
-  const uint32_t e0 = L | (w4[0] << 16), m0 = 0xFFFF00FFu;          // ntok byte masked out
-  const uint32_t e1 = (w4[0] >> 16) | (w4[1] << 16);
-  const uint32_t e2 = (w4[1] >> 16) | (w4[2] << 16);
-  const uint32_t e3 = (w4[2] >> 16) | (w4[3] << 16);
-  if (tag == h && (q0.z & m0) == e0 && q0.w == e1 && q1.x == e2 && q1.y == e3) {
-    const uint32_t mt = (q0.z >> 8) & 0xFFu;
-    const int tk[MEMO_MAX_TOK] = {(int)q1.z, (int)q1.w, (int)q2.x, (int)q2.y, (int)q2.z, (int)q2.w, (int)q3.x, (int)q3.y, (int)q3.z};
-    uint32_t ck = (uint32_t)h ^ (uint32_t)(h >> 32) ^ mt;
-#pragma unroll
-    for (int k = 0; k < MEMO_MAX_TOK; k++) ck ^= (uint32_t)tk[k] * (2u * k + 3u);
-    if (ck == q3.w && mt >= 1 && mt <= MEMO_MAX_TOK && mt <= L) {
-#pragma unroll
-      for (int k = 0; k < MEMO_MAX_TOK; k++) if (k < (int)mt) ids[k] = tk[k];
-      return mt;
-    }
-  }
-  for (uint32_t k = 0; k < L; k++) ids[k] = bmap[(w4[k >> 2] >> (8 * (k & 3))) & 0xFFu];
-  const uint32_t nt = enc_word(ids, L, tbl);
-  if (tag == 0ull && nt <= MEMO_MAX_TOK && atomicCAS(&slot->tag, 0ull, h) == 0ull) {  // first encoder fills the slot
+  for (uint32_t q = 0; q < L; q++) ids[q] = bmap[(k.w4[q >> 2] >> (8 * (q & 3))) & 0xFFu];
+  nt = enc_word(ids, L, tbl);
+  if (tag == 0ull && nt <= MEMO_MAX_TOK && atomicCAS(&slot->tag, 0ull, k.h) == 0ull) {  // first encoder fills the slot
     int tk[MEMO_MAX_TOK];
-    uint32_t ck = (uint32_t)h ^ (uint32_t)(h >> 32) ^ nt;
+    uint32_t ck = (uint32_t)k.h ^ (uint32_t)(k.h >> 32) ^ nt;
 #pragma unroll
-    for (int k = 0; k < MEMO_MAX_TOK; k++) { tk[k] = k < (int)nt ? ids[k] : 0; ck ^= (uint32_t)tk[k] * (2u * k + 3u); }
+    for (int q = 0; q < MEMO_MAX_TOK; q++) { tk[q] = q < (int)nt ? ids[q] : 0; ck ^= (uint32_t)tk[q] * (2u * q + 3u); }
     uint4 *dst = reinterpret_cast<uint4 *>(slot);
-    // (the tag, in q0.x/q0.y, is already there: written by the CAS)
-    reinterpret_cast<uint32_t *>(slot)[2] = e0 | (nt << 8);
-    reinterpret_cast<uint32_t *>(slot)[3] = e1;
-    dst[1] = make_uint4(e2, e3, (uint32_t)tk[0], (uint32_t)tk[1]);
+    // (the tag, in words 0..1, is already there: written by the CAS)
+    reinterpret_cast<uint32_t *>(slot)[2] = k.e0 | (nt << 8);
+    reinterpret_cast<uint32_t *>(slot)[3] = k.e1;
+    dst[1] = make_uint4(k.e2, k.e3, (uint32_t)tk[0], (uint32_t)tk[1]);
     dst[2] = make_uint4((uint32_t)tk[2], (uint32_t)tk[3], (uint32_t)tk[4], (uint32_t)tk[5]);
     dst[3] = make_uint4((uint32_t)tk[6], (uint32_t)tk[7], (uint32_t)tk[8], ck);
   }
@@ -537,7 +533,7 @@ class EncoderImpl {
     SWB_CUDA(cudaMemcpyAsync(d_bmap_.get(), dev_bmap_, sizeof dev_bmap_, cudaMemcpyHostToDevice, stream_));
     SWB_CUDA(cudaStreamSynchronize(stream_));
     tbl_ = RankTableDev{slots_.get(), (uint32_t)(cap - 1)};
-    const uint64_t memo_cap = 1ull << 20;  // 64 MB: the hot words of Zipfian text stay L2 resident
+    const uint64_t memo_cap = 1ull << 22;  // 256 MB, two-way: room for millions of distinct words; the hot ones stay L2 resident
     memo_slots_.alloc(memo_cap);
     SWB_CUDA(cudaMemsetAsync(memo_slots_.get(), 0, memo_cap * sizeof(MemoSlot), stream_));
     SWB_CUDA(cudaStreamSynchronize(stream_));

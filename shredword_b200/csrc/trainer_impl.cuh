@@ -1242,7 +1242,7 @@ class TrainerImpl {
     if (tr_->config.unk_id < 0) throw Error("profile_scripted: negative unk_id is not supported");
     ensure_pair_table(8ull * (258ull + n + 2));
     ensure_global_table(std::max<uint64_t>(gt_cap_ * 4, 16ull * (258ull + n + 2)));  // (the script cannot stop to let the table grow)
-    if (!hcmd2_.size()) { hcmd2_.alloc(4); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(16); }
+    if (!hcmd2_.size()) { hcmd2_.alloc(4); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(32); }
     if (recs_b_.size() != recs_.size()) recs_b_.alloc(recs_.size());
     if (!hdr_b_.size()) hdr_b_.alloc(HDR_WORDS);
     SWB_CUDA(cudaMemsetAsync(cl_acct_.get(), 0, cl_acct_.bytes(), stream_));
@@ -1286,7 +1286,7 @@ class TrainerImpl {
     ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
     maybe_grow_global_table(gt_flagged_);
     gt_flagged_ = false;
-    if (!hcmd2_.size()) { hcmd2_.alloc(4); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(16); }
+    if (!hcmd2_.size()) { hcmd2_.alloc(4); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(32); }
     if (recs_b_.size() != recs_.size()) recs_b_.alloc(recs_.size());  // second record buffer + header: merges started from a hint
     if (!hdr_b_.size()) hdr_b_.alloc(HDR_WORDS);
     memset(hdr_b_.host(), 0, HDR_WORDS * sizeof(unsigned long long));
@@ -1418,8 +1418,9 @@ class TrainerImpl {
     sync();
     {  // device time of this launch's merges (command seen -> result published), per mode
       check_debug_bounds();
-      unsigned long long ac[8];
+      unsigned long long ac[32];
       SWB_CUDA(cudaMemcpy(ac, cl_acct_.get(), sizeof ac, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < 4; i++) { stats.local_by_log[i] += ac[16 + i]; stats.local_by_log_ms[i] += (double)ac[24 + i] * 1e-6; stats.local_by_log_recs[i] += ac[20 + i]; }
       stats.hints_rejected += ac[5]; stats.resident_spill_merges += ac[7];
       stats.resident_local_merges += ac[0]; stats.resident_local_ms += (double)ac[1] * 1e-6;
       stats.resident_grid_merges += ac[2]; stats.resident_grid_ms += (double)ac[3] * 1e-6;

@@ -184,7 +184,13 @@ class BPETrainer:
   def stats(self) -> dict:
     s = SwbStats()
     lib.swb_get_stats(self.trainer, ctypes.byref(s))
-    return {k: getattr(s, k) for k, _ in SwbStats._fields_ if not k.endswith("_")}
+    out = {}
+    for k, _ in SwbStats._fields_:
+      if k.endswith("_"):
+        continue
+      v = getattr(s, k)
+      out[k] = list(v) if hasattr(v, "__len__") else v
+    return out
 
   def profile_scripted_merges(self, merge_triples: np.ndarray) -> float:
     """Profiling aid (swb_profile_scripted_merges): after init() on a fresh load, runs the given merges inside one
