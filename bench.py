@@ -306,23 +306,36 @@ def main():
   last = {}
   digests = set()
 
+  retried = []
+
   def step(resident: bool, timing: bool):
     STATE["step"] += 1
     w0 = time.perf_counter()
     old = last.pop("trainer", None)
     if old is not None:
       old.destroy()  # the previous step's handle: its device memory goes back before the next step allocates
-    w1 = time.perf_counter()
-    t = new_trainer()
-    t.set_kernel_timing(timing)
-    if world > 1:
-      t.load_shard(d_corpus[:nbytes] if resident else arr, goff)
-    elif resident:
-      t.load_device(d_corpus.data_ptr(), nbytes)
-    else:
-      t.load_buffer(arr)
-    w2 = time.perf_counter()
-    merges = t.train_quiet()
+    for attempt in range(3):
+      w1 = time.perf_counter()
+      t = new_trainer()
+      t.set_kernel_timing(timing)
+      if world > 1:
+        t.load_shard(d_corpus[:nbytes] if resident else arr, goff)
+      elif resident:
+        t.load_device(d_corpus.data_ptr(), nbytes)
+      else:
+        t.load_buffer(arr)
+      w2 = time.perf_counter()
+      try:
+        merges = t.train_quiet()
+        break
+      except RuntimeError as e:
+        # A failed training step is repeated from scratch INSIDE the timed region (its cost stays in the number) and is
+        # reported in the JSON line (`retried_steps`); the library marks the handle failed, nothing of it is reused.
+        log(f"[bench] rank {rank} step {STATE['step']} attempt {attempt}: training failed, repeating the step: {e}")
+        retried.append({"step": STATE["step"], "error": str(e)[:600]})
+        t.destroy()
+        if attempt == 2:
+          raise
     w3 = time.perf_counter()
     m = t.merges_array()  # the step's result, read on the host
     st = t.stats()
@@ -460,7 +473,7 @@ def main():
     "dtype": "int32 symbols, uint64 counts", "data": "synthetic", "config": config, "clocks": clocks,
     "e2e": {"value": e2e_value, "unit": "GB/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(total_bytes),
             "d2h_bytes_per_step": int(st_e2e[-1]["merge_bytes"])},
-    "gpu_launches": launches, "roofline": roofline, "parity": parity,
+    "gpu_launches": launches, "roofline": roofline, "parity": parity, "retried_steps": retried,
     "extra": {"merges": merges, "merges_per_s": merges / (phase(st_res, "merge_ms") / 1e3) if (rank == 0 and phase(st_res, "merge_ms")) else None,
               "us_per_merge": phase(st_res, "merge_ms") * 1e3 / max(merges, 1),
               "phase_ms": {k: phase(st_res, k) for k in ("load_ms", "count_ms", "merge_ms")},

@@ -161,55 +161,9 @@ void oracle_destroy(OracleTrainer *t) {
   free_corpus(t); pm_free(&t->pm); free(t->heap.d); free(t->merges); free(t);
 }
 
-/* ------------------------------------------------------------------ load (T1-T3)
- * csrc/bpe/bpe.cpp:229-252 + hash.cpp:29-53: whitespace split, word -> count.
- * Word order = StrMap iteration order (hash.cpp:67-71): bucket = djb2(word) & 4095 ascending,
- * within a bucket in order of first occurrence (new entries are appended at the chain tail). */
-int oracle_load_corpus_buffer(OracleTrainer *t, const uint8_t *data, size_t n) {
-  if (!t || (!data && n)) return -1;
-  if (memchr(data, 0, n)) { fprintf(stderr, "oracle: NUL byte in corpus is outside the parity domain\n"); return -1; }
-  free_corpus(t);
-  /* pass 1: unique words in first-occurrence order */
-  size_t ucap = 1 << 16, un = 0;
-  uint64_t *uoff = xmalloc(ucap * sizeof *uoff);  /* offset of the first occurrence */
-  uint32_t *ulen = xmalloc(ucap * sizeof *ulen);
-  uint64_t *ucnt = xmalloc(ucap * sizeof *ucnt);
-  uint64_t *uhash = xmalloc(ucap * sizeof *uhash);
-  size_t nslots = 1 << 18; uint32_t *slots = xcalloc(nslots, sizeof *slots);
-  size_t i = 0;
-  while (i < n) {
-    while (i < n && is_delim(data[i])) i++;
-    if (i >= n) break;
-    size_t s = i; uint64_t h = 1469598103934665603ULL;
-    while (i < n && !is_delim(data[i])) { h = (h ^ data[i]) * 1099511628211ULL; i++; }
-    size_t len = i - s;
-    if (len > 0xffffffffu) { fprintf(stderr, "oracle: word longer than 4 GiB\n"); return -1; }
-    h = mix64(h);
-    size_t p = (size_t)h & (nslots - 1);
-    for (;;) {
-      uint32_t v = slots[p];
-      if (!v) break;
-      size_t u = v - 1;
-      if (uhash[u] == h && ulen[u] == len && memcmp(data + uoff[u], data + s, len) == 0) { ucnt[u]++; goto next_word; }
-      p = (p + 1) & (nslots - 1);
-    }
-    if (un == ucap) {
-      ucap *= 2;
-      uoff = xrealloc(uoff, ucap * sizeof *uoff); ulen = xrealloc(ulen, ucap * sizeof *ulen);
-      ucnt = xrealloc(ucnt, ucap * sizeof *ucnt); uhash = xrealloc(uhash, ucap * sizeof *uhash);
-    }
-    uoff[un] = s; ulen[un] = (uint32_t)len; ucnt[un] = 1; uhash[un] = h; slots[p] = (uint32_t)(++un);
-    if (un * 2 > nslots) {
-      free(slots); nslots *= 4; slots = xcalloc(nslots, sizeof *slots);
-      for (size_t u = 0; u < un; u++) {
-        size_t q = (size_t)uhash[u] & (nslots - 1);
-        while (slots[q]) q = (q + 1) & (nslots - 1);
-        slots[q] = (uint32_t)(u + 1);
-      }
-    }
-  next_word:;
-  }
-  free(slots); free(uhash);
+/* Unique words in first-occurrence order (bytes at data + uoff[u]) -> the word table in reference order, kept bytes, symbols.
+ * Frees uoff / ulen / ucnt. */
+static int build_table(OracleTrainer *t, const uint8_t *data, size_t un, uint64_t *uoff, uint32_t *ulen, uint64_t *ucnt) {
   /* pass 2: stable counting sort by djb2 bucket (hash.cpp:35-39; only the low 12 bits matter) */
   uint32_t *bucket = xmalloc(un * sizeof *bucket);
   size_t start[WORD_BUCKETS + 1]; memset(start, 0, sizeof start);
@@ -264,6 +218,58 @@ int oracle_load_corpus_buffer(OracleTrainer *t, const uint8_t *data, size_t n) {
   return 0;
 }
 
+/* ------------------------------------------------------------------ load (T1-T3)
+ * csrc/bpe/bpe.cpp:229-252 + hash.cpp:29-53: whitespace split, word -> count.
+ * Word order = StrMap iteration order (hash.cpp:67-71): bucket = djb2(word) & 4095 ascending,
+ * within a bucket in order of first occurrence (new entries are appended at the chain tail). */
+int oracle_load_corpus_buffer(OracleTrainer *t, const uint8_t *data, size_t n) {
+  if (!t || (!data && n)) return -1;
+  if (memchr(data, 0, n)) { fprintf(stderr, "oracle: NUL byte in corpus is outside the parity domain\n"); return -1; }
+  free_corpus(t);
+  /* pass 1: unique words in first-occurrence order */
+  size_t ucap = 1 << 16, un = 0;
+  uint64_t *uoff = xmalloc(ucap * sizeof *uoff);  /* offset of the first occurrence */
+  uint32_t *ulen = xmalloc(ucap * sizeof *ulen);
+  uint64_t *ucnt = xmalloc(ucap * sizeof *ucnt);
+  uint64_t *uhash = xmalloc(ucap * sizeof *uhash);
+  size_t nslots = 1 << 18; uint32_t *slots = xcalloc(nslots, sizeof *slots);
+  size_t i = 0;
+  while (i < n) {
+    while (i < n && is_delim(data[i])) i++;
+    if (i >= n) break;
+    size_t s = i; uint64_t h = 1469598103934665603ULL;
+    while (i < n && !is_delim(data[i])) { h = (h ^ data[i]) * 1099511628211ULL; i++; }
+    size_t len = i - s;
+    if (len > 0xffffffffu) { fprintf(stderr, "oracle: word longer than 4 GiB\n"); return -1; }
+    h = mix64(h);
+    size_t p = (size_t)h & (nslots - 1);
+    for (;;) {
+      uint32_t v = slots[p];
+      if (!v) break;
+      size_t u = v - 1;
+      if (uhash[u] == h && ulen[u] == len && memcmp(data + uoff[u], data + s, len) == 0) { ucnt[u]++; goto next_word; }
+      p = (p + 1) & (nslots - 1);
+    }
+    if (un == ucap) {
+      ucap *= 2;
+      uoff = xrealloc(uoff, ucap * sizeof *uoff); ulen = xrealloc(ulen, ucap * sizeof *ulen);
+      ucnt = xrealloc(ucnt, ucap * sizeof *ucnt); uhash = xrealloc(uhash, ucap * sizeof *uhash);
+    }
+    uoff[un] = s; ulen[un] = (uint32_t)len; ucnt[un] = 1; uhash[un] = h; slots[p] = (uint32_t)(++un);
+    if (un * 2 > nslots) {
+      free(slots); nslots *= 4; slots = xcalloc(nslots, sizeof *slots);
+      for (size_t u = 0; u < un; u++) {
+        size_t q = (size_t)uhash[u] & (nslots - 1);
+        while (slots[q]) q = (q + 1) & (nslots - 1);
+        slots[q] = (uint32_t)(u + 1);
+      }
+    }
+  next_word:;
+  }
+  free(slots); free(uhash);
+  return build_table(t, data, un, uoff, ulen, ucnt);
+}
+
 int oracle_load_corpus(OracleTrainer *t, const char *path) {
   if (!t || !path) return -1;
   FILE *f = fopen(path, "rb");
@@ -277,6 +283,77 @@ int oracle_load_corpus(OracleTrainer *t, const char *path) {
   fclose(f);
   int rc = got == (size_t)sz ? oracle_load_corpus_buffer(t, buf, got) : -1;
   free(buf);
+  return rc;
+}
+
+/* ---- streaming load (test infrastructure for corpora larger than host memory: the 50 GB configuration) ----
+ * The same pass 1 as oracle_load_corpus_buffer, fed chunk by chunk: a chunk must end on a delimiter (no word straddles two
+ * chunks). The bytes of a word are copied into an arena when it is first seen, so the chunk can be dropped afterwards. */
+struct OracleStream {
+  uint8_t *arena; size_t an, acap;
+  uint64_t *uoff; uint32_t *ulen; uint64_t *ucnt; uint64_t *uhash; size_t un, ucap;
+  uint32_t *slots; size_t nslots;
+  int bad;
+};
+OracleStream *oracle_stream_begin(void) {
+  OracleStream *s = xcalloc(1, sizeof *s);
+  s->acap = 1 << 20; s->arena = xmalloc(s->acap);
+  s->ucap = 1 << 16;
+  s->uoff = xmalloc(s->ucap * sizeof *s->uoff); s->ulen = xmalloc(s->ucap * sizeof *s->ulen);
+  s->ucnt = xmalloc(s->ucap * sizeof *s->ucnt); s->uhash = xmalloc(s->ucap * sizeof *s->uhash);
+  s->nslots = 1 << 18; s->slots = xcalloc(s->nslots, sizeof *s->slots);
+  return s;
+}
+int oracle_stream_feed(OracleStream *s, const uint8_t *data, size_t n) {
+  if (!s || (!data && n)) return -1;
+  if (n && memchr(data, 0, n)) { s->bad = 1; return -1; }
+  size_t i = 0;
+  while (i < n) {
+    while (i < n && is_delim(data[i])) i++;
+    if (i >= n) break;
+    size_t st = i; uint64_t h = 1469598103934665603ULL;
+    while (i < n && !is_delim(data[i])) { h = (h ^ data[i]) * 1099511628211ULL; i++; }
+    size_t len = i - st;
+    h = mix64(h);
+    size_t p = (size_t)h & (s->nslots - 1);
+    int found = 0;
+    for (;;) {
+      uint32_t v = s->slots[p];
+      if (!v) break;
+      size_t u = v - 1;
+      if (s->uhash[u] == h && s->ulen[u] == len && memcmp(s->arena + s->uoff[u], data + st, len) == 0) { s->ucnt[u]++; found = 1; break; }
+      p = (p + 1) & (s->nslots - 1);
+    }
+    if (found) continue;
+    if (s->un == s->ucap) {
+      s->ucap *= 2;
+      s->uoff = xrealloc(s->uoff, s->ucap * sizeof *s->uoff); s->ulen = xrealloc(s->ulen, s->ucap * sizeof *s->ulen);
+      s->ucnt = xrealloc(s->ucnt, s->ucap * sizeof *s->ucnt); s->uhash = xrealloc(s->uhash, s->ucap * sizeof *s->uhash);
+    }
+    while (s->an + len > s->acap) { s->acap *= 2; s->arena = xrealloc(s->arena, s->acap); }
+    memcpy(s->arena + s->an, data + st, len);
+    s->uoff[s->un] = s->an; s->ulen[s->un] = (uint32_t)len; s->ucnt[s->un] = 1; s->uhash[s->un] = h; s->an += len;
+    s->slots[p] = (uint32_t)(++s->un);
+    if (s->un * 2 > s->nslots) {
+      free(s->slots); s->nslots *= 4; s->slots = xcalloc(s->nslots, sizeof *s->slots);
+      for (size_t u = 0; u < s->un; u++) {
+        size_t q = (size_t)s->uhash[u] & (s->nslots - 1);
+        while (s->slots[q]) q = (q + 1) & (s->nslots - 1);
+        s->slots[q] = (uint32_t)(u + 1);
+      }
+    }
+  }
+  return 0;
+}
+int oracle_stream_finish(OracleStream *s, OracleTrainer *t) {
+  if (!s || !t) return -1;
+  int rc = -1;
+  free(s->slots); free(s->uhash);
+  if (!s->bad) {
+    free_corpus(t);
+    rc = build_table(t, s->arena, s->un, s->uoff, s->ulen, s->ucnt);  /* (frees uoff / ulen / ucnt) */
+  } else { free(s->uoff); free(s->ulen); free(s->ucnt); }
+  free(s->arena); free(s);
   return rc;
 }
 

@@ -35,6 +35,11 @@ void oracle_destroy(OracleTrainer *t);
 /* csrc/bpe/bpe.cpp:208-297. Returns 0, or -1 (unreadable file / NUL byte in corpus). */
 int oracle_load_corpus(OracleTrainer *t, const char *path);
 int oracle_load_corpus_buffer(OracleTrainer *t, const uint8_t *data, size_t n);
+/* The same load fed chunk by chunk (chunks end on a delimiter), for corpora larger than host memory. */
+typedef struct OracleStream OracleStream;
+OracleStream *oracle_stream_begin(void);
+int oracle_stream_feed(OracleStream *s, const uint8_t *data, size_t n);
+int oracle_stream_finish(OracleStream *s, OracleTrainer *t); /* builds t's word table; frees s */
 
 void oracle_init(OracleTrainer *t);           /* csrc/bpe/bpe.cpp:171-185 */
 void oracle_count_bigrams(OracleTrainer *t);  /* csrc/bpe/bpe.cpp:315-370 */

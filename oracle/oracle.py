@@ -39,6 +39,9 @@ def lib():
     L.oracle_destroy.argtypes = [vp]; L.oracle_destroy.restype = None
     L.oracle_load_corpus.argtypes = [vp, C.c_char_p]; L.oracle_load_corpus.restype = C.c_int
     L.oracle_load_corpus_buffer.argtypes = [vp, vp, sz]; L.oracle_load_corpus_buffer.restype = C.c_int
+    L.oracle_stream_begin.argtypes = []; L.oracle_stream_begin.restype = vp
+    L.oracle_stream_feed.argtypes = [vp, vp, sz]; L.oracle_stream_feed.restype = C.c_int
+    L.oracle_stream_finish.argtypes = [vp, vp]; L.oracle_stream_finish.restype = C.c_int
     L.oracle_init.argtypes = [vp]; L.oracle_init.restype = None
     L.oracle_count_bigrams.argtypes = [vp]; L.oracle_count_bigrams.restype = None
     L.oracle_merge_batch.argtypes = [vp, C.c_int]; L.oracle_merge_batch.restype = C.c_int
@@ -86,6 +89,15 @@ class Oracle:
     a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
     a = np.ascontiguousarray(a)
     return lib().oracle_load_corpus_buffer(self.h, _p(a), a.size)
+
+  def load_chunks(self, chunks) -> int:
+    """Streaming load: `chunks` yields uint8 arrays that end on a delimiter (corpora larger than host memory)."""
+    st = lib().oracle_stream_begin()
+    for c in chunks:
+      a = np.ascontiguousarray(c, dtype=np.uint8)
+      if lib().oracle_stream_feed(st, _p(a), a.size) != 0:
+        break
+    return lib().oracle_stream_finish(st, self.h)
 
   def init(self):
     lib().oracle_init(self.h)

@@ -35,13 +35,14 @@ constexpr int CL_REC_STAGE = 512;          // records staged per CTA and merge
 constexpr unsigned int CL_LOCAL_MAX = CL_SIZE * CL_THREADS * 64;  // longest birth log the leader cluster takes alone (entries)
 constexpr int CL_CAND_CAP = 1024;          // candidate words listed per CTA and merge (more: rewritten where they are found)
 constexpr int CL_MAX_PROBES = 256;
+constexpr unsigned int CL_SOLO_MAX = 8 * CL_THREADS;  // SOLO: a log of up to 8 entries per thread of ONE CTA (no DSMEM exchange, no cluster barrier)
 // Effective limits of one launch. The defaults are the compile-time capacities above; the parity tests shrink them
 // (SWB_TEST_* environment variables, see TrainerImpl::cluster_tune) so that the overflow paths -- candidate lists past
 // the shared-memory list, inbox and table spills into the global pair table, records and log entries past their stages,
 // GRID merges from long logs -- run on corpora small enough for the CPU oracle.
-struct ClusterTune { unsigned int local_max, cand_cap, inbox_cap, rec_stage, birth_stage, max_probes; };
+struct ClusterTune { unsigned int local_max, cand_cap, inbox_cap, rec_stage, birth_stage, max_probes, solo_max /* longest log CTA 0 of the leader cluster takes all by itself */; };
 __host__ __device__ __forceinline__ ClusterTune cluster_tune_default() {
-  return ClusterTune{CL_LOCAL_MAX, (unsigned int)CL_CAND_CAP, (unsigned int)CL_INBOX, (unsigned int)CL_REC_STAGE, (unsigned int)CL_BIRTH_STAGE, (unsigned int)CL_MAX_PROBES};
+  return ClusterTune{CL_LOCAL_MAX, (unsigned int)CL_CAND_CAP, (unsigned int)CL_INBOX, (unsigned int)CL_REC_STAGE, (unsigned int)CL_BIRTH_STAGE, (unsigned int)CL_MAX_PROBES, (unsigned int)CL_SOLO_MAX};
 }
 constexpr unsigned int CL_IP_LOCAL_MAX = 8192;  // longest occurrence list of a pair of two initial symbols the leader cluster takes alone (every entry is a candidate word: two per thread)
 
@@ -63,7 +64,7 @@ __host__ __device__ __forceinline__ unsigned int cmd3_word(unsigned long long se
   return w ? w : 0x5BD1E995u;
 }
 // leader -> other clusters (device memory)
-struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, t_cmd /* %globaltimer when the command arrived */, spec /* started from a hint */, tail_done /* GRID merges whose tail (emit + publish, run by whichever block finished last) is complete */; };
+struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, t_cmd /* %globaltimer when the command arrived */, spec /* started from a hint */, tail_done /* GRID merges whose tail (emit + publish, run by whichever block finished last) is complete */, done_count /* blocks that have finished their part of a GRID merge, summed over all GRID merges of this launch: never reset, so no reset can race with the next merge's arrivals */; };
 __host__ __device__ __forceinline__ unsigned long long cmd2_check(unsigned long long seq, unsigned long long pair,
                                                                   unsigned long long nio, unsigned long long lr) {
   return (seq * HDR_MAGIC) ^ pair ^ (nio << 7 | nio >> 57) ^ (lr * 0xD6E8FEB86659FD93ull);
@@ -77,7 +78,8 @@ __host__ __device__ __forceinline__ unsigned long long cmd2_check(unsigned long 
 struct ClusterCtl {
   // the command, written into every CTA of the leader cluster by its CTA 0
   unsigned long long pair, new_id_op, log_range, k;
-  unsigned int mode, stop;             // mode 0 = LOCAL, 1 = GRID
+  unsigned int mode, stop;             // mode 0 = LOCAL (the leader cluster), 1 = GRID (all clusters), 2 = SOLO (CTA 0 of the leader cluster alone)
+  unsigned int go;                     // CTAs 1.. of the leader cluster: bumped (remote store by CTA 0) when a command is for them too
   unsigned int log_cursor, births_total;  // CTA 0: log entries before this merge / appended by this merge so far
   unsigned long long t_cmd;               // %globaltimer when the command of this merge arrived
   // per CTA, per merge
@@ -265,8 +267,8 @@ __device__ __forceinline__ void cluster_fold_inbox(const ClusterSmem &m, const P
 // LOCAL merge, phase 2 of one CTA: apply this CTA's pairs to the device frequency table and stage the records
 __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const EmitMode &em, const PairTableDev &t, bool spill,
                                                   unsigned long long &cx, unsigned long long &cs, unsigned int &inserted,
-                                                  unsigned long long &maxpush, Rec *__restrict__ out, size_t out_cap, cg::cluster_group &cluster, int32_t new_id, const ClusterTune &tune) {
-  const unsigned int n_occ = m.ctl->n_occ;  // (listed while T2 was filled; the caller has synchronised the block)
+                                                  unsigned long long &maxpush, Rec *__restrict__ out, size_t out_cap, cg::cluster_group &cluster, int32_t new_id, const ClusterTune &tune,
+                                                  unsigned int n_occ /* entries listed in m.occ (the caller has synchronised the block) */) {
   ClusterCtl *c0 = cluster.map_shared_rank(m.ctl, 0);
 #pragma unroll 1
   for (unsigned int i = threadIdx.x; i < n_occ; i += CL_THREADS) {
@@ -311,7 +313,7 @@ __device__ __forceinline__ void cluster_emit_part(const ClusterSmem &m, const Em
 __global__ void __launch_bounds__(CL_THREADS, 1)
 merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *removed_total, Rec *__restrict__ out0, Rec *__restrict__ out1, size_t out_cap,
               unsigned long long *__restrict__ out_hdr0, unsigned long long *__restrict__ out_hdr1, unsigned long long seq_base, unsigned long long op_base,
-              volatile HostCmd2 *hcmd /* [3] in mapped host memory: the command, the hints for even / odd sequence numbers */, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace,
+              volatile HostCmd2 *hcmd /* [8] in mapped host memory: [0] the command, [1], [2] the hints for even / odd sequence numbers (host -> device); [4] status (device -> host) */, DevCmd2 *dcmd, unsigned long long timeout_ns, unsigned long long *trace,
               uint4 *ovf /* [CL_LOCAL_MAX]: candidate words that did not fit a CTA's shared-memory list */,
               const HostCmd2 *__restrict__ script /* nullptr, or [script_n] commands in DEVICE memory that replace the mailbox: the kernel then runs without the host (profiling under ncu's kernel replay, see TrainerImpl::profile_scripted) */, unsigned long long script_n, ClusterTune tune,
               unsigned long long *acct /* [32]: LOCAL merges, their device ns, GRID merges, their device ns, hints accepted, hints rejected, hints accepted without a PCIe trip, LOCAL merges that spilled to the global table, [8] sequence number the watchdog gave up on, [9] after how many ns */) {
@@ -336,6 +338,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
   bool hint_ok = false;
   unsigned long long prev_maxpush = 0;
   unsigned int prev_new_id = 0;
+  unsigned int last_pub_lo = 0, last_pub_path = 0;  // (CTA 0 / thread 0) low half of the last sequence number it published itself, and through which path (1 LOCAL/SOLO, 2 spill tail)
+  unsigned int go_sent = 0, go_seen = 0;  // (CTA 0 / thread 0) commands handed to the other CTAs of the leader cluster; (other CTAs / thread 0) seen
   uint4 pre_hv = make_uint4(0u, 0u, 0u, 0u);  // the hint word for the NEXT merge, requested while this one runs (a read of mapped host memory takes microseconds)
   long long tr_poll = 0, tr_p1 = 0, tr_p2 = 0, tr_pub = 0;
   for (unsigned long long k = 0;; k++) {
@@ -405,10 +409,17 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         }
         const unsigned long long t_cmd = gtime_ns();
         const unsigned int stop = (unsigned int)(nio >> 32);
-        const unsigned int mode = (lr == ~0ull || (unsigned int)(lr & 0xFFFFFFFFu) > tune.local_max) ? 1u : 0u;
-        for (unsigned int r = 0; r < CL_SIZE; r++) {
+        const unsigned int ln = (unsigned int)(lr & 0xFFFFFFFFu);
+        const unsigned int mode = (lr == ~0ull || ln > tune.local_max) ? 1u : (!stop && ln <= tune.solo_max) ? 2u : 0u;
+        // SOLO: only this CTA learns about the merge; the other CTAs of the cluster keep waiting for their `go`
+        for (unsigned int r = 0; r < (mode == 2u ? 1u : (unsigned int)CL_SIZE); r++) {
           ClusterCtl *c = cluster.map_shared_rank(m.ctl, r);
           c->pair = pair; c->new_id_op = nio; c->log_range = lr; c->k = k; c->mode = mode; c->stop = stop; c->t_cmd = t_cmd; c->spec = spec;
+        }
+        if (mode != 2u) {
+          asm volatile("fence.acq_rel.cluster;" ::: "memory");
+          go_sent++;
+          for (unsigned int r = 1; r < CL_SIZE; r++) *(volatile unsigned int *)&cluster.map_shared_rank(m.ctl, r)->go = go_sent;
         }
         if (mode == 1u) cursor_stale = true;  // a GRID merge appends through the global cursor
         if (stop || mode == 1u) {  // the other clusters take part (or leave)
@@ -417,12 +428,22 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           *(volatile unsigned long long *)&dcmd->epoch = grid_epoch + 1;
         }
         *(volatile unsigned long long *)&dcmd->alive_ns = gtime_ns();
+        {  // device -> host status (mailbox word 4, its own 64-byte line): which command was just accepted and how, what was
+           // published last. Diagnostics only: the host prints it when a result does not arrive.
+          const unsigned int sx = (unsigned int)want, sy = mode | (spec << 8) | (stop << 16) | ((unsigned int)(grid_epoch & 0xFFFFu) << 20), sz = last_pub_lo, sw = last_pub_path;
+          asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(hcmd + 4), "r"(sx), "r"(sy), "r"(sz), "r"(sw) : "memory");
+        }
         tr_poll += clock64() - c0;
         // the hint for the merge after this one may already be in the mailbox (the host sends it a merge ahead when it can):
         // ask for it now, look at it when this merge is done
         if (!stop) asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pre_hv.x), "=r"(pre_hv.y), "=r"(pre_hv.z), "=r"(pre_hv.w) : "l"(hcmd + 1 + ((want + 1) & 1ull)) : "memory");
       }
-      cluster_barrier(cluster);  // (release/acquire: the command is visible in every CTA of the leader cluster)
+      if (crank != 0 && threadIdx.x == 0) {  // wait for a command that concerns the whole cluster (SOLO merges pass these CTAs by)
+        while (*(volatile unsigned int *)&m.ctl->go == go_seen) { }
+        go_seen = *(volatile unsigned int *)&m.ctl->go;
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+      }
+      __syncthreads();
     } else {
       if (threadIdx.x == 0) {
         unsigned long long pair = 0, nio = 3ull << 32, lr = ~0ull, kk = 0;
@@ -466,7 +487,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       __syncthreads();
       if (threadIdx.x == 0) {
         __threadfence();
-        is_last = atomicAdd(t.done_blocks, 1u) == gridDim.x - 1;
+        is_last = atomicAdd(&dcmd->done_count, 1ull) + 1ull == grid_epoch * (unsigned long long)gridDim.x;
       }
       __syncthreads();
       if (is_last) {
@@ -476,6 +497,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         if (threadIdx.x == 0) {  // (one publisher at a time)
           __threadfence();
           *(volatile unsigned long long *)&dcmd->tail_done = grid_epoch;
+          acct[10] = seq; acct[11] = blockIdx.x;  // (diagnostics: the last GRID merge whose tail ran, and where)
           const unsigned long long dt = gtime_ns() - m.ctl->t_cmd;
           acct[2] += 1; acct[3] += dt;
           if (trace) {  // development aid: how long do GRID merges take? [16..23] = counts, [24..31] = ns, by duration class
@@ -491,7 +513,11 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       continue;
     }
 
-    // ---------------------------------------------------------------- LOCAL: the leader cluster alone
+    // ---------------------------------------------------------------- LOCAL: the leader cluster alone; SOLO: its CTA 0 alone
+    // (SOLO = the same code with one CTA's worth of log entries, the deltas emitted straight from this CTA's own table T1,
+    //  no exchange through the other CTAs' shared memory and no cluster barrier: most merges touch a few hundred words)
+    const bool solo = mode == 2u;
+    const unsigned int n_cta = solo ? 1u : (unsigned int)CL_SIZE, my_cta = solo ? 0u : crank;
     const long long c1 = clock64();
     {
       const unsigned long long lr = m.ctl->log_range;
@@ -505,11 +531,11 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       // Eight log entries per thread are requested together (one round trip); the matching ones are listed in
       // shared memory and then dealt out evenly, so that no thread rewrites more words than its neighbours.
       long long cA = 0;
-      for (uint64_t base = 0; have_log && base < n; base += 8ull * CL_SIZE * CL_THREADS) {
+      for (uint64_t base = 0; have_log && base < n; base += 8ull * n_cta * CL_THREADS) {
         uint4 ev[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-          const uint64_t i = base + (uint64_t)u * (CL_SIZE * CL_THREADS) + crank * CL_THREADS + threadIdx.x;
+          const uint64_t i = base + (uint64_t)u * (n_cta * CL_THREADS) + my_cta * CL_THREADS + threadIdx.x;
           ev[u] = (i < n && SWB_DBG_OK(ent == em.log.ip_ent || lo + i < em.log.cap, 1, lo, i, n)) ? __ldcg(&ent[lo + i]) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
         }
 #pragma unroll
@@ -552,8 +578,10 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
     }
     __syncthreads();
     if (trace && crank == 0 && threadIdx.x == 0) trace[7] += (unsigned long long)(clock64() - c1);
-    cluster_exchange(m, t, cluster, crank, tune);
-    cluster_barrier(cluster);  // every partial sum of this merge has reached the CTA that owns its pair
+    if (!solo) {
+      cluster_exchange(m, t, cluster, crank, tune);
+      cluster_barrier(cluster);  // every partial sum of this merge has reached the CTA that owns its pair
+    }
     const long long c2 = clock64();
     {
       ClusterCtl *c0 = cluster.map_shared_rank(m.ctl, 0);
@@ -571,7 +599,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         em.g.slots[gt_upsert(em.g, em.merged_key, em.stamp_base | delta_bucket(em, em.merged_key), 0ull, ins)].freq = 0;
         if (ins) atomicAdd(em.g.n_used, ins);
       }
-      cluster_fold_inbox(m, t, cluster, tune);
+      if (!solo) cluster_fold_inbox(m, t, cluster, tune);
       unsigned long long cx = 0, cs = 0;
       unsigned int inserted = 0;
       if (threadIdx.x == 64) {  // this CTA's range in the birth log: requested now, needed after the records are staged
@@ -579,7 +607,12 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         m.ctl->birth_base = c0->log_cursor + (nb ? atomicAdd(&c0->births_total, nb) : 0u);
       }
       unsigned long long maxpush = 0;
-      cluster_emit_part(m, em, t, spill, cx, cs, inserted, maxpush, out, out_cap, cluster, new_id, tune);
+      if (!solo) cluster_emit_part(m, em, t, spill, cx, cs, inserted, maxpush, out, out_cap, cluster, new_id, tune, m.ctl->n_occ);
+      else {  // T1 is the whole delta table of this merge
+        ClusterSmem m1 = m;
+        m1.keys = m.k1; m1.val = m.v1; m1.mk = m.m1; m1.occ = m.occ1;
+        cluster_emit_part(m1, em, t, spill, cx, cs, inserted, maxpush, out, out_cap, cluster, new_id, tune, m.ctl->n_occ1);
+      }
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) {
         inserted += __shfl_down_sync(0xffffffffu, inserted, d);
@@ -614,7 +647,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         m.ctl->n_births = 0; m.ctl->n_recs = 0; m.ctl->n_occ = 0; m.ctl->n_cand = 0; m.ctl->n_occ1 = 0; m.ctl->inbox_n = 0; m.ctl->n_ovf = 0;
       }
     }
-    cluster_barrier(cluster);  // all records, checksums and log entries of this merge are out
+    if (!solo) cluster_barrier(cluster);  // all records, checksums and log entries of this merge are out
+    else __syncthreads();
     const long long c3 = clock64();
     if (crank == 0) {
       ClusterCtl *c = m.ctl;
@@ -629,7 +663,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag);
         __syncthreads();
         cluster_clear_tables(m);
-        if (threadIdx.x == 0) { acct[0] += 1; acct[1] += gtime_ns() - c->t_cmd; acct[7] += 1; }
+        if (threadIdx.x == 0) { acct[0] += 1; acct[1] += gtime_ns() - c->t_cmd; acct[7] += 1; last_pub_lo = (unsigned int)seq; last_pub_path = 2u; }
         if (threadIdx.x == 0) {
           c->log_cursor += c->births_total;  // (the births of this merge are in the log: the next LOCAL merge appends after them)
           c->spill = 0; c->n_recs_total = 0; c->removed = 0;
@@ -647,7 +681,10 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         unsigned long long x = 0, sm = 0;
         unsigned long long mxp = 0;
 #pragma unroll
-        for (int r = 0; r < CL_SIZE; r++) { x ^= c->part_cx[r]; sm += c->part_cs[r]; mxp = c->part_max[r] > mxp ? c->part_max[r] : mxp; }
+        for (int r = 0; r < CL_SIZE; r++) {
+          if (solo && r > 0) break;  // (the other CTAs' parts are those of an earlier merge)
+          x ^= c->part_cx[r]; sm += c->part_cs[r]; mxp = c->part_max[r] > mxp ? c->part_max[r] : mxp;
+        }
         // the next merge may start from a hint: this one was LOCAL, complete and raised no flag
         hint_ok = pre_flags == 0u && n <= out_cap && script == nullptr;
         prev_maxpush = mxp; prev_new_id = (unsigned int)new_id;
@@ -659,6 +696,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(out_hdr + 6), "l"(chk), "l"(seq) : "memory");
           const unsigned long long dt = gtime_ns() - c->t_cmd;
           acct[0] += 1; acct[1] += dt;
+          last_pub_lo = (unsigned int)seq; last_pub_path = 1u;
           {  // LOCAL merges by length of the log they read: [16 + cls] merges, [24 + cls] their ns (cls: <=512, <=4096, <=32768, more entries)
             const unsigned int ln = (unsigned int)(c->log_range & 0xFFFFFFFFu);
             const int cls = ln <= 512u ? 0 : ln <= 4096u ? 1 : ln <= 32768u ? 2 : 3;

@@ -350,12 +350,16 @@ __device__ __forceinline__ void pt_publish(const PairTableDev &t, unsigned int n
     if (__ldcg(lg->flags)) flags |= 32u;
     flags |= (unsigned long long)cur << 32;
   }
-  out_hdr[1] = n; out_hdr[2] = flags; out_hdr[3] = rem; out_hdr[4] = cx; out_hdr[5] = cs;
-  out_hdr[6] = hdr_check(seq, n, flags, rem, cx, cs);
-  out_hdr[0] = seq; out_hdr[7] = seq;
+  // The counters go back to zero BEFORE the header can be seen: whoever sees the header may start the next operation on this
+  // table at once (the host answers within microseconds), and a reset that lands after the first blocks of the next
+  // operation have counted themselves in would leave that operation without a last block -- and its result unpublished.
   if (removed && !(extra_flags & 8u) && !keep_state) *removed = 0;
   if (!(extra_flags & 8u) && !keep_state) { *t.n_touched = 0; *t.flags = 0; }
   *t.done_blocks = 0;
+  __threadfence();
+  out_hdr[1] = n; out_hdr[2] = flags; out_hdr[3] = rem; out_hdr[4] = cx; out_hdr[5] = cs;
+  out_hdr[6] = hdr_check(seq, n, flags, rem, cx, cs);
+  out_hdr[0] = seq; out_hdr[7] = seq;
 }
 
 // full-grid emit (more records than the fused tail takes, long words present, or the count pass): every
@@ -866,30 +870,38 @@ struct GlobalSink {
   }
 };
 
-// The indexed scan of one merge over the whole grid: one thread per log entry of the merge that created
-// max(a, b); the entries with the wanted neighbour and side name the words to rewrite.
-// Returns this thread's removed-symbol count.
-__device__ __forceinline__ uint32_t scan_log_words(const StreamDev &s, const PairTableDev &t, const BirthLogDev &lg, uint32_t merge,
-                                                   uint32_t want_other, uint32_t want_side, int32_t a, int32_t b, int32_t new_id) {
-  const uint64_t lo = __ldcg(&lg.start[merge]);
-  const uint64_t n = __ldcg(&lg.start[merge + 1]) - lo;
+// The indexed scan of one merge over the whole grid: one thread per entry of a list of (neighbour, side, word) entries --
+// the birth log of the merge that created max(a, b), or the occurrence index of a pair of two initial symbols; the entries
+// with the wanted neighbour and side name the words to rewrite. Returns this thread's removed-symbol count.
+__device__ __forceinline__ uint32_t scan_entry_words(const StreamDev &s, const PairTableDev &t, const BirthLogDev &lg, const uint4 *__restrict__ ent,
+                                                     uint64_t lo, uint64_t n, uint64_t ent_cap, uint32_t want_other, uint32_t want_side, int32_t a, int32_t b,
+                                                     int32_t new_id) {
   GlobalSink sink{t, lg};
   uint32_t removed = 0;
 #pragma unroll 1
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    if (!SWB_DBG_OK(lo + i < lg.cap, 4, lo, i, n)) break;
-    const uint4 e = __ldcg(&lg.ent[lo + i]);
+    if (!SWB_DBG_OK(lo + i < ent_cap, 4, lo, i, n)) break;
+    const uint4 e = __ldcg(&ent[lo + i]);
     if (e.x == want_other && (e.y & 0x80000000u) == want_side && SWB_DBG_OK((((uint64_t)e.w << 32) | e.z) < s.n_rows * ROW, 5, ((uint64_t)e.w << 32) | e.z, e.y, i))
       removed += merge_one_word(s, ((uint64_t)e.w << 32) | e.z, e.y & 0x7FFFFFFFu, a, b, new_id, sink);
   }
   return removed;
 }
 
-// One merge over the whole grid: the indexed word scan when the pair has a birth log, the row-signature scan otherwise.
+// One merge over the whole grid: the indexed word scan when the pair has a birth log or (two initial symbols) an occurrence
+// list, the row-signature scan otherwise.
 __device__ __forceinline__ uint32_t scan_merge(const StreamDev &s, const PairTableDev &t, const BirthLogDev &lg, int32_t a, int32_t b,
                                                int32_t new_id, int (*sm)[ROW], Match (*ml)[MATCH_CAP], unsigned int *n_match) {
   uint32_t merge, other, side;
-  if (log_lookup(lg, a, b, merge, other, side)) return scan_log_words(s, t, lg, merge, other, side, a, b, new_id);
+  if (log_lookup(lg, a, b, merge, other, side)) {
+    const uint64_t lo = __ldcg(&lg.start[merge]), hi = __ldcg(&lg.start[merge + 1]);
+    return scan_entry_words(s, t, lg, lg.ent, lo, hi >= lo ? hi - lo : 0, lg.cap, other, side, a, b, new_id);
+  }
+  if (ip_lookup(lg, a, b)) {  // every word that held (a, b) when the corpus was loaded (a superset of those that still do)
+    const uint32_t pk = (uint32_t)a * 256u + (uint32_t)b;
+    const uint64_t lo = __ldcg(&lg.ip_start[pk]), hi = __ldcg(&lg.ip_start[pk + 1]);
+    return scan_entry_words(s, t, lg, lg.ip_ent, lo, hi - lo, ~0ull, (uint32_t)a, 0u, a, b, new_id);
+  }
   return scan_rows(s, t, lg, a, b, new_id, sm, ml, n_match);
 }
 

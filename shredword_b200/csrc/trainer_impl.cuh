@@ -241,9 +241,9 @@ class TrainerImpl {
     unsigned long long *d_u64 = reinterpret_cast<unsigned long long *>(scalars_.get() + 8);  // [0]=long syms [1]=bytes [2]=cursor
     // ---- 1. tokenise + dedupe
     // Unique words grow far slower than the corpus (Heaps' law): the table starts at one 32-byte slot per 256 corpus bytes, at
-    // most 8 M slots (256 MB; what the tail of the distribution touches of it should stay in the 126 MB L2), and is rebuilt
+    // most 16 M slots (512 MB; only the occupied 32-byte sectors are ever touched again, and for a few million unique words those mostly stay in the 126 MB L2), and is rebuilt
     // four times as large if the corpus turns out to hold more unique words than 60 % of that.
-    uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(1ull << 16, pow2_ceil(n / 256)), 1ull << 23);
+    uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(1ull << 16, pow2_ceil(n / 256)), 1ull << 24);
     DevBuf<WSlot> wslots;
     unsigned int h_scal[4];
     const int tok_grid = (int)std::max<uint64_t>((uint64_t)sms_, (n >> 31) + 1);  // one block per SM; a block's span stays below 4 GB
@@ -739,6 +739,37 @@ class TrainerImpl {
       const double t = now_ms();
       if (t_wait0 == 0) { t_wait0 = t; return; }
       if (t - t_wait0 < 5.0) return;
+      if (resident_wait_ && t - t_wait0 > 200.0) {
+        // The resident kernel reports which command it accepted last (mailbox word 4). If it has moved on to waiting for the
+        // command AFTER the merge whose result we are waiting for, that result is lost and neither side will ever move
+        // again: fail now (with everything that can help to find out why) instead of when the kernel's watchdog fires.
+        const volatile HostCmd2 *stw = hcmd2_.host() + 4;
+        const unsigned int sx = stw->x, sy = stw->y, sz = stw->z, sw = stw->w;
+        if (sx == (unsigned int)(seq + 1) && ((sy >> 16) & 0xFu) == 0u) {
+          volatile unsigned long long *ho = (h == hdr_.host()) ? hdr_b_.host() : hdr_.host();
+          char msg[768];
+          snprintf(msg, sizeof msg, "lost result: the resident kernel has accepted command %u (mode %u, from a hint %u, GRID merges so far %u; it last published seq ..%u through path %u) "
+                   "while the result of merge %llu never arrived (this header: seq %llu/%llu n %llu flags %llx check %s; other header: seq %llu/%llu n %llu flags %llx)",
+                   sx, sy & 0xFFu, (sy >> 8) & 0xFFu, sy >> 20, sz, sw, seq, (unsigned long long)h[0], (unsigned long long)h[7], (unsigned long long)h[1],
+                   (unsigned long long)h[2], h[6] == hdr_check(h[0], h[1], h[2], h[3], h[4], h[5]) ? "ok" : "BAD", (unsigned long long)ho[0], (unsigned long long)ho[7],
+                   (unsigned long long)ho[1], (unsigned long long)ho[2]);
+          std::string full(msg);
+          {  // stop the kernel (it accepts a stop addressed to the merge before the one it is waiting for) and read its counters
+            HostCmd2Sender stopper;
+            stopper.c = hcmd2_.host(); stopper.next_seq = seq;
+            stopper.send(0, 0, 1);
+            unsigned long long ac[16] = {0};
+            unsigned int sc[3] = {0, 0, 0};
+            if (cudaStreamSynchronize(stream_) == cudaSuccess && cudaMemcpy(ac, cl_acct_.get(), sizeof ac, cudaMemcpyDeviceToHost) == cudaSuccess) {
+              if (pt_scal_.size()) cudaMemcpy(sc, pt_scal_.get(), sizeof sc, cudaMemcpyDeviceToHost);
+              snprintf(msg, sizeof msg, "; LOCAL %llu GRID %llu merges done in this launch, last GRID tail: seq %llu in block %llu; pair table: touched %u flags %u done_blocks %u",
+                       ac[0], ac[2], ac[10], ac[11], sc[0], sc[1], sc[2]);
+              full += msg;
+            }
+          }
+          throw Error(full);
+        }
+      }
       cudaError_t e = cudaStreamQuery(stream_);
       if (e == cudaSuccess) {
         if (++idle_polls_ > 64) {
@@ -757,7 +788,10 @@ class TrainerImpl {
           if (cl_acct_.size() >= 16) {  // did the resident kernel's watchdog give up on the host?
             unsigned long long ac[16] = {0};
             if (cudaMemcpy(ac, cl_acct_.get(), sizeof ac, cudaMemcpyDeviceToHost) == cudaSuccess && ac[8]) {
-              snprintf(msg, sizeof msg, "; the resident kernel's watchdog gave up waiting for command %llu after %.1f ms (SWB_HOST_TIMEOUT_MS)", ac[8], (double)ac[9] * 1e-6);
+              unsigned int sc[3] = {0, 0, 0};
+              if (pt_scal_.size()) cudaMemcpy(sc, pt_scal_.get(), sizeof sc, cudaMemcpyDeviceToHost);
+              snprintf(msg, sizeof msg, "; the resident kernel's watchdog gave up waiting for command %llu after %.1f ms (SWB_HOST_TIMEOUT_MS); LOCAL %llu GRID %llu merges done, "
+                       "last GRID tail: seq %llu in block %llu; pair table: touched %u flags %u done_blocks %u", ac[8], (double)ac[9] * 1e-6, ac[0], ac[2], ac[10], ac[11], sc[0], sc[1], sc[2]);
               full += msg;
             }
           }
@@ -1183,7 +1217,7 @@ class TrainerImpl {
         if (e && *e) { const unsigned long x = strtoul(e, nullptr, 10); if (x < v) v = (unsigned int)x; }
       };
       shrink("SWB_TEST_LOCAL_MAX", c.local_max); shrink("SWB_TEST_CAND_CAP", c.cand_cap); shrink("SWB_TEST_INBOX", c.inbox_cap);
-      shrink("SWB_TEST_REC_STAGE", c.rec_stage); shrink("SWB_TEST_BIRTH_STAGE", c.birth_stage); shrink("SWB_TEST_MAX_PROBES", c.max_probes);
+      shrink("SWB_TEST_REC_STAGE", c.rec_stage); shrink("SWB_TEST_BIRTH_STAGE", c.birth_stage); shrink("SWB_TEST_MAX_PROBES", c.max_probes); shrink("SWB_TEST_SOLO_MAX", c.solo_max);
       if (c.max_probes < 1) c.max_probes = 1;
       return c;
     }();
@@ -1242,11 +1276,11 @@ class TrainerImpl {
     if (tr_->config.unk_id < 0) throw Error("profile_scripted: negative unk_id is not supported");
     ensure_pair_table(8ull * (258ull + n + 2));
     ensure_global_table(std::max<uint64_t>(gt_cap_ * 4, 16ull * (258ull + n + 2)));  // (the script cannot stop to let the table grow)
-    if (!hcmd2_.size()) { hcmd2_.alloc(4); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(32); }
+    if (!hcmd2_.size()) { hcmd2_.alloc(8); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(32); }
     if (recs_b_.size() != recs_.size()) recs_b_.alloc(recs_.size());
     if (!hdr_b_.size()) hdr_b_.alloc(HDR_WORDS);
     SWB_CUDA(cudaMemsetAsync(cl_acct_.get(), 0, cl_acct_.bytes(), stream_));
-    memset((void *)hcmd2_.host(), 0, 4 * sizeof(HostCmd2));
+    memset((void *)hcmd2_.host(), 0, 8 * sizeof(HostCmd2));
     SWB_CUDA(cudaMemsetAsync(dcmd2_.get(), 0, sizeof(DevCmd2), stream_));
     EmitMode em = emit_mode(1, 0, 0);
     em.log = birth_log(256, (uint32_t)n + 1);
@@ -1286,12 +1320,12 @@ class TrainerImpl {
     ensure_pair_table(8ull * (258ull + tr_->num_merges + (uint64_t)max_merges + 2));
     maybe_grow_global_table(gt_flagged_);
     gt_flagged_ = false;
-    if (!hcmd2_.size()) { hcmd2_.alloc(4); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(32); }
+    if (!hcmd2_.size()) { hcmd2_.alloc(8); dcmd2_.alloc(1); cl_ovf_.alloc(CL_LOCAL_MAX); cl_acct_.alloc(32); }
     if (recs_b_.size() != recs_.size()) recs_b_.alloc(recs_.size());  // second record buffer + header: merges started from a hint
     if (!hdr_b_.size()) hdr_b_.alloc(HDR_WORDS);
     memset(hdr_b_.host(), 0, HDR_WORDS * sizeof(unsigned long long));
     SWB_CUDA(cudaMemsetAsync(cl_acct_.get(), 0, cl_acct_.bytes(), stream_));
-    memset((void *)hcmd2_.host(), 0, 4 * sizeof(HostCmd2));
+    memset((void *)hcmd2_.host(), 0, 8 * sizeof(HostCmd2));
     SWB_CUDA(cudaMemsetAsync(dcmd2_.get(), 0, sizeof(DevCmd2), stream_));
     const int32_t unk = tr_->config.unk_id;
     EmitMode em = emit_mode(1, 0, 0);
@@ -1364,7 +1398,9 @@ class TrainerImpl {
       const unsigned long long q = seq_base + done + 1;
       unsigned long long *hh = (q & 1ull) ? hdr_b_.host() : hdr_.host();
       Rec *hr = (q & 1ull) ? recs_b_.host() : recs_.host();
+      resident_wait_ = true;
       wait_seq_at(q, hh, hr, recs_.size());
+      resident_wait_ = false;
       const double tw1 = now_ms();
       stats.host_wait_ms += tw1 - tw0;
       const size_t n = (size_t)hh[1];
@@ -1614,6 +1650,7 @@ class TrainerImpl {
   DevBuf<unsigned long long> ptrace_;
   // device-resident loop
   bool trace_wait_ = getenv("SWB_TRACE_WAIT") != nullptr;
+  bool resident_wait_ = false;  // wait_seq_at is waiting for a result of the resident kernel (its status word is meaningful)
   std::vector<float> wait_trace_;
   std::vector<uint32_t> trace_removed_, trace_nrec_, trace_cand_, trace_mrows_;
   std::vector<uint64_t> trace_logn_;

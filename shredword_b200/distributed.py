@@ -153,21 +153,28 @@ class DistributedBPETrainer(BPETrainer):
   def _idle_rank(self) -> bool:
     return self.merge_loop == "rank0" and self.rank != 0
 
-  def _broadcast_result(self):
+  def _broadcast_result(self, failed: bool = False):
     """merge_loop == "rank0": rank 0's merge list, byte map and token histogram go to every rank (one broadcast of sizes,
-    one of the payload; NCCL when the device is a GPU)."""
+    one of the payload; NCCL when the device is a GPU). failed (rank 0 only): training failed there -- every rank learns it
+    (a negative merge count) and raises, instead of waiting for a payload that never comes."""
     if self.merge_loop != "rank0":
       return
-    if self.rank == 0:
+    if self.rank == 0 and not failed:
       m = super().merges_array().astype(np.int64).reshape(-1)
       bm = super().byte_map().astype(np.int64)
       tf = super().token_freq().astype(np.int64)
       payload = np.concatenate([m, bm, tf])
       hdr = torch.tensor([m.size // 3, payload.size], dtype=torch.int64, device=self.device)
+    elif self.rank == 0:
+      hdr = torch.tensor([-1, 0], dtype=torch.int64, device=self.device)
     else:
       hdr = torch.zeros(2, dtype=torch.int64, device=self.device)
     dist.broadcast(hdr, src=0, group=self.group)
     n_merges, n = int(hdr[0].item()), int(hdr[1].item())
+    if n_merges < 0:
+      if self.rank != 0:
+        raise RuntimeError("training failed on rank 0 (which runs the merge loop)")
+      return
     buf = torch.from_numpy(payload).to(self.device) if self.rank == 0 else torch.empty(n, dtype=torch.int64, device=self.device)
     dist.broadcast(buf, src=0, group=self.group)
     self.collectives += 2
@@ -202,8 +209,15 @@ class DistributedBPETrainer(BPETrainer):
 
   def train_quiet(self) -> int:
     if self.merge_loop == "rank0":
-      got = super().train_quiet() if self.rank == 0 else 0
-      self._broadcast_result()
+      got, err = 0, None
+      if self.rank == 0:
+        try:
+          got = super().train_quiet()
+        except RuntimeError as e:  # the other ranks are waiting for the result: tell them before raising
+          err = e
+      self._broadcast_result(failed=err is not None)
+      if err is not None:
+        raise err
       return got if self.rank == 0 else self._bcast[0].shape[0]
     if self.native:
       return super().train_quiet()

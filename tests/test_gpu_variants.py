@@ -24,6 +24,8 @@ VARIANTS = {
   "host_frequency_table": {"SWB_HOST_TABLE": "1"},
   "no_load_pipeline": {"SWB_NO_LOAD_PIPELINE": "1"},
   "small_load_pieces": {"SWB_LOAD_PIECE": "65536", "SWB_ENCODE_PIECE": "65536"},
+  "no_solo_merges": {"SWB_TEST_SOLO_MAX": "0"},          # every LOCAL merge through the whole leader cluster (DSMEM exchange)
+  "solo_only_tiny_logs": {"SWB_TEST_SOLO_MAX": "40"},
   # forced overflow paths of merge_cluster
   "grid_from_long_logs": {"SWB_TEST_LOCAL_MAX": "64"},
   "candidate_overflow": {"SWB_TEST_CAND_CAP": "3"},
@@ -32,7 +34,8 @@ VARIANTS = {
   "record_stage_overflow": {"SWB_TEST_REC_STAGE": "1"},
   "birth_stage_overflow": {"SWB_TEST_BIRTH_STAGE": "1"},
   "frequency_table_rehash": {"SWB_TEST_SMALL_GT": "1"},
-  "everything_small": {"SWB_TEST_LOCAL_MAX": "4096", "SWB_TEST_CAND_CAP": "5", "SWB_TEST_INBOX": "7", "SWB_TEST_MAX_PROBES": "3",
+  "solo_table_spill": {"SWB_TEST_MAX_PROBES": "1", "SWB_TEST_REC_STAGE": "1", "SWB_TEST_BIRTH_STAGE": "2", "SWB_TEST_CAND_CAP": "4"},
+  "everything_small": {"SWB_TEST_LOCAL_MAX": "4096", "SWB_TEST_SOLO_MAX": "300", "SWB_TEST_CAND_CAP": "5", "SWB_TEST_INBOX": "7", "SWB_TEST_MAX_PROBES": "3",
                        "SWB_TEST_REC_STAGE": "2", "SWB_TEST_BIRTH_STAGE": "3", "SWB_TEST_SMALL_GT": "1"},
 }
 

@@ -116,3 +116,13 @@ def test_encode_decode_roundtrip(oracle_mod):
       seq = res
     out += seq
   assert out == list(ids[: len(out)])
+
+
+def test_streaming_load_equals_buffer_load(oracle_mod):
+  """The chunk-fed loader (used for the 50 GB configuration, which does not fit host memory) builds the same word table."""
+  from shredword_b200 import synth
+  spec = synth.small_spec(6_000_000, 40_000, 5, "multi")
+  kw = dict(target_vocab_size=700, unk_id=0, character_coverage=0.995, min_pair_freq=20)
+  a = oracle_mod.Oracle(**kw); a.load_buffer(np.concatenate(list(synth.generate(spec, chunk_words=120_000)))); na = a.train()
+  b = oracle_mod.Oracle(**kw); assert b.load_chunks(synth.generate(spec, chunk_words=120_000)) == 0
+  assert b.train() == na and np.array_equal(a.merges, b.merges) and np.array_equal(a.token_freq(), b.token_freq())
