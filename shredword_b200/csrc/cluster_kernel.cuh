@@ -35,7 +35,7 @@ constexpr int CL_REC_STAGE = 512;          // records staged per CTA and merge
 constexpr unsigned int CL_LOCAL_MAX = CL_SIZE * CL_THREADS * 64;  // longest birth log the leader cluster takes alone (entries)
 constexpr int CL_CAND_CAP = 1024;          // candidate words listed per CTA and merge (more: rewritten where they are found)
 constexpr int CL_MAX_PROBES = 256;
-constexpr unsigned int CL_SOLO_MAX = 8 * CL_THREADS;  // SOLO: a log of up to 8 entries per thread of ONE CTA (no DSMEM exchange, no cluster barrier)
+constexpr unsigned int CL_SOLO_MAX = 2 * CL_THREADS;  // SOLO: a log of up to 2 entries (hence at most 2 candidate words) per thread of ONE CTA; measured: at 8 per thread the words of one CTA take longer than the exchange saves
 // Effective limits of one launch. The defaults are the compile-time capacities above; the parity tests shrink them
 // (SWB_TEST_* environment variables, see TrainerImpl::cluster_tune) so that the overflow paths -- candidate lists past
 // the shared-memory list, inbox and table spills into the global pair table, records and log entries past their stages,
@@ -456,7 +456,14 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
             m.ctl->spec = (unsigned int)*(volatile unsigned long long *)&dcmd->spec;
             break;
           }
-          if ((spin & 255) == 255 && gtime_ns() - *(volatile unsigned long long *)&dcmd->alive_ns > 4 * timeout_ns) break;  // leader gone
+          if ((spin & 255) == 255) {  // leader gone?
+            // %globaltimer of two SMs can differ by a tick: the leader's stamp may be AHEAD of this SM's clock, and an unsigned
+            // difference would then be huge -- this block would leave, the next GRID merge would wait for it for ever (144
+            // blocks expected, 143 arrive, nobody is last, nothing is published). Signed difference; 0 = the leader has not
+            // accepted its first command yet.
+            const unsigned long long alive = *(volatile unsigned long long *)&dcmd->alive_ns;
+            if (alive != 0ull && (long long)(gtime_ns() - alive) > (long long)(4 * timeout_ns)) break;
+          }
         }
         m.ctl->pair = pair; m.ctl->new_id_op = nio; m.ctl->log_range = lr; m.ctl->k = kk; m.ctl->mode = 1u; m.ctl->stop = (unsigned int)(nio >> 32);
       }

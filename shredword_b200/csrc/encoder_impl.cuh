@@ -237,7 +237,6 @@ enc_fused(const uint8_t *__restrict__ text, uint64_t n, uint64_t lo_b, uint64_t 
           unsigned int *__restrict__ fallback, unsigned long long tok_base, unsigned long long word_base, int32_t *__restrict__ out,
           uint64_t cap_ids, uint32_t *__restrict__ word_ntok, uint64_t cap_words, int32_t neg_id) {
   __shared__ int stok[ENC_TILE + ENC_SHORT];       // tokens of the word that starts at byte r of the tile: stok[r ...]
-  __shared__ int ctok[ENC_TILE];                   // the tile's tokens, compacted in text order
   __shared__ uint16_t wstart[ENCF_MAX_WORDS];      // ordered word starts (byte position in the tile)
   __shared__ uint16_t wnt[ENCF_MAX_WORDS];         // tokens per word
   __shared__ uint16_t woff[ENCF_MAX_WORDS];        // exclusive token offset of each word inside the tile
@@ -329,37 +328,48 @@ enc_fused(const uint8_t *__restrict__ text, uint64_t n, uint64_t lo_b, uint64_t 
         if (threadIdx.x == 0) *(volatile unsigned long long *)&desc[tile] = (1ull << 62) | agg;
         long long idx = (long long)tile - 1;
         for (;;) {
-          const long long my = idx - (long long)threadIdx.x;
-          unsigned long long d = 2ull << 62;  // (before the first tile: an empty prefix)
-          if (my >= 0) { do { d = *(volatile unsigned long long *)&desc[my]; } while ((d >> 62) == 0ull); }
-          const unsigned int pm = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
-          const int first = __ffs(pm) - 1;  // nearest tile (lowest lane) that already knows its inclusive prefix
-          unsigned long long v = ((int)threadIdx.x <= first || first < 0) ? (d & 0x3FFFFFFFFFFFFFFFull) : 0ull;
+          // four windows of 32 descriptors are requested together (one L2 round trip), then looked at nearest first
+          unsigned long long dq[4];
 #pragma unroll
-          for (int dd = 16; dd > 0; dd >>= 1) v += __shfl_down_sync(0xffffffffu, v, dd);
-          v = __shfl_sync(0xffffffffu, v, 0);
-          excl += v;
-          if (first >= 0) break;
-          idx -= 32;
+          for (int u = 0; u < 4; u++) {
+            const long long my = idx - 32 * u - (long long)threadIdx.x;
+            dq[u] = my >= 0 ? *(volatile unsigned long long *)&desc[my] : (2ull << 62);  // (before the first tile: an empty prefix)
+          }
+          bool found = false;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (found) continue;
+            const long long my = idx - 32 * u - (long long)threadIdx.x;
+            unsigned long long d = dq[u];
+            while ((d >> 62) == 0ull) d = *(volatile unsigned long long *)&desc[my];  // that tile has not even published its own totals yet
+            const unsigned int pm = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+            const int first = __ffs(pm) - 1;  // nearest tile (lowest lane) that already knows its inclusive prefix
+            unsigned long long v = ((int)threadIdx.x <= first || first < 0) ? (d & 0x3FFFFFFFFFFFFFFFull) : 0ull;
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) v += __shfl_down_sync(0xffffffffu, v, dd);
+            v = __shfl_sync(0xffffffffu, v, 0);
+            excl += v;
+            found = first >= 0;
+          }
+          if (found) break;
+          idx -= 128;
         }
         if (threadIdx.x == 0) *(volatile unsigned long long *)&desc[tile] = (2ull << 62) | (excl + agg);
       }
       if (threadIdx.x == 0) s_excl = excl;
     }
     __syncthreads();
-    // ---- compact in shared memory, then coalesced stores
-    for (uint32_t j = threadIdx.x; j < nw; j += ENC_THREADS) {
-      const uint32_t rel = wstart[j], nt = wnt[j], o = woff[j];
-      for (uint32_t k = 0; k < nt; k++) ctok[o + k] = stok[rel + k];
-    }
-    __syncthreads();
+    // ---- write: word j's tokens go to out[to + woff[j] ...]; consecutive words are consecutive threads of a warp, so a
+    // warp's stores cover one contiguous stretch of the output
     const unsigned long long excl = s_excl;
     const uint64_t to = tok_base + (excl >> 31), wo = word_base + (excl & 0x7FFFFFFFull);
-    for (uint32_t k = threadIdx.x; k < ntok; k += ENC_THREADS)
-      if (to + k < cap_ids) { const int v = ctok[k]; out[to + k] = (v == UNK_CODE) ? neg_id : v; }
-    if (word_ntok)
-      for (uint32_t j = threadIdx.x; j < nw; j += ENC_THREADS)
-        if (wo + j < cap_words) word_ntok[wo + j] = wnt[j];
+    for (uint32_t j = threadIdx.x; j < nw; j += ENC_THREADS) {
+      const uint32_t rel = wstart[j], nt = wnt[j];
+      const uint64_t o = to + woff[j];
+      for (uint32_t k = 0; k < nt; k++)
+        if (o + k < cap_ids) { const int v = stok[rel + k]; out[o + k] = (v == UNK_CODE) ? neg_id : v; }
+      if (word_ntok && wo + j < cap_words) word_ntok[wo + j] = nt;
+    }
   }
 }
 
@@ -557,7 +567,7 @@ class EncoderImpl {
       if (desc_.size() < n_tiles + 1) desc_.alloc(n_tiles + 1);  // [n_tiles] = {tile counter, fallback flag}
       SWB_CUDA(cudaMemsetAsync(desc_.get(), 0, (n_tiles + 1) * 8, stream_));
       unsigned int *ctr = reinterpret_cast<unsigned int *>(desc_.get() + n_tiles);
-      const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)sms_ * 4);
+      const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)sms_ * 6);  // 30 KB of shared memory and 40 registers per thread: six blocks per SM
       enc_fused<<<grid, ENC_THREADS, 0, stream_>>>(d_text, n, lo, hi, tbl_, memo_, d_bmap_.get(), desc_.get(), ctr, ctr + 1, tok_base + tt,
                                                    word_base + tw, d_out, cap_ids, d_word_ntok, cap_words, neg_id_);
       launches++;
