@@ -561,9 +561,12 @@ def main():
       torch.cuda.synchronize(); t0 = time.perf_counter()
       t.load_buffer(arr[:sb]); got = t.train_quiet(); t.merges_array()
       same_s = time.perf_counter() - t0
-    t.destroy()
+    sst = t.stats()
     cb["ours_on_same_sample"] = {"seconds": same_s, "GB_per_s": sb / 1e9 / same_s, "merges": got, "speedup": cb["seconds"] / same_s,
-                                 "merges_equal_count": got == cb["merges"]}
+                                 "merges_equal_count": got == cb["merges"],
+                                 "phase_ms": {k: sst[k] for k in ("load_ms", "count_ms", "merge_ms")},
+                                 "note": "end to end from host memory incl. handle creation; a 32 MB corpus leaves the GPU mostly idle (fixed costs dominate)"}
+    t.destroy()
     full = full_config_reference()
     if full:
       cb["full_config2"] = full

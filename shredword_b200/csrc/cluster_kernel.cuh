@@ -505,7 +505,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           __threadfence();
           *(volatile unsigned long long *)&dcmd->tail_done = grid_epoch;
           acct[10] = seq; acct[11] = blockIdx.x;  // (diagnostics: the last GRID merge whose tail ran, and where)
-          const unsigned long long dt = gtime_ns() - m.ctl->t_cmd;
+          const long long dts = (long long)(gtime_ns() - m.ctl->t_cmd);  // (stamps of two SMs: may come out a tick negative)
+          const unsigned long long dt = dts > 0 ? (unsigned long long)dts : 0ull;
           acct[2] += 1; acct[3] += dt;
           if (trace) {  // development aid: how long do GRID merges take? [16..23] = counts, [24..31] = ns, by duration class
             const int cls = dt < 16000 ? 0 : dt < 24000 ? 1 : dt < 32000 ? 2 : dt < 48000 ? 3 : dt < 64000 ? 4 : dt < 128000 ? 5 : dt < 256000 ? 6 : 7;

@@ -1232,13 +1232,18 @@ class TrainerImpl {
     const ClusterFacts &cf = cluster_facts(device_);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)(cf.clusters * CL_SIZE)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES; cfg.stream = stream_;
+    // (profiling switches: SWB_CLUSTERS=n caps the number of clusters, SWB_NO_COOP=1 drops the cooperative attribute -- a profiler
+    //  that takes SMs for itself can make the full cooperative grid "too large"; fewer clusters only slow GRID merges down)
+    static const int cap_clusters = getenv("SWB_CLUSTERS") ? atoi(getenv("SWB_CLUSTERS")) : 0;
+    static const bool no_coop = getenv("SWB_NO_COOP") && atoi(getenv("SWB_NO_COOP")) > 0;
+    const int n_clusters = cap_clusters > 0 ? std::min(cap_clusters, cf.clusters) : cf.clusters;
+    cfg.gridDim = dim3((unsigned)(n_clusters * CL_SIZE)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES; cfg.stream = stream_;
     cudaLaunchAttribute at[3];
     int n_at = 0;
     at[n_at].id = cudaLaunchAttributeClusterDimension;
     at[n_at].val.clusterDim.x = CL_SIZE; at[n_at].val.clusterDim.y = 1; at[n_at].val.clusterDim.z = 1;
     n_at++;
-    if (cf.cooperative) { at[n_at].id = cudaLaunchAttributeCooperative; at[n_at].val.cooperative = 1; n_at++; }
+    if (cf.cooperative && !no_coop) { at[n_at].id = cudaLaunchAttributeCooperative; at[n_at].val.cooperative = 1; n_at++; }
     {  // keep the symbol rows resident in L2 across the merges of this launch (the birth log streams through it)
       static const bool no_persist = getenv("SWB_NO_L2_PERSIST") && atoi(getenv("SWB_NO_L2_PERSIST")) > 0;
       int max_persist = 0, max_window = 0;
