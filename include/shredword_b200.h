@@ -200,6 +200,14 @@ uint64_t swb_encoder_kernel_launches(const SwbEncoder *enc);
  * written; 3 * nbytes always suffices), or -1 on error. */
 int64_t swb_normalize(const void *text, size_t nbytes, void *out, size_t cap, int on_device);
 
+/* ---- optional pre-pass: the reference's regex pre-tokenisation (reference shredword/base.py:38-58,
+ * apply_regex: regex.findall of its GPT-4 style split pattern). The result is `text` with one ' ' behind every piece of the
+ * pattern and the bytes ' ' \t \n \r inside pieces replaced by 0x1C 0x1D 0x1E 0x1F, so that the whitespace-splitting
+ * trainer / encoder treats exactly the reference's pieces as its words; dropping the ' ' bytes and mapping 0x1C-0x1F back
+ * restores the text. `text` is UTF-8 (bytes that are not well-formed UTF-8 count as characters outside \p{L} \p{N} \s).
+ * Pointers and return value as for swb_normalize; 2 * nbytes always suffices. */
+int64_t swb_pretokenize(const void *text, size_t nbytes, void *out, size_t cap, int on_device);
+
 /* ---- building blocks of the multi-GPU merge loop ----
  * Unique words are sharded over ranks (word wi belongs to rank wi % nranks); every rank keeps an
  * identical replica of the pair table + heap. A record is 4 x int64: first, second, delta, key

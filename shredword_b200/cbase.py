@@ -98,6 +98,7 @@ _sigs = {
   "swb_decode": ([c_void_p, c_void_p, c_size_t, c_void_p, c_size_t], c_size_t),
   "swb_encoder_kernel_launches": ([c_void_p], c_uint64),
   "swb_normalize": ([c_void_p, c_size_t, c_void_p, c_size_t, c_int], c_int64),
+  "swb_pretokenize": ([c_void_p, c_size_t, c_void_p, c_size_t, c_int], c_int64),
   "swb_set_shard": ([T, c_int, c_int], c_int),
   "swb_device_pci_bus_id": ([c_int, c_char_p, c_size_t], c_int),
   "swb_dist_reduce_records": ([c_void_p, c_size_t], c_size_t),

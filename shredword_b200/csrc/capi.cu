@@ -12,6 +12,7 @@
 #include "../../include/shredword_b200.h"
 #include "encoder_impl.cuh"
 #include "normalize.cuh"
+#include "pretok.cuh"
 #include "trainer_impl.cuh"
 
 using swb::EncoderImpl;
@@ -340,6 +341,35 @@ int64_t swb_normalize(const void *text, size_t nbytes, void *out, size_t cap, in
       swb::DevBuf<uint8_t> d_in(nbytes + 16), d_out(cap + 16);
       if (nbytes) SWB_CUDA(cudaMemcpyAsync(d_in.get(), text, nbytes, cudaMemcpyHostToDevice, st));
       total = swb::normalize_device(d_in.get(), nbytes, d_out.get(), cap, st, sms, nullptr);
+      const size_t back = (size_t)std::min<uint64_t>(total, cap);
+      if (back) SWB_CUDA(cudaMemcpyAsync(out, d_out.get(), back, cudaMemcpyDeviceToHost, st));
+      SWB_CUDA(cudaStreamSynchronize(st));
+    }
+  } catch (...) { cudaStreamDestroy(st); throw; }
+  cudaStreamDestroy(st);
+  return (int64_t)total;
+  SWB_CATCH(-1)
+}
+
+// ---- optional pre-pass: the reference's regex pre-tokenisation (reference shredword/base.py:38-58, apply_regex)
+int64_t swb_pretokenize(const void *text, size_t nbytes, void *out, size_t cap, int on_device) {
+  if ((!text && nbytes) || (!out && cap)) { set_err("swb_pretokenize: NULL argument"); return -1; }
+  SWB_TRY
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) { cudaGetLastError(); throw swb::Error("no CUDA device (this library has no CPU fallback)"); }
+  int dev = 0, sms = 0;
+  SWB_CUDA(cudaGetDevice(&dev));
+  SWB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st;
+  SWB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  uint64_t total = 0;
+  try {
+    if (on_device) {
+      total = swb::pretokenize_device(static_cast<const uint8_t *>(text), nbytes, static_cast<uint8_t *>(out), cap, st, dev, sms, nullptr);
+    } else {
+      swb::DevBuf<uint8_t> d_in(nbytes + 16), d_out(cap + 16);
+      if (nbytes) SWB_CUDA(cudaMemcpyAsync(d_in.get(), text, nbytes, cudaMemcpyHostToDevice, st));
+      total = swb::pretokenize_device(d_in.get(), nbytes, d_out.get(), cap, st, dev, sms, nullptr);
       const size_t back = (size_t)std::min<uint64_t>(total, cap);
       if (back) SWB_CUDA(cudaMemcpyAsync(out, d_out.get(), back, cudaMemcpyDeviceToHost, st));
       SWB_CUDA(cudaStreamSynchronize(st));

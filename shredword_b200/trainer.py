@@ -53,6 +53,35 @@ def normalize(text) -> bytes:
   return out[:n].tobytes()
 
 
+_PT_UNMAP = bytes.maketrans(b"\x1c\x1d\x1e\x1f", b" \t\n\r")
+
+
+def pretokenize(text) -> bytes:
+  """Optional pre-pass on the GPU: the reference's regex pre-tokenisation (reference shredword/base.py:38-58). Returns the
+  UTF-8 text with one ' ' behind every piece of the reference's split pattern and the bytes ' ' \\t \\n \\r inside pieces
+  mapped to 0x1C-0x1F: feed it to load_buffer / encode and the trainer's words are exactly the reference's pieces.
+  `undo_pretokenize` restores the text."""
+  if isinstance(text, str):
+    text = text.encode("utf-8")
+  a = text if isinstance(text, np.ndarray) else np.frombuffer(bytes(text), dtype=np.uint8)
+  a = np.ascontiguousarray(a, dtype=np.uint8)
+  out = np.empty(2 * a.size + 16, dtype=np.uint8)
+  n = lib.swb_pretokenize(_ptr(a), a.size, _ptr(out), out.size, 0)
+  if n < 0:
+    raise RuntimeError(f"pretokenize failed: {last_error()}")
+  return out[:n].tobytes()
+
+
+def undo_pretokenize(data) -> bytes:
+  return bytes(data).replace(b" ", b"").translate(_PT_UNMAP)
+
+
+def apply_regex(text: str) -> list:
+  """Same result as the reference's apply_regex (shredword/base.py:38-58): the list of pieces, computed on the GPU."""
+  out = pretokenize(text)
+  return [p.translate(_PT_UNMAP).decode("utf-8") for p in out.split(b" ")[:-1]] if out else []
+
+
 class BPETrainer:
   def __init__(self, target_vocab_size=8192, unk_id=0, character_coverage=0.995, min_pair_freq=2000):
     self.config = BPEConfig(
