@@ -12,7 +12,9 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#if defined(__x86_64__) || defined(_M_X64)
 #include <emmintrin.h>
+#endif
 
 #include <chrono>
 #include <map>
@@ -1176,19 +1178,31 @@ class TrainerImpl {
     volatile HostCmd2 *c = nullptr;
     unsigned long long next_seq = 0;
     bool running = false;
+    // One mailbox word = 16 bytes {x, y, z, check(seq, x, y, z)}. On x86-64 it is written with ONE aligned 16-byte SSE store
+    // (single-copy atomic on every CPU this has run on, not architecturally promised); elsewhere as two 8-byte stores, the
+    // half that carries the 32-bit check word last, behind a release fence. Either way the device accepts a word only when
+    // the check matches the sequence number it expects (cluster_kernel.cuh), so a torn read is read again, never acted on.
+    static void store16(volatile HostCmd2 *dst, unsigned int x, unsigned int y, unsigned int z, unsigned int check) {
+#if defined(__x86_64__) || defined(_M_X64)
+      const __m128i v = _mm_set_epi32((int)check, (int)z, (int)y, (int)x);
+      _mm_store_si128(reinterpret_cast<__m128i *>(const_cast<HostCmd2 *>(dst)), v);
+#else
+      volatile unsigned long long *w = reinterpret_cast<volatile unsigned long long *>(dst);
+      __atomic_store_n(const_cast<unsigned long long *>(w), (unsigned long long)x | ((unsigned long long)y << 32), __ATOMIC_RELAXED);
+      __atomic_thread_fence(__ATOMIC_RELEASE);
+      __atomic_store_n(const_cast<unsigned long long *>(w + 1), (unsigned long long)z | ((unsigned long long)check << 32), __ATOMIC_RELEASE);
+#endif
+      __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    }
     void send(unsigned long long pair, unsigned int new_id, unsigned int op) {
       const unsigned int x = (unsigned int)pair, y = (unsigned int)(pair >> 32), z = (new_id & 0x0FFFFFFFu) | (op << 28);
-      const __m128i v = _mm_set_epi32((int)cmd3_word(next_seq, x, y, z), (int)z, (int)y, (int)x);
-      _mm_store_si128(reinterpret_cast<__m128i *>(const_cast<HostCmd2 *>(c)), v);  // one 16-byte store: the device never sees half a command
-      __atomic_thread_fence(__ATOMIC_SEQ_CST);
+      store16(c, x, y, z, cmd3_word(next_seq, x, y, z));
     }
     // hint for the merge with sequence number `seq`: mailbox word 1 + (seq & 1) (two hint words used in turn, so that the
     // hint for merge q+2 can be written while the device may still be reading the one for merge q+1)
     void hint(unsigned long long seq, unsigned long long pair, unsigned int freq) {
       const unsigned int x = (unsigned int)pair, y = (unsigned int)(pair >> 32), z = freq;
-      const __m128i v = _mm_set_epi32((int)cmd3_word(seq, x, y, z), (int)z, (int)y, (int)x);
-      _mm_store_si128(reinterpret_cast<__m128i *>(const_cast<HostCmd2 *>(c + 1 + (seq & 1ull))), v);
-      __atomic_thread_fence(__ATOMIC_SEQ_CST);
+      store16(c + 1 + (seq & 1ull), x, y, z, cmd3_word(seq, x, y, z));
     }
     ~HostCmd2Sender() { if (running) send(0, 0, 1); }
   };
