@@ -15,6 +15,9 @@
 #if defined(__x86_64__) || defined(_M_X64)
 #include <emmintrin.h>
 #endif
+#include <atomic>
+#include <exception>
+#include <thread>
 
 #include <chrono>
 #include <map>
@@ -772,6 +775,7 @@ class TrainerImpl {
           throw Error(full);
         }
       }
+      if (resident_wait_ && !launch_returned_.load(std::memory_order_acquire)) return;  // the launch call itself has not returned (a serialising tool): the stream has nothing to say yet
       cudaError_t e = cudaStreamQuery(stream_);
       if (e == cudaSuccess) {
         if (++idle_polls_ > 64) {
@@ -1399,14 +1403,41 @@ class TrainerImpl {
       if (!ptrace_.size()) { ptrace_.alloc(32); SWB_CUDA(cudaMemsetAsync(ptrace_.get(), 0, ptrace_.bytes(), stream_)); }
       trace_p = ptrace_.get();
     }
+    // The launch call is made from a helper thread. Normally it returns within microseconds and the thread is gone before the
+    // first result arrives. Under a tool that serialises kernels (ncu's launch list, compute-sanitizer) cudaLaunchKernel does
+    // not return until the kernel has finished -- and this kernel only finishes once THIS thread has served its mailbox: a
+    // launch from this thread would wait for itself until the watchdog fires. (Declared before `sender`: on an exception the
+    // sender's destructor tells the kernel to stop first, then this one joins.)
+    struct Launcher {
+      std::thread th;
+      std::exception_ptr err;
+      std::atomic<int> *returned = nullptr;
+      ~Launcher() { if (th.joinable()) th.join(); if (returned) returned->store(1); }
+    } launcher;
+    launcher.returned = &launch_returned_;
     HostCmd2Sender sender;
     sender.c = hcmd2_.host();
     sender.next_seq = seq_base + 1;  // the first merge travels through the mailbox like all the others
     int32_t da = to_dev(a), db = to_dev(b);
     sender.send(((unsigned long long)(uint32_t)da << 32) | (uint32_t)db, (unsigned int)new_id, 0);
-    launch_merge_cluster(s, em, removed_p, out0, out1, out_cap, out_hdr0, out_hdr1, seq_base, op_base, hc, dc, timeout_ns, trace_p, nullptr, 0);
+    launch_returned_.store(0);
+    sender.running = true;  // (from here on the kernel may be running: a stop must reach it whatever happens)
+    launcher.th = std::thread([&]() {
+      try {
+        SWB_CUDA(cudaSetDevice(device_));
+        launch_merge_cluster(s, em, removed_p, out0, out1, out_cap, out_hdr0, out_hdr1, seq_base, op_base, hc, dc, timeout_ns, trace_p, nullptr, 0);
+      } catch (...) { launcher.err = std::current_exception(); }
+      launch_returned_.store(1, std::memory_order_release);
+    });
+    {  // the normal case: wait the few microseconds the launch takes, so that a launch error surfaces here and not as a time-out
+      const double tl0 = now_ms();
+      while (!launch_returned_.load(std::memory_order_acquire) && now_ms() - tl0 < 20.0) std::this_thread::yield();
+      if (launch_returned_.load(std::memory_order_acquire)) {
+        launcher.th.join();
+        if (launcher.err) { sender.running = false; std::rethrow_exception(launcher.err); }
+      }
+    }
     launched(); stats.merge_launches++;
-    sender.running = true;
     int done = 0;
     unsigned long long cur_key = ((unsigned long long)(uint32_t)da << 32) | (uint32_t)db;
     const uint64_t minf = tr_->config.min_pair_freq;
@@ -1470,6 +1501,8 @@ class TrainerImpl {
       look_ahead();
       if (npk >= 1 && done + 1 < max_merges) send_hint(seq_base + done + 2, pk[0], 1, sender);  // late hint for the merge after this command's
     }
+    if (launcher.th.joinable()) launcher.th.join();  // (a serialising tool: the launch call returns now that the kernel has been told to stop)
+    if (launcher.err) std::rethrow_exception(launcher.err);
     sync();
     {  // device time of this launch's merges (command seen -> result published), per mode
       check_debug_bounds();
@@ -1658,6 +1691,7 @@ class TrainerImpl {
   PairTableDev pt_{};
   DevBuf<unsigned long long> pt_keys_, pt_val_, pt_min_, removed_, emit_partial_;
   int idle_polls_ = 0;
+  std::atomic<int> launch_returned_{1};  // 0 while the launch call of the resident kernel is still inside the driver (see run_resident)
   uint64_t gt_used_estimate_ = 0;
   bool gt_flagged_ = false;
   // persistent merge kernel
