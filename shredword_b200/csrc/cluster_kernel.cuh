@@ -52,7 +52,7 @@ constexpr unsigned int CL_IP_LOCAL_MAX = 8192;  // longest occurrence list of a 
 // The sequence number is not carried in the clear: the device knows which one it waits for, and a word that was written
 // for any other sequence number (a stale command, an old hint) fails the check. The check is never 0, so a zeroed mailbox
 // word matches nothing. Atomicity assumption: a 16-byte aligned store of the host reaches memory as one unit (true for SSE
-// stores on every x86-64 with AVX, and for the two-register store pair used elsewhere, see host_store16 in trainer_impl.cuh);
+// stores on every x86-64 with AVX; other hosts write two 8-byte halves, the one with the check word last: HostCmd2Sender::store16 in trainer_impl.cuh);
 // a torn word would still have to pass the 32-bit check to be taken.
 struct __align__(16) HostCmd2 { unsigned int x, y, z, w; };
 __host__ __device__ __forceinline__ unsigned int cmd3_word(unsigned long long seq, unsigned int x, unsigned int y, unsigned int z) {

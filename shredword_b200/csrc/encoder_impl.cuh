@@ -7,7 +7,8 @@
 // trainer's final segmentation of that word (a merge of rank r only creates pairs containing id
 // 256+r, which can only match ranks > r), which is how the tests pin it.
 //
-// Three kernels per chunk of text:
+// enc_fused (below, "single-pass encoder") is the path every text takes: one kernel, the text read once, the ids written once.
+// A text that holds a word longer than ENC_SHORT bytes falls back, piece by piece, to three kernels:
 //   enc_words  : 16 bytes per thread -> delimiter bit-mask -> word list in shared memory -> one thread
 //                encodes one word in shared memory (merge-rank table: 16-byte slots, L2 resident) and
 //                parks the tokens in tmp[word start ...] (a word of L bytes yields <= L tokens, so the

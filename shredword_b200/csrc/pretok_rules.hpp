@@ -79,7 +79,8 @@ SWB_HD uint32_t pt_class(const uint8_t *__restrict__ tab, uint32_t cp) {
 }
 
 // the character whose first byte is text[i] (i < n; text[i] is not a continuation byte unless i == 0 or the text is malformed)
-SWB_HD PtChar pt_at(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *__restrict__ tab, uint64_t i) {
+template <class T>
+SWB_HD PtChar pt_at(const T &text, uint64_t n, const uint8_t *__restrict__ tab, uint64_t i) {
   PtChar c;
   c.at = i;
   const uint32_t b0 = text[i];
@@ -113,11 +114,13 @@ SWB_HD PtChar pt_at(const uint8_t *__restrict__ text, uint64_t n, const uint8_t 
 
 SWB_HD PtChar pt_none() { PtChar c; c.cp = PT_INVALID; c.cls = PT_NONE; c.at = c.nx = 0; return c; }
 
-SWB_HD PtChar pt_next(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *__restrict__ tab, const PtChar &c) {
+template <class T>
+SWB_HD PtChar pt_next(const T &text, uint64_t n, const uint8_t *__restrict__ tab, const PtChar &c) {
   return c.nx < n ? pt_at(text, n, tab, c.nx) : pt_none();
 }
 
-SWB_HD PtChar pt_prev(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *__restrict__ tab, const PtChar &c) {
+template <class T>
+SWB_HD PtChar pt_prev(const T &text, uint64_t n, const uint8_t *__restrict__ tab, const PtChar &c) {
   if (c.at == 0) return pt_none();
   uint64_t i = c.at - 1;
   while (i > 0 && pt_is_cont(text[i])) --i;
@@ -126,7 +129,8 @@ SWB_HD PtChar pt_prev(const uint8_t *__restrict__ text, uint64_t n, const uint8_
 
 // alternative (1) at the apostrophe text[a]: true iff a match starts there and the contraction letters follow; *end = index
 // of the first byte behind it
-SWB_HD bool pt_contraction(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *__restrict__ tab, uint64_t a, uint64_t *end) {
+template <class T>
+SWB_HD bool pt_contraction(const T &text, uint64_t n, const uint8_t *__restrict__ tab, uint64_t a, uint64_t *end) {
   PtChar ap;
   ap.cp = '\''; ap.cls = PT_O; ap.at = a; ap.nx = a + 1;
   if (a + 1 < n && pt_is_cont(text[a + 1])) return false;  // malformed: not an apostrophe character
@@ -145,7 +149,8 @@ SWB_HD bool pt_contraction(const uint8_t *__restrict__ text, uint64_t n, const u
 }
 
 // does a piece end behind character c?
-SWB_HD bool pt_piece_ends(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *__restrict__ tab, const PtChar &c) {
+template <class T>
+SWB_HD bool pt_piece_ends(const T &text, uint64_t n, const uint8_t *__restrict__ tab, const PtChar &c) {
   const PtChar f = pt_next(text, n, tab, c);
   if (f.cls == PT_NONE) return true;
   switch (c.cls) {
@@ -198,7 +203,8 @@ SWB_HD bool pt_piece_ends(const uint8_t *__restrict__ text, uint64_t n, const ui
 
 // what input byte i contributes to the pre-tokenised stream: itself (the trainer's four delimiter bytes mapped to 0x1C-0x1F),
 // followed by one ' ' if it is the last byte of a character that ends a piece. Returns the byte count (1 or 2).
-SWB_HD uint32_t pt_emit(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *__restrict__ tab, uint64_t i, uint8_t *b0) {
+template <class T>
+SWB_HD uint32_t pt_emit(const T &text, uint64_t n, const uint8_t *__restrict__ tab, uint64_t i, uint8_t *b0) {
   const uint8_t b = text[i];
   *b0 = b == ' ' ? 0x1C : b == '\t' ? 0x1D : b == '\n' ? 0x1E : b == '\r' ? 0x1F : b;
   if (i + 1 < n && pt_is_cont(text[i + 1])) return 1;  // not the last byte of its character
