@@ -1243,6 +1243,23 @@ class TrainerImpl {
   }
   // One launch of the resident kernel: clusters of CL_SIZE CTAs, co-resident (cooperative attribute where available: GRID
   // merges spin on a grid-wide counter), the symbol rows pinned in L2 for the duration of the launch.
+  // Nsight Compute refuses a launch that carries both a cluster dimension and the cooperative attribute ("LaunchFailed", and
+  // the process is gone). The attribute is a launch-time check only (this kernel never calls grid.sync(); its grid is sized
+  // from the occupancy query), so it is dropped when the profiler's injection library is in the process.
+  static bool profiler_attached() {
+    static const bool attached = [] {
+      if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_PORT_BASE") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) return true;
+      FILE *f = fopen("/proc/self/maps", "r");
+      if (!f) return false;
+      char line[1024];
+      bool hit = false;
+      while (!hit && fgets(line, sizeof line, f))
+        hit = strstr(line, "nsight-compute") || strstr(line, "libcuda-injection") || strstr(line, "libInterceptorInjectionTarget");
+      fclose(f);
+      return hit;
+    }();
+    return attached;
+  }
   void launch_merge_cluster(const StreamDev &s, const EmitMode &em, unsigned long long *removed_p, Rec *out0, Rec *out1, size_t out_cap,
                             unsigned long long *out_hdr0, unsigned long long *out_hdr1, unsigned long long seq_base, unsigned long long op_base,
                             volatile HostCmd2 *hc, DevCmd2 *dc, unsigned long long timeout_ns, unsigned long long *trace_p,
@@ -1253,7 +1270,7 @@ class TrainerImpl {
     // (profiling switches: SWB_CLUSTERS=n caps the number of clusters, SWB_NO_COOP=1 drops the cooperative attribute -- a profiler
     //  that takes SMs for itself can make the full cooperative grid "too large"; fewer clusters only slow GRID merges down)
     static const int cap_clusters = getenv("SWB_CLUSTERS") ? atoi(getenv("SWB_CLUSTERS")) : 0;
-    static const bool no_coop = getenv("SWB_NO_COOP") && atoi(getenv("SWB_NO_COOP")) > 0;
+    static const bool no_coop = (getenv("SWB_NO_COOP") && atoi(getenv("SWB_NO_COOP")) > 0) || profiler_attached();
     const int n_clusters = cap_clusters > 0 ? std::min(cap_clusters, cf.clusters) : cf.clusters;
     cfg.gridDim = dim3((unsigned)(n_clusters * CL_SIZE)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES; cfg.stream = stream_;
     cudaLaunchAttribute at[3];
