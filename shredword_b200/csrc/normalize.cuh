@@ -18,61 +18,23 @@
 // output once.
 #pragma once
 
+#include "normalize_rules.hpp"
 #include "stream_map.cuh"
 
 namespace swb {
 
-__device__ __forceinline__ bool norm_is_ws(uint8_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }  // normalize.cpp:13-15
-
-// bytes that text[i] contributes (0, 1 or 4); *marker = the 3 marker bytes come first
-template <class T>
-__device__ __forceinline__ uint32_t norm_emit(const T &text, uint64_t n, uint64_t i, bool &marker) {
-  marker = false;
-  const uint8_t c = text[i];
-  if (c == '\n') return 1;     // line separator, kept
-  if (norm_is_ws(c)) return 0;
-  // the literal bytes E2 96 81 at the very end of a line (which then ends with a non-whitespace byte) are dropped
-  {
-    // k = position of this byte among the last three bytes of the line, if it is one of them
-    for (int k = 0; k < 3; k++) {
-      const uint64_t e = i + (uint64_t)(3 - k);  // candidate line end (index one past the last byte) if this is byte k of the triple
-      if (e > n || (e < n && text[e] != '\n')) continue;
-      if (e < 3) continue;
-      const uint64_t s = e - 3;
-      if (text[s] == 0xE2 && text[s + 1] == 0x96 && text[s + 2] == 0x81) {
-        // the three bytes must belong to this line (no newline among them: none of them is one)
-        if (k == 0) {  // the marker in front of the triple, if any, is still emitted
-          bool mk = false;
-          if (i > 0 && norm_is_ws(text[i - 1]) && text[i - 1] != '\n') {
-            uint64_t j = i - 1;
-            while (j > 0 && norm_is_ws(text[j]) && text[j] != '\n') --j;
-            mk = !norm_is_ws(text[j]);
-          }
-          marker = mk;
-          return mk ? 3u : 0u;
-        }
-        return 0;
-      }
-    }
-  }
-  uint32_t len = 1;
-  if (i > 0 && norm_is_ws(text[i - 1]) && text[i - 1] != '\n') {
-    uint64_t j = i - 1;
-    while (j > 0 && norm_is_ws(text[j]) && text[j] != '\n') --j;
-    if (!norm_is_ws(text[j])) { marker = true; len = 4; }  // (j == 0 and whitespace, or a newline: the run starts the line)
-  }
-  return len;
-}
-
-struct NormEmit {
+struct NormEmit {  // code = what norm_emit returns: 0 nothing, 1 the byte, 3 the marker, 4 marker + byte
   static constexpr int MAX_OUT = 4;
-  __device__ __forceinline__ uint32_t operator()(const TextWin &t, uint64_t n, uint64_t i, uint8_t *out) const {
+  __device__ __forceinline__ bool fast(const TextWin &t, uint64_t n, uint64_t i, uint32_t &code) const { return norm_fast(t, n, i, &code); }
+  __device__ __forceinline__ uint32_t slow(const TextWin &t, uint64_t n, uint64_t i) const {
     bool mk;
-    const uint32_t e = norm_emit(t, n, i, mk);
+    return norm_emit(t, n, i, mk);
+  }
+  __device__ __forceinline__ uint32_t expand(const TextWin &t, uint64_t i, uint32_t code, uint8_t *out) const {
     uint32_t k = 0;
-    if (mk) { out[0] = 0xE2; out[1] = 0x96; out[2] = 0x81; k = 3; }
-    if (e == 1 || e == 4) {
-      const uint8_t c = t[i];
+    if (code >= 3u) { out[0] = 0xE2; out[1] = 0x96; out[2] = 0x81; k = 3; }
+    if (code == 1u || code == 4u) {
+      const uint8_t c = tx_near(t, i);
       out[k++] = (c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c;
     }
     return k;

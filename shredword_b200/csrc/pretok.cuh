@@ -15,13 +15,19 @@
 
 namespace swb {
 
-struct PretokEmit {
+struct PretokEmit {  // code: 1 = a piece ends behind this byte
   static constexpr int MAX_OUT = 2;
   const uint8_t *__restrict__ tab;  // 2-bit class per code point
-  __device__ __forceinline__ uint32_t operator()(const TextWin &t, uint64_t n, uint64_t i, uint8_t *out) const {
-    const uint32_t e = pt_emit(t, n, tab, i, &out[0]);
+  __device__ __forceinline__ bool fast(const TextWin &t, uint64_t n, uint64_t i, uint32_t &code) const { return pt_fast(t, n, i, &code); }
+  __device__ __forceinline__ uint32_t slow(const TextWin &t, uint64_t n, uint64_t i) const {
+    uint8_t b0;
+    return pt_emit(t, n, tab, i, &b0) - 1u;
+  }
+  __device__ __forceinline__ uint32_t expand(const TextWin &t, uint64_t i, uint32_t code, uint8_t *out) const {
+    const uint8_t b = tx_near(t, i);
+    out[0] = b == ' ' ? 0x1C : b == '\t' ? 0x1D : b == '\n' ? 0x1E : b == '\r' ? 0x1F : b;
     out[1] = ' ';
-    return e;
+    return 1u + code;
   }
 };
 

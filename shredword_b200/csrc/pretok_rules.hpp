@@ -37,10 +37,12 @@
 #include <cstdint>
 #include <cstring>
 
+#ifndef SWB_HD
 #ifdef __CUDACC__
 #define SWB_HD __host__ __device__ __forceinline__
 #else
 #define SWB_HD inline
+#endif
 #endif
 
 namespace swb {
@@ -64,6 +66,13 @@ struct PtChar {
   uint64_t at;   // index of its first byte
   uint64_t nx;   // index of the next character's first byte
 };
+
+#ifndef SWB_TX_NEAR
+#define SWB_TX_NEAR
+// text[i] for an i within 128 bytes of the byte being decided (a windowed text answers it from its staged copy, unchecked)
+template <class T>
+SWB_HD uint8_t tx_near(const T &text, uint64_t i) { return text[i]; }
+#endif
 
 SWB_HD bool pt_is_cont(uint8_t b) { return (b & 0xC0) == 0x80; }
 SWB_HD bool pt_is_nl(const PtChar &c) { return c.cp == '\n' || c.cp == '\r'; }
@@ -212,6 +221,34 @@ SWB_HD uint32_t pt_emit(const T &text, uint64_t n, const uint8_t *__restrict__ t
   while (s > 0 && pt_is_cont(text[s])) --s;
   const PtChar c = pt_at(text, n, tab, s);
   return pt_piece_ends(text, n, tab, c) ? 2u : 1u;
+}
+
+// The cases that settle most bytes of ordinary text without decoding anything (by class of c and of the character f behind
+// it, see the top of this file); *ends = a piece ends behind byte i. Returns false when the general rule (pt_emit) is needed.
+//   * not the last byte of its character                       -> no
+//   * ASCII letter, f an ASCII non-letter (or end of text)      -> yes ("c in L: f not in L")
+//   * ASCII letter, f an ASCII letter, no apostrophe 1 or 2 bytes before (so c cannot end a contraction) -> no
+//   * ASCII space / \t / \v / \f, f an ASCII letter             -> no (it is the prefix character of alternative (2))
+template <class T>
+SWB_HD bool pt_fast(const T &text, uint64_t n, uint64_t i, uint32_t *ends) {
+  const uint32_t b = tx_near(text, i);
+  const bool has_next = i + 1 < n;
+  const uint32_t nb = has_next ? tx_near(text, i + 1) : 0u;
+  if (has_next && pt_is_cont((uint8_t)nb)) { *ends = 0; return true; }
+  if (b >= 0x80u) return false;
+  if (!has_next) { *ends = 1; return true; }
+  if (nb >= 0x80u) return false;
+  // (f counts as a letter only if it is well formed: an ASCII byte with continuation bytes glued to it is a class-O character)
+  const bool next_letter = ((nb | 32u) - 'a') < 26u && !(i + 2 < n && pt_is_cont(tx_near(text, i + 2)));
+  if (((nb | 32u) - 'a') < 26u && !next_letter) return false;
+  if (((b | 32u) - 'a') < 26u) {
+    if (!next_letter) { *ends = 1; return true; }
+    if ((i >= 1 && tx_near(text, i - 1) == '\'') || (i >= 2 && tx_near(text, i - 2) == '\'')) return false;
+    *ends = 0;
+    return true;
+  }
+  if (next_letter && (b == ' ' || b == '\t' || b == 0x0Bu || b == 0x0Cu)) { *ends = 0; return true; }
+  return false;
 }
 
 }  // namespace swb

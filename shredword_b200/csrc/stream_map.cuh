@@ -5,8 +5,11 @@
 //     side are staged in shared memory by ONE bulk copy (cp.async.bulk global -> shared, completion on an mbarrier), double
 //     buffered: the copy of a block's next tile runs while it works on the current one. The per-byte functions read their
 //     neighbourhood through TextWin (shared memory inside the window, global memory beyond it -- long runs only).
-//   * Lane l of a warp handles bytes l, l+32, ... of the warp's 512-byte segment (conflict-free shared-memory reads; the
-//     bytes a group of 32 input bytes produces are placed by a warp scan), the output of a warp is staged in shared memory.
+//   * A warp owns a 512-byte segment; lane l handles bytes l, l+32, ... (conflict-free shared-memory reads). What a byte
+//     contributes is first a small CODE: most bytes are settled by a cheap test (F::fast); the ones that need the general rule
+//     (F::slow: long, data dependent) are listed and then dealt out evenly over the lanes, so the warp pays for the general
+//     rule once per 32 such bytes, not once per group of 32 input bytes that happens to contain one. The codes are then
+//     expanded to bytes, placed by a warp scan and staged in shared memory.
 //   * Where the tile's output goes is learnt from the tiles before it with a decoupled look-back over one 64-bit
 //     descriptor per tile (status << 62 | bytes: 1 = this tile's own count, 2 = count of all tiles up to it), then every
 //     warp copies its staged bytes out with coalesced stores.
@@ -27,16 +30,19 @@ constexpr int SM_HALO = 128;
 constexpr int SM_WIN = SM_TILE + 2 * SM_HALO;
 constexpr unsigned int SM_SPIN_LIMIT = 1u << 28;  // a wait that long is a bug: trap instead of hanging the GPU
 
-// The text as the per-byte functions see it: bytes [w0, w1) come from shared memory, the rest from global memory.
+// The text as the per-byte functions see it: bytes [w0, w0 + len) come from shared memory, the rest from global memory.
 struct TextWin {
   const uint8_t *__restrict__ g;
-  const uint8_t *s;    // s[i - w0] for w0 <= i < w1
-  long long w0, w1;
+  const uint8_t *s;    // s[i - w0] for w0 <= i < w0 + len
+  uint64_t w0;
+  uint32_t len;
   __device__ __forceinline__ uint8_t operator[](uint64_t i) const {
-    const long long k = (long long)i;
-    return (k >= w0 && k < w1) ? s[k - w0] : __ldg(g + i);
+    const uint64_t r = i - w0;  // (wraps for i < w0: then r >= len)
+    return r < (uint64_t)len ? s[(uint32_t)r] : __ldg(g + i);
   }
 };
+// a byte within SM_HALO of the byte being decided (which lies in the tile): always inside the staged window, no range check
+__device__ __forceinline__ uint8_t tx_near(const TextWin &t, uint64_t i) { return t.s[(uint32_t)(i - t.w0)]; }
 
 __device__ __forceinline__ uint32_t sm_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -91,8 +97,11 @@ __device__ __forceinline__ unsigned long long sm_look_back(unsigned long long *_
   return excl;
 }
 
-// F: struct with `static constexpr int MAX_OUT` (most bytes one input byte can produce) and
-//    `__device__ uint32_t operator()(const TextWin &t, uint64_t n, uint64_t i, uint8_t *out) const` (writes its bytes, returns how many)
+// F: struct with
+//   static constexpr int MAX_OUT                                   most bytes one input byte can produce
+//   bool     fast(const TextWin &t, n, i, uint32_t &code) const    the cheap cases: true = code is set
+//   uint32_t slow(const TextWin &t, n, i) const                    the general rule -> code (< 256)
+//   uint32_t expand(const TextWin &t, i, code, uint8_t *out) const writes the bytes of input byte i, returns how many
 template <class F>
 __global__ void __launch_bounds__(SM_THREADS)
 stream_map(const uint8_t *__restrict__ text, uint64_t n, F f, unsigned long long *__restrict__ desc, unsigned int *__restrict__ tile_counter,
@@ -100,6 +109,8 @@ stream_map(const uint8_t *__restrict__ text, uint64_t n, F f, unsigned long long
   __shared__ __align__(128) uint8_t win[2][SM_WIN];
   __shared__ __align__(16) uint8_t stage[SM_WARPS][SM_SEG * F::MAX_OUT];
   __shared__ __align__(8) unsigned long long bar[2];
+  __shared__ uint8_t code[SM_WARPS][SM_SEG];
+  __shared__ uint16_t slow_list[SM_WARPS][SM_SEG];
   __shared__ uint32_t wtot[SM_WARPS];
   __shared__ unsigned int s_first, s_next;
   __shared__ unsigned long long s_excl;
@@ -160,16 +171,32 @@ stream_map(const uint8_t *__restrict__ text, uint64_t n, F f, unsigned long long
     }
     __syncthreads();
     TextWin t;
-    t.g = text; t.w0 = lo; t.w1 = w1;
+    t.g = text; t.w0 = (uint64_t)lo; t.len = (uint32_t)(w1 - lo);
     t.s = win[b] + (lo - w0);  // s[i - lo]
     // ---- this warp's segment: 16 groups of 32 consecutive bytes
     const uint64_t seg0 = tile * SM_TILE + (uint64_t)w * SM_SEG;
+    uint32_t n_slow = 0;
+    for (int k = 0; k < SM_SEG / 32; k++) {  // codes of the cheap cases, list of the others
+      const uint64_t i = seg0 + 32ull * k + lane;
+      uint32_t c = 0;
+      const bool need = i < n && !f.fast(t, n, i, c);
+      if (i < n && !need) code[w][32 * k + lane] = (uint8_t)c;
+      const unsigned int mask = __ballot_sync(0xffffffffu, need);
+      if (need) slow_list[w][n_slow + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)(32 * k + lane);
+      n_slow += __popc(mask);
+    }
+    __syncwarp();
+    for (uint32_t q = lane; q < n_slow; q += 32) {  // the general rule, every lane busy
+      const uint32_t j = slow_list[w][q];
+      code[w][j] = (uint8_t)f.slow(t, n, seg0 + j);
+    }
+    __syncwarp();
     uint32_t run = 0;  // bytes staged by this warp so far
     for (int k = 0; k < SM_SEG / 32; k++) {
       const uint64_t i = seg0 + 32ull * k + lane;
       uint8_t ob[F::MAX_OUT];
       uint32_t cnt = 0;
-      if (i < n) cnt = f(t, n, i, ob);
+      if (i < n) cnt = f.expand(t, i, code[w][32 * k + lane], ob);
       uint32_t inc = cnt;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += u; }
