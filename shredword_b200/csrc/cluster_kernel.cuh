@@ -64,7 +64,7 @@ __host__ __device__ __forceinline__ unsigned int cmd3_word(unsigned long long se
   return w ? w : 0x5BD1E995u;
 }
 // leader -> other clusters (device memory)
-struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, t_cmd /* %globaltimer when the command arrived */, spec /* started from a hint */, tail_done /* GRID merges whose tail (emit + publish, run by whichever block finished last) is complete */, done_count /* blocks that have finished their part of a GRID merge, summed over all GRID merges of this launch: never reset, so no reset can race with the next merge's arrivals */; };
+struct DevCmd2 { unsigned long long epoch, pair, new_id_op, log_range, alive_ns, k /* index of the merge within this launch */, t_cmd /* %globaltimer when the command arrived */, spec /* started from a hint */, tail_done /* GRID merges whose tail (emit + publish, run by whichever block finished last) is complete */, done_count /* blocks that have finished their part of a GRID merge, summed over all GRID merges of this launch: never reset, so no reset can race with the next merge's arrivals */, tail_max /* largest frequency the last GRID merge makes the host push (its tail's atomicMax; zeroed with the command) */, tail_flags /* flag word of the header that tail published */; };
 __host__ __device__ __forceinline__ unsigned long long cmd2_check(unsigned long long seq, unsigned long long pair,
                                                                   unsigned long long nio, unsigned long long lr) {
   return (seq * HDR_MAGIC) ^ pair ^ (nio << 7 | nio >> 57) ^ (lr * 0xD6E8FEB86659FD93ull);
@@ -338,6 +338,8 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
   bool hint_ok = false;
   unsigned long long prev_maxpush = 0;
   unsigned int prev_new_id = 0;
+  bool grid_pending = false;  // (CTA 0 / thread 0) the previous merge was GRID: its tail (any block) reports through dcmd->tail_max / tail_flags
+  unsigned int grid_new_id = 0;
   unsigned int last_pub_lo = 0, last_pub_path = 0;  // (CTA 0 / thread 0) low half of the last sequence number it published itself, and through which path (1 LOCAL/SOLO, 2 spill tail)
   unsigned int go_sent = 0, go_seen = 0;  // (CTA 0 / thread 0) commands handed to the other CTAs of the leader cluster; (other CTAs / thread 0) seen
   uint4 pre_hv = make_uint4(0u, 0u, 0u, 0u);  // the hint word for the NEXT merge, requested while this one runs (a read of mapped host memory takes microseconds)
@@ -351,6 +353,20 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
         const unsigned long long t0 = gtime_ns();
         unsigned long long pair = 0, nio = 3ull << 32, lr = ~0ull;
         unsigned int spec = 0;
+        if (grid_pending && script == nullptr) {
+          // The merge before was GRID: whichever block finished last ran its tail. The host answers only once it has seen that
+          // tail's header, so waiting for the tail costs nothing -- and with what the tail reports (largest pushed frequency,
+          // flags) the merge after a GRID merge can start from a hint like any other.
+          while (*(volatile unsigned long long *)&dcmd->tail_done < grid_epoch) { if (gtime_ns() - t0 > timeout_ns) break; }
+          __threadfence();
+          if (*(volatile unsigned long long *)&dcmd->tail_done >= grid_epoch) {
+            const unsigned long long fl = *(volatile unsigned long long *)&dcmd->tail_flags;
+            hint_ok = (fl & 0xFFFFFFFFull & ~64ull) == 0ull;
+            prev_maxpush = *(volatile unsigned long long *)&dcmd->tail_max;
+            prev_new_id = grid_new_id;
+          }
+          grid_pending = false;
+        }
         for (unsigned long long spin = 0;; spin++) {
           uint4 v = make_uint4(0u, 0u, 0u, 0u), hv = make_uint4(0u, 0u, 0u, 0u);  // one 16-byte load from mapped host memory = one PCIe read (the two are in flight together)
           bool have_v = true;
@@ -422,7 +438,9 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
           for (unsigned int r = 1; r < CL_SIZE; r++) *(volatile unsigned int *)&cluster.map_shared_rank(m.ctl, r)->go = go_sent;
         }
         if (mode == 1u) cursor_stale = true;  // a GRID merge appends through the global cursor
+        if (mode == 1u && !stop) { grid_pending = true; grid_new_id = (unsigned int)(nio & 0x0FFFFFFFull); }
         if (stop || mode == 1u) {  // the other clusters take part (or leave)
+          dcmd->tail_max = 0ull;
           dcmd->pair = pair; dcmd->new_id_op = nio; dcmd->log_range = lr; dcmd->k = k; dcmd->t_cmd = t_cmd; dcmd->spec = spec;
           __threadfence();
           *(volatile unsigned long long *)&dcmd->epoch = grid_epoch + 1;
@@ -500,7 +518,7 @@ merge_cluster(StreamDev s, PairTableDev t, EmitMode em, unsigned long long *remo
       if (is_last) {
         __threadfence();
         TailSmem ts{m.tail_stage, m.csum, m.tail_count};
-        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag);
+        fused_tail(t, em, ts, out, out_cap, out_hdr, removed_total, seq, spec_flag, nullptr, &dcmd->tail_max, &dcmd->tail_flags);
         if (threadIdx.x == 0) {  // (one publisher at a time)
           __threadfence();
           *(volatile unsigned long long *)&dcmd->tail_done = grid_epoch;

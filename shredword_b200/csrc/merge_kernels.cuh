@@ -293,7 +293,7 @@ __device__ __forceinline__ void pt_emit_range(const PairTableDev &t, const EmitM
                                               unsigned int n, unsigned int first, unsigned int stride,
                                               unsigned int *out_count, unsigned long long &cx, unsigned long long &cs,
                                               unsigned int &inserted, Rec *__restrict__ direct = nullptr,
-                                              unsigned int stage_cap = 0xFFFFFFFFu) {
+                                              unsigned int stage_cap = 0xFFFFFFFFu, unsigned long long *maxpush = nullptr /* this thread's largest new frequency >= min_freq */) {
 #pragma unroll 1
   for (unsigned int i = first; i < n; i += stride) {
     const uint4 tc = __ldcg(&t.touched[i]);
@@ -321,6 +321,7 @@ __device__ __forceinline__ void pt_emit_range(const PairTableDev &t, const EmitM
     if (d < 0) { const unsigned long long ad = (unsigned long long)(-d); nw = old >= ad ? old - ad : 0ull; }
     else nw = old + (unsigned long long)d;
     em.g.slots[g].freq = nw;
+    if (maxpush && nw >= em.min_freq && nw > *maxpush) *maxpush = nw;  // the host pushes this pair (reference bpe.cpp:512-515)
     if (old >= em.min_freq || nw >= em.min_freq)
       rec_out(out, out_cap, atomicAdd(out_count, 1u), k, (long long)nw, mk, cx, cs, direct, stage_cap);
   }
@@ -338,7 +339,7 @@ __device__ __forceinline__ void block_checksum(unsigned long long &cx, unsigned 
     cx = x; cs = sm;
   }
 }
-__device__ __forceinline__ void pt_publish(const PairTableDev &t, unsigned int n, size_t out_cap, unsigned int extra_flags,
+__device__ __forceinline__ unsigned long long pt_publish(const PairTableDev &t, unsigned int n, size_t out_cap, unsigned int extra_flags,
                                            volatile unsigned long long *out_hdr, unsigned long long *removed,
                                            unsigned long long seq, unsigned long long cx, unsigned long long cs,
                                            const BirthLogDev *lg = nullptr, bool keep_state = false) {
@@ -360,6 +361,7 @@ __device__ __forceinline__ void pt_publish(const PairTableDev &t, unsigned int n
   out_hdr[1] = n; out_hdr[2] = flags; out_hdr[3] = rem; out_hdr[4] = cx; out_hdr[5] = cs;
   out_hdr[6] = hdr_check(seq, n, flags, rem, cx, cs);
   out_hdr[0] = seq; out_hdr[7] = seq;
+  return flags;
 }
 
 // full-grid emit (more records than the fused tail takes, long words present, or the count pass): every
@@ -412,7 +414,9 @@ constexpr unsigned int STAGE_RECS = 384;        // records staged in shared memo
 struct TailSmem { Rec *stage; unsigned long long *csum; unsigned int *count; };
 __device__ __forceinline__ void fused_tail(const PairTableDev &t, const EmitMode &em, const TailSmem &ts, Rec *__restrict__ out,
                                            size_t out_cap, unsigned long long *__restrict__ out_hdr, unsigned long long *removed,
-                                           unsigned long long seq, unsigned int extra_flags, unsigned long long *trace = nullptr) {
+                                           unsigned long long seq, unsigned int extra_flags, unsigned long long *trace = nullptr,
+                                           unsigned long long *tail_max = nullptr /* global, zeroed by the caller: largest frequency the host will push */,
+                                           unsigned long long *tail_flags = nullptr /* global: the header's flag word */) {
   const long long tc0 = clock64();
   const unsigned int n = __ldcg(t.n_touched);
   const bool small = n <= em.fused_max;
@@ -421,7 +425,13 @@ __device__ __forceinline__ void fused_tail(const PairTableDev &t, const EmitMode
   __syncthreads();
   unsigned int inserted = 0;
   const long long tc1 = clock64();
-  if (small) pt_emit_range(t, em, ts.stage, out_cap, n, threadIdx.x, blockDim.x, ts.count, cx, cs, inserted, out, STAGE_RECS);
+  unsigned long long mp = 0;
+  if (small) pt_emit_range(t, em, ts.stage, out_cap, n, threadIdx.x, blockDim.x, ts.count, cx, cs, inserted, out, STAGE_RECS, tail_max ? &mp : nullptr);
+  if (tail_max) {  // (ahead of the block barrier inside block_checksum, which is ahead of the publisher's fence)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_down_sync(0xffffffffu, mp, d); mp = o > mp ? o : mp; }
+    if ((threadIdx.x & 31) == 0 && mp) atomicMax(tail_max, mp);
+  }
   const long long tc2 = clock64();
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) inserted += __shfl_down_sync(0xffffffffu, inserted, d);
@@ -453,7 +463,8 @@ __device__ __forceinline__ void fused_tail(const PairTableDev &t, const EmitMode
       out_hdr[21] = (nw_ >= 256 && (uint32_t)(nw_ - 256) < em.log.m_cur) ? em.log.start[nw_ - 256 + 1] - em.log.start[nw_ - 256] : ~0ull;
     }
 #endif
-    pt_publish(t, n_out, out_cap, (small ? 0u : 8u) | gflag | extra_flags, out_hdr, removed, seq, cx, cs, &em.log);
+    const unsigned long long fl = pt_publish(t, n_out, out_cap, (small ? 0u : 8u) | gflag | extra_flags, out_hdr, removed, seq, cx, cs, &em.log);
+    if (tail_flags) *(volatile unsigned long long *)tail_flags = fl;
     if (trace) {
       const long long tc6 = clock64();
       trace[9] += (unsigned long long)(tc1 - tc0); trace[10] += (unsigned long long)(tc2 - tc1); trace[11] += (unsigned long long)(tc3 - tc2);
