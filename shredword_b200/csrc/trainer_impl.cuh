@@ -240,7 +240,16 @@ class TrainerImpl {
                         const uint8_t *host_src = nullptr) {
     if (n >= (1ull << 40) || global_offset + n >= (1ull << 40)) throw Error("corpus larger than 1 TiB is not supported (40-bit offsets)");
     if (split && !comm_) throw Error("a range-split load needs swb_dist_init first");
+    static const bool trace_load = getenv("SWB_TRACE_INIT") != nullptr;
+    double t_tr = now_ms();
+    auto tr = [&](const char *what) {  // (SWB_TRACE_INIT=1: where a load spends its host time)
+      if (!trace_load) return;
+      const double t = now_ms();
+      fprintf(stderr, "[trace] load: %-28s %9.3f ms\n", what, t - t_tr);
+      t_tr = t;
+    };
     free_corpus_state();
+    tr("free previous state");
     unsigned int *d_nuniq = scalars_.get() + 0, *d_flags = scalars_.get() + 1, *d_cursor = scalars_.get() + 2,
                  *d_nlong = scalars_.get() + 3;
     unsigned long long *d_u64 = reinterpret_cast<unsigned long long *>(scalars_.get() + 8);  // [0]=long syms [1]=bytes [2]=cursor
@@ -248,7 +257,11 @@ class TrainerImpl {
     // Unique words grow far slower than the corpus (Heaps' law): the table starts at one 32-byte slot per 256 corpus bytes, at
     // most 16 M slots (512 MB; only the occupied 32-byte sectors are ever touched again, and for a few million unique words those mostly stay in the 126 MB L2), and is rebuilt
     // four times as large if the corpus turns out to hold more unique words than 60 % of that.
-    uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(1ull << 16, pow2_ceil(n / 256)), 1ull << 24);
+    uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(1ull << 20, pow2_ceil(n / 256)), 1ull << 24);  // (small corpora hold far more unique words per byte: at least 1 M slots = 32 MB)
+    {  // SWB_TEST_WT_CAP=<slots> (tests): start with a table that is too small, so that the grow-and-run-again path is taken
+      static const uint64_t test_cap = getenv("SWB_TEST_WT_CAP") ? strtoull(getenv("SWB_TEST_WT_CAP"), nullptr, 10) : 0;
+      if (test_cap) cap = std::max<uint64_t>(64, pow2_ceil(test_cap));
+    }
     DevBuf<WSlot> wslots;
     unsigned int h_scal[4];
     const int tok_grid = (int)std::max<uint64_t>((uint64_t)sms_, (n >> 31) + 1);  // one block per SM; a block's span stays below 4 GB
@@ -302,6 +315,7 @@ class TrainerImpl {
       if (!(h_scal[1] & 1u)) break;
       cap *= 4;  // more unique words than expected: bigger table, run again
     }
+    tr("tokenise (all tries)");
     W = h_scal[0];
     DevBuf<uint64_t> woff;
     if (!split) {
@@ -394,6 +408,7 @@ class TrainerImpl {
       corpus = std::move(arena_all);
       n = base_n;
     }
+    tr("compact + sort");
     // ---- 3. lengths, byte histogram, long words
     DevBuf<uint32_t> wlen(W);
     long_index_.alloc(W);
@@ -412,6 +427,7 @@ class TrainerImpl {
     n_long_ = h_scal[3];
     const uint64_t long_total = h_u64[0];
     word_bytes_total_ = h_u64[1];
+    tr("word info");
     // ---- 4. character coverage rule on the host (256 values; reference bpe.cpp:257-279)
     apply_keep_rule(h_hist);
     DevBuf<int32_t> d_bmap(256);
@@ -443,6 +459,7 @@ class TrainerImpl {
       launched();
       sync();
     }
+    tr("pack rows");
     // ---- 6. long words
     long_off_.alloc(n_long_); long_len_.alloc(n_long_); long_word_.alloc(n_long_); long_syms_.alloc(long_total);
     if (n_long_) {
@@ -451,6 +468,7 @@ class TrainerImpl {
                                                   d_bmap.get(), long_off_.get(), long_syms_.get(), long_len_.get(), long_word_.get());
       launched(2);
     }
+    tr("long words");
     // ---- 7. keep the bytes of the unique words (accessors, encoder pin checks); release the corpus
     word_boff_.alloc(W + 1);
     word_bytes_.alloc(word_bytes_total_);
@@ -477,9 +495,11 @@ class TrainerImpl {
       if (W) SWB_CUDA(cudaMemcpy(h_len.data(), wlen.get(), W * 4, cudaMemcpyDeviceToHost));
       for (uint64_t w = mrank(); w < W; w += mnranks()) live_symbols_ += h_len[w];
     }
+    tr("word bytes + counts");
     corpus.release();
     SWB_CUDA(cudaMemsetAsync(scalars_.get(), 0, scalars_.bytes(), stream_));
     setup_birth_log();
+    tr("birth log / occurrence index");
     // public mirror fields (reference Corpus)
     tr_->corpus.vocab_size = W;
     tr_->corpus.word_counts = h_counts.data();
@@ -492,6 +512,7 @@ class TrainerImpl {
     device_tables_ = false;
     tables_fresh_ = true;
     gt_used_estimate_ = 0;
+    tr("host tables reset");
   }
 
   // reference bpe.cpp:262-279 + histogram.cpp:47-53: bytes listed in the bucket

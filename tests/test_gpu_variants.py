@@ -34,6 +34,7 @@ VARIANTS = {
   "record_stage_overflow": {"SWB_TEST_REC_STAGE": "1"},
   "birth_stage_overflow": {"SWB_TEST_BIRTH_STAGE": "1"},
   "frequency_table_rehash": {"SWB_TEST_SMALL_GT": "1"},
+  "word_table_growth": {"SWB_TEST_WT_CAP": "256"},       # the load's hash table starts far too small: overflow, 4x, tokenise again (several times)
   "solo_table_spill": {"SWB_TEST_MAX_PROBES": "1", "SWB_TEST_REC_STAGE": "1", "SWB_TEST_BIRTH_STAGE": "2", "SWB_TEST_CAND_CAP": "4"},
   "everything_small": {"SWB_TEST_LOCAL_MAX": "4096", "SWB_TEST_SOLO_MAX": "300", "SWB_TEST_CAND_CAP": "5", "SWB_TEST_INBOX": "7", "SWB_TEST_MAX_PROBES": "3",
                        "SWB_TEST_REC_STAGE": "2", "SWB_TEST_BIRTH_STAGE": "3", "SWB_TEST_SMALL_GT": "1"},
