@@ -110,12 +110,12 @@ __device__ __forceinline__ void wt_global_insert(const WordTableDev &t, const ui
                                                  unsigned long long cnt, bool short_word, uint64_t lo, uint64_t hi) {
   const unsigned long long key = (off << WT_TAG_BITS) | tag;
   uint64_t slot = h64 & t.mask;
-  // Once the table has been declared too small the host throws this run away and tokenises again into a larger one: every
-  // further insert would only walk ever longer probe sequences through a table that is filling up (a 32 MB corpus with 350 k
-  // unique words spent 650 ms that way in a table of 131 072 slots).
-  if (__ldcg(t.flags) & 1u) return;
   for (uint64_t probe = 0; probe <= t.mask; probe++) {
-    if ((probe & 63u) == 63u && (__ldcg(t.flags) & 1u)) return;
+    // Once the table has been declared too small the host throws this run away and tokenises again into a larger one: every
+    // further insert would only walk ever longer probe sequences through a table that is filling up (a 32 MB corpus with 350 k
+    // unique words spent 650 ms that way in a table of 131 072 slots). Looked at only on long probe sequences: the flag is
+    // one word that every SM would otherwise read on every insert.
+    if ((probe & 31u) == 31u && (__ldcg(t.flags) & 1u)) return;
     WSlot *sl = t.slots + slot;
     unsigned long long cur = __ldcg(&sl->key);
     if (cur == WT_EMPTY) {
