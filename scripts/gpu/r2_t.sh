@@ -3,7 +3,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 ( timeout 1800 python -m pytest tests -q -m gpu -p no:cacheprovider 2>&1 | tail -30 > gpurun_out/pytest_t.log; echo "pytest done"; tail -3 gpurun_out/pytest_t.log )
-( timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_pretok.py tests/test_normalize.py -q -m gpu -p no:cacheprovider -x > gpurun_out/memcheck_prepass.log 2>&1; echo "memcheck prepass rc=$?"; tail -4 gpurun_out/memcheck_prepass.log )
+# (compute-sanitizer is closed on this pool: the memcheck run of the pre-pass tests was refused)
 ( timeout 1500 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_final_n1.json 2> gpurun_out/bench_final_n1.log; echo "bench n1 rc=$?"; grep -v "warmup" gpurun_out/bench_final_n1.log | tail -2 | cut -c1-300 )
 python - <<'PY'
 import json
