@@ -357,6 +357,12 @@ class HostCore {
     }
     return got;
   }
+  // Is a look-ahead entry made earlier still what it was (its pair untouched since)? A merge in between that changed the
+  // pair's frequency has made the heap entry stale: the list it came from has to be made again.
+  bool peek_still_valid(const Peek &e) const {
+    const PairInfo *info = pairs_.find(e.a, e.b);
+    return info && info->freq == e.freq;
+  }
   bool peek_next(int32_t *a, int32_t *b, uint64_t *freq) {  // the first entry only
     Peek p;
     if (peek_next(&p, 1) != 1) return false;

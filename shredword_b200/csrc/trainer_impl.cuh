@@ -1415,8 +1415,22 @@ class TrainerImpl {
     //   late hint  for q+1: sent right after the look-ahead (the device checks merge q)
     //   early hint for q+2: sent as soon as the records of merge q have arrived and show that q pushed nothing >= F
     //                       (the device checks merge q+1) -- it is on its way a whole merge before it is needed
-    HostCore::Peek pk[2];
+    // The hints need two look-ahead entries. SWB_PEEK_DEPTH=n (3..8) asks for a longer list and reuses its tail for the following
+    // merges instead of walking the heap again (entry i names merge q+1+i under conditions that do not depend on WHEN the host
+    // looks, so one merge later the list minus its first entry is still valid if the merge applied in between pushed nothing
+    // at or above the entries kept and left their frequencies alone). Exact (tests/test_dist_host_logic.py checks the claims
+    // to depth 6) and it takes 46 ms of heap walking off a config-3 step -- but the step got 25-35 ms SLOWER in an alternating
+    // A/B on one box (fewer hints accepted, the device waits longer for the host), so the default stays at 2: a fresh walk per merge.
+    constexpr size_t PEEK_MAX = 8;
+    static const size_t peek_depth = [] {
+      const char *e = getenv("SWB_PEEK_DEPTH");
+      const size_t v = e ? (size_t)strtoul(e, nullptr, 10) : 2;
+      return std::min<size_t>(std::max<size_t>(v, 2), (size_t)8);
+    }();
+    static_assert(PEEK_MAX == 8, "SWB_PEEK_DEPTH is clamped to the list's capacity");
+    HostCore::Peek pk[PEEK_MAX];
     size_t npk = 0;
+    uint64_t last_mp = ~0ull;  // largest frequency the merge applied last made the heap push; ~0 = unknown
     unsigned long long n_early = 0;
     static const bool no_early = getenv("SWB_NO_EARLY_HINTS") && atoi(getenv("SWB_NO_EARLY_HINTS")) > 0;
     unsigned long long hint_ring[4][2];  // what was sent for sequence number q: [q & 3] = {early, late}
@@ -1429,11 +1443,18 @@ class TrainerImpl {
       hint_ring[hint_seq & 3][which] = key;
       stats.hints_sent++;
     };
-    auto look_ahead = [&]() {
-      npk = 0;
-      if (!hints) return;
+    auto look_ahead = [&](int32_t ca, int32_t cb) {  // (ca, cb) = the merge that has just been chosen (host ids)
+      if (!hints) { npk = 0; return; }
       const double th0 = now_ms();
-      npk = core.peek_next(pk, 2);
+      while (npk > 0 && pk[npk - 1].freq <= last_mp) npk--;  // entries the merge applied last may have overtaken (or: nothing known about it)
+      bool reuse = npk >= 3 && pk[0].a == ca && pk[0].b == cb;
+      for (size_t i = 1; reuse && i < npk; i++) reuse = core.peek_still_valid(pk[i]);  // (a pair the last merge touched: its entry is stale now)
+      if (reuse) {
+        for (size_t i = 1; i < npk; i++) pk[i - 1] = pk[i];
+        npk--;
+      } else {
+        npk = core.peek_next(pk, peek_depth);
+      }
       stats.host_peek_ms += now_ms() - th0;
     };
     unsigned long long *trace_p = nullptr;
@@ -1479,7 +1500,7 @@ class TrainerImpl {
     int done = 0;
     unsigned long long cur_key = ((unsigned long long)(uint32_t)da << 32) | (uint32_t)db;
     const uint64_t minf = tr_->config.min_pair_freq;
-    look_ahead();
+    look_ahead(a, b);
     if (npk >= 1 && max_merges > 1) send_hint(seq_base + 2, pk[0], 1, sender);
     for (;;) {
       const double tw0 = now_ms();
@@ -1501,10 +1522,14 @@ class TrainerImpl {
         stats.hints_taken++;
       }
       hint_ring[(q + 2) & 3][0] = hint_ring[(q + 2) & 3][1] = NO_HINT;
-      if (npk >= 2 && done + 2 < max_merges && !(flags & ~64u) && n <= recs_.size()) {  // early hint for merge q+2
+      last_mp = ~0ull;
+      if (hints && !(flags & ~64u) && n <= recs_.size()) {  // the largest frequency this merge makes the heap push (records carry the new frequency)
         uint64_t mp = 0;
         for (size_t i = 0; i < n; i++) { const uint64_t f = (uint64_t)hr[i].delta; if (f >= minf && f > mp) mp = f; }
-        if (mp < pk[1].freq && !no_early) {
+        last_mp = mp;
+      }
+      if (npk >= 2 && done + 2 < max_merges && last_mp != ~0ull) {  // early hint for merge q+2
+        if (last_mp < pk[1].freq && !no_early) {
           // With this hint the device may start merge q+2 -- whose results go into THIS record buffer -- before the records of
           // merge q have been applied below: they move to private memory first.
           rec_copy_.assign(hr, hr + n);
@@ -1536,7 +1561,7 @@ class TrainerImpl {
       da = to_dev(na); db = to_dev(nb);
       cur_key = ((unsigned long long)(uint32_t)da << 32) | (uint32_t)db;
       sender.send(cur_key, (unsigned int)nn, 0);
-      look_ahead();
+      look_ahead(na, nb);
       if (npk >= 1 && done + 1 < max_merges) send_hint(seq_base + done + 2, pk[0], 1, sender);  // late hint for the merge after this command's
     }
     if (launcher.th.joinable()) launcher.th.join();  // (a serialising tool: the launch call returns now that the kernel has been told to stop)

@@ -113,3 +113,24 @@ def test_reference_python_package_binds_our_library(product, tmp_path):
   ) % (str(tmp_path), str(corpus), str(corpus), str(tmp_path / "m.model"), str(tmp_path / "m.vocab"))
   r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
   assert "BOUND_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_build_staleness_is_decided_by_source_digest_not_mtimes():
+  """The tree is copied to the GPU box (modification times change, N ranks import the package at once): the library is
+  rebuilt only when the digest of its sources differs from the one recorded next to it, and one builder at a time."""
+  import os
+  from shredword_b200 import build as B
+  B.build()
+  assert not B.needs_build()
+  stamp = open(B.STAMP).read()
+  assert stamp.strip() == B.source_digest()
+  now = os.path.getmtime(B.OUT)
+  try:
+    os.utime(B.OUT, (now - 10_000, now - 10_000))  # an "old" library next to "newer" sources: still current
+    assert not B.needs_build()
+    open(B.STAMP, "w").write("0" * 64 + "\n")      # another digest: stale
+    assert B.needs_build()
+  finally:
+    open(B.STAMP, "w").write(stamp)
+    os.utime(B.OUT, (now, now))
+  assert not B.needs_build()

@@ -96,7 +96,7 @@ def test_look_ahead_is_exact_and_leaves_the_heap_alone(name, product, oracle_mod
   from shredword_b200.trainer import _ptr
   kw = cases.kwargs(name)
   minf = kw["min_pair_freq"]
-  DEPTH = 3
+  DEPTH = 6  # (the resident loop keeps a list of up to 8 and reuses its tail for the following merges)
   sh = oracle_mod.Oracle(kw["target_vocab_size"], kw.get("unk_id", 0), kw.get("character_coverage", 0.995), minf)
   sh.load_buffer(cases.corpus(name))
   t = product.BPETrainer(**kw)
