@@ -245,3 +245,53 @@ def test_random_small_corpora_replica_matches_oracle(block, product, oracle_mod)
       done += 1
     assert done == n_full, (seed, kw, done, n_full)
     assert np.array_equal(full.merges, t.merges_array()), (seed, kw)
+
+
+class OracleEncoder:
+  """Stands in for this rank's BPEEncoder in the CPU test of the document-parallel encode (same `encode` method)."""
+
+  def __init__(self, O, merges, byte_map):
+    self.O, self.merges, self.byte_map = O, merges, byte_map
+
+  def encode(self, text):
+    return self.O.encode(self.merges, self.byte_map, bytes(text))
+
+
+def _encode_worker(rank, world, port, out_dir):
+  sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+  import torch.distributed as dist
+  import oracle as O
+  from shredword_b200.distributed import DistributedBPEEncoder
+  dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+  merges = np.load(os.path.join(out_dir, "merges.npy"))
+  byte_map = np.load(os.path.join(out_dir, "byte_map.npy"))
+  text = np.frombuffer(open(os.path.join(out_dir, "text.bin"), "rb").read(), dtype=np.uint8)
+  enc = DistributedBPEEncoder(OracleEncoder(O, merges, byte_map))
+  ids, off, total = enc.encode_whole(text)
+  np.save(os.path.join(out_dir, f"ids_{rank}.npy"), np.asarray(ids, dtype=np.int32))
+  np.save(os.path.join(out_dir, f"meta_{rank}.npy"), np.array([off, total], dtype=np.int64))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_gloo_world2_document_parallel_encode(product, oracle_mod, tmp_path):
+  """Document-parallel encode (BASELINE config 4) over gloo, world_size 2: every rank encodes its newline-cut share, the
+  token counts are all-gathered; the shares placed at the gathered offsets are the encoding of the whole text."""
+  import socket
+  name = "multi_ties"
+  kw = cases.kwargs(name)
+  o = oracle_mod.Oracle(kw["target_vocab_size"], kw.get("unk_id", 0), kw.get("character_coverage", 0.995), kw["min_pair_freq"])
+  data = cases.corpus(name)
+  o.load_buffer(data); o.train()
+  byte_map = np.asarray(o.byte_map(kw.get("unk_id", 0)), dtype=np.int32)
+  np.save(tmp_path / "merges.npy", o.merges); np.save(tmp_path / "byte_map.npy", byte_map)
+  (tmp_path / "text.bin").write_bytes(bytes(data))
+  want = np.asarray(oracle_mod.encode(o.merges, byte_map, bytes(data)), dtype=np.int32)
+  s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+  mp.spawn(_encode_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  got = np.full(want.size, -7, dtype=np.int32)
+  for r in range(2):
+    ids = np.load(tmp_path / f"ids_{r}.npy"); off, total = np.load(tmp_path / f"meta_{r}.npy")
+    assert total == want.size and len(ids) > 0
+    got[off: off + len(ids)] = ids
+  assert np.array_equal(got, want)
