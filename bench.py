@@ -484,7 +484,9 @@ def main():
               "look_ahead": {k: st_res[-1].get(k) for k in ("hints_sent", "hints_taken", "hints_rejected", "host_peek_ms")},
               "host_split_ms": {k: st_res[-1].get(k) for k in ("host_pop_ms", "host_wait_ms", "host_apply_ms")},
               "merge_loop": MERGE_LOOP if world > 1 else "single GPU",
-              "collectives_per_step": st_res[-1].get("collectives"), "exchange_bytes_per_step": st_res[-1].get("exchange_bytes"), "wall_ms_per_step": wall_res,
+              "collectives_per_step": st_res[-1].get("collectives"), "exchange_bytes_per_step": st_res[-1].get("exchange_bytes"),
+              "exchange_ms": float(np.mean([s_.get("exchange_ns", 0) for s_ in st_res])) / 1e6,  # (inside load_ms: sizes + word arenas + metadata all-gathers, merge of the N tables)
+              "wall_ms_per_step": wall_res,
               "ms_per_step_with_kernel_timing": ms_tim},
   }
 

@@ -144,7 +144,8 @@ typedef struct SwbStats {
   uint64_t records, heap_pushes, heap_pops, heap_peak;             /* host replica counters */
   uint64_t collectives, exchange_bytes;                            /* multi-GPU: NCCL all-gathers and their bytes */
   uint64_t resident_spill_merges; /* LOCAL merges of the resident kernel whose deltas overflowed shared memory into the global pair table */
-  uint64_t reserved_[4];
+  uint64_t exchange_ns;                                             /* multi-GPU load: host time from the first all-gather to the merged global word table */
+  uint64_t reserved_[3];
   /* resident cluster kernel: merges done by the leader cluster alone / by the whole grid, and the device time
    * they took (command seen -> result published, %globaltimer; also added to merge_kernel_ms) */
   uint64_t resident_local_merges, resident_grid_merges;

@@ -43,7 +43,7 @@ class SwbStats(Structure):
               ("host_pop_ms", c_double), ("host_launch_ms", c_double), ("host_wait_ms", c_double), ("host_apply_ms", c_double),
               ("records", c_uint64), ("heap_pushes", c_uint64), ("heap_pops", c_uint64), ("heap_peak", c_uint64),
               ("collectives", c_uint64), ("exchange_bytes", c_uint64),
-              ("resident_spill_merges", c_uint64), ("reserved_", c_uint64 * 4),
+              ("resident_spill_merges", c_uint64), ("exchange_ns", c_uint64), ("reserved_", c_uint64 * 3),
               ("resident_local_merges", c_uint64), ("resident_grid_merges", c_uint64),
               ("resident_local_ms", c_double), ("resident_grid_ms", c_double),
               ("hints_sent", c_uint64), ("hints_taken", c_uint64), ("hints_rejected", c_uint64), ("host_peek_ms", c_double),

@@ -354,6 +354,7 @@ class TrainerImpl {
         sync();
       }
       wslots.release();
+      const double t_ex0 = now_ms();  // (the stream is idle here: the exchange's host time is its device time)
       DevBuf<unsigned long long> d_sizes(2 * (size_t)nranks);
       const unsigned long long mine[2] = {Wl, arena_bytes};
       SWB_CUDA(cudaMemcpyAsync(d_sizes.get() + 2 * rank, mine, 16, cudaMemcpyHostToDevice, stream_));
@@ -389,6 +390,7 @@ class TrainerImpl {
       launched();
       SWB_CUDA(cudaMemcpyAsync(h_scal, scalars_.get(), sizeof h_scal, cudaMemcpyDeviceToHost, stream_));
       sync();
+      stats.exchange_ns += (uint64_t)((now_ms() - t_ex0) * 1e6);
       W = h_scal[0];
       if (W >= (1ull << 31)) throw Error("more than 2^31 unique words");
       DevBuf<unsigned long long> sk(W), sv(W), sk2(W), sv2(W);

@@ -134,3 +134,22 @@ def test_build_staleness_is_decided_by_source_digest_not_mtimes():
     open(B.STAMP, "w").write(stamp)
     os.utime(B.OUT, (now, now))
   assert not B.needs_build()
+
+
+def test_stats_struct_layout_matches_the_header(tmp_path):
+  """The ctypes mirror of SwbStats (shredword_b200/cbase.py) against the C declaration in include/shredword_b200.h,
+  compiled here with gcc: same size, same offsets of every field."""
+  import ctypes
+  import subprocess
+  from shredword_b200.cbase import SwbStats
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  fields = [k for k, _ in SwbStats._fields_]
+  src = tmp_path / "layout.c"
+  src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(void) { printf("%%zu", sizeof(SwbStats));\n%s\nreturn 0; }\n'
+                 % (os.path.join(root, "include", "shredword_b200.h"),
+                    "\n".join('printf(" %%zu", offsetof(SwbStats, %s));' % f for f in fields)))
+  exe = tmp_path / "layout"
+  subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+  got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+  assert got[0] == ctypes.sizeof(SwbStats)
+  assert got[1:] == [getattr(SwbStats, f).offset for f in fields]
